@@ -1,0 +1,208 @@
+/*
+ * sparseconv_b200.h — C ABI of the B200-native sparse-convolution hot path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (POSTECH-CVLab/NeRF-Downstream) reaches this path only through the Python
+ * package `MinkowskiEngine`, whose native backend (`MinkowskiEngineBackend._C`,
+ * third-party, not vendored) it imports at
+ *   co3d_3d/src/models/mink/modules/sparse_conv.py:7-12.
+ * Every entry point below cites the reference call site whose behaviour it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; the text of the last
+ *     error on the calling thread is returned by spc_last_error();
+ *   - all data pointers are DEVICE pointers (torch `tensor.data_ptr()`), sizes
+ *     are int64_t, `stream` is a cudaStream_t passed as void*;
+ *   - nothing is allocated inside: callers pass outputs and workspaces;
+ *   - no function synchronises the stream; sizes that are only known on the
+ *     device (number of unique voxels) are written to a device int32 the caller
+ *     reads back when it needs them.
+ *
+ * Coordinate rows are int32 [M,4] = (batch, x, y, z)  (co3d_3d/src/data/co3d.py:121
+ * strips column 0 as the batch index).  Supported range: batch in [0,1022],
+ * x,y,z in [-131072,131071]; anything else sets the error flag (`status[0]`).
+ */
+#ifndef SPARSECONV_B200_H_
+#define SPARSECONV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPC_ABI_VERSION 1
+
+/* bytes per hash-table slot: {u64 key, u32 first_row, u32 map_row} */
+#define SPC_SLOT_BYTES 16
+
+/* coordinate source kinds for spc_coords_insert */
+#define SPC_SRC_FLOAT 0   /* float32 [N,4]; quantised with floor(x/ts)*ts  */
+#define SPC_SRC_INT 1     /* int32   [N,4]; inserted as is                  */
+#define SPC_SRC_STRIDE 2  /* int32   [N,4]; floor_div(c, ts)*ts per axis    */
+
+/* precision modes of the convolution kernels */
+#define SPC_PREC_FP32 0   /* CUDA-core FP32 FMA, fp32-faithful             */
+#define SPC_PREC_TF32 1   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+
+int spc_abi_version(void);
+const char* spc_last_error(void);
+
+/* Number of table slots to allocate for n keys (power of two, load <= 0.5). */
+int64_t spc_table_slots(int64_t n);
+/* Workspace bytes needed by spc_coords_insert for n source rows. */
+int64_t spc_coords_insert_workspace(int64_t n);
+
+/*
+ * Voxel quantisation + coordinate hashing + unique / inverse map.
+ * Replaces ME.TensorField(...).sparse() (co3d_3d/src/models/mink/resnet.py:164,
+ * res16unet.py:392, base_model.py:10-13) and CoordinateManager.stride()
+ * (modules/sparse_conv.py:403-405).
+ *   src        [n,4] float32 or int32 (see SPC_SRC_*)
+ *   ts[3]      tensor stride applied when quantising (1,1,1 for plain floor)
+ *   slots      n_slots*16 bytes, n_slots = spc_table_slots(n); (re)initialised here
+ *   out_coords [n,4] int32; rows [0,M) valid, first-occurrence order
+ *   out_first  [n] int32;  out_first[r] = first source row of voxel r (ME unique_index)
+ *   out_inverse[n] int32;  voxel row of every source row (ME inverse_mapping)
+ *   out_count  [n] int32;  rows [0,M): number of source rows per voxel
+ *   status     [2] int32;  status[0]=M, status[1]=error flag (1 = coordinate out of range)
+ */
+int spc_coords_insert(const void* src, int64_t n, int src_kind, const int32_t* ts,
+                      void* slots, int64_t n_slots,
+                      int32_t* out_coords, int32_t* out_first, int32_t* out_inverse,
+                      int32_t* out_count, int32_t* status,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Kernel-map construction (CoordinateManager.kernel_map, sparse_conv.py:90-96,
+ * :197-204).  For every out row o and offset k: nbr[k*M_out+o] = in row whose
+ * coordinate is coord_out[o] + offsets[k], or -1.
+ *   offsets  HOST pointer, [K,3] int32, already scaled by in tensor stride x dilation;
+ *            index order: first spatial axis fastest (sparse_conv.py:375-379)
+ *   nbr      [K, M_out] int32 (offset-major)
+ *   tap_count[K] int32 device: number of pairs per offset (zeroed here)
+ */
+int spc_kernel_map(const void* in_slots, int64_t in_n_slots,
+                   const int32_t* out_coords, int64_t m_out,
+                   const int32_t* offsets_host, int K,
+                   int32_t* nbr, int32_t* tap_count, void* stream);
+
+/*
+ * Per-tile offset mask: bit k of mask[t] is set iff some row of the 128-row tile t has a
+ * neighbour at offset k.  The tcgen05 convolution skips offsets whose bit is clear.
+ *   mask [ceil(m/128)] uint32, K <= 32.
+ */
+int spc_tile_mask(const int32_t* nbr, int64_t m, int K, uint32_t* mask, void* stream);
+
+/* Transposed dense map: nbr_t[k*M_in + i] = o  iff  nbr[k*M_out + o] = i. */
+int spc_kernel_map_transpose(const int32_t* nbr, int64_t m_out, int64_t m_in, int K,
+                             int32_t* nbr_t, void* stream);
+
+/*
+ * ME-style pair lists (sparse_conv.py:122-143): for each offset k the pairs
+ * (in,out) ascending in out row, concatenated k-major.
+ *   pairs [2, P] int32 (row 0 = in rows, row 1 = out rows), P = sum tap_count
+ *   tap_offset [K+1] int32 device: start of each offset's segment
+ *   workspace: spc_pairs_workspace(m_out, K) bytes
+ */
+int64_t spc_pairs_workspace(int64_t m_out, int K);
+int spc_kernel_map_pairs(const int32_t* nbr, int64_t m_out, int K, int64_t pair_capacity,
+                         int32_t* pairs, int32_t* tap_offset,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Per-voxel feature reduction of TensorField.sparse() (UNWEIGHTED_AVERAGE,
+ * res16unet.py:665-667): out[r] = mean/sum of feats[j] over inverse[j]==r.
+ *   mode 0 = average, 1 = sum.  `out` [m, C] is zeroed here.
+ */
+int spc_segment_reduce(const float* feats, const int32_t* inverse, const int32_t* count,
+                       int64_t n, int64_t m, int C, int mode, float* out, void* stream);
+/* Backward of the above and SparseTensor.slice (res16unet.py:435):
+ * out[j] = src[index[j]] * (count ? 1/count[index[j]] : 1). */
+int spc_gather_rows(const float* src, const int32_t* index, const int32_t* count,
+                    int64_t n, int C, float* out, void* stream);
+/* out[index[j]] += src[j]  (backward of slice); out zeroed here. m rows. */
+int spc_scatter_add_rows(const float* src, const int32_t* index, int64_t n, int64_t m, int C,
+                         float* out, void* stream);
+
+/*
+ * Sparse convolution (MinkowskiConvolution / MinkowskiConvolutionTranspose,
+ * modules/common.py:117-125,172-180; arithmetic restated at sparse_conv.py:122-143).
+ *   fwd  : out[o,:]  = sum_k  in[nbr[k,o],:] @ W[k]            (+ bias)
+ *   dgrad: din[i,:]  = sum_k  dout[nbr_t[k,i],:] @ W[k]^T
+ *   wgrad: dW[k]     = sum_o  in[nbr[k,o],:]^T  dout[o,:]
+ *   W is [K, Cin, Cout] row-major fp32.
+ *   tile_mask / tile_mask_t: spc_tile_mask of nbr / nbr_t, or NULL (= all offsets active).
+ *   workspace: spc_conv_workspace(...) bytes (packed weights for the TF32 path).
+ */
+void spc_debug_force_mt(int mt);
+int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
+int spc_conv_fwd(const float* in, const float* w, const float* bias, const int32_t* nbr,
+                 const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
+                 float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int spc_conv_dgrad(const float* dout, const float* w, const int32_t* nbr_t,
+                   const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
+                   float* din, void* workspace, int64_t workspace_bytes, void* stream);
+int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
+                   int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
+                   float* dw, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * BatchNorm over voxel rows (MinkowskiBatchNorm == nn.BatchNorm1d on .F,
+ * modules/common.py:24) with optional fused ReLU and residual add
+ * (resnet_block.py:66-67).
+ *   stats  : sum[c], sumsq[c] over m rows -> mean, biased var (double-accumulated)
+ *   apply  : y = (x-mean)*rsqrt(var+eps)*gamma+beta (+res) ; relu optional
+ *   bwd    : dx, dgamma, dbeta (and dres = masked dy when res was fused)
+ */
+int64_t spc_bn_workspace(int64_t m, int C);
+int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
+                 const float* beta, const float* residual, int64_t m, int C, float eps,
+                 int relu, float* y, void* stream);
+int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mean,
+               const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+               int training, float* dx, float* dresidual, float* dgamma, float* dbeta,
+               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* y = relu(x) ; dx = dy * (y > 0) ; y = a + b  (MinkowskiReLU, SparseTensor +=). */
+int spc_relu_fwd(const float* x, int64_t n, float* y, void* stream);
+int spc_relu_bwd(const float* y, const float* dy, int64_t n, float* dx, void* stream);
+int spc_add(const float* a, const float* b, int64_t n, float* y, void* stream);
+
+/*
+ * Local pooling with kernel_size == stride (MinkowskiSumPooling / AvgPooling,
+ * resnet.py:62-64, co3d.py:107-111) over the stride map `parent` (in row ->
+ * out row, the inverse map of spc_coords_insert with SPC_SRC_STRIDE).
+ *   fwd: out[o] = sum_k in[nbr[k,o]]  (avg: / number of present inputs), a gather over the
+ *        kernel map `nbr` [K, m_out] of the pooling region, so no atomics are needed.
+ *   bwd: din[j] = dout[parent[j]] (avg: / count[parent[j]]) == spc_gather_rows(dout, parent, count).
+ */
+int spc_pool_fwd(const float* in, const int32_t* nbr, int64_t m_out, int C, int K, int avg,
+                 float* out, void* stream);
+
+/*
+ * Global average / sum pooling (MinkowskiGlobalAvgPooling, resnet.py:18,175):
+ * out[b,:] = mean over rows with batch index b; rows ordered by batch index.
+ *   coords [m,4] int32; n_batch rows of output; cnt [n_batch] int32 (written).
+ */
+int spc_global_pool_fwd(const float* in, const int32_t* coords, int64_t m, int C, int n_batch,
+                        int avg, float* out, int32_t* cnt, void* stream);
+int spc_global_pool_bwd(const float* dout, const int32_t* coords, const int32_t* cnt, int64_t m,
+                        int C, int n_batch, int avg, float* din, void* stream);
+
+/* Fused SGD step on a flat arena (co3d_cls.gin:33-39; optim.py:60-69):
+ * g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf. */
+int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
+                 float momentum, float weight_decay, float grad_scale, int first_step,
+                 void* stream);
+
+/* Number of kernels launched through this library since load (bench `gpu_launches`). */
+int64_t spc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSECONV_B200_H_ */

@@ -1,0 +1,112 @@
+// common.cuh — shared helpers for the sparseconv_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/sparseconv_b200.h"
+
+namespace spc {
+
+// ---- error plumbing -------------------------------------------------------
+extern thread_local char g_last_error[512];
+extern std::atomic<long long> g_launch_count;
+
+inline int fail(const char* what, const char* detail) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, detail);
+  return -1;
+}
+inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail(what, cudaGetErrorString(e));
+}
+#define SPC_CUDA(expr)                                    \
+  do {                                                    \
+    int _rc = ::spc::check_cuda((expr), #expr);           \
+    if (_rc) return _rc;                                  \
+  } while (0)
+// call right after a kernel launch
+#define SPC_LAUNCHED(name)                                        \
+  do {                                                            \
+    ::spc::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+    int _rc = ::spc::check_cuda(cudaGetLastError(), name);        \
+    if (_rc) return _rc;                                          \
+  } while (0)
+#define SPC_REQUIRE(cond, msg)                 \
+  do {                                         \
+    if (!(cond)) return ::spc::fail(__func__, msg); \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- coordinate keys --------------------------------------------------------
+// 64-bit key = batch:10 | x:18 | y:18 | z:18 (offset binary).  All-ones = empty.
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kCoordBias = 131072;         // 2^17
+constexpr unsigned kCoordRange = 262144u;  // 2^18
+constexpr unsigned kBatchMax = 1023u;      // batch index must be < 1023
+
+struct __align__(16) Slot {
+  unsigned long long key;
+  unsigned int first;  // smallest source row that produced this key
+  unsigned int row;    // row in the coordinate map
+};
+static_assert(sizeof(Slot) == SPC_SLOT_BYTES, "slot size");
+
+__device__ __forceinline__ bool pack_key(int b, int x, int y, int z, unsigned long long& key) {
+  unsigned ux = (unsigned)(x + kCoordBias), uy = (unsigned)(y + kCoordBias),
+           uz = (unsigned)(z + kCoordBias);
+  bool ok = ((unsigned)b < kBatchMax) & (ux < kCoordRange) & (uy < kCoordRange) & (uz < kCoordRange);
+  key = ((unsigned long long)(unsigned)b << 54) | ((unsigned long long)ux << 36) |
+        ((unsigned long long)uy << 18) | (unsigned long long)uz;
+  return ok;
+}
+__device__ __forceinline__ int4 unpack_key(unsigned long long key) {
+  int4 c;
+  c.x = (int)(key >> 54);
+  c.y = (int)((key >> 36) & 0x3FFFFu) - kCoordBias;
+  c.z = (int)((key >> 18) & 0x3FFFFu) - kCoordBias;
+  c.w = (int)(key & 0x3FFFFu) - kCoordBias;
+  return c;
+}
+// splitmix64 finaliser; buckets are pairs of slots (one 32-byte sector).
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
+  k ^= k >> 30;
+  k *= 0xbf58476d1ce4e5b9ull;
+  k ^= k >> 27;
+  k *= 0x94d049bb133111ebull;
+  k ^= k >> 31;
+  return k;
+}
+
+// Read-only probe of a 2-slot bucket table.  Returns map row or -1.
+__device__ __forceinline__ int table_lookup(const Slot* __restrict__ slots,
+                                            unsigned long long bucket_mask,
+                                            unsigned long long key) {
+  unsigned long long b = hash_key(key) & bucket_mask;
+  const uint4* base = reinterpret_cast<const uint4*>(slots);
+  for (;;) {
+    uint4 s0 = __ldg(base + 2 * b);
+    uint4 s1 = __ldg(base + 2 * b + 1);
+    unsigned long long k0 = ((unsigned long long)s0.y << 32) | s0.x;
+    unsigned long long k1 = ((unsigned long long)s1.y << 32) | s1.x;
+    if (k0 == key) return (int)s0.w;
+    if (k1 == key) return (int)s1.w;
+    // slots of a bucket fill in order and nothing is ever deleted
+    if (k0 == kEmptyKey || k1 == kEmptyKey) return -1;
+    b = (b + 1) & bucket_mask;
+  }
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+}  // namespace spc

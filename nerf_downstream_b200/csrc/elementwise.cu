@@ -1,0 +1,483 @@
+// elementwise.cu — bandwidth-bound kernels on voxel feature rows [M, C] (fp32, row-major):
+// BatchNorm statistics / apply / backward with fused ReLU and residual add, ReLU, add,
+// local and global pooling, fused SGD.  SURVEY.md §8a rows a7-a10.
+//
+// Thread mapping for all [M,C] kernels: a block owns R consecutive rows per iteration and
+// every thread a fixed group of VEC channels (VEC = 4 when C % 4 == 0, else 1), so
+//   - per-channel parameters (scale/shift) live in registers,
+//   - a warp always touches one contiguous span of memory (rows are contiguous),
+//   - the grid is a multiple of the SM count and strides over row groups.
+#include "common.cuh"
+
+namespace spc {
+
+struct RowMap {
+  int lanes;    // threads per row = C / VEC
+  int rows;     // rows per block iteration
+  int threads;  // lanes * rows
+};
+static inline RowMap make_row_map(int C, int vec) {
+  RowMap r;
+  r.lanes = C / vec;
+  r.rows = r.lanes >= 256 ? 1 : 256 / r.lanes;
+  r.threads = r.lanes * r.rows;
+  return r;
+}
+static inline int pick_vec(int C, const void* a, const void* b = nullptr, const void* c = nullptr,
+                           const void* d = nullptr) {
+  auto al = [](const void* p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
+  return (C % 4 == 0 && al(a) && al(b) && al(c) && al(d)) ? 4 : 1;
+}
+static inline int pick_grid(int64_t m, int rows_per_iter, int blocks_per_sm) {
+  int64_t need = ceil_div(m, rows_per_iter);
+  int64_t cap = (int64_t)kNumSMs * blocks_per_sm;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <int VEC> struct Vec;
+template <> struct Vec<1> {
+  float v[1];
+  __device__ static Vec load(const float* p) { Vec r; r.v[0] = *p; return r; }
+  __device__ void store(float* p) const { *p = v[0]; }
+};
+template <> struct Vec<4> {
+  float v[4];
+  __device__ static Vec load(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+  }
+  __device__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// column reductions: up to two sums per channel, partials per block, double finalise
+// ---------------------------------------------------------------------------
+// MODE 0: s0 = sum x, s1 = sum x^2                     (BN statistics)
+// MODE 1: s0 = sum dy', s1 = sum dy' * (x - mean)      (BN backward; dy' = relu-masked dy)
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(1024)
+col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                  const float* __restrict__ dy, const float* __restrict__ mean, long long m, int C,
+                  int lanes, int rows, int relu, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [rows][2*C]
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const int c0 = lane * VEC;
+  float s0[VEC], s1[VEC], mu[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { s0[j] = 0.f; s1[j] = 0.f; mu[j] = MODE == 1 ? mean[c0 + j] : 0.f; }
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
+    const long long off = r * C + c0;
+    Vec<VEC> xv = Vec<VEC>::load(x + off);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s0[j] += xv.v[j]; s1[j] += xv.v[j] * xv.v[j]; }
+    } else {
+      Vec<VEC> g = Vec<VEC>::load(dy + off);
+      if (relu) {
+        Vec<VEC> yv = Vec<VEC>::load(y + off);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) if (!(yv.v[j] > 0.f)) g.v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s0[j] += g.v[j]; s1[j] += g.v[j] * (xv.v[j] - mu[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sm[rl * 2 * C + c0 + j] = s0[j];
+    sm[rl * 2 * C + C + c0 + j] = s1[j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < rows; ++q) acc += sm[q * 2 * C + idx];
+    partial[(long long)blockIdx.x * 2 * C + idx] = acc;
+  }
+}
+
+// out0[c] = S0/m, out1[c] = S1/m - (S0/m)^2          (MODE 0: mean, biased var)
+// out0[c] = S0,   out1[c] = S1 * rsqrt(var+eps)       (MODE 1: dbeta, dgamma)
+template <int MODE>
+__global__ void col_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                    long long m, const float* __restrict__ var, float eps,
+                                    float* __restrict__ out0, float* __restrict__ out1,
+                                    float* __restrict__ raw /* [2C] sums, optional */) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += (double)partial[(long long)i * 2 * C + c];
+    b += (double)partial[(long long)i * 2 * C + C + c];
+  }
+  if (raw) { raw[c] = (float)a; raw[C + c] = (float)b; }
+  if (MODE == 0) {
+    double mu = a / (double)m;
+    double v = b / (double)m - mu * mu;
+    out0[c] = (float)mu;
+    out1[c] = (float)(v > 0.0 ? v : 0.0);
+  } else {
+    out0[c] = (float)a;
+    out1[c] = (float)(b / sqrt((double)var[c] + (double)eps));
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(1024)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                const float* __restrict__ var, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ res, long long m, int C,
+                int lanes, int rows, float eps, int relu, float* __restrict__ y) {
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const int c0 = lane * VEC;
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float g = gamma ? gamma[c0 + j] : 1.f, b = beta ? beta[c0 + j] : 0.f;
+    sc[j] = g * rsqrtf(var[c0 + j] + eps);
+    sh[j] = b - mean[c0 + j] * sc[j];
+  }
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
+    const long long off = r * C + c0;
+    Vec<VEC> xv = Vec<VEC>::load(x + off), o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = fmaf(xv.v[j], sc[j], sh[j]);
+    if (res) {
+      Vec<VEC> rv = Vec<VEC>::load(res + off);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] += rv.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
+    }
+    o.store(y + off);
+  }
+}
+
+// dx = scale * (dy' - sum_dy/m - (x-mean) * invstd^2 * sum_dy_xmu/m), dres = dy'
+template <int VEC>
+__global__ void __launch_bounds__(1024)
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                    const float* __restrict__ dy, const float* __restrict__ mean,
+                    const float* __restrict__ var, const float* __restrict__ gamma,
+                    const float* __restrict__ sums /* [2C]: sum dy', sum dy'(x-mean) */,
+                    long long m, int C, int lanes, int rows, float eps, int relu, int training,
+                    float* __restrict__ dx, float* __restrict__ dres) {
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const int c0 = lane * VEC;
+  float sc[VEC], mu[VEC], k0[VEC], k1[VEC];
+  const float inv_m = 1.f / (float)m;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float istd = rsqrtf(var[c0 + j] + eps);
+    sc[j] = (gamma ? gamma[c0 + j] : 1.f) * istd;
+    mu[j] = mean[c0 + j];
+    k0[j] = training ? sums[c0 + j] * inv_m : 0.f;
+    k1[j] = training ? sums[C + c0 + j] * inv_m * istd * istd : 0.f;
+  }
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
+    const long long off = r * C + c0;
+    Vec<VEC> g = Vec<VEC>::load(dy + off);
+    if (relu) {
+      Vec<VEC> yv = Vec<VEC>::load(y + off);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) if (!(yv.v[j] > 0.f)) g.v[j] = 0.f;
+    }
+    if (dres) g.store(dres + off);
+    Vec<VEC> xv = Vec<VEC>::load(x + off), o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = sc[j] * (g.v[j] - k0[j] - (xv.v[j] - mu[j]) * k1[j]);
+    o.store(dx + off);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// flat elementwise
+// ---------------------------------------------------------------------------
+// OP 0: y = max(a,0)   OP 1: y = b * (a > 0)   OP 2: y = a + b
+template <int OP>
+__global__ void __launch_bounds__(256)
+flat_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+            float* __restrict__ y, int vec_ok) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n4 = vec_ok ? n / 4 : 0;
+  for (long long q = i; q < n4; q += stride) {
+    float4 av = reinterpret_cast<const float4*>(a)[q], o;
+    if (OP == 0) {
+      o = make_float4(fmaxf(av.x, 0.f), fmaxf(av.y, 0.f), fmaxf(av.z, 0.f), fmaxf(av.w, 0.f));
+    } else {
+      float4 bv = reinterpret_cast<const float4*>(b)[q];
+      if (OP == 1) o = make_float4(av.x > 0.f ? bv.x : 0.f, av.y > 0.f ? bv.y : 0.f,
+                                   av.z > 0.f ? bv.z : 0.f, av.w > 0.f ? bv.w : 0.f);
+      else o = make_float4(av.x + bv.x, av.y + bv.y, av.z + bv.z, av.w + bv.w);
+    }
+    reinterpret_cast<float4*>(y)[q] = o;
+  }
+  for (long long q = n4 * 4 + i; q < n; q += stride) {
+    float av = a[q];
+    if (OP == 0) y[q] = fmaxf(av, 0.f);
+    else if (OP == 1) y[q] = av > 0.f ? b[q] : 0.f;
+    else y[q] = av + b[q];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+           float lr, float mom, float wd, float gscale, int first) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float w = p[i];
+    float d = fmaf(wd, w, g[i] * gscale);
+    float b = first ? d : fmaf(mom, buf[i], d);
+    buf[i] = b;
+    p[i] = w - lr * b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pooling
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(1024)
+pool_fwd_kernel(const float* __restrict__ in, const int* __restrict__ nbr, long long m_out, int C,
+                int K, int lanes, int rows, int avg, float* __restrict__ out) {
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const int c0 = lane * VEC;
+  for (long long o = (long long)blockIdx.x * rows + rl; o < m_out; o += (long long)gridDim.x * rows) {
+    Vec<VEC> acc;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc.v[j] = 0.f;
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) {
+      int i = nbr[(long long)k * m_out + o];
+      if (i >= 0) {
+        Vec<VEC> v = Vec<VEC>::load(in + (long long)i * C + c0);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc.v[j] += v.v[j];
+        ++cnt;
+      }
+    }
+    if (avg && cnt > 1) {
+      float s = 1.f / (float)cnt;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc.v[j] *= s;
+    }
+    acc.store(out + o * C + c0);
+  }
+}
+
+// global pooling: rows of one batch index are (almost always) contiguous, so each thread
+// keeps a running sum and flushes with one atomic per (batch change, channel).
+__global__ void __launch_bounds__(1024)
+global_pool_fwd_kernel(const float* __restrict__ in, const int4* __restrict__ coords, long long m,
+                       int C, int n_batch, int lanes, int rows, int rows_per_block,
+                       float* __restrict__ out, int* __restrict__ cnt) {
+  const int c = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block < m ? r0 + rows_per_block : m;
+  float acc = 0.f;
+  int cur = -1, n = 0;
+  for (long long r = r0 + rl; r < r1; r += rows) {
+    int b = coords[r].x;
+    if (b != cur) {
+      if (cur >= 0 && cur < n_batch) {
+        atomicAdd(out + (long long)cur * C + c, acc);
+        if (c == 0) atomicAdd(cnt + cur, n);
+      }
+      cur = b; acc = 0.f; n = 0;
+    }
+    acc += in[r * C + c];
+    ++n;
+  }
+  if (cur >= 0 && cur < n_batch) {
+    atomicAdd(out + (long long)cur * C + c, acc);
+    if (c == 0) atomicAdd(cnt + cur, n);
+  }
+}
+
+__global__ void global_pool_norm_kernel(float* __restrict__ out, const int* __restrict__ cnt,
+                                        int n_batch, int C) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_batch * C) return;
+  int n = cnt[e / C];
+  if (n > 1) out[e] = out[e] / (float)n;
+}
+
+__global__ void __launch_bounds__(256)
+global_pool_bwd_kernel(const float* __restrict__ dout, const int4* __restrict__ coords,
+                       const int* __restrict__ cnt, long long total, int C, int n_batch, int avg,
+                       float* __restrict__ din) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  long long r = e / C;
+  int c = (int)(e - r * C);
+  int b = coords[r].x;
+  float v = 0.f;
+  if (b >= 0 && b < n_batch) {
+    v = dout[(long long)b * C + c];
+    if (avg) v = v / (float)cnt[b];
+  }
+  din[e] = v;
+}
+
+}  // namespace spc
+
+using namespace spc;
+
+#define DISPATCH_VEC(vec, ...)        \
+  if ((vec) == 4) { constexpr int VEC = 4; __VA_ARGS__; } \
+  else { constexpr int VEC = 1; __VA_ARGS__; }
+
+extern "C" {
+
+int64_t spc_bn_workspace(int64_t m, int C) {
+  (void)m;
+  return (int64_t)kNumSMs * 4 * 2 * C * 4 + 2 * C * 4 + 256;
+}
+
+static int col_reduce_launch(int mode, const float* x, const float* y, const float* dy,
+                             const float* mean, int64_t m, int C, int relu, float* partial,
+                             int* nblocks_out, cudaStream_t stream) {
+  int vec = pick_vec(C, x, y, dy);
+  RowMap rm = make_row_map(C, vec);
+  if (rm.threads > 1024) return fail("col_reduce", "C too large (max 1024 scalar / 4096 vec4)");
+  int grid = pick_grid(m, rm.rows, 4);
+  size_t smem = (size_t)rm.rows * 2 * C * sizeof(float);
+  if (smem > 48 * 1024) return fail("col_reduce", "shared memory");
+  DISPATCH_VEC(vec,
+    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, partial);
+    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, partial));
+  SPC_LAUNCHED("col_reduce_kernel");
+  *nblocks_out = grid;
+  return 0;
+}
+
+int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, void* workspace,
+                 int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
+  SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
+  float* partial = (float*)workspace;
+  int nb = 0;
+  int rc = col_reduce_launch(0, x, nullptr, nullptr, nullptr, m, C, 0, partial, &nb, stream);
+  if (rc) return rc;
+  col_finalize_kernel<0><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, nullptr, 0.f, mean, var, nullptr);
+  SPC_LAUNCHED("col_finalize_kernel");
+  return 0;
+}
+
+int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
+                 const float* beta, const float* residual, int64_t m, int C, float eps, int relu,
+                 float* y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1, "bad C");
+  if (m == 0) return 0;
+  int vec = pick_vec(C, x, residual, y);
+  RowMap rm = make_row_map(C, vec);
+  SPC_REQUIRE(rm.threads <= 1024, "C too large");
+  int grid = pick_grid(m, rm.rows, 8);
+  DISPATCH_VEC(vec, bn_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
+      x, mean, var, gamma, beta, residual, m, C, rm.lanes, rm.rows, eps, relu, y));
+  SPC_LAUNCHED("bn_apply_kernel");
+  return 0;
+}
+
+int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mean,
+               const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+               int training, float* dx, float* dresidual, float* dgamma, float* dbeta,
+               void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
+  SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
+  SPC_REQUIRE(!relu || y, "relu backward needs y");
+  float* partial = (float*)workspace;
+  float* sums = partial + (int64_t)kNumSMs * 4 * 2 * C;
+  int nb = 0;
+  int rc = col_reduce_launch(1, x, y, dy, mean, m, C, relu, partial, &nb, stream);
+  if (rc) return rc;
+  col_finalize_kernel<1><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, var, eps, dbeta, dgamma, sums);
+  SPC_LAUNCHED("col_finalize_kernel");
+  int vec = pick_vec(C, x, y, dy, dx);
+  if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;
+  RowMap rm = make_row_map(C, vec);
+  SPC_REQUIRE(rm.threads <= 1024, "C too large");
+  int grid = pick_grid(m, rm.rows, 8);
+  DISPATCH_VEC(vec, bn_bwd_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
+      x, y, dy, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx, dresidual));
+  SPC_LAUNCHED("bn_bwd_apply_kernel");
+  return 0;
+}
+
+static int flat_launch(int op, const float* a, const float* b, int64_t n, float* y, cudaStream_t stream) {
+  if (n == 0) return 0;
+  int vec_ok = ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!b || (uintptr_t)b % 16 == 0);
+  int64_t want = ceil_div(ceil_div(n, 4), 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  if (op == 0) flat_kernel<0><<<grid, 256, 0, stream>>>(a, b, n, y, vec_ok);
+  else if (op == 1) flat_kernel<1><<<grid, 256, 0, stream>>>(a, b, n, y, vec_ok);
+  else flat_kernel<2><<<grid, 256, 0, stream>>>(a, b, n, y, vec_ok);
+  SPC_LAUNCHED("flat_kernel");
+  return 0;
+}
+int spc_relu_fwd(const float* x, int64_t n, float* y, void* stream) { return flat_launch(0, x, nullptr, n, y, (cudaStream_t)stream); }
+int spc_relu_bwd(const float* y, const float* dy, int64_t n, float* dx, void* stream) { return flat_launch(1, y, dy, n, dx, (cudaStream_t)stream); }
+int spc_add(const float* a, const float* b, int64_t n, float* y, void* stream) { return flat_launch(2, a, b, n, y, (cudaStream_t)stream); }
+
+int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
+                 float momentum, float weight_decay, float grad_scale, int first_step, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n == 0) return 0;
+  int64_t want = ceil_div(n, 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  sgd_kernel<<<grid, 256, 0, stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step);
+  SPC_LAUNCHED("sgd_kernel");
+  return 0;
+}
+
+int spc_pool_fwd(const float* in, const int32_t* nbr, int64_t m_out, int C, int K, int avg,
+                 float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && K >= 1, "bad shape");
+  if (m_out == 0) return 0;
+  int vec = pick_vec(C, in, out);
+  RowMap rm = make_row_map(C, vec);
+  SPC_REQUIRE(rm.threads <= 1024, "C too large");
+  int grid = pick_grid(m_out, rm.rows, 8);
+  DISPATCH_VEC(vec, pool_fwd_kernel<VEC><<<grid, rm.threads, 0, stream>>>(in, nbr, m_out, C, K, rm.lanes, rm.rows, avg, out));
+  SPC_LAUNCHED("pool_fwd_kernel");
+  return 0;
+}
+
+int spc_global_pool_fwd(const float* in, const int32_t* coords, int64_t m, int C, int n_batch,
+                        int avg, float* out, int32_t* cnt, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && C <= 1024 && n_batch >= 1, "bad shape");
+  SPC_CUDA(cudaMemsetAsync(out, 0, (size_t)n_batch * C * sizeof(float), stream));
+  SPC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_batch * sizeof(int), stream));
+  if (m == 0) return 0;
+  RowMap rm = make_row_map(C, 1);
+  const int rows_per_block = rm.rows * 64;
+  int grid = (int)ceil_div(m, rows_per_block);
+  global_pool_fwd_kernel<<<grid, rm.threads, 0, stream>>>(in, (const int4*)coords, m, C, n_batch, rm.lanes, rm.rows, rows_per_block, out, cnt);
+  SPC_LAUNCHED("global_pool_fwd_kernel");
+  if (avg) {
+    global_pool_norm_kernel<<<(int)ceil_div((int64_t)n_batch * C, 256), 256, 0, stream>>>(out, cnt, n_batch, C);
+    SPC_LAUNCHED("global_pool_norm_kernel");
+  }
+  return 0;
+}
+
+int spc_global_pool_bwd(const float* dout, const int32_t* coords, const int32_t* cnt, int64_t m,
+                        int C, int n_batch, int avg, float* din, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (m == 0) return 0;
+  long long total = (long long)m * C;
+  global_pool_bwd_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(dout, (const int4*)coords, cnt, total, C, n_batch, avg, din);
+  SPC_LAUNCHED("global_pool_bwd_kernel");
+  return 0;
+}
+
+}  // extern "C"
