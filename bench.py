@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — MinkUNet34C (Res16UNet34C) fwd+bwd+SGD voxels/s on synthetic ScanNet-shaped plenoxel
+scenes (BASELINE.json configs[1]; metric "MinkUNet fwd+bwd voxels/sec").
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels behind the ME surface)
+  python bench.py --impl reference ...                      CPU arm: the oracle port of ME's CPU algorithm
+                                                            (ME itself is not installable here)
+
+A step = one pass of the hot path over one batch: voxel quantisation + hashing, kernel maps, every
+conv fwd/dgrad/wgrad, BN/ReLU/pooling, loss, gradient all-reduce (N>1) and the SGD update.  The
+coordinate manager is rebuilt every step, as in the reference where each step makes a new TensorField.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "MinkUNet34C fwd+bwd voxels/sec"
+UNIT = "voxels/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half ~ samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: oracle port of ME's CPU algorithm (gather -> sgemm -> scatter, OpenMP kernel maps)
+# ---------------------------------------------------------------------------
+def cpu_step_fn(voxels: int, seed: int = 777):
+    import numpy as np
+    import torch
+    from nerf_downstream_b200 import models, synth
+    from oracle import nets
+
+    torch.manual_seed(0)
+    coords, feats, labels = synth.room_batch(seed, 1, voxels)
+    model = models.Res16UNet34C(27, 20)
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k)
+              for k, v in model.state_dict().items()}
+    f = torch.from_numpy(feats)
+    y = torch.from_numpy(labels)
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        logits = nets.resunet_forward(params, coords, f, use_c=True)
+        loss = torch.nn.functional.cross_entropy(logits, y, ignore_index=255)
+        loss.backward()
+        return float(loss)
+
+    return step, coords.shape[0]
+
+
+def cpu_baseline(voxels: int, budget_s: float = 20.0):
+    import torch
+    step, n = cpu_step_fn(voxels)
+    step()  # warm-up (builds the C oracle, touches MKL)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        step()
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 5:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"Res16UNet34C(27,20) fwd+bwd on one {n}-voxel synthetic room, fp32, {reps} reps; "
+                      "CPU restatement of ME's algorithm (ME not installable)",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = oracle port, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    voxels = args.cpu_voxels
+    step, n = cpu_step_fn(voxels)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = (f"each step = Res16UNet34C(27,20) fwd+bwd on one {n}-voxel synthetic room (bounded sample of the "
+              f"{args.voxels}-voxel workload), fp32, oracle port of ME's CPU algorithm (ME not installable)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"MinkUNet34C (Res16UNet34C 27->20) fwd+bwd, synthetic ScanNet-shaped plenoxel "
+                                   f"scenes, {args.voxels} voxels/scene, {args.scenes} scene(s)/GPU",
+                       "sample_voxels": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from nerf_downstream_b200 import lib as L
+    from nerf_downstream_b200 import me as ME
+    from nerf_downstream_b200 import models, ops, synth, trainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    ops.set_default_precision(args.precision)
+
+    torch.manual_seed(0)
+    model = models.Res16UNet34C(27, 20).to(dev).train()
+    tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
+
+    coords, feats, labels = synth.room_batch(777 + rank, args.scenes, args.voxels)
+    h_coords = torch.from_numpy(coords).pin_memory()
+    h_feats = torch.from_numpy(feats).pin_memory()
+    h_labels = torch.from_numpy(labels).pin_memory()
+    d_coords, d_feats, d_labels = h_coords.to(dev), h_feats.to(dev), h_labels.to(dev)
+    voxels_per_step = [0]
+
+    def step(c, f, y):
+        field = ME.TensorField(coordinates=c, features=f)
+        logits = model(field)
+        loss = F.cross_entropy(logits, y, ignore_index=255)
+        tr.backward_and_step(loss)
+        key = field.coordinate_manager.get_unique_coordinate_map_key(1)
+        voxels_per_step[0] = field.coordinate_manager.size(key)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident timed region -------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(d_coords, d_feats, d_labels)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    ms = timed(args.steps, lambda: step(d_coords, d_feats, d_labels))
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    vox = torch.tensor([float(voxels_per_step[0])], device=dev)
+    if world > 1:
+        dist.all_reduce(vox, op=dist.ReduceOp.SUM)
+    total_voxels = float(vox.item())
+    value = total_voxels * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------
+    def e2e_step():
+        c = h_coords.to(dev, non_blocking=True)
+        f = h_feats.to(dev, non_blocking=True)
+        y = h_labels.to(dev, non_blocking=True)
+        loss = step(c, f, y)
+        return loss.item()  # device -> host read of the step's result
+
+    e2e_step()
+    e2e_steps = max(3, args.steps // 2)
+    ms_e2e = timed(e2e_steps, e2e_step)
+    e2e_value = total_voxels * e2e_steps / (ms_e2e * 1e-3)
+    h2d = h_coords.numel() * 4 + h_feats.numel() * 4 + h_labels.numel() * 8
+    d2h = 4 + 8 * 5  # loss scalar + the per-level map sizes the host reads back (2 int32 each)
+
+    # ---- per-kernel-class device times inside a (separately) timed region -> roofline -------------
+    roofline = None
+    classes = {}
+    if rank == 0:
+        prof = ops.KernelProfiler()
+        ops.set_profiler(prof)
+        for _ in range(2):
+            step(d_coords, d_feats, d_labels)
+        torch.cuda.synchronize()
+        ops.set_profiler(None)
+        classes = prof.summary()
+        peaks = _peaks()
+        if classes:
+            top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+            name, s = top
+            t = s["ms"] * 1e-3
+            step_ms_prof = sum(v["ms"] for v in classes.values()) / 2
+            traffic = None
+            tfile = ROOT / "profiles" / "roofline_traffic.json"
+            if tfile.exists():
+                traffic = json.loads(tfile.read_text()).get(name)
+            if name.startswith("conv") and s["flops"] > 0:
+                tf32_peak = peaks["bf16_sustained"] / 2.0
+                ach = s["flops"] / t / 1e12
+                roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                            "frac": ach / tf32_peak, "traffic": traffic,
+                            "peak_note": f"kind::tf32 peak taken as half the {peaks['source']} sustained bf16 rate "
+                                         f"({peaks['bf16_sustained']} TFLOP/s); no TF32 figure in MEASURED_PEAKS.json",
+                            "launches": s["n"], "avg_launch_ms": s["ms"] / s["n"],
+                            "algorithmic_gbs": s["bytes"] / t / 1e9, "share_of_step": s["ms"] / 2 / step_ms_prof}
+            else:
+                ach = s["bytes"] / t / 1e9
+                roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_note": peaks["source"],
+                            "launches": s["n"], "avg_launch_ms": s["ms"] / s["n"],
+                            "share_of_step": s["ms"] / 2 / step_ms_prof}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        cpu = cpu_baseline(args.cpu_voxels) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"MinkUNet34C (Res16UNet34C 27->20) fwd+bwd+SGD, synthetic ScanNet-shaped "
+                                       f"plenoxel scenes, {args.voxels} voxels/scene, {args.scenes} scene(s)/GPU, "
+                                       f"BASELINE.json configs[1]",
+                           "voxels_per_step_all_gpus": total_voxels, "parallelism": f"dp{world}",
+                           "l2_policy": "inputs_exceed_l2 (activations per step >> 126 MB)",
+                           "precision": args.precision},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / e2e_steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline,
+                "cpu_baseline": cpu,
+                "kernel_classes_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in
+                                               sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voxels", type=int, default=1_000_000, help="voxels per scene")
+    ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU per step")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

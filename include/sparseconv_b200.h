@@ -158,6 +158,7 @@ int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
  */
 int64_t spc_bn_workspace(int64_t m, int C);
 int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
+                 float* running_mean, float* running_var, float momentum, /* nullable */
                  void* workspace, int64_t workspace_bytes, void* stream);
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,

@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lcudart"]
+           "-cudart", "static"]
     subprocess.run(cmd, check=True)
     STAMP.write_text(digest)
     return LIB_PATH

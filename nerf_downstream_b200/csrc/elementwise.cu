@@ -103,7 +103,9 @@ template <int MODE>
 __global__ void col_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
                                     long long m, const float* __restrict__ var, float eps,
                                     float* __restrict__ out0, float* __restrict__ out1,
-                                    float* __restrict__ raw /* [2C] sums, optional */) {
+                                    float* __restrict__ raw /* [2C] sums, optional */,
+                                    float* __restrict__ run_mean, float* __restrict__ run_var,
+                                    float momentum) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
@@ -115,8 +117,14 @@ __global__ void col_finalize_kernel(const float* __restrict__ partial, int nbloc
   if (MODE == 0) {
     double mu = a / (double)m;
     double v = b / (double)m - mu * mu;
+    v = v > 0.0 ? v : 0.0;
     out0[c] = (float)mu;
-    out1[c] = (float)(v > 0.0 ? v : 0.0);
+    out1[c] = (float)v;
+    if (run_mean) {  // nn.BatchNorm1d: running_var tracks the UNBIASED variance
+      double unb = m > 1 ? v * (double)m / (double)(m - 1) : v;
+      run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * mu);
+      run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
+    }
   } else {
     out0[c] = (float)a;
     out1[c] = (float)(b / sqrt((double)var[c] + (double)eps));
@@ -355,8 +363,9 @@ static int col_reduce_launch(int mode, const float* x, const float* y, const flo
   return 0;
 }
 
-int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, void* workspace,
-                 int64_t workspace_bytes, void* stream_) {
+int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, float* running_mean,
+                 float* running_var, float momentum, void* workspace, int64_t workspace_bytes,
+                 void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
@@ -364,7 +373,7 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, void
   int nb = 0;
   int rc = col_reduce_launch(0, x, nullptr, nullptr, nullptr, m, C, 0, partial, &nb, stream);
   if (rc) return rc;
-  col_finalize_kernel<0><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, nullptr, 0.f, mean, var, nullptr);
+  col_finalize_kernel<0><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, nullptr, 0.f, mean, var, nullptr, running_mean, running_var, momentum);
   SPC_LAUNCHED("col_finalize_kernel");
   return 0;
 }
@@ -398,7 +407,7 @@ int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mea
   int nb = 0;
   int rc = col_reduce_launch(1, x, y, dy, mean, m, C, relu, partial, &nb, stream);
   if (rc) return rc;
-  col_finalize_kernel<1><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, var, eps, dbeta, dgamma, sums);
+  col_finalize_kernel<1><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, var, eps, dbeta, dgamma, sums, nullptr, nullptr, 0.f);
   SPC_LAUNCHED("col_finalize_kernel");
   int vec = pick_vec(C, x, y, dy, dx);
   if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;

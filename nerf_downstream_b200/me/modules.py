@@ -1,0 +1,407 @@
+"""ME-compatible layers backed by the sm_100a kernels.
+
+Constructor signatures, attribute names and state-dict keys follow MinkowskiEngine 0.5.x as
+the reference uses them (co3d_3d/src/models/mink/modules/common.py:22-180,
+modules/sparse_conv.py:267-452 for parameter shapes / init, resnet.py:18,61-64 for pooling).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+from torch.nn import Parameter
+
+from .. import lib as L
+from .. import ops
+from .core import (ConvolutionMode, CoordinateMapKey, KernelGenerator, RegionType, SparseTensor, TensorField,
+                   _to_list)
+
+
+class MinkowskiModuleBase(nn.Module):
+    pass
+
+
+class MinkowskiNetwork(nn.Module):
+    def __init__(self, D):
+        super().__init__()
+        self.D = D
+
+
+def _wrap_like(input, feats):
+    """Re-wrap features with the key/manager of `input` (layernorm.py:16-30 pattern)."""
+    if isinstance(input, TensorField):
+        return TensorField(feats, coordinate_field_map_key=input.coordinate_field_map_key,
+                           coordinate_manager=input.coordinate_manager, quantization_mode=input.quantization_mode)
+    return SparseTensor(feats, coordinate_map_key=input.coordinate_map_key,
+                        coordinate_manager=input.coordinate_manager)
+
+
+# ---------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------
+class MinkowskiConvolutionBase(MinkowskiModuleBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, is_transpose=False, expand_coordinates=False,
+                 convolution_mode=ConvolutionMode.DEFAULT, dimension=-1):
+        super().__init__()
+        assert dimension > 0, f"Invalid dimension. Please provide a valid dimension argument. dimension={dimension}"
+        if kernel_generator is None:
+            kernel_generator = KernelGenerator(kernel_size=kernel_size, stride=stride, dilation=dilation,
+                                               expand_coordinates=expand_coordinates, dimension=dimension)
+        elif kernel_generator.expand_coordinates != expand_coordinates:
+            kernel_generator.expand_coordinates = expand_coordinates
+        if expand_coordinates:
+            raise NotImplementedError("expand_coordinates (generative transposed conv) is not built")
+        self.is_transpose = is_transpose
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_generator = kernel_generator
+        self.dimension = dimension
+        self.use_mm = False  # kernel_volume == 1 and all strides 1 -> plain matrix product
+        self.convolution_mode = convolution_mode
+        # 'tf32' / 'fp32' / None (= ops.default_precision())
+        self.precision: Optional[str] = None
+        Tensor = torch.FloatTensor
+        if self.kernel_generator.kernel_volume == 1 and self.kernel_generator.requires_strided_coordinates:
+            kernel_shape = (self.in_channels, self.out_channels)
+            self.use_mm = True
+        else:
+            kernel_shape = (self.kernel_generator.kernel_volume, self.in_channels, self.out_channels)
+        self.kernel = Parameter(Tensor(*kernel_shape))
+        self.bias = Parameter(Tensor(1, out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self, is_transpose=False):
+        # sparse_conv.py:427-435
+        with torch.no_grad():
+            n = (self.out_channels if is_transpose else self.in_channels) * self.kernel_generator.kernel_volume
+            stdv = 1.0 / math.sqrt(n)
+            self.kernel.data.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.data.uniform_(-stdv, stdv)
+
+    def _precision(self) -> int:
+        if self.precision is None:
+            return ops.default_precision()
+        return {"tf32": L.PREC_TF32, "fp32": L.PREC_FP32}[self.precision]
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        assert isinstance(input, SparseTensor), "MinkowskiConvolution expects a SparseTensor"
+        assert input.D == self.dimension
+        if coordinates is not None:
+            raise NotImplementedError("explicit output coordinates are not built")
+        mgr = input.coordinate_manager
+        in_key = input.coordinate_map_key
+        kg = self.kernel_generator
+        if self.use_mm:
+            out_key = in_key
+            km = mgr.identity_map(in_key)
+            w = self.kernel.view(1, self.in_channels, self.out_channels)
+        else:
+            if self.is_transpose:
+                # existing map at tensor_stride / stride with id "" (sparse_conv.py:397-401)
+                ts = input.tensor_stride
+                out_ts = []
+                for t, s in zip(ts, kg.kernel_stride):
+                    if t % s != 0:
+                        raise RuntimeError(f"tensor stride {ts} is not divisible by upsample stride {kg.kernel_stride}")
+                    out_ts.append(t // s)
+                out_key = CoordinateMapKey(out_ts, "")
+                if not mgr.exists_coordinate_map_key(out_key):
+                    raise RuntimeError(f"transposed convolution needs an existing coordinate map {out_key}")
+            else:
+                out_key = mgr.stride(in_key, kg.kernel_stride)
+            km = mgr.get_kernel_map(in_key, out_key, kg, is_transpose=self.is_transpose)
+            w = self.kernel
+        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision())
+        return SparseTensor(outfeat, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def __repr__(self):
+        s = f"(in={self.in_channels}, out={self.out_channels}, kernel_size={self.kernel_generator.kernel_size}, " \
+            f"stride={self.kernel_generator.kernel_stride}, dilation={self.kernel_generator.kernel_dilation})"
+        return self.__class__.__name__ + s
+
+
+class MinkowskiConvolution(MinkowskiConvolutionBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=ConvolutionMode.DEFAULT,
+                 dimension=None):
+        MinkowskiConvolutionBase.__init__(self, in_channels, out_channels, kernel_size, stride, dilation, bias,
+                                          kernel_generator, is_transpose=False,
+                                          expand_coordinates=expand_coordinates,
+                                          convolution_mode=convolution_mode, dimension=dimension)
+        self.reset_parameters()
+
+
+class MinkowskiConvolutionTranspose(MinkowskiConvolutionBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=ConvolutionMode.DEFAULT,
+                 dimension=None):
+        MinkowskiConvolutionBase.__init__(self, in_channels, out_channels, kernel_size, stride, dilation, bias,
+                                          kernel_generator, is_transpose=True,
+                                          expand_coordinates=expand_coordinates,
+                                          convolution_mode=convolution_mode, dimension=dimension)
+        self.reset_parameters(True)
+
+
+# ---------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------
+class MinkowskiBatchNorm(nn.Module):
+    """`self.bn` is a real nn.BatchNorm1d (state-dict keys bn.weight ... bn.num_batches_tracked,
+    fcnn.py:138-140); the arithmetic runs in the fused sm_100a BN kernels."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def _run(self, feats, relu=False, residual=None):
+        bn = self.bn
+        training = bn.training or not bn.track_running_stats
+        momentum = bn.momentum
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        return ops.BatchNormFn.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                     0.0 if momentum is None else momentum, bn.eps, relu, residual)
+
+    def forward(self, input):
+        return _wrap_like(input, self._run(input.F))
+
+    def __repr__(self):
+        bn = self.bn
+        return f"{self.__class__.__name__}({bn.num_features}, eps={bn.eps}, momentum={bn.momentum}, " \
+               f"affine={bn.affine}, track_running_stats={bn.track_running_stats})"
+
+
+class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
+    """Cross-rank statistics via nn.SyncBatchNorm (train.py:106-107).  Off by default in the
+    reference (`use_sync_batchnorm`), so this wrapper simply defers to torch on `.F`."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True,
+                 process_group=None):
+        nn.Module.__init__(self)
+        self.bn = nn.SyncBatchNorm(num_features, eps=eps, momentum=momentum, affine=affine,
+                                   track_running_stats=track_running_stats, process_group=process_group)
+
+    def forward(self, input):
+        return _wrap_like(input, self.bn(input.F))
+
+    @classmethod
+    def convert_sync_batchnorm(cls, module, process_group=None):
+        module_output = module
+        if isinstance(module, MinkowskiBatchNorm) and not isinstance(module, MinkowskiSyncBatchNorm):
+            bn = module.bn
+            module_output = MinkowskiSyncBatchNorm(bn.num_features, bn.eps, bn.momentum, bn.affine,
+                                                   bn.track_running_stats, process_group)
+            if bn.affine:
+                with torch.no_grad():
+                    module_output.bn.weight = bn.weight
+                    module_output.bn.bias = bn.bias
+            module_output.bn.running_mean = bn.running_mean
+            module_output.bn.running_var = bn.running_var
+            module_output.bn.num_batches_tracked = bn.num_batches_tracked
+            return module_output
+        for name, child in module.named_children():
+            module_output.add_module(name, cls.convert_sync_batchnorm(child, process_group))
+        del module
+        return module_output
+
+
+class MinkowskiInstanceNorm(MinkowskiModuleBase):
+    """Constructed by get_norm('IN') only (common.py:25-26); not on the hot path -> not built."""
+
+    def __init__(self, num_features):
+        super().__init__()
+        self.num_features = num_features
+        self.weight = Parameter(torch.ones(1, num_features))
+        self.bias = Parameter(torch.zeros(1, num_features))
+
+    def forward(self, input):
+        raise NotImplementedError("MinkowskiInstanceNorm is outside the built hot path (SURVEY.md §8f rank 4)")
+
+
+# ---------------------------------------------------------------------------
+# non-linearities
+# ---------------------------------------------------------------------------
+class MinkowskiNonlinearityBase(MinkowskiModuleBase):
+    MODULE = None
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.module = self.MODULE(*args, **kwargs)
+
+    def forward(self, input):
+        return _wrap_like(input, self.module(input.F))
+
+    def __repr__(self):
+        return self.__class__.__name__ + "()"
+
+
+class MinkowskiReLU(MinkowskiNonlinearityBase):
+    MODULE = nn.ReLU
+
+    def forward(self, input):
+        return _wrap_like(input, ops.ReLUFn.apply(input.F))
+
+
+class MinkowskiPReLU(MinkowskiNonlinearityBase):
+    MODULE = nn.PReLU
+
+
+class MinkowskiLeakyReLU(MinkowskiNonlinearityBase):
+    MODULE = nn.LeakyReLU
+
+
+class MinkowskiELU(MinkowskiNonlinearityBase):
+    MODULE = nn.ELU
+
+
+class MinkowskiCELU(MinkowskiNonlinearityBase):
+    MODULE = nn.CELU
+
+
+class MinkowskiSELU(MinkowskiNonlinearityBase):
+    MODULE = nn.SELU
+
+
+class MinkowskiGELU(MinkowskiNonlinearityBase):
+    MODULE = nn.GELU
+
+
+class MinkowskiSigmoid(MinkowskiNonlinearityBase):
+    MODULE = nn.Sigmoid
+
+
+class MinkowskiTanh(MinkowskiNonlinearityBase):
+    MODULE = nn.Tanh
+
+
+class MinkowskiSoftmax(MinkowskiNonlinearityBase):
+    MODULE = nn.Softmax
+
+
+class MinkowskiDropout(MinkowskiNonlinearityBase):
+    MODULE = nn.Dropout
+
+
+class MinkowskiLinear(MinkowskiModuleBase):
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+
+    def forward(self, input):
+        return _wrap_like(input, self.linear(input.F))
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(in_features={self.linear.in_features}, " \
+               f"out_features={self.linear.out_features}, bias={self.linear.bias is not None})"
+
+
+# ---------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------
+class MinkowskiLocalPoolingBase(MinkowskiModuleBase):
+    AVG = False
+
+    def __init__(self, kernel_size, stride=1, dilation=1, kernel_generator=None, dimension=None):
+        super().__init__()
+        assert dimension is not None and dimension > 0, f"invalid dimension: {dimension}"
+        if kernel_generator is None:
+            kernel_generator = KernelGenerator(kernel_size=kernel_size, stride=stride, dilation=dilation,
+                                               dimension=dimension)
+        self.kernel_generator = kernel_generator
+        self.dimension = dimension
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        in_key = input.coordinate_map_key
+        out_key = mgr.stride(in_key, self.kernel_generator.kernel_stride)
+        km = mgr.get_kernel_map(in_key, out_key, self.kernel_generator, is_pool=True)
+        out = ops.LocalPoolFn.apply(input.F, km, self.AVG)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(kernel_size={self.kernel_generator.kernel_size}, " \
+               f"stride={self.kernel_generator.kernel_stride}, dilation={self.kernel_generator.kernel_dilation})"
+
+
+class MinkowskiSumPooling(MinkowskiLocalPoolingBase):
+    AVG = False
+
+
+class MinkowskiAvgPooling(MinkowskiLocalPoolingBase):
+    AVG = True
+
+
+class MinkowskiMaxPooling(MinkowskiLocalPoolingBase):
+    def forward(self, input, coordinates=None):
+        raise NotImplementedError("MinkowskiMaxPooling is outside the built hot path (SURVEY.md §8f rank 4)")
+
+
+class MinkowskiGlobalPooling(MinkowskiModuleBase):
+    AVG = True
+
+    def __init__(self, mode=None):
+        super().__init__()
+        self.pooling_mode = mode
+
+    def forward(self, input: SparseTensor):
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        out_key = mgr.origin()
+        nb = mgr.size(out_key)
+        out = ops.GlobalPoolFn.apply(input.F, input.C, nb, self.AVG)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "()"
+
+
+class MinkowskiGlobalAvgPooling(MinkowskiGlobalPooling):
+    AVG = True
+
+
+class MinkowskiGlobalSumPooling(MinkowskiGlobalPooling):
+    AVG = False
+
+
+class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
+    def __init__(self, mode=None):
+        super().__init__()
+
+    def forward(self, input):
+        raise NotImplementedError("MinkowskiGlobalMaxPooling is outside the built hot path (SURVEY.md §8f rank 4)")
+
+
+# ---------------------------------------------------------------------------
+# tensor ops
+# ---------------------------------------------------------------------------
+def cat(*sparse_tensors):
+    """Channel concatenation of tensors sharing a coordinate map (res16unet.py:410-425)."""
+    if len(sparse_tensors) == 1 and isinstance(sparse_tensors[0], (list, tuple)):
+        sparse_tensors = tuple(sparse_tensors[0])
+    for s in sparse_tensors:
+        assert isinstance(s, (SparseTensor, TensorField)), "Inputs must be sparse tensors."
+    first = sparse_tensors[0]
+    mgr = first.coordinate_manager
+    if isinstance(first, TensorField):
+        key = first.coordinate_field_map_key
+        for s in sparse_tensors:
+            assert mgr is s.coordinate_manager, "different coordinate managers"
+            assert key == s.coordinate_field_map_key, "different coordinate field keys"
+        return TensorField(torch.cat([s.F for s in sparse_tensors], dim=1), coordinate_field_map_key=key,
+                           coordinate_manager=mgr, quantization_mode=first.quantization_mode)
+    key = first.coordinate_map_key
+    for s in sparse_tensors:
+        assert mgr is s.coordinate_manager, \
+            "Invalid coordinate manager. All inputs must have the same coordinate manager."
+        assert key == s.coordinate_map_key, \
+            f"Invalid coordinate map key: {key} != {s.coordinate_map_key}. Inputs must share a coordinate map."
+    return SparseTensor(torch.cat([s.F for s in sparse_tensors], dim=1), coordinate_map_key=key,
+                        coordinate_manager=mgr)

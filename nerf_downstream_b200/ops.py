@@ -1,0 +1,588 @@
+"""Functional layer over the C ABI: coordinate maps, kernel maps and autograd Functions.
+
+Host-side mirror of what MinkowskiEngine's `CoordinateMapManager` + conv/pool/BN functions do
+for the reference's call sites.  All arithmetic happens in
+`libsparseconv_b200.so`; torch is used for memory, streams and autograd bookkeeping only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+_I3 = ctypes.c_int32 * 3
+
+# precision used by convolution layers unless a layer overrides it
+_default_precision = L.PREC_TF32
+
+
+def set_default_precision(mode: str) -> None:
+    """'tf32' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FFMA, fp32-faithful)."""
+    global _default_precision
+    _default_precision = {"tf32": L.PREC_TF32, "fp32": L.PREC_FP32}[mode]
+
+
+def default_precision() -> int:
+    return _default_precision
+
+
+def _empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+# ---------------------------------------------------------------------------
+# optional per-kernel-class timing (bench.py roofline); off unless a profiler is installed
+# ---------------------------------------------------------------------------
+class KernelProfiler:
+    """CUDA-event timing of every library call on the launching stream, grouped by kernel class,
+    with the ALGORITHMIC flops / bytes of each call (formulas: SURVEY.md §8d)."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def end(self, name, e0, flops=0.0, nbytes=0.0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.records.append((name, e0, e1, float(flops), float(nbytes)))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl, by in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+_profiler: Optional[KernelProfiler] = None
+
+
+def set_profiler(p: Optional[KernelProfiler]) -> None:
+    global _profiler
+    _profiler = p
+
+
+# ---------------------------------------------------------------------------
+# coordinate maps
+# ---------------------------------------------------------------------------
+class CoordMap:
+    """One coordinate map: unique int32 rows (b,x,y,z) + the hash table that indexes them."""
+
+    __slots__ = ("coords", "table", "n_slots", "size", "tensor_stride", "n_batch_cache")
+
+    def __init__(self, coords, table, n_slots, size, tensor_stride):
+        self.coords = coords            # int32 [M,4]
+        self.table = table              # uint8 [n_slots*16]
+        self.n_slots = n_slots
+        self.size = size
+        self.tensor_stride = tuple(int(t) for t in tensor_stride)
+        self.n_batch_cache = None
+
+
+def coords_insert(src: torch.Tensor, kind: int, ts: Sequence[int]):
+    """Quantise + hash + unique.  Returns (CoordMap, first_idx, inverse, count).
+
+    first_idx[r] is ME's `unique_index`, inverse[j] ME's `inverse_mapping` (both int32 here).
+    One host synchronisation: the number of unique rows is read back to size the outputs.
+    """
+    lib = L.load()
+    if src.dim() != 2 or src.shape[1] != 4:
+        raise RuntimeError(f"coordinates must be [N,4] (batch,x,y,z), got {tuple(src.shape)}")
+    want = torch.float32 if kind == L.SRC_FLOAT else torch.int32
+    if src.dtype != want:
+        raise RuntimeError(f"coordinate dtype {src.dtype} does not match source kind {kind}")
+    src = src.contiguous()
+    dev = src.device
+    n = src.shape[0]
+    n_slots = int(lib.spc_table_slots(n))
+    table = _empty(n_slots * L.SLOT_BYTES, torch.uint8, dev)
+    coords = _empty((n, 4), torch.int32, dev)
+    first = _empty(n, torch.int32, dev)
+    inverse = _empty(n, torch.int32, dev)
+    count = _empty(n, torch.int32, dev)
+    status = _empty(2, torch.int32, dev)
+    ws_bytes = int(lib.spc_coords_insert_workspace(n))
+    ws = _empty(ws_bytes, torch.uint8, dev)
+    ts_arr = _I3(*[int(t) for t in ts])
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_coords_insert(L.ptr(src), n, kind, ctypes.cast(ts_arr, ctypes.c_void_p), L.ptr(table),
+                                  n_slots, L.ptr(coords), L.ptr(first), L.ptr(inverse), L.ptr(count),
+                                  L.ptr(status), L.ptr(ws), ws_bytes, L.stream()), "spc_coords_insert")
+    if e0 is not None:
+        _profiler.end("coords_insert(hash)", e0, 0, 20.0 * n + 36.0 * n)
+    m, err = status.tolist()  # host sync
+    if err:
+        raise RuntimeError("coordinate out of the supported range: batch index must be in [0,1022] and "
+                           "x,y,z in [-131072,131071] (and finite)")
+    cmap = CoordMap(coords[:m], table, n_slots, m, ts)
+    return cmap, first[:m], inverse, count[:m]
+
+
+def kernel_offsets(kernel_size: Sequence[int], tensor_stride: Sequence[int], dilation: Sequence[int]):
+    """HYPER_CUBE offsets; index order: first spatial axis fastest (sparse_conv.py:375-379).
+
+    Odd kernel sizes are centred, even ones start at 0; offsets are scaled by the INPUT tensor
+    stride times the dilation."""
+    ks = [int(k) for k in kernel_size]
+    axes = []
+    for a in range(3):
+        k, step = ks[a], int(tensor_stride[a]) * int(dilation[a])
+        lo = -(k - 1) // 2 if k % 2 == 1 else 0
+        axes.append([(lo + j) * step for j in range(k)])
+    offs = []
+    for jz in range(ks[2]):
+        for jy in range(ks[1]):
+            for jx in range(ks[0]):
+                offs.append((axes[0][jx], axes[1][jy], axes[2][jz]))
+    return offs
+
+
+class KernelMap:
+    """Dense offset-major kernel map nbr[K, M_out] (+ lazily its transpose, masks, pair lists)."""
+
+    def __init__(self, nbr, tap_count, K, m_in, m_out):
+        self.nbr = nbr
+        self.tap_count = tap_count
+        self.K = K
+        self.m_in = m_in
+        self.m_out = m_out
+        self._mask = None
+        self._nbr_t = None
+        self._mask_t = None
+        self._pairs = None
+        self._n_pairs = None
+
+    @property
+    def n_pairs(self) -> int:
+        """Number of (in,out) pairs; host sync, used for reporting only."""
+        if self._n_pairs is None:
+            self._n_pairs = int(self.tap_count.sum().item()) if self.tap_count is not None else int(self.m_out)
+        return self._n_pairs
+
+    @property
+    def mask(self):
+        if self._mask is None and self.K <= 32:
+            self._mask = tile_mask(self.nbr, self.m_out, self.K)
+        return self._mask
+
+    @property
+    def nbr_t(self):
+        if self._nbr_t is None:
+            lib = L.load()
+            t = _empty((self.K, self.m_in), torch.int32, self.nbr.device)
+            L.check(lib.spc_kernel_map_transpose(L.ptr(self.nbr), self.m_out, self.m_in, self.K, L.ptr(t),
+                                                 L.stream()), "spc_kernel_map_transpose")
+            self._nbr_t = t
+        return self._nbr_t
+
+    @property
+    def mask_t(self):
+        if self._mask_t is None and self.K <= 32:
+            self._mask_t = tile_mask(self.nbr_t, self.m_in, self.K)
+        return self._mask_t
+
+    def swapped(self) -> "KernelMap":
+        """The same pairs with in/out roles exchanged (transposed convolution)."""
+        km = KernelMap(self.nbr_t, self.tap_count, self.K, self.m_out, self.m_in)
+        km._n_pairs = self._n_pairs
+        km._mask = self.mask_t
+        km._nbr_t = self.nbr
+        km._mask_t = self.mask
+        return km
+
+    def pairs(self):
+        """ME-style dict {k: IntTensor[2, n_k]} (row 0 = in rows, row 1 = out rows, ascending out
+        row), only non-empty offsets (sparse_conv.py:122-143)."""
+        if self._pairs is None:
+            lib = L.load()
+            dev = self.nbr.device
+            counts = self.tap_count.tolist()
+            total = int(sum(counts))
+            pairs = _empty((2, max(total, 1)), torch.int32, dev)
+            tap_off = _empty(self.K + 1, torch.int32, dev)
+            ws_bytes = int(lib.spc_pairs_workspace(self.m_out, self.K))
+            ws = _empty(ws_bytes, torch.uint8, dev)
+            L.check(lib.spc_kernel_map_pairs(L.ptr(self.nbr), self.m_out, self.K, max(total, 1), L.ptr(pairs),
+                                             L.ptr(tap_off), L.ptr(ws), ws_bytes, L.stream()),
+                    "spc_kernel_map_pairs")
+            out, start = {}, 0
+            for k, c in enumerate(counts):
+                if c > 0:
+                    out[k] = pairs[:, start:start + c]
+                start += c
+            self._pairs = out
+        return self._pairs
+
+
+def tile_mask(nbr, m, K):
+    lib = L.load()
+    n_tiles = (m + 127) // 128
+    mask = _empty(max(n_tiles, 1), torch.int32, nbr.device)
+    L.check(lib.spc_tile_mask(L.ptr(nbr), m, K, L.ptr(mask), L.stream()), "spc_tile_mask")
+    return mask
+
+
+def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
+    lib = L.load()
+    K = len(offsets)
+    dev = out_map.coords.device
+    flat = (ctypes.c_int32 * (3 * K))(*[int(v) for off in offsets for v in off])
+    nbr = _empty((K, out_map.size), torch.int32, dev)
+    tap_count = _empty(K, torch.int32, dev)
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_kernel_map(L.ptr(in_map.table), in_map.n_slots, L.ptr(out_map.coords), out_map.size,
+                               ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
+                               L.stream()), "spc_kernel_map")
+    if e0 is not None:
+        _profiler.end("kernel_map", e0, 0, (16.0 + 8.0 * K + 4.0 * K) * out_map.size)
+    return KernelMap(nbr, tap_count, K, in_map.size, out_map.size)
+
+
+# ---------------------------------------------------------------------------
+# feature-row ops
+# ---------------------------------------------------------------------------
+def _feat(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"features must be float32, got {x.dtype}")
+    return x.contiguous()
+
+
+def segment_reduce(feats, inverse, count, m, mode):
+    lib = L.load()
+    feats = _feat(feats)
+    n, C = feats.shape
+    out = _empty((m, C), torch.float32, feats.device)
+    L.check(lib.spc_segment_reduce(L.ptr(feats), L.ptr(inverse), L.ptr(count), n, m, C, mode, L.ptr(out),
+                                   L.stream()), "spc_segment_reduce")
+    return out
+
+
+def gather_rows(src, index, count=None):
+    lib = L.load()
+    src = _feat(src)
+    n, C = index.shape[0], src.shape[1]
+    out = _empty((n, C), torch.float32, src.device)
+    L.check(lib.spc_gather_rows(L.ptr(src), L.ptr(index), L.ptr(count), n, C, L.ptr(out), L.stream()),
+            "spc_gather_rows")
+    return out
+
+
+def scatter_add_rows(src, index, m):
+    lib = L.load()
+    src = _feat(src)
+    n, C = src.shape
+    out = _empty((m, C), torch.float32, src.device)
+    L.check(lib.spc_scatter_add_rows(L.ptr(src), L.ptr(index), n, m, C, L.ptr(out), L.stream()),
+            "spc_scatter_add_rows")
+    return out
+
+
+class SegmentReduceFn(torch.autograd.Function):
+    """TensorField -> SparseTensor feature reduction (mode 0 average, 1 sum, 2 first/subsample)."""
+
+    @staticmethod
+    def forward(ctx, feats, inverse, count, first, m, mode):
+        ctx.mode = mode
+        ctx.n = feats.shape[0]
+        if mode == 2:
+            ctx.save_for_backward(first)
+            return gather_rows(feats, first)
+        ctx.save_for_backward(inverse, count)
+        return segment_reduce(feats, inverse, count, m, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _feat(g)
+        if ctx.mode == 2:
+            (first,) = ctx.saved_tensors
+            return scatter_add_rows(g, first, ctx.n), None, None, None, None, None
+        inverse, count = ctx.saved_tensors
+        return gather_rows(g, inverse, count if ctx.mode == 0 else None), None, None, None, None, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """out[j] = src[index[j]]  (SparseTensor.slice, res16unet.py:435)."""
+
+    @staticmethod
+    def forward(ctx, src, index):
+        ctx.save_for_backward(index)
+        ctx.m = src.shape[0]
+        return gather_rows(src, index)
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        return scatter_add_rows(_feat(g), index, ctx.m), None
+
+
+# ---------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------
+def _conv_bytes(km, K, c_in, c_out) -> float:
+    """Algorithmic bytes of one conv pass: every feature row once, weights once, dense map once."""
+    return 4.0 * km.m_in * c_in + 4.0 * km.m_out * c_out + 4.0 * K * c_in * c_out + 4.0 * K * km.m_out
+
+
+def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
+    lib = L.load()
+    K, c_in, c_out = w.shape
+    out = _empty((km.m_out, c_out), torch.float32, x.device)
+    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
+    ws = _empty(ws_bytes, torch.uint8, x.device)
+    mask = km.mask if precision == L.PREC_TF32 else None
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
+                             c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
+            "spc_conv_fwd")
+    if e0 is not None:
+        _profiler.end("conv_fwd", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+    return out
+
+
+def conv_dgrad_raw(g, w, km: KernelMap, precision):
+    lib = L.load()
+    K, c_in, c_out = w.shape
+    din = _empty((km.m_in, c_in), torch.float32, g.device)
+    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
+    ws = _empty(ws_bytes, torch.uint8, g.device)
+    mask_t = km.mask_t if precision == L.PREC_TF32 else None
+    nbr_t = km.nbr_t
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_conv_dgrad(L.ptr(g), L.ptr(w), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out, c_in,
+                               c_out, K, precision, L.ptr(din), L.ptr(ws), ws_bytes, L.stream()),
+            "spc_conv_dgrad")
+    if e0 is not None:
+        _profiler.end("conv_dgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+    return din
+
+
+def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision):
+    lib = L.load()
+    dw = _empty((K, c_in, c_out), torch.float32, x.device)
+    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
+    ws = _empty(ws_bytes, torch.uint8, x.device)
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), km.m_in, km.m_out, c_in, c_out, K,
+                               precision, L.ptr(dw), L.ptr(ws), ws_bytes, L.stream()), "spc_conv_wgrad")
+    if e0 is not None:
+        _profiler.end("conv_wgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+    return dw
+
+
+class SparseConvFn(torch.autograd.Function):
+    """out[o] = sum_k x[nbr[k,o]] @ W[k] (+bias); backward = dgrad / wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, km, precision):
+        x = _feat(x)
+        w3 = w.contiguous()
+        if x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
+            raise RuntimeError(f"conv input {tuple(x.shape)} does not match map rows {km.m_in} / kernel {tuple(w3.shape)}")
+        b = bias.contiguous().view(-1) if bias is not None else None
+        out = conv_fwd_raw(x, w3, b, km, precision)
+        ctx.save_for_backward(x, w3)
+        ctx.km = km
+        ctx.precision = precision
+        ctx.has_bias = bias is not None
+        ctx.bias_shape = bias.shape if bias is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w3 = ctx.saved_tensors
+        km, prec = ctx.km, ctx.precision
+        g = _feat(g)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad_raw(g, w3, km, prec)
+        if ctx.needs_input_grad[1]:
+            K, c_in, c_out = w3.shape
+            dw = conv_wgrad_raw(x, g, km, K, c_in, c_out, prec)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(0).view(ctx.bias_shape)
+        return dx, dw, db, None, None
+
+
+# ---------------------------------------------------------------------------
+# batch norm / relu / add
+# ---------------------------------------------------------------------------
+class BatchNormFn(torch.autograd.Function):
+    """nn.BatchNorm1d semantics on [M,C] rows, optional fused ReLU and residual add."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual):
+        lib = L.load()
+        x = _feat(x)
+        m, C = x.shape
+        dev = x.device
+        ws_bytes = int(lib.spc_bn_workspace(m, C))
+        ws = _empty(ws_bytes, torch.uint8, dev)
+        use_batch = training or running_mean is None
+        e0 = _profiler.begin() if _profiler else None
+        if use_batch:
+            if m < 1:
+                raise RuntimeError("batch norm over zero rows")
+            mean = _empty(C, torch.float32, dev)
+            var = _empty(C, torch.float32, dev)
+            upd = training and running_mean is not None
+            L.check(lib.spc_bn_stats(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
+                                     L.ptr(running_mean) if upd else None,
+                                     L.ptr(running_var) if upd else None, float(momentum), L.ptr(ws), ws_bytes,
+                                     L.stream()), "spc_bn_stats")
+        else:
+            mean, var = running_mean, running_var
+        res = _feat(residual) if residual is not None else None
+        y = _empty((m, C), torch.float32, dev)
+        L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res), m, C,
+                                 float(eps), int(relu), L.ptr(y), L.stream()), "spc_bn_apply")
+        if e0 is not None:
+            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)) * m * C)
+        ctx.save_for_backward(x, y if relu else None, mean, var, gamma)
+        ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, y, mean, var, gamma = ctx.saved_tensors
+        eps, relu, use_batch, has_res, affine = ctx.cfg
+        dy = _feat(dy)
+        m, C = x.shape
+        dev = x.device
+        ws_bytes = int(lib.spc_bn_workspace(m, C))
+        ws = _empty(ws_bytes, torch.uint8, dev)
+        dx = _empty((m, C), torch.float32, dev)
+        dres = _empty((m, C), torch.float32, dev) if has_res else None
+        dgamma = _empty(C, torch.float32, dev)
+        dbeta = _empty(C, torch.float32, dev)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y), L.ptr(dy), L.ptr(mean), L.ptr(var), L.ptr(gamma), m, C, eps,
+                               relu, use_batch, L.ptr(dx), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
+                               ws_bytes, L.stream()), "spc_bn_bwd")
+        if e0 is not None:
+            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)) * m * C)
+        return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,
+                dres)
+
+
+class ReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = L.load()
+        x = _feat(x)
+        y = torch.empty_like(x)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_relu_fwd(L.ptr(x), x.numel(), L.ptr(y), L.stream()), "spc_relu_fwd")
+        if e0 is not None:
+            _profiler.end("relu_fwd", e0, 0, 8.0 * x.numel())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        (y,) = ctx.saved_tensors
+        g = _feat(g)
+        dx = torch.empty_like(g)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_relu_bwd(L.ptr(y), L.ptr(g), g.numel(), L.ptr(dx), L.stream()), "spc_relu_bwd")
+        if e0 is not None:
+            _profiler.end("relu_bwd", e0, 0, 12.0 * g.numel())
+        return dx
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = L.load()
+        a, b = _feat(a), _feat(b)
+        if a.shape != b.shape:
+            raise RuntimeError("add: shape mismatch")
+        y = torch.empty_like(a)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_add(L.ptr(a), L.ptr(b), a.numel(), L.ptr(y), L.stream()), "spc_add")
+        if e0 is not None:
+            _profiler.end("add", e0, 0, 12.0 * a.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+# ---------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------
+class LocalPoolFn(torch.autograd.Function):
+    """Sum / average pooling over a kernel map region (kernel_size == stride in the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, km, avg):
+        lib = L.load()
+        x = _feat(x)
+        C = x.shape[1]
+        out = _empty((km.m_out, C), torch.float32, x.device)
+        L.check(lib.spc_pool_fwd(L.ptr(x), L.ptr(km.nbr), km.m_out, C, km.K, int(avg), L.ptr(out), L.stream()),
+                "spc_pool_fwd")
+        ctx.km = km
+        ctx.avg = avg
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # din[i] = sum_k dout[nbr_t[k,i]] (/ count of the out row): a pooling over the swapped map
+        lib = L.load()
+        km = ctx.km
+        g = _feat(g)
+        C = g.shape[1]
+        if ctx.avg:
+            # scale rows of g by 1/(number of present inputs) first
+            cnt = (km.nbr >= 0).sum(0).clamp_(min=1).to(torch.float32).unsqueeze(1)
+            g = (g / cnt).contiguous()
+        din = _empty((km.m_in, C), torch.float32, g.device)
+        L.check(lib.spc_pool_fwd(L.ptr(g), L.ptr(km.nbr_t), km.m_in, C, km.K, 0, L.ptr(din), L.stream()),
+                "spc_pool_fwd(bwd)")
+        return din, None, None
+
+
+class GlobalPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coords, n_batch, avg):
+        lib = L.load()
+        x = _feat(x)
+        m, C = x.shape
+        out = _empty((n_batch, C), torch.float32, x.device)
+        cnt = _empty(n_batch, torch.int32, x.device)
+        L.check(lib.spc_global_pool_fwd(L.ptr(x), L.ptr(coords), m, C, n_batch, int(avg), L.ptr(out), L.ptr(cnt),
+                                        L.stream()), "spc_global_pool_fwd")
+        ctx.save_for_backward(coords, cnt)
+        ctx.cfg = (m, C, n_batch, int(avg))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        coords, cnt = ctx.saved_tensors
+        m, C, n_batch, avg = ctx.cfg
+        g = _feat(g)
+        din = _empty((m, C), torch.float32, g.device)
+        L.check(lib.spc_global_pool_bwd(L.ptr(g), L.ptr(coords), L.ptr(cnt), m, C, n_batch, avg, L.ptr(din),
+                                        L.stream()), "spc_global_pool_bwd")
+        return din, None, None, None
+
+
+def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):
+    lib = L.load()
+    L.check(lib.spc_sgd_step(L.ptr(param), L.ptr(grad), L.ptr(buf), param.numel(), float(lr), float(momentum),
+                             float(weight_decay), float(grad_scale), int(first_step), L.stream()), "spc_sgd_step")

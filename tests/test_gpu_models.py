@@ -1,0 +1,110 @@
+"""Whole-network parity: the from-scratch ResNet14 / Res16UNet34C (same parameters and layer tables
+as the reference's resnet.py / res16unet.py, see tests/test_dropin.py) on the CUDA engine against the
+functional CPU oracle (oracle/nets.py) with identical weights.
+
+Tolerances (stated, end to end through 14 / 50+ layers with batch-norm in between):
+  fp32 mode : logits  |d| <= 2e-3 * max|ref| ; parameter gradients  cosine >= 0.9999, |d| <= 1e-2 * max|ref|
+  tf32 mode : logits  cosine >= 0.9999, |d| <= 3e-2 * max|ref|
+"""
+import numpy as np
+import pytest
+import torch
+
+from nerf_downstream_b200 import models, ops, synth
+from nerf_downstream_b200 import me as ME
+from oracle import nets
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def _compare(model, fwd, coords, feats, target_fn, mode, dev):
+    ops.set_default_precision(mode)
+    try:
+        model = model.to(dev).train()
+        params = {k: v.detach().double().cpu().clone().requires_grad_(v.is_floating_point() and "running" not in k)
+                  for k, v in model.state_dict().items()}
+        ref = fwd(params, coords, torch.from_numpy(feats).double())
+        loss_ref = target_fn(ref)
+        loss_ref.backward()
+        field = ME.TensorField(coordinates=torch.from_numpy(coords).to(dev), features=torch.from_numpy(feats).to(dev))
+        out = model(field)
+        loss = target_fn(out)
+        loss.backward()
+        scale = ref.abs().max().item()
+        err = (out.detach().double().cpu() - ref.detach()).abs().max().item()
+        cos = _cos(out.detach(), ref.detach())
+        if mode == "fp32":
+            assert err <= 2e-3 * scale, (err, scale)
+            assert cos >= 0.99999
+        else:
+            assert cos >= 0.9999, cos
+            assert err <= 3e-2 * scale, (err, scale)
+        worst = 1.0
+        for name, p in model.named_parameters():
+            g_ref = params[name].grad
+            assert p.grad is not None and g_ref is not None, name
+            c = _cos(p.grad, g_ref)
+            worst = min(worst, c)
+            if mode == "fp32":
+                gs = g_ref.abs().max().item()
+                ge = (p.grad.double().cpu() - g_ref).abs().max().item()
+                assert c >= 0.9999 and ge <= 1e-2 * max(gs, 1e-12), (name, c, ge, gs)
+            else:
+                assert c >= 0.99, (name, c)
+        return cos, worst
+    finally:
+        ops.set_default_precision("tf32")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_resnet14_matches_oracle(cuda_device, mode):
+    torch.manual_seed(0)
+    coords, feats, labels = synth.co3d_batch(777, 3, lattice=64)
+    model = models.ResNet14(27, 51)
+    y = torch.from_numpy(labels)
+
+    def target(logits):
+        return torch.nn.functional.cross_entropy(logits, y.to(logits.device))
+    _compare(model, nets.resnet_forward, coords, feats, target, mode, cuda_device)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_res16unet34c_matches_oracle(cuda_device, mode):
+    torch.manual_seed(1)
+    coords, feats, labels = synth.room_batch(777, 2, 12_000)
+    model = models.Res16UNet34C(27, 20)
+    y = torch.from_numpy(labels)
+
+    def target(logits):
+        return torch.nn.functional.cross_entropy(logits, y.to(logits.device), ignore_index=255)
+    _compare(model, nets.resunet_forward, coords, feats, target, mode, cuda_device)
+
+
+def test_manager_semantics(cuda_device):
+    """Key rules the models silently rely on (SURVEY.md §7 hard parts)."""
+    coords, feats = synth.random_cloud(3, 4000, extent=10, n_batch=2, channels=8)
+    x = ME.TensorField(coordinates=torch.from_numpy(coords).to(cuda_device),
+                       features=torch.from_numpy(feats).to(cuda_device)).sparse()
+    mgr = x.coordinate_manager
+    a = ME.MinkowskiConvolution(8, 8, kernel_size=3, stride=2, dimension=3).to(cuda_device)(x)
+    b = ME.MinkowskiConvolution(8, 8, kernel_size=1, stride=2, dimension=3).to(cuda_device)(x)
+    assert a.coordinate_map_key == b.coordinate_map_key and a.tensor_stride == [2, 2, 2]
+    a += b                                                      # legal because the keys are equal
+    up = ME.MinkowskiConvolutionTranspose(8, 4, kernel_size=2, stride=2, dimension=3).to(cuda_device)(a)
+    assert up.coordinate_map_key == x.coordinate_map_key        # lands on the encoder's map
+    cat = ME.cat(up, x)
+    assert cat.F.shape == (x.F.shape[0], 12)
+    with pytest.raises(AssertionError):
+        ME.cat(a, x)
+    g = ME.MinkowskiGlobalAvgPooling()(a)
+    assert g.F.shape == (2, 8) and g.C.cpu().tolist() == [[0, 0, 0, 0], [1, 0, 0, 0]]
+    km = mgr.kernel_map(x.coordinate_map_key, x.coordinate_map_key, 1, 3, 1)
+    assert 13 in km and km[13].shape[0] == 2 and bool((km[13][0] == km[13][1]).all())
+    assert mgr.size(x.coordinate_map_key) == x.F.shape[0]
+    k2 = mgr.stride(x.coordinate_map_key, [2, 2, 2])
+    assert k2 == a.coordinate_map_key

@@ -1,0 +1,365 @@
+"""Parity of the CUDA path (called through the C ABI) against the CPU oracle.
+
+Bars:
+  integer outputs (coordinates, unique / inverse maps, kernel maps, pair lists)  : bit-exact
+  fp32-faithful conv / BN / pooling vs fp64 oracle                               : |d| <= 1e-4 * (1 + |ref|)
+  TF32 tensor-core conv vs fp64 oracle                                            : |d| <= 3e-3 * max|ref|
+"""
+import numpy as np
+import pytest
+import torch
+
+from nerf_downstream_b200 import lib as L
+from nerf_downstream_b200 import ops, synth
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+TF32_TOL = 3e-3
+
+
+def assert_fp32(got: torch.Tensor, ref: torch.Tensor, what=""):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs()
+    bound = FP32_TOL * (1 + ref.abs())
+    assert bool((err <= bound).all()), f"{what}: max err {err.max().item():.3e} (ref max {ref.abs().max().item():.3e})"
+
+
+def assert_tf32(got: torch.Tensor, ref: torch.Tensor, what=""):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= TF32_TOL * max(scale, 1e-30), f"{what}: max err {err:.3e} vs {TF32_TOL} * {scale:.3e}"
+
+
+def gpu(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev)
+
+
+# ---------------------------------------------------------------------------
+# coordinates
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,extent,seed", [(1, 3, 0), (37, 2, 1), (5000, 9, 2), (200_000, 40, 3), (1024, 1, 4)])
+def test_quantize_hash_unique_exact(cuda_device, n, extent, seed):
+    c, _ = synth.random_cloud(seed, n, extent=extent, n_batch=3)
+    cmap, first, inverse, count = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    uc, ui, inv = R.unique_first_np(R.quantize_np(c))
+    assert cmap.size == uc.shape[0]
+    assert (cmap.coords.cpu().numpy() == uc).all()
+    assert (first.cpu().numpy() == ui).all()
+    assert (inverse.cpu().numpy() == inv).all()
+    assert (count.cpu().numpy() == np.bincount(inv, minlength=uc.shape[0])).all()
+
+
+def test_quantize_with_tensor_stride(cuda_device):
+    c, _ = synth.random_cloud(7, 3000, extent=20, n_batch=2)
+    cmap, first, inverse, _ = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (4, 4, 4))
+    uc, ui, inv = R.unique_first_np(R.quantize_np(c, (4, 4, 4)))
+    assert (cmap.coords.cpu().numpy() == uc).all() and (inverse.cpu().numpy() == inv).all()
+
+
+def test_empty_and_out_of_range(cuda_device):
+    cmap, first, inverse, count = ops.coords_insert(torch.zeros((0, 4), device=cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    assert cmap.size == 0 and inverse.numel() == 0
+    bad = torch.tensor([[0, 0, 0, 0], [0, 200000.0, 0, 0]], device=cuda_device)
+    with pytest.raises(RuntimeError, match="out of the supported range"):
+        ops.coords_insert(bad, L.SRC_FLOAT, (1, 1, 1))
+    nan = torch.tensor([[0, float("nan"), 0, 0]], device=cuda_device)
+    with pytest.raises(RuntimeError, match="out of the supported range"):
+        ops.coords_insert(nan, L.SRC_FLOAT, (1, 1, 1))
+    edge = torch.tensor([[1022, -131072, 131071, 0], [0, 131071, -131072, 5]], dtype=torch.int32, device=cuda_device)
+    cmap, _, _, _ = ops.coords_insert(edge, L.SRC_INT, (1, 1, 1))
+    assert cmap.coords.cpu().tolist() == edge.cpu().tolist()
+
+
+def _maps(cuda_device, seed, n, extent):
+    c, f = synth.random_cloud(seed, n, extent=extent, n_batch=2)
+    cmap, first, inverse, count = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    uc, ui, inv = R.unique_first_np(R.quantize_np(c))
+    return c, f, cmap, uc, inverse, inv
+
+
+@pytest.mark.parametrize("stride", [2, 4])
+def test_stride_map_exact(cuda_device, stride):
+    _, _, cmap, uc, _, _ = _maps(cuda_device, 11, 20000, 24)
+    ts = (stride,) * 3
+    smap, first, parent, count = ops.coords_insert(cmap.coords, L.SRC_STRIDE, ts)
+    suc, sui, sinv = R.unique_first_np(R.stride_coords_np(uc, ts))
+    assert (smap.coords.cpu().numpy() == suc).all()
+    assert (first.cpu().numpy() == sui).all() and (parent.cpu().numpy() == sinv).all()
+    # and with the C restatement (ME CPU algorithm structure)
+    assert (R.unique_first_c(R.stride_coords_c(uc, ts))[0] == suc).all()
+
+
+KMAP_CASES = [((3, 3, 3), 1), ((3, 3, 3), 2), ((2, 2, 2), 2), ((1, 1, 1), 2), ((5, 5, 5), 1), ((3, 1, 3), 1)]
+
+
+@pytest.mark.parametrize("ks,stride", KMAP_CASES)
+def test_kernel_map_exact(cuda_device, ks, stride):
+    _, _, cmap, uc, _, _ = _maps(cuda_device, 21, 30000, 20)
+    if stride == 1:
+        out_map, out_np = cmap, uc
+    else:
+        ts = (stride,) * 3
+        out_map, _, _, _ = ops.coords_insert(cmap.coords, L.SRC_STRIDE, ts)
+        out_map.tensor_stride = ts
+        out_np = R.unique_first_np(R.stride_coords_np(uc, ts))[0]
+    offs = ops.kernel_offsets(ks, (1, 1, 1), (1, 1, 1))
+    km = ops.build_kernel_map(cmap, out_map, offs)
+    ref = R.kernel_map_np(uc, out_np, R.kernel_offsets(ks, (1, 1, 1)))
+    assert (km.nbr.cpu().numpy() == ref).all()
+    assert (km.tap_count.cpu().numpy() == (ref >= 0).sum(1)).all()
+    ref_t = R.transpose_dense(ref, uc.shape[0])
+    assert (km.nbr_t.cpu().numpy() == ref_t).all()
+    # ME-style pair lists (sparse_conv.py:122-143)
+    pairs = km.pairs()
+    ref_pairs = R.pairs_from_dense(ref)
+    assert sorted(pairs) == sorted(ref_pairs)
+    for k in ref_pairs:
+        assert pairs[k].dtype == torch.int32 and (pairs[k].cpu().numpy() == ref_pairs[k]).all()
+    if km.K <= 32:
+        m = km.mask.cpu().numpy().astype(np.uint32)
+        for t in range(m.shape[0]):
+            want = 0
+            for k in range(km.K):
+                if (ref[k, t * 128:(t + 1) * 128] >= 0).any():
+                    want |= 1 << k
+            assert int(m[t]) == want
+
+
+def test_kernel_map_with_strided_input(cuda_device):
+    # 3^3 stride-1 map at tensor stride 2: offsets scale with the input tensor stride
+    _, _, cmap, uc, _, _ = _maps(cuda_device, 22, 30000, 24)
+    ts = (2, 2, 2)
+    m2, _, _, _ = ops.coords_insert(cmap.coords, L.SRC_STRIDE, ts)
+    m2.tensor_stride = ts
+    u2 = R.unique_first_np(R.stride_coords_np(uc, ts))[0]
+    km = ops.build_kernel_map(m2, m2, ops.kernel_offsets((3, 3, 3), ts, (1, 1, 1)))
+    ref = R.kernel_map_c(u2, u2, R.kernel_offsets((3, 3, 3), ts))
+    assert (km.nbr.cpu().numpy() == ref).all()
+    assert (ref[13] == np.arange(u2.shape[0])).all()
+
+
+# ---------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------
+def _conv_case(cuda_device, seed, n, extent, ks, stride, cin, cout, transpose=False):
+    c, _ = synth.random_cloud(seed, n, extent=extent, n_batch=2)
+    mgr = R.OracleManager(c)
+    cmap, _, _, _ = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    ts_in = (1, 1, 1)
+    if stride == 1:
+        out_map, ts_out = cmap, ts_in
+    else:
+        ts_out = (stride,) * 3
+        out_map, _, _, _ = ops.coords_insert(cmap.coords, L.SRC_STRIDE, ts_out)
+        out_map.tensor_stride = ts_out
+        mgr.stride(ts_in, (stride,) * 3)
+    km = ops.build_kernel_map(cmap, out_map, ops.kernel_offsets(ks, ts_in, (1, 1, 1)))
+    nbr = mgr.kernel_map(ts_in, ts_out, ks)
+    if transpose:
+        km = km.swapped()
+        nbr = R.transpose_dense(nbr, cmap.size)
+    K = len(R.kernel_offsets(ks, ts_in))
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(km.m_in, cin, generator=g, dtype=torch.float64)
+    w = torch.randn(K, cin, cout, generator=g, dtype=torch.float64) / (K * cin) ** 0.5
+    b = torch.randn(1, cout, generator=g, dtype=torch.float64)
+    go = torch.randn(km.m_out, cout, generator=g, dtype=torch.float64)
+    return km, nbr, x, w, b, go
+
+
+def _run_conv(cuda_device, km, nbr, x, w, b, go, precision, check):
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = R.conv_forward(xr, wr, nbr, br)
+    ref.backward(go)
+    xg = x.float().to(cuda_device).requires_grad_()
+    wg = w.float().to(cuda_device).requires_grad_()
+    bg = b.float().to(cuda_device).requires_grad_()
+    out = ops.SparseConvFn.apply(xg, wg, bg, km, precision)
+    out.backward(go.float().to(cuda_device))
+    check(out, ref, "forward")
+    check(xg.grad, xr.grad, "dgrad")
+    check(wg.grad, wr.grad, "wgrad")
+    assert_fp32(bg.grad, br.grad, "dbias")
+
+
+FP32_CONV_CASES = [
+    ((3, 3, 3), 1, 27, 32, False), ((3, 3, 3), 1, 32, 32, False), ((3, 3, 3), 2, 64, 64, False),
+    ((2, 2, 2), 2, 32, 32, False), ((2, 2, 2), 2, 48, 40, True), ((1, 1, 1), 2, 64, 128, False),
+    ((3, 3, 3), 1, 5, 7, False), ((3, 3, 3), 2, 16, 24, True), ((3, 3, 3), 1, 96, 20, False),
+]
+
+
+@pytest.mark.parametrize("ks,stride,cin,cout,transpose", FP32_CONV_CASES)
+def test_conv_fp32_vs_fp64_oracle(cuda_device, ks, stride, cin, cout, transpose):
+    case = _conv_case(cuda_device, 31, 6000, 10, ks, stride, cin, cout, transpose)
+    _run_conv(cuda_device, *case, L.PREC_FP32, assert_fp32)
+
+
+TF32_CONV_CASES = [
+    ((3, 3, 3), 1, 32, 32, False, 0), ((3, 3, 3), 1, 64, 96, False, 0), ((3, 3, 3), 1, 128, 96, False, 2),
+    ((3, 3, 3), 1, 96, 96, False, 1), ((3, 3, 3), 1, 256, 256, False, 0), ((3, 3, 3), 2, 64, 128, False, 0),
+    ((2, 2, 2), 2, 32, 32, False, 0), ((2, 2, 2), 2, 256, 128, True, 0), ((1, 1, 1), 2, 128, 256, False, 0),
+    ((3, 3, 3), 1, 384, 256, False, 0), ((3, 3, 3), 2, 256, 512, False, 0), ((3, 3, 3), 1, 32, 16, False, 2),
+]
+
+
+@pytest.mark.parametrize("ks,stride,cin,cout,transpose,force_mt", TF32_CONV_CASES)
+def test_conv_tf32_tensor_core(cuda_device, ks, stride, cin, cout, transpose, force_mt):
+    lib = L.load()
+    case = _conv_case(cuda_device, 41, 9000, 11, ks, stride, cin, cout, transpose)
+    lib.spc_debug_force_mt(force_mt)
+    try:
+        _run_conv(cuda_device, *case, L.PREC_TF32, assert_tf32)
+    finally:
+        lib.spc_debug_force_mt(0)
+
+
+def test_conv_tf32_matches_fp32_kernels_large(cuda_device):
+    # on-device cross-check at a size the CPU oracle would not finish quickly (~150 K voxels)
+    c, _, _ = synth.room_batch(5, 1, 150_000, channels=1)
+    cmap, _, _, _ = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(cmap.size, 64, generator=g).to(cuda_device)
+    w = (torch.randn(27, 64, 96, generator=g) / (27 * 64) ** 0.5).to(cuda_device)
+    go = torch.randn(cmap.size, 96, generator=g).to(cuda_device)
+    a = ops.conv_fwd_raw(x, w, None, km, L.PREC_TF32)
+    b = ops.conv_fwd_raw(x, w, None, km, L.PREC_FP32)
+    assert_tf32(a, b, "fwd")
+    assert_tf32(ops.conv_dgrad_raw(go, w, km, L.PREC_TF32), ops.conv_dgrad_raw(go, w, km, L.PREC_FP32), "dgrad")
+    # linearity (size-independent property): conv(2x + y) == 2 conv(x) + conv(y)
+    y = torch.randn(cmap.size, 64, generator=g).to(cuda_device)
+    lhs = ops.conv_fwd_raw(2 * x + y, w, None, km, L.PREC_FP32)
+    rhs = 2 * b + ops.conv_fwd_raw(y, w, None, km, L.PREC_FP32)
+    assert_fp32(lhs, rhs, "linearity")
+    # 3^3 stride-1 maps are symmetric: nbr[k][o] = i  <=>  nbr[26-k][i] = o
+    assert bool((km.nbr_t == km.nbr.flip(0)).all())
+
+
+# ---------------------------------------------------------------------------
+# BN / ReLU / add / pooling / reduction
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("m,C,relu,res", [(1000, 32, False, False), (4097, 27, True, False), (3000, 96, True, True),
+                                          (257, 512, False, True), (2, 64, True, False), (50000, 128, True, True)])
+def test_batchnorm_matches_torch(cuda_device, m, C, relu, res):
+    g = torch.Generator().manual_seed(m + C)
+    x = torch.randn(m, C, generator=g, dtype=torch.float64) * 2 + 0.5
+    gamma = torch.rand(C, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(C, generator=g, dtype=torch.float64)
+    r = torch.randn(m, C, generator=g, dtype=torch.float64) if res else None
+    go = torch.randn(m, C, generator=g, dtype=torch.float64)
+    rm, rv = torch.zeros(C, dtype=torch.float64), torch.ones(C, dtype=torch.float64)
+    xr, gr, br = x.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    rr = r.clone().requires_grad_() if res else None
+    ref = torch.nn.functional.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5)
+    if res:
+        ref = ref + rr
+    if relu:
+        ref = torch.relu(ref)
+    ref.backward(go)
+    d = cuda_device
+    xg, gg, bg = (t.float().to(d).requires_grad_() for t in (x, gamma, beta))
+    rg = r.float().to(d).requires_grad_() if res else None
+    rmg, rvg = torch.zeros(C, device=d), torch.ones(C, device=d)
+    out = ops.BatchNormFn.apply(xg, gg, bg, rmg, rvg, True, 0.1, 1e-5, relu, rg)
+    out.backward(go.float().to(d))
+    assert_fp32(out, ref, "bn fwd")
+    assert_fp32(xg.grad, xr.grad, "bn dx")
+    assert_fp32(gg.grad, gr.grad, "bn dgamma")
+    assert_fp32(bg.grad, br.grad, "bn dbeta")
+    if res:
+        assert_fp32(rg.grad, rr.grad, "bn dres")
+    assert_fp32(rmg, rm, "running_mean")
+    assert_fp32(rvg, rv, "running_var")
+    # eval mode uses the running statistics
+    ev = ops.BatchNormFn.apply(xg.detach(), gg.detach(), bg.detach(), rmg, rvg, False, 0.1, 1e-5, False, None)
+    assert_fp32(ev, torch.nn.functional.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-5), "bn eval")
+
+
+def test_relu_add(cuda_device):
+    x = torch.randn(1001, 37, device=cuda_device, requires_grad=True)
+    y = ops.ReLUFn.apply(x)
+    y.backward(torch.ones_like(y))
+    assert torch.equal(y, torch.relu(x.detach())) and torch.equal(x.grad, (x.detach() > 0).float())
+    a, b = torch.randn(999, 5, device=cuda_device), torch.randn(999, 5, device=cuda_device)
+    assert torch.equal(ops.AddFn.apply(a, b), a + b)
+
+
+def test_pooling_and_global_pool(cuda_device):
+    c, f = synth.random_cloud(51, 20000, extent=16, n_batch=3, channels=64)
+    mgr = R.OracleManager(c)
+    feats = torch.from_numpy(f)
+    x0 = R.segment_mean(feats.double(), mgr.inverse, mgr.maps[(1, 1, 1)].shape[0])
+    cmap, first, inverse, count = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    xg = ops.SegmentReduceFn.apply(feats.to(cuda_device), inverse, count, first, cmap.size, 0)
+    assert_fp32(xg, x0, "segment mean")
+    assert_fp32(ops.SegmentReduceFn.apply(feats.to(cuda_device), inverse, count, first, cmap.size, 1),
+                R.segment_mean(feats.double(), mgr.inverse, cmap.size, "sum"), "segment sum")
+    ts2 = mgr.stride((1, 1, 1), (2, 2, 2))
+    m2, _, parent, cnt2 = ops.coords_insert(cmap.coords, L.SRC_STRIDE, ts2)
+    km = ops.build_kernel_map(cmap, m2, ops.kernel_offsets((2, 2, 2), (1, 1, 1), (1, 1, 1)))
+    nbr = mgr.kernel_map((1, 1, 1), ts2, (2, 2, 2))
+    for avg in (False, True):
+        xr = x0.clone().requires_grad_()
+        ref = R.sum_pool(xr, nbr, avg)
+        xq = xg.detach().clone().requires_grad_()
+        out = ops.LocalPoolFn.apply(xq, km, avg)
+        go = torch.randn(ref.shape, dtype=torch.float64)
+        ref.backward(go)
+        out.backward(go.float().to(cuda_device))
+        assert_fp32(out, ref, f"pool avg={avg}")
+        assert_fp32(xq.grad, xr.grad, f"pool bwd avg={avg}")
+    xr = x0.clone().requires_grad_()
+    ref = R.global_avg_pool(xr, mgr.maps[(1, 1, 1)], 3)
+    xq = xg.detach().clone().requires_grad_()
+    out = ops.GlobalPoolFn.apply(xq, cmap.coords, 3, True)
+    go = torch.randn(3, 64, dtype=torch.float64)
+    ref.backward(go)
+    out.backward(go.float().to(cuda_device))
+    assert_fp32(out, ref, "global avg")
+    assert_fp32(xq.grad, xr.grad, "global avg bwd")
+    # slice back to points
+    sl = ops.GatherRowsFn.apply(xg, inverse)
+    assert_fp32(sl, x0[torch.from_numpy(mgr.inverse.astype(np.int64))], "slice")
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (BASELINE config 2/4 scale: 1 M voxels)
+# ---------------------------------------------------------------------------
+def test_full_size_round_trips(cuda_device):
+    c, _, _ = synth.room_batch(777, 1, 1_000_000, channels=1)
+    cg = gpu(c, cuda_device)
+    cmap, first, inverse, count = ops.coords_insert(cg, L.SRC_FLOAT, (1, 1, 1))
+    assert cmap.size == 1_000_000
+    q = torch.floor(cg).int()
+    assert bool((cmap.coords[inverse.long()] == q).all())            # inverse map round trip
+    assert bool((first[1:] > first[:-1]).all())                      # first-occurrence order
+    assert bool((q[first.long()] == cmap.coords).all())
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    ar = torch.arange(cmap.size, device=cuda_device, dtype=torch.int32)
+    assert bool((km.nbr[13] == ar).all())                            # centre offset is the identity
+    assert bool((km.nbr_t == km.nbr.flip(0)).all())                  # symmetry of 3^3 s1 maps
+    # every pair satisfies coord_in == coord_out + offset
+    offs = ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1))
+    for k in (0, 5, 26):
+        o = torch.nonzero(km.nbr[k] >= 0).view(-1)
+        d = cmap.coords[km.nbr[k][o].long()] - cmap.coords[o]
+        assert bool((d == torch.tensor([0, *offs[k]], device=cuda_device, dtype=torch.int32)).all())
+    assert int(km.tap_count.sum()) == int((km.nbr >= 0).sum())
+    # stride map: idempotence and parent consistency
+    m2, _, parent, _ = ops.coords_insert(cmap.coords, L.SRC_STRIDE, (2, 2, 2))
+    want = cmap.coords.clone()
+    want[:, 1:] = torch.div(want[:, 1:], 2, rounding_mode="floor") * 2
+    assert bool((m2.coords[parent.long()] == want).all())
+    m2b, _, parent_b, _ = ops.coords_insert(m2.coords, L.SRC_STRIDE, (2, 2, 2))
+    assert m2b.size == m2.size and bool((parent_b == torch.arange(m2.size, device=cuda_device)).all())

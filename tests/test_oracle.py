@@ -1,0 +1,126 @@
+"""Oracle pinned on hand-checkable known answers and on itself
+(numpy restatement vs C restatement).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+
+
+def test_offset_numbering_z_axis():
+    # sparse_conv.py:375-379: valid_kernel=[4,13,22] is "the z axis" of a 3x3x3 kernel
+    offs = R.kernel_offsets((3, 3, 3), (1, 1, 1))
+    assert len(offs) == 27
+    assert offs[4] == (0, 0, -1) and offs[13] == (0, 0, 0) and offs[22] == (0, 0, 1)
+    assert offs[0] == (-1, -1, -1) and offs[1] == (0, -1, -1) and offs[3] == (-1, 0, -1)
+    # even kernels start at 0, offsets scale with the input tensor stride
+    assert R.kernel_offsets((2, 2, 2), (2, 2, 2)) == [(0, 0, 0), (2, 0, 0), (0, 2, 0), (2, 2, 0),
+                                                       (0, 0, 2), (2, 0, 2), (0, 2, 2), (2, 2, 2)]
+
+
+def test_quantize_negative_and_duplicates():
+    c = np.array([[0, -0.5, 0.2, 1.9], [0, -1.0, 0.99, 1.0], [0, 3.1, 0, 0], [1, -0.5, 0.2, 1.9],
+                  [0, -0.01, 0.5, 1.5]], np.float32)
+    for q in (R.quantize_np(c), R.quantize_c(c)):
+        assert q.tolist() == [[0, -1, 0, 1], [0, -1, 0, 1], [0, 3, 0, 0], [1, -1, 0, 1], [0, -1, 0, 1]]
+    for fn in (R.unique_first_np, R.unique_first_c):
+        uc, ui, inv = fn(R.quantize_np(c))
+        assert uc.tolist() == [[0, -1, 0, 1], [0, 3, 0, 0], [1, -1, 0, 1]]
+        assert ui.tolist() == [0, 2, 3]            # first occurrence, ascending
+        assert inv.tolist() == [0, 0, 1, 2, 0]
+    f = torch.tensor([[1.0], [3.0], [10.0], [7.0], [5.0]])
+    assert R.segment_mean(f, inv, 3).view(-1).tolist() == [3.0, 10.0, 7.0]
+    assert R.segment_mean(f, inv, 3, "sum").view(-1).tolist() == [9.0, 10.0, 7.0]
+
+
+def test_stride_floor_division():
+    c = np.array([[0, -1, 0, 3], [0, -2, 1, 4], [0, -3, 2, 5], [1, 7, -8, 0]], np.int32)
+    for fn in (R.stride_coords_np, R.stride_coords_c):
+        assert fn(c, (2, 2, 2)).tolist() == [[0, -2, 0, 2], [0, -2, 0, 4], [0, -4, 2, 4], [1, 6, -8, 0]]
+        assert fn(c, (4, 4, 4)).tolist() == [[0, -4, 0, 0], [0, -4, 0, 4], [0, -4, 0, 4], [1, 4, -8, 0]]
+
+
+def test_line_conv_shifts():
+    # (i) five voxels on the x axis, one-hot weights -> shifts
+    coords = np.array([[0, x, 0, 0] for x in range(5)], np.int32)
+    offs = R.kernel_offsets((3, 3, 3), (1, 1, 1))
+    for fn in (R.kernel_map_np, R.kernel_map_c):
+        nbr = fn(coords, coords, offs)
+        assert nbr[13].tolist() == [0, 1, 2, 3, 4]
+        assert nbr[12].tolist() == [-1, 0, 1, 2, 3]   # offset (-1,0,0): in = out - 1
+        assert nbr[14].tolist() == [1, 2, 3, 4, -1]
+        assert (np.delete(nbr, [12, 13, 14], axis=0) == -1).all()
+    feats = torch.arange(1.0, 6.0).view(5, 1)
+    w = torch.zeros(27, 1, 1)
+    w[14] = 1.0
+    assert R.conv_forward(feats, w, nbr).view(-1).tolist() == [2.0, 3.0, 4.0, 5.0, 0.0]
+    pairs = R.pairs_from_dense(nbr)
+    assert sorted(pairs) == [12, 13, 14] and pairs[12].tolist() == [[0, 1, 2, 3], [1, 2, 3, 4]]
+
+
+def test_block_conv_k2s2_and_transpose():
+    # (ii)/(iii) a 2x2x2 block through conv k2 s2 and back through convtr k2 s2
+    block = np.array([[0, x, y, z] for z in range(2) for y in range(2) for x in range(2)], np.int32)
+    mgr = R.OracleManager(block.astype(np.float32))
+    ts2 = mgr.stride((1, 1, 1), (2, 2, 2))
+    assert mgr.maps[ts2].tolist() == [[0, 0, 0, 0]]
+    nbr = mgr.kernel_map((1, 1, 1), ts2, (2, 2, 2))
+    assert nbr.reshape(-1).tolist() == list(range(8))          # k = x + 2y + 4z
+    feats = torch.arange(1.0, 9.0).view(8, 1)
+    w = torch.arange(1.0, 9.0).view(8, 1, 1) * 10
+    assert R.conv_forward(feats, w, nbr).item() == sum(10.0 * (i + 1) ** 2 for i in range(8))
+    nbr_t = mgr.kernel_map(ts2, (1, 1, 1), (2, 2, 2), transpose=True)
+    assert nbr_t.shape == (8, 8)
+    up = R.conv_forward(torch.tensor([[2.0]]), w, nbr_t)
+    assert up.view(-1).tolist() == [20.0 * (i + 1) for i in range(8)]      # fine voxel f gets in*W[k(f-c)]
+
+
+def test_kernel1_stride2_keeps_even_lattice():
+    # (vi) kernel 1, stride 2: only voxels on the coarse lattice contribute
+    coords = np.array([[0, 0, 0, 0], [0, 1, 0, 0], [0, 2, 0, 0], [0, 3, 1, 0]], np.float32)
+    mgr = R.OracleManager(coords)
+    ts2 = mgr.stride((1, 1, 1), (2, 2, 2))
+    assert mgr.maps[ts2].tolist() == [[0, 0, 0, 0], [0, 2, 0, 0]]
+    nbr = mgr.kernel_map((1, 1, 1), ts2, (1, 1, 1))
+    assert nbr.tolist() == [[0, 2]]
+    assert mgr.parents[ts2].tolist() == [0, 0, 1, 1]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_numpy_and_c_restatements_agree(seed):
+    rng = np.random.default_rng(seed)
+    n = 5000
+    c = np.empty((n, 4), np.float32)
+    c[:, 0] = rng.integers(0, 3, n)
+    c[:, 1:] = rng.uniform(-9, 9, (n, 3))
+    q = R.quantize_np(c)
+    assert (q == R.quantize_c(c)).all()
+    a, b = R.unique_first_np(q), R.unique_first_c(q)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    uc = a[0]
+    assert (uc[a[2]] == q).all() and (np.diff(a[1]) > 0).all()
+    for ts_in, k, s in [((1, 1, 1), 3, 1), ((1, 1, 1), 3, 2), ((1, 1, 1), 2, 2), ((1, 1, 1), 1, 2)]:
+        out = uc if s == 1 else R.unique_first_np(R.stride_coords_np(uc, (s, s, s)))[0]
+        offs = R.kernel_offsets((k,) * 3, ts_in)
+        n1, n2 = R.kernel_map_np(uc, out, offs), R.kernel_map_c(uc, out, offs)
+        assert (n1 == n2).all()
+        # definition check: coord_in == coord_out + offset for every pair
+        for kk in (0, len(offs) // 2, len(offs) - 1):
+            o = np.nonzero(n1[kk] >= 0)[0]
+            assert (uc[n1[kk, o]][:, 1:] == out[o][:, 1:] + np.array(offs[kk])).all()
+            assert (uc[n1[kk, o]][:, 0] == out[o][:, 0]).all()
+        t = R.transpose_dense(n1, uc.shape[0])
+        assert ((t >= 0).sum() == (n1 >= 0).sum())
+
+
+def test_conv_autograd_gradcheck():
+    # (viii) fp64 gradcheck of the oracle convolution on a tiny map
+    rng = np.random.default_rng(3)
+    c = np.unique(rng.integers(0, 4, (40, 4)).astype(np.int32), axis=0)
+    c[:, 0] = 0
+    c = np.unique(c, axis=0)
+    nbr = R.kernel_map_np(c, c, R.kernel_offsets((3, 3, 3), (1, 1, 1)))
+    x = torch.randn(c.shape[0], 2, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(27, 2, 3, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: R.conv_forward(a, b, nbr), (x, w))
