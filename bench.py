@@ -270,6 +270,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         ops.set_profiler(None)
         classes = prof.summary()
+        if args.detail:
+            det = prof.summary_detail()
+            for (name, detail), v in sorted(det.items(), key=lambda kv: -kv[1]["ms"])[:40]:
+                t = v["ms"] / v["n"]
+                print(f"# {name:12s} {detail:34s} n={v['n']:3d} avg={t:8.3f} ms  "
+                      f"{v['flops'] / v['n'] / (t * 1e-3) / 1e12 if t > 0 else 0:7.1f} TFLOP/s  "
+                      f"{v['bytes'] / v['n'] / (t * 1e-3) / 1e9 if t > 0 else 0:7.0f} GB/s(alg)", file=sys.stderr)
         peaks = _peaks()
         if classes:
             top = max(classes.items(), key=lambda kv: kv[1]["ms"])
@@ -334,6 +341,7 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

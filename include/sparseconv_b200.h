@@ -137,6 +137,7 @@ int spc_scatter_add_rows(const float* src, const int32_t* index, int64_t n, int6
  *   workspace: spc_conv_workspace(...) bytes (packed weights for the TF32 path).
  */
 void spc_debug_force_mt(int mt);
+void spc_debug_set(int idx, int val); /* test hook: wgrad operand-layout knobs, 0 = default */
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
 int spc_conv_fwd(const float* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
@@ -145,7 +146,7 @@ int spc_conv_dgrad(const float* dout, const float* w, const int32_t* nbr_t,
                    const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* din, void* workspace, int64_t workspace_bytes, void* stream);
 int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
-                   int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
+                   const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* dw, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*

@@ -19,10 +19,11 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
                   void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 bool umma_wgrad_supported(int c_in, int c_out);
 int64_t umma_wgrad_workspace(int K, int c_in, int c_out);
-int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, int64_t m_out, int c_in,
-                    int c_out, int K, float* dw, void* workspace, int64_t workspace_bytes,
-                    cudaStream_t stream);
+int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const uint32_t* tile_mask,
+                    int64_t m_out, int c_in, int c_out, int K, float* dw, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t stream);
 void umma_set_force_mt(int mt);
+void umma_debug_set(int idx, int val);
 }  // namespace spc
 
 using namespace spc;
@@ -31,6 +32,8 @@ extern "C" {
 
 /* test hook: force the number of 128-row sub-tiles per CTA of the tcgen05 kernel (0 = auto) */
 void spc_debug_force_mt(int mt) { umma_set_force_mt(mt); }
+/* test hook: operand-layout knobs of the tcgen05 wgrad kernel (0 = built-in default) */
+void spc_debug_set(int idx, int val) { umma_debug_set(idx, val); }
 
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision) {
   if (precision != SPC_PREC_TF32) return 256;
@@ -67,14 +70,15 @@ int spc_conv_dgrad(const float* dout, const float* w, const int32_t* nbr_t,
   return conv_fwd_simt(dout, w, nullptr, nbr_t, m_in, c_out, c_in, K, true, din, (cudaStream_t)stream);
 }
 
-int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr, int64_t m_in,
+int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
+                   const uint32_t* tile_mask, int64_t m_in,
                    int64_t m_out, int c_in, int c_out, int K, int precision, float* dw,
                    void* workspace, int64_t workspace_bytes, void* stream) {
   (void)m_in;
   SPC_REQUIRE(c_in >= 1 && c_out >= 1 && K >= 1, "bad shape");
   SPC_REQUIRE(precision == SPC_PREC_FP32 || precision == SPC_PREC_TF32, "bad precision mode");
-  if (precision == SPC_PREC_TF32 && umma_wgrad_supported(c_in, c_out))
-    return conv_wgrad_umma(in, dout, nbr, m_out, c_in, c_out, K, dw, workspace, workspace_bytes,
+  if (precision == SPC_PREC_TF32 && K <= 32 && umma_wgrad_supported(c_in, c_out))
+    return conv_wgrad_umma(in, dout, nbr, tile_mask, m_out, c_in, c_out, K, dw, workspace, workspace_bytes,
                            (cudaStream_t)stream);
   return conv_wgrad_simt(in, dout, nbr, m_out, c_in, c_out, K, dw, (cudaStream_t)stream);
 }

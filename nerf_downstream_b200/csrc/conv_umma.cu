@@ -309,6 +309,7 @@ static int launch_conv_umma(const UmmaConvParams& p, int grid, size_t smem, cuda
 }
 
 static int g_umma_force_mt = 0;  // test hook: 0 = auto
+static int g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // test hook spc_debug_set: 0 = default
 
 int conv_fwd_umma(const float* in, const float* w, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
@@ -366,12 +367,341 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
 }
 
 void umma_set_force_mt(int mt) { g_umma_force_mt = mt; }
+void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_dbg[idx] = val; }
 
-bool umma_wgrad_supported(int, int) { return false; }
-int64_t umma_wgrad_workspace(int, int, int) { return 0; }
-int conv_wgrad_umma(const float*, const float*, const int*, int64_t, int, int, int, float*, void*,
-                    int64_t, cudaStream_t) {
-  return fail("conv_wgrad_umma", "not built");
+// =====================================================================================
+// wgrad on tcgen05:  dW[k][ci][co] = sum_o in[nbr[k,o]][ci] * dout[o][co]
+// =====================================================================================
+// GEMM view: D[M x N] += A[M x Kred] * B[Kred x N] with the REDUCTION over out rows o:
+//   M = 128 = four 32-channel "chunks", each chunk = (kernel offset k, channel group cc) — so for
+//       Cin = 32 four different offsets share one MMA, for Cin = 128 one offset fills it;
+//   N = Cout;  Kred = 8 rows per tcgen05.mma (tf32).
+// Both operands are MN-major: a gathered input row IS 32 consecutive M elements, a dout row IS
+// Cout consecutive N elements, so rows are laid down as [rows x 128 B] blocks like in the forward
+// kernel; MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3),
+// LBO = distance between 32-element column groups, SBO = distance between 4-row groups.
+// TMEM holds `mb_per_pass` accumulators (512 columns); a work item = (row range, pass) and ends
+// with an fp32 red.global.add of its partial dW — the only atomics of the convolution path.
+constexpr int kWgR = 64;                         // reduction rows per pipeline step
+constexpr int kWgChunkBlock = kWgR * kChunkBytes;  // 8 KB: [64 rows x 128 B]
+constexpr int kWgAStage = 4 * kWgChunkBlock;     // 32 KB: four chunks = one 128-row M block
+constexpr int kWgMaxAStages = 6;
+constexpr int kWgBStages = 2;
+
+struct UmmaWgradParams {
+  const float* in;            // [m_in, Cin]
+  const float* dout;          // [m_out, Cout]
+  const int* nbr;             // [K, m_out]
+  const uint32_t* tile_mask;  // [ceil(m_out/128)] or null
+  float* dw;                  // [K, Cin, Cout], zeroed
+  int m_out, Cin, Cout, K;
+  int ncc, nq;                // chunks per offset, total chunks
+  int n_mb, mb_per_pass, n_pass;
+  int n_rb, rb_per_split, n_split;
+  int a_stages;
+  int dbg_layout, dbg_swz, dbg_lbo, dbg_sbo;  // operand layout knobs (test hook spc_debug_set)
+  int n_work;
+};
+
+// byte offset of 16-byte piece j (0..7) of row r inside its 128-byte line under
+// SWIZZLE_128B_BASE32B = Swizzle<2,5,2>: the 32-byte chunk index is XORed with (row & 3)
+__device__ __forceinline__ uint32_t wg_swz(int j, int r, int mode) {
+  if (mode == 0) return (uint32_t)((j ^ (r & 7)) << 4);  // SWIZZLE_128B (16-byte base)
+  return (uint32_t)((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4));
+}
+
+// offsets (bitmask) that the chunks of M block `mb` (global index) belong to
+__device__ __forceinline__ uint32_t mblock_taps(int mb, int ncc, int nq) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    int q = mb * 4 + s;
+    if (q < nq) t |= 1u << (q / ncc);
+  }
+  return t;
+}
+
+template <int LOOKAHEAD>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_wgrad_umma_kernel(const UmmaWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_stage_bytes = (p.Cout / 32) * kWgChunkBlock;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)p.a_stages * kWgAStage;
+  const uint32_t bar_base = b_base + (uint32_t)kWgBStages * b_stage_bytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kWgMaxAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kWgMaxAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kWgMaxAStages + kWgBStages + s); };
+  const uint32_t t_full = bar_base + 8u * (2 * kWgMaxAStages + 2 * kWgBStages);
+  const uint32_t t_empty = t_full + 8u;
+  const uint32_t tmem_slot = t_full + 16u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), kNumProducerThreads); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), kNumProducerThreads); mbar_init(b_empty(s), 1); }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, kNumEpilogueThreads);
+    fence_mbar_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t all_taps = p.K >= 32 ? 0xFFFFFFFFu : ((1u << p.K) - 1u);
+
+  // (row block -> offset mask); tile masks are per 128 rows = 2 row blocks
+  auto rb_mask = [&](int rb) -> uint32_t {
+    return p.tile_mask ? (p.tile_mask[rb >> 1] & all_taps) : all_taps;
+  };
+
+  if (warp < 4) {
+    // ============================ producers ============================
+    int a_stage = 0, b_stage = 0, arr_a = 0, arr_b = 0, outstanding = 0;
+    uint32_t a_phase = 0, b_phase = 0, hasb_fifo = 0;  // bit i = i-th oldest outstanding group carries B
+    auto arrive_oldest = [&]() {
+      if (hasb_fifo & 1u) { mbar_arrive(b_full(arr_b)); if (++arr_b == kWgBStages) arr_b = 0; }
+      mbar_arrive(a_full(arr_a));
+      if (++arr_a == p.a_stages) arr_a = 0;
+      hasb_fifo >>= 1;
+      --outstanding;
+    };
+    // Before blocking on a free slot, publish every group issued so far: the B ring is shallower
+    // than the look-ahead window, so the consumer may need those groups to release the slot.
+    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
+      if (mbar_try_wait(bar, parity)) return;
+      if (outstanding > 0) {
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        while (outstanding > 0) arrive_oldest();
+      }
+      mbar_wait(bar, parity);
+    };
+    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+      const int split = w / p.n_pass, pass = w - split * p.n_pass;
+      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
+      for (int rb = rb0; rb < rb1; ++rb) {
+        const uint32_t mask = rb_mask(rb);
+        const int o0 = rb * kWgR;
+        bool b_loaded = false;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          if (!(mblock_taps(mb, p.ncc, p.nq) & mask)) continue;
+          bool with_b = false;
+          if (!b_loaded) {
+            b_loaded = with_b = true;
+            wait_empty(b_empty(b_stage), b_phase ^ 1u);
+            const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
+            const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
+            for (int e = threadIdx.x; e < n16; e += kNumProducerThreads) {
+              const int j = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
+              const int o = o0 + r;
+              const bool ok = o < p.m_out;
+              const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + j * 4;
+              cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(j, r, p.dbg_swz), src, ok ? 16u : 0u);
+            }
+          }
+          wait_empty(a_empty(a_stage), a_phase ^ 1u);
+          {
+            // warp w gathers chunk slot w of this M block: 64 rows x 128 B
+            const int q = mb * 4 + warp;
+            if (q < p.nq) {
+              const int k = q / p.ncc, cc = q - k * p.ncc;
+              const int oa = o0 + lane, ob = o0 + 32 + lane;
+              const int idx0 = oa < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + oa) : -1;
+              const int idx1 = ob < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + ob) : -1;
+              const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + warp * kWgChunkBlock;
+              const int j = lane & 7, sub = lane >> 3;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = i * 4 + sub;
+                const int v0 = __shfl_sync(0xffffffffu, idx0, r & 31);
+                const int v1 = __shfl_sync(0xffffffffu, idx1, r & 31);
+                const int src_row = i < 8 ? v0 : v1;
+                const float* src = p.in + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin + cc * 32 + j * 4;
+                cp_async_16(dsta + r * kChunkBytes + wg_swz(j, r, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
+              }
+            }
+          }
+          cp_async_commit();
+          hasb_fifo |= (with_b ? 1u : 0u) << outstanding;
+          ++outstanding;
+          if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
+          if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
+          if (outstanding > LOOKAHEAD) {
+            cp_async_wait<LOOKAHEAD>();
+            fence_proxy_async_smem();
+            arrive_oldest();
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    while (outstanding > 0) arrive_oldest();
+  } else if (warp == 8) {
+    // ============================ MMA issuer ============================
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0, t_phase = 0;
+    const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
+    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+      const int split = w / p.n_pass, pass = w - split * p.n_pass;
+      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
+      mbar_wait(t_empty, t_phase ^ 1u);  // epilogue drained the accumulators of the previous item
+      tc_fence_after();
+      uint32_t touched = 0;
+      for (int rb = rb0; rb < rb1; ++rb) {
+        const uint32_t mask = rb_mask(rb);
+        bool b_ready = false;
+        int b_used = -1;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          if (!(mblock_taps(mb, p.ncc, p.nq) & mask)) continue;
+          if (!b_ready) {
+            mbar_wait(b_full(b_stage), b_phase);
+            b_ready = true;
+            b_used = b_stage;
+          }
+          mbar_wait(a_full(a_stage), a_phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = a_base + (uint32_t)a_stage * kWgAStage;
+            const uint32_t b_addr = b_base + (uint32_t)b_used * b_stage_bytes;
+            const uint32_t d = tmem_base + (uint32_t)((mb - mb0) * p.Cout);
+            const uint32_t was = (touched >> (mb - mb0)) & 1u;
+#pragma unroll
+            for (int r8 = 0; r8 < kWgR / 8; ++r8) {
+              const uint64_t adesc = make_desc(a_addr + r8 * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+              const uint64_t bdesc = make_desc(b_addr + r8 * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+              mma_tf32(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
+            }
+            mma_commit(a_empty(a_stage));
+          }
+          __syncwarp();
+          touched |= 1u << (mb - mb0);
+          if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
+        }
+        if (b_ready) {
+          if (lane == 0) mma_commit(b_empty(b_used));
+          __syncwarp();
+          if (++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
+        }
+      }
+      if (lane == 0) mma_commit(t_full);
+      __syncwarp();
+      t_phase ^= 1u;
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int ew = warp & 3;
+    uint32_t t_phase = 0;
+    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+      const int split = w / p.n_pass, pass = w - split * p.n_pass;
+      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
+      // which accumulators received at least one MMA (same rule as the issuer)
+      uint32_t seen = 0;
+      for (int rb = rb0 + lane; rb < rb1; rb += 32) seen |= rb_mask(rb);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
+      mbar_wait(t_full, t_phase);
+      tc_fence_after();
+      for (int mb = mb0; mb < mb1; ++mb) {
+        if (!(mblock_taps(mb, p.ncc, p.nq) & seen)) continue;
+        const int q = mb * 4 + ew;
+        if (q >= p.nq) continue;  // padding chunk of the last M block (warp-uniform)
+        const int k = q / p.ncc, cc = q - k * p.ncc;
+        if (!((seen >> k) & 1u)) continue;  // this offset has no pair in the row range: stays zero
+        float* dst = p.dw + ((size_t)k * p.Cin + cc * 32 + lane) * p.Cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((mb - mb0) * p.Cout);
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(v[i]),
+                         "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(t_empty);
+      t_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+bool umma_wgrad_supported(int c_in, int c_out) {
+  return c_in >= 32 && c_in % 32 == 0 && c_out >= 32 && c_out % 32 == 0 && c_out <= 256;
+}
+int64_t umma_wgrad_workspace(int, int, int) { return 256; }
+
+template <int LOOKAHEAD>
+static int launch_wgrad_umma(const UmmaWgradParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = conv_wgrad_umma_kernel<LOOKAHEAD>;
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kNumThreads, smem, stream>>>(p);
+  SPC_LAUNCHED("conv_wgrad_umma_kernel");
+  return 0;
+}
+
+int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const uint32_t* tile_mask,
+                    int64_t m_out, int c_in, int c_out, int K, float* dw, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  SPC_REQUIRE(umma_wgrad_supported(c_in, c_out), "shape not supported by the tcgen05 wgrad path");
+  SPC_REQUIRE(K <= 32, "tcgen05 path supports kernel volume <= 32");
+  SPC_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dw % 16) == 0,
+              "rows must be 16-byte aligned");
+  SPC_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
+  if (m_out == 0) return 0;
+  UmmaWgradParams p;
+  p.in = in; p.dout = dout; p.nbr = nbr; p.tile_mask = tile_mask; p.dw = dw;
+  p.m_out = (int)m_out; p.Cin = c_in; p.Cout = c_out; p.K = K;
+  p.ncc = c_in / 32;
+  p.nq = K * p.ncc;
+  p.n_mb = (p.nq + 3) / 4;
+  int cap = 512 / c_out;                       // accumulators that fit in TMEM
+  p.n_pass = (p.n_mb + cap - 1) / cap;
+  p.mb_per_pass = (p.n_mb + p.n_pass - 1) / p.n_pass;
+  p.n_pass = (p.n_mb + p.mb_per_pass - 1) / p.mb_per_pass;
+  p.n_rb = (int)ceil_div(m_out, kWgR);
+  int want_split = (2 * kNumSMs + p.n_pass - 1) / p.n_pass;
+  if (want_split > p.n_rb) want_split = p.n_rb;
+  if (want_split < 1) want_split = 1;
+  p.rb_per_split = (p.n_rb + want_split - 1) / want_split;
+  if (p.rb_per_split & 1) ++p.rb_per_split;    // keep splits aligned to 128-row mask tiles
+  p.n_split = (p.n_rb + p.rb_per_split - 1) / p.rb_per_split;
+  p.n_work = p.n_split * p.n_pass;
+  const int b_stage_bytes = (c_out / 32) * kWgChunkBlock;
+  int a_stages = (kSmemLimit - 1024 - 256 - kWgBStages * b_stage_bytes) / kWgAStage;
+  if (a_stages > kWgMaxAStages) a_stages = kWgMaxAStages;
+  SPC_REQUIRE(a_stages >= 2, "wgrad tile does not fit in shared memory");
+  p.a_stages = a_stages;
+  // MN-major 32-bit operands: SWIZZLE_128B_BASE32B, LBO = chunk-block pitch, SBO = 4-row group pitch
+  p.dbg_layout = g_dbg[0] ? g_dbg[0] : 1;
+  p.dbg_swz = g_dbg[1] ? g_dbg[1] - 1 : 1;
+  p.dbg_lbo = g_dbg[2] ? g_dbg[2] : kWgChunkBlock;
+  p.dbg_sbo = g_dbg[3] ? g_dbg[3] : 512;
+  const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256;
+  const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
+  const int la = a_stages >= 6 ? 5 : (a_stages >= 4 ? 3 : 1);
+  switch (la) {
+    case 5: return launch_wgrad_umma<5>(p, grid, smem, stream);
+    case 3: return launch_wgrad_umma<3>(p, grid, smem, stream);
+    default: return launch_wgrad_umma<1>(p, grid, smem, stream);
+  }
 }
 
 }  // namespace spc

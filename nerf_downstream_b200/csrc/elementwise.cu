@@ -56,23 +56,39 @@ template <> struct Vec<4> {
 // ---------------------------------------------------------------------------
 // MODE 0: s0 = sum x, s1 = sum x^2                     (BN statistics)
 // MODE 1: s0 = sum dy', s1 = sum dy' * (x - mean)      (BN backward; dy' = relu-masked dy)
+// Per-channel double sums live in `gsum[2C]` (zeroed by the host wrapper); the block that takes
+// the last ticket of `counter` finalises, so statistics cost ONE launch.
+struct ColFinal {
+  double* gsum;          // [2C]
+  unsigned* counter;
+  float* out0;           // MODE 0: mean    | MODE 1: dbeta
+  float* out1;           // MODE 0: var     | MODE 1: dgamma
+  float* raw;            // MODE 1: float sums [2C] for the apply kernel
+  float* run_mean;       // MODE 0, optional
+  float* run_var;
+  const float* var;      // MODE 1
+  float momentum, eps;
+};
+
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(1024)
 col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
                   const float* __restrict__ dy, const float* __restrict__ mean, long long m, int C,
-                  int lanes, int rows, int relu, float* __restrict__ partial) {
+                  int lanes, int rows, int relu, ColFinal fin) {
   extern __shared__ float sm[];  // [rows][2*C]
+  __shared__ bool s_last;
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
   const int c0 = lane * VEC;
   float s0[VEC], s1[VEC], mu[VEC];
+  // MODE 0 accumulates around a pivot (row 0) so that E[x^2] - E[x]^2 does not cancel
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { s0[j] = 0.f; s1[j] = 0.f; mu[j] = MODE == 1 ? mean[c0 + j] : 0.f; }
+  for (int j = 0; j < VEC; ++j) { s0[j] = 0.f; s1[j] = 0.f; mu[j] = MODE == 1 ? mean[c0 + j] : x[c0 + j]; }
   for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
     const long long off = r * C + c0;
     Vec<VEC> xv = Vec<VEC>::load(x + off);
     if (MODE == 0) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s0[j] += xv.v[j]; s1[j] += xv.v[j] * xv.v[j]; }
+      for (int j = 0; j < VEC; ++j) { float d = xv.v[j] - mu[j]; s0[j] += d; s1[j] += d * d; }
     } else {
       Vec<VEC> g = Vec<VEC>::load(dy + off);
       if (relu) {
@@ -93,41 +109,34 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
   for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
     float acc = 0.f;
     for (int q = 0; q < rows; ++q) acc += sm[q * 2 * C + idx];
-    partial[(long long)blockIdx.x * 2 * C + idx] = acc;
+    atomicAdd(fin.gsum + idx, (double)acc);
   }
-}
-
-// out0[c] = S0/m, out1[c] = S1/m - (S0/m)^2          (MODE 0: mean, biased var)
-// out0[c] = S0,   out1[c] = S1 * rsqrt(var+eps)       (MODE 1: dbeta, dgamma)
-template <int MODE>
-__global__ void col_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
-                                    long long m, const float* __restrict__ var, float eps,
-                                    float* __restrict__ out0, float* __restrict__ out1,
-                                    float* __restrict__ raw /* [2C] sums, optional */,
-                                    float* __restrict__ run_mean, float* __restrict__ run_var,
-                                    float momentum) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblocks; ++i) {
-    a += (double)partial[(long long)i * 2 * C + c];
-    b += (double)partial[(long long)i * 2 * C + C + c];
-  }
-  if (raw) { raw[c] = (float)a; raw[C + c] = (float)b; }
-  if (MODE == 0) {
-    double mu = a / (double)m;
-    double v = b / (double)m - mu * mu;
-    v = v > 0.0 ? v : 0.0;
-    out0[c] = (float)mu;
-    out1[c] = (float)v;
-    if (run_mean) {  // nn.BatchNorm1d: running_var tracks the UNBIASED variance
-      double unb = m > 1 ? v * (double)m / (double)(m - 1) : v;
-      run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * mu);
-      run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double a = __ldcg(fin.gsum + c), b = __ldcg(fin.gsum + C + c);
+    if (MODE == 0) {
+      const double dm = a / (double)m;
+      const double mu0 = (double)x[c] + dm;            // pivot + mean of the deviations
+      double v = b / (double)m - dm * dm;              // biased variance
+      v = v > 0.0 ? v : 0.0;
+      fin.out0[c] = (float)mu0;
+      fin.out1[c] = (float)v;
+      if (fin.run_mean) {  // nn.BatchNorm1d: running_var tracks the UNBIASED variance
+        const double unb = m > 1 ? v * (double)m / (double)(m - 1) : v;
+        fin.run_mean[c] = (float)((1.0 - fin.momentum) * fin.run_mean[c] + fin.momentum * mu0);
+        fin.run_var[c] = (float)((1.0 - fin.momentum) * fin.run_var[c] + fin.momentum * unb);
+      }
+    } else {
+      fin.raw[c] = (float)a;
+      fin.raw[C + c] = (float)b;
+      fin.out0[c] = (float)a;                                                // dbeta
+      fin.out1[c] = (float)(b / sqrt((double)fin.var[c] + (double)fin.eps)); // dgamma
     }
-  } else {
-    out0[c] = (float)a;
-    out1[c] = (float)(b / sqrt((double)var[c] + (double)eps));
   }
 }
 
@@ -343,23 +352,37 @@ extern "C" {
 
 int64_t spc_bn_workspace(int64_t m, int C) {
   (void)m;
-  return (int64_t)kNumSMs * 4 * 2 * C * 4 + 2 * C * 4 + 256;
+  return (int64_t)2 * C * 8 + 2 * C * 4 + 256;  // double sums [2C], counter, float sums [2C]
+}
+
+struct BnWs {
+  double* gsum;
+  unsigned* counter;
+  float* raw;
+};
+static BnWs bn_ws(void* workspace, int C) {
+  BnWs w;
+  char* base = (char*)(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
+  w.gsum = (double*)base;
+  w.counter = (unsigned*)(base + (size_t)2 * C * 8);
+  w.raw = (float*)(base + (size_t)2 * C * 8 + 64);
+  return w;
 }
 
 static int col_reduce_launch(int mode, const float* x, const float* y, const float* dy,
-                             const float* mean, int64_t m, int C, int relu, float* partial,
-                             int* nblocks_out, cudaStream_t stream) {
+                             const float* mean, int64_t m, int C, int relu, ColFinal fin,
+                             cudaStream_t stream) {
   int vec = pick_vec(C, x, y, dy);
   RowMap rm = make_row_map(C, vec);
   if (rm.threads > 1024) return fail("col_reduce", "C too large (max 1024 scalar / 4096 vec4)");
   int grid = pick_grid(m, rm.rows, 4);
   size_t smem = (size_t)rm.rows * 2 * C * sizeof(float);
-  if (smem > 48 * 1024) return fail("col_reduce", "shared memory");
+  if (smem > 40 * 1024) return fail("col_reduce", "shared memory");
+  SPC_CUDA(cudaMemsetAsync(fin.gsum, 0, (size_t)2 * C * 8 + 64, stream));  // sums + ticket counter
   DISPATCH_VEC(vec,
-    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, partial);
-    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, partial));
+    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, fin);
+    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, dy, mean, m, C, rm.lanes, rm.rows, relu, fin));
   SPC_LAUNCHED("col_reduce_kernel");
-  *nblocks_out = grid;
   return 0;
 }
 
@@ -369,13 +392,12 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
-  float* partial = (float*)workspace;
-  int nb = 0;
-  int rc = col_reduce_launch(0, x, nullptr, nullptr, nullptr, m, C, 0, partial, &nb, stream);
-  if (rc) return rc;
-  col_finalize_kernel<0><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, nullptr, 0.f, mean, var, nullptr, running_mean, running_var, momentum);
-  SPC_LAUNCHED("col_finalize_kernel");
-  return 0;
+  BnWs w = bn_ws(workspace, C);
+  ColFinal fin;
+  fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
+  fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
+  fin.momentum = momentum; fin.eps = 0.f;
+  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, m, C, 0, fin, stream);
 }
 
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
@@ -402,13 +424,13 @@ int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mea
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
   SPC_REQUIRE(!relu || y, "relu backward needs y");
-  float* partial = (float*)workspace;
-  float* sums = partial + (int64_t)kNumSMs * 4 * 2 * C;
-  int nb = 0;
-  int rc = col_reduce_launch(1, x, y, dy, mean, m, C, relu, partial, &nb, stream);
+  BnWs w = bn_ws(workspace, C);
+  float* sums = w.raw;
+  ColFinal fin;
+  fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = dbeta; fin.out1 = dgamma; fin.raw = sums;
+  fin.run_mean = nullptr; fin.run_var = nullptr; fin.var = var; fin.momentum = 0.f; fin.eps = eps;
+  int rc = col_reduce_launch(1, x, y, dy, mean, m, C, relu, fin, stream);
   if (rc) return rc;
-  col_finalize_kernel<1><<<(int)ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, m, var, eps, dbeta, dgamma, sums, nullptr, nullptr, 0.f);
-  SPC_LAUNCHED("col_finalize_kernel");
   int vec = pick_vec(C, x, y, dy, dx);
   if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;
   RowMap rm = make_row_map(C, vec);

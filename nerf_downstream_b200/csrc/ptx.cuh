@@ -108,14 +108,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1.
 // `lbo_bytes` is only meaningful for MN-major operands (distance between 128-byte column
 // groups); K-major swizzled layouts ignore it (canonical value 16 B).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
+}
+// K-major operand, SWIZZLE_128B (16-byte chunks XOR row&7), 8-row groups `sbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
+}
+// MN-major 32-bit operand: the only legal layout is SWIZZLE_128B_BASE32B (32-byte chunks XOR
+// row&3; atom = 4 K-rows x 128 B).  LBO = distance between 32-element groups along MN,
+// SBO = distance between 4-row groups along K.
+__device__ __forceinline__ uint64_t make_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                          uint32_t sbo_bytes) {
+  return make_desc(smem_addr, lbo_bytes, sbo_bytes, 1u);
 }
 // Instruction descriptor for kind::tf32 with fp32 accumulation.
 // a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.

@@ -38,10 +38,11 @@ SIGNATURES = {
     "spc_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "spc_scatter_add_rows": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "spc_debug_force_mt": (None, [c_int]),
+    "spc_debug_set": (None, [c_int, c_int]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
-    "spc_conv_wgrad": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
+    "spc_conv_wgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_bn_workspace": (c_int64, [c_int64, c_int]),
     "spc_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "spc_bn_apply": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P, _P]),

@@ -48,15 +48,27 @@ class KernelProfiler:
         e.record(torch.cuda.current_stream())
         return e
 
-    def end(self, name, e0, flops=0.0, nbytes=0.0):
+    def end(self, name, e0, flops=0.0, nbytes=0.0, detail=""):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream())
-        self.records.append((name, e0, e1, float(flops), float(nbytes)))
+        self.records.append((name, e0, e1, float(flops), float(nbytes), detail))
+
+    def summary_detail(self):
+        """{(class, detail): {...}} — per layer shape."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl, by, detail in self.records:
+            d = out.setdefault((name, detail), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, fl, by in self.records:
+        for name, e0, e1, fl, by, _ in self.records:
             d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += e0.elapsed_time(e1)
             d["n"] += 1
@@ -346,7 +358,8 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
                              c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
             "spc_conv_fwd")
     if e0 is not None:
-        _profiler.end("conv_fwd", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+        _profiler.end("conv_fwd", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
+                      f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
     return out
 
 
@@ -363,7 +376,8 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision):
                                c_out, K, precision, L.ptr(din), L.ptr(ws), ws_bytes, L.stream()),
             "spc_conv_dgrad")
     if e0 is not None:
-        _profiler.end("conv_dgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+        _profiler.end("conv_dgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
+                      f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
     return din
 
 
@@ -372,11 +386,13 @@ def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision):
     dw = _empty((K, c_in, c_out), torch.float32, x.device)
     ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
     ws = _empty(ws_bytes, torch.uint8, x.device)
+    mask = km.mask if precision == L.PREC_TF32 else None
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), km.m_in, km.m_out, c_in, c_out, K,
+    L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out, K,
                                precision, L.ptr(dw), L.ptr(ws), ws_bytes, L.stream()), "spc_conv_wgrad")
     if e0 is not None:
-        _profiler.end("conv_wgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out))
+        _profiler.end("conv_wgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
+                      f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
     return dw
 
 
