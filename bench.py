@@ -194,7 +194,7 @@ def run_ours(args):
     model = models.Res16UNet34C(27, 20).to(dev).train()
     tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
 
-    coords, feats, labels = synth.room_batch(777 + rank, args.scenes, args.voxels)
+    coords, feats, labels = synth.room_batch(777 + rank, args.scenes, args.voxels, shuffle=args.shuffle)
     h_coords = torch.from_numpy(coords).pin_memory()
     h_feats = torch.from_numpy(feats).pin_memory()
     h_labels = torch.from_numpy(labels).pin_memory()
@@ -316,6 +316,7 @@ def run_ours(args):
                                        f"BASELINE.json configs[1]",
                            "voxels_per_step_all_gpus": total_voxels, "parallelism": f"dp{world}",
                            "l2_policy": "inputs_exceed_l2 (activations per step >> 126 MB)",
+                           "voxel_order": "shuffled" if args.shuffle else "raster (as the reference loaders deliver)",
                            "precision": args.precision},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -342,6 +343,8 @@ def main():
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
+    ap.add_argument("--shuffle", action="store_true",
+                    help="deliver voxels in random order instead of the loaders' raster order (adversarial locality)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -471,74 +471,110 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       hasb_fifo >>= 1;
       --outstanding;
     };
-    // Before blocking on a free slot, publish every group issued so far: the B ring is shallower
-    // than the look-ahead window, so the consumer may need those groups to release the slot.
-    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
-      if (mbar_try_wait(bar, parity)) return;
-      if (outstanding > 0) {
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        while (outstanding > 0) arrive_oldest();
+    // Wait for a free slot WITHOUT starving the consumer: the B ring is shallower than the look-ahead
+    // window, so the MMA warp may need groups this thread has issued but not yet published.  While
+    // the slot is busy, publish the oldest outstanding group (its copies are the next to land
+    // anyway); once nothing is outstanding, block.
+    auto wait_oldest = [&]() {
+      switch (outstanding) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        case 4: cp_async_wait<3>(); break;
+        case 5: cp_async_wait<4>(); break;
+        default: cp_async_wait<5>(); break;
       }
-      mbar_wait(bar, parity);
+      fence_proxy_async_smem();
     };
+    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
+      while (!mbar_test_wait(bar, parity)) {
+        if (outstanding == 0) { mbar_wait(bar, parity); return; }
+        wait_oldest();
+        arrive_oldest();
+      }
+    };
+    const int g16 = (lane >> 3) * 16;  // this lane group gathers rows [g16, g16+16) of the row block
+    const int j = lane & 7;            // 16-byte piece of the 128-byte line
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int split = w / p.n_pass, pass = w - split * p.n_pass;
-      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
       const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
-      for (int rb = rb0; rb < rb1; ++rb) {
-        const uint32_t mask = rb_mask(rb);
-        const int o0 = rb * kWgR;
-        bool b_loaded = false;
-        for (int mb = mb0; mb < mb1; ++mb) {
-          if (!(mblock_taps(mb, p.ncc, p.nq) & mask)) continue;
-          bool with_b = false;
-          if (!b_loaded) {
-            b_loaded = with_b = true;
-            wait_empty(b_empty(b_stage), b_phase ^ 1u);
-            const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
-            const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
-            for (int e = threadIdx.x; e < n16; e += kNumProducerThreads) {
-              const int j = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
-              const int o = o0 + r;
-              const bool ok = o < p.m_out;
-              const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + j * 4;
-              cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(j, r, p.dbg_swz), src, ok ? 16u : 0u);
-            }
+      // iterator over the active (row block, M block) steps of this work item
+      auto advance = [&](int& rb, int& mb, uint32_t& mask) -> bool {
+        for (;;) {
+          if (++mb >= mb1) {
+            mb = mb0;
+            if (++rb >= rb1) return false;
+            mask = rb_mask(rb);
           }
-          wait_empty(a_empty(a_stage), a_phase ^ 1u);
-          {
-            // warp w gathers chunk slot w of this M block: 64 rows x 128 B
-            const int q = mb * 4 + warp;
-            if (q < p.nq) {
-              const int k = q / p.ncc, cc = q - k * p.ncc;
-              const int oa = o0 + lane, ob = o0 + 32 + lane;
-              const int idx0 = oa < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + oa) : -1;
-              const int idx1 = ob < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + ob) : -1;
-              const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + warp * kWgChunkBlock;
-              const int j = lane & 7, sub = lane >> 3;
+          if (mblock_taps(mb, p.ncc, p.nq) & mask) return true;
+        }
+      };
+      // neighbour rows of this warp's chunk (offset k of chunk mb*4+warp) for the lane's 16 rows
+      auto load_idx = [&](int rb, int mb, int* idx) {
+        const int q = mb * 4 + warp;
+        const int k = q < p.nq ? q / p.ncc : -1;
+        const int o = rb * kWgR + g16;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int r = i * 4 + sub;
-                const int v0 = __shfl_sync(0xffffffffu, idx0, r & 31);
-                const int v1 = __shfl_sync(0xffffffffu, idx1, r & 31);
-                const int src_row = i < 8 ? v0 : v1;
-                const float* src = p.in + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin + cc * 32 + j * 4;
-                cp_async_16(dsta + r * kChunkBytes + wg_swz(j, r, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
-              }
-            }
-          }
-          cp_async_commit();
-          hasb_fifo |= (with_b ? 1u : 0u) << outstanding;
-          ++outstanding;
-          if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
-          if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
-          if (outstanding > LOOKAHEAD) {
-            cp_async_wait<LOOKAHEAD>();
-            fence_proxy_async_smem();
-            arrive_oldest();
+        for (int i = 0; i < 16; ++i)
+          idx[i] = (k >= 0 && o + i < p.m_out) ? __ldg(p.nbr + (size_t)k * p.m_out + o + i) : -1;
+      };
+      int rb = rb0 - 1, mb = mb1;  // so that the first advance() lands on (rb0, mb0)
+      uint32_t mask = 0;
+      bool have = advance(rb, mb, mask);
+      int idx_cur[16], idx_next[16];
+      if (have) load_idx(rb, mb, idx_cur);
+      int b_rb = -1;
+      while (have) {
+        int nrb = rb, nmb = mb;
+        uint32_t nmask = mask;
+        const bool have_next = advance(nrb, nmb, nmask);
+        if (have_next) load_idx(nrb, nmb, idx_next);  // prefetch: hides the index-load latency
+        const int o0 = rb * kWgR;
+        bool with_b = false;
+        if (b_rb != rb) {  // first active M block of this row block brings the dout rows along
+          b_rb = rb;
+          with_b = true;
+          wait_empty(b_empty(b_stage), b_phase ^ 1u);
+          const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
+          const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
+          for (int e = threadIdx.x; e < n16; e += kNumProducerThreads) {
+            const int jj = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
+            const int o = o0 + r;
+            const bool ok = o < p.m_out;
+            const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + jj * 4;
+            cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(jj, r, p.dbg_swz), src, ok ? 16u : 0u);
           }
         }
+        wait_empty(a_empty(a_stage), a_phase ^ 1u);
+        {
+          // warp w gathers chunk slot w of this M block: 64 rows x 128 B
+          const int q = mb * 4 + warp;
+          if (q < p.nq) {
+            const int cc = q % p.ncc;
+            const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + warp * kWgChunkBlock + g16 * kChunkBytes;
+            const float* srcb = p.in + cc * 32 + j * 4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int src_row = idx_cur[i];
+              const float* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin;
+              cp_async_16(dsta + i * kChunkBytes + wg_swz(j, i, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        hasb_fifo |= (with_b ? 1u : 0u) << outstanding;
+        ++outstanding;
+        if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
+        if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
+        if (outstanding > LOOKAHEAD) {
+          cp_async_wait<LOOKAHEAD>();
+          fence_proxy_async_smem();
+          arrive_oldest();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) idx_cur[i] = idx_next[i];
+        rb = nrb; mb = nmb; mask = nmask; have = have_next;
       }
     }
     cp_async_wait<0>();
@@ -551,7 +587,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int split = w / p.n_pass, pass = w - split * p.n_pass;
-      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
       const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
       mbar_wait(t_empty, t_phase ^ 1u);  // epilogue drained the accumulators of the previous item
       tc_fence_after();
@@ -602,7 +638,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     uint32_t t_phase = 0;
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int split = w / p.n_pass, pass = w - split * p.n_pass;
-      const int mb0 = pass * p.mb_per_pass, mb1 = min(mb0 + p.mb_per_pass, p.n_mb);
+      const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
       const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
       // which accumulators received at least one MMA (same rule as the issuer)
       uint32_t seen = 0;
@@ -675,7 +711,6 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
   int cap = 512 / c_out;                       // accumulators that fit in TMEM
   p.n_pass = (p.n_mb + cap - 1) / cap;
   p.mb_per_pass = (p.n_mb + p.n_pass - 1) / p.n_pass;
-  p.n_pass = (p.n_mb + p.mb_per_pass - 1) / p.mb_per_pass;
   p.n_rb = (int)ceil_div(m_out, kWgR);
   int want_split = (2 * kNumSMs + p.n_pass - 1) / p.n_pass;
   if (want_split > p.n_rb) want_split = p.n_rb;

@@ -61,14 +61,18 @@ def room_scene(rng: np.random.Generator, target_voxels: int = 1_000_000, base=(3
 
 
 def room_batch(seed: int, n_scenes: int, target_voxels: int, channels: int = 27, num_classes: int = 20,
-               ignore_label: int = 255) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+               ignore_label: int = 255, shuffle: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(coords float32 [N,4], feats float32 [N,C], labels int64 [N]) for a batch of rooms."""
     rng = np.random.default_rng(seed)
     cs, fs, ls = [], [], []
     for b in range(n_scenes):
         vox = room_scene(rng, target_voxels)
-        perm = rng.permutation(vox.shape[0])  # loaders do not deliver voxels in raster order
-        vox = vox[perm]
+        # The reference's loaders hand voxels over in the raster order of the plenoxel grid they were
+        # decoded from (np.nonzero of `links`, co3d_3d/src/data/co3d.py:164-172, scannet.py:558-583;
+        # crops / dropout are boolean masks and keep that order).  shuffle=True is the adversarial
+        # case: neighbouring voxels land far apart in memory and gathers miss the L2.
+        if shuffle:
+            vox = vox[rng.permutation(vox.shape[0])]
         xyz = vox.astype(np.float32) + rng.random(vox.shape, dtype=np.float32) * np.float32(0.999)
         c = np.empty((vox.shape[0], 4), np.float32)
         c[:, 0] = b
