@@ -138,6 +138,7 @@ int spc_scatter_add_rows(const float* src, const int32_t* index, int64_t n, int6
  */
 void spc_debug_force_mt(int mt);
 void spc_debug_set(int idx, int val); /* test hook: wgrad operand-layout knobs, 0 = default */
+int spc_debug_read(long long* host, int n); /* test hook: wgrad role cycle counters -> host buffer */
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
 int spc_conv_fwd(const float* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,

@@ -24,6 +24,7 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
                     int64_t workspace_bytes, cudaStream_t stream);
 void umma_set_force_mt(int mt);
 void umma_debug_set(int idx, int val);
+int umma_debug_read(long long* host, int n);
 }  // namespace spc
 
 using namespace spc;
@@ -34,6 +35,8 @@ extern "C" {
 void spc_debug_force_mt(int mt) { umma_set_force_mt(mt); }
 /* test hook: operand-layout knobs of the tcgen05 wgrad kernel (0 = built-in default) */
 void spc_debug_set(int idx, int val) { umma_debug_set(idx, val); }
+/* test hook: cycle counters of the last tcgen05 wgrad launch (8 x int64 per CTA) into a HOST buffer */
+int spc_debug_read(long long* host, int n) { return umma_debug_read(host, n); }
 
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision) {
   if (precision != SPC_PREC_TF32) return 256;
@@ -77,7 +80,7 @@ int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
   (void)m_in;
   SPC_REQUIRE(c_in >= 1 && c_out >= 1 && K >= 1, "bad shape");
   SPC_REQUIRE(precision == SPC_PREC_FP32 || precision == SPC_PREC_TF32, "bad precision mode");
-  if (precision == SPC_PREC_TF32 && K <= 32 && umma_wgrad_supported(c_in, c_out))
+  if (precision == SPC_PREC_TF32 && K <= 32 && (int64_t)K * c_in <= 128 * 128 && umma_wgrad_supported(c_in, c_out))
     return conv_wgrad_umma(in, dout, nbr, tile_mask, m_out, c_in, c_out, K, dw, workspace, workspace_bytes,
                            (cudaStream_t)stream);
   return conv_wgrad_simt(in, dout, nbr, m_out, c_in, c_out, K, dw, (cudaStream_t)stream);

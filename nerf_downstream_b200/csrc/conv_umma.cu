@@ -30,10 +30,17 @@ constexpr int kTileM = 128;          // rows per accumulator (UMMA M)
 constexpr int kChunkBytes = 128;     // one swizzle row = 32 fp32 channels
 constexpr int kAStageBytes = kTileM * kChunkBytes;  // 16 KB per sub-tile per stage
 constexpr int kMaxStages = 8;
-constexpr int kNumProducerThreads = 128;
+// Every role is latency-bound on instruction issue when it is the only warp on its scheduler, so
+// the gather runs on TWO producer warps per scheduler.
+constexpr int kNumProducerWarps = 8;
+constexpr int kNumProducerThreads = kNumProducerWarps * 32;
 constexpr int kNumEpilogueThreads = 128;
-constexpr int kNumThreads = 288;     // 4 producer + 4 epilogue + 1 MMA warp
+constexpr int kMmaWarp = kNumProducerWarps + 4;
+constexpr int kNumThreads = (kMmaWarp + 1) * 32;  // 8 producer + 4 epilogue + 1 MMA warp
 constexpr int kSmemLimit = 227 * 1024;
+
+// cycle counters of the wgrad roles (test hook spc_debug_read): per CTA 8 x int64
+__device__ long long g_wg_counters[kNumSMs * 8];
 
 struct UmmaConvParams {
   const float* A;            // [*, Ck]
@@ -115,7 +122,7 @@ conv_umma_kernel(const UmmaConvParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -126,11 +133,10 @@ conv_umma_kernel(const UmmaConvParams p) {
 
   const int rows_per_work = kTileM * MT;
 
-  if (warp < 4) {
+  if (warp < kNumProducerWarps) {
     // ============================ producers ============================
     int stage = 0;
     uint32_t phase = 0;
-    int arr_stage = 0, outstanding = 0;
     const int sub = lane >> 3;  // row within a group of 4
     const int j = lane & 7;     // 16-byte chunk within the 128-byte row
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
@@ -149,8 +155,8 @@ conv_umma_kernel(const UmmaConvParams p) {
       auto load_idx = [&](int kk, int* idx) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          int o = o0 + mt * kTileM + (int)threadIdx.x;
-          idx[mt] = (kk >= 0 && o < p.m_out) ? __ldg(p.nbr + (size_t)kk * p.m_out + o) : -1;
+          int o = o0 + mt * kTileM + warp * 16 + lane;  // lanes 0-15 hold this warp's 16 rows
+          idx[mt] = (lane < 16 && kk >= 0 && o < p.m_out) ? __ldg(p.nbr + (size_t)kk * p.m_out + o) : -1;
         }
       };
       load_idx(k, idx_next);
@@ -172,37 +178,24 @@ conv_umma_kernel(const UmmaConvParams p) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int rl = q * 4 + sub;            // row within this warp's 32 rows
-              const int r = warp * 32 + rl;          // row within the 128-row sub-tile
+            for (int q = 0; q < 4; ++q) {
+              const int rl = q * 4 + sub;            // row within this warp's 16 rows
+              const int r = warp * 16 + rl;          // row within the 128-row sub-tile
               const int src_row = __shfl_sync(0xffffffffu, idx[mt], rl);
               const float* src = p.A + (size_t)(src_row >= 0 ? src_row : 0) * p.Ck + kc * 32 + j * 4;
               const uint32_t dst = stage_addr + mt * kAStageBytes + r * kChunkBytes + ((j ^ (r & 7)) << 4);
               cp_async_16(dst, src, src_row >= 0 ? 16u : 0u);
             }
           }
-          cp_async_commit();
-          ++outstanding;
+          // the stage's "full" barrier is signalled by the hardware when this thread's copies have
+          // landed (cp.async.mbarrier.arrive.noinc): no wait_group, no fence, nothing blocks here
+          cp_async_mbar_arrive_noinc(full_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          if (outstanding > LOOKAHEAD) {
-            cp_async_wait<LOOKAHEAD>();
-            fence_proxy_async_smem();
-            mbar_arrive(full_bar(arr_stage));
-            if (++arr_stage == p.stages) arr_stage = 0;
-            --outstanding;
-          }
         }
         k = k_next;
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    while (outstanding > 0) {
-      mbar_arrive(full_bar(arr_stage));
-      if (++arr_stage == p.stages) arr_stage = 0;
-      --outstanding;
-    }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
     int stage = 0;
     uint32_t phase = 0;
@@ -223,6 +216,7 @@ conv_umma_kernel(const UmmaConvParams p) {
       tc_fence_after();
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(full_bar(stage), phase);
+        fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
         tc_fence_after();
         if (lane == 0) {
           const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
@@ -259,7 +253,7 @@ conv_umma_kernel(const UmmaConvParams p) {
         if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
       }
       if (p.K < 32) mask &= (1u << p.K) - 1u;
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait_sleep(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -293,7 +287,7 @@ conv_umma_kernel(const UmmaConvParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -326,6 +320,17 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
   p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
   p.m_out = (int)m_out; p.Ck = c_in; p.Cn = c_out; p.K = K;
   p.cn_tile = pick_cn_tile(c_out);
+  // Small maps (deep UNet levels): too few 128-row tiles to fill 148 SMs, so split the output
+  // channels over more CTAs when that shortens the critical path = waves x bytes per stage.
+  {
+    const int64_t m_tiles = ceil_div(m_out, kTileM);
+    int64_t best = ceil_div(m_tiles * (c_out / p.cn_tile), kNumSMs) * (kAStageBytes + p.cn_tile * kChunkBytes);
+    for (int t = p.cn_tile - 16; t >= 32; t -= 16) {
+      if (c_out % t) continue;
+      int64_t cost = ceil_div(m_tiles * (c_out / t), kNumSMs) * (kAStageBytes + t * kChunkBytes);
+      if (cost < best) { best = cost; p.cn_tile = t; }
+    }
+  }
   p.n_ntiles = c_out / p.cn_tile;
   p.kc_count = c_in / 32;
 
@@ -367,6 +372,10 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
 }
 
 void umma_set_force_mt(int mt) { g_umma_force_mt = mt; }
+int umma_debug_read(long long* host, int n) {
+  if (n > kNumSMs * 8) n = kNumSMs * 8;
+  return (int)cudaMemcpyFromSymbol(host, g_wg_counters, (size_t)n * sizeof(long long));
+}
 void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_dbg[idx] = val; }
 
 // =====================================================================================
@@ -387,6 +396,11 @@ constexpr int kWgChunkBlock = kWgR * kChunkBytes;  // 8 KB: [64 rows x 128 B]
 constexpr int kWgAStage = 4 * kWgChunkBlock;     // 32 KB: four chunks = one 128-row M block
 constexpr int kWgMaxAStages = 6;
 constexpr int kWgBStages = 2;
+constexpr int kWgIdxRing = 16;   // per-warp ring of index rows (64 int32 each)
+constexpr int kWgIdxDist = 8;    // steps of index prefetch distance (> max LOOKAHEAD + 1)
+constexpr int kWgIdxBytes = kNumProducerWarps * kWgIdxRing * 32 * 4;  // 16 KB: 32 rows per warp and slot
+constexpr int kWgMaxMb = 128;    // M blocks (K * Cin / 128): 27 offsets x 512 channels = 108
+constexpr int kWgTabBytes = kWgMaxMb * 4 + kWgMaxMb * 4 * 2;  // per-M-block offset masks, per-chunk (k, cc)
 
 struct UmmaWgradParams {
   const float* in;            // [m_in, Cin]
@@ -400,6 +414,7 @@ struct UmmaWgradParams {
   int n_rb, rb_per_split, n_split;
   int a_stages;
   int dbg_layout, dbg_swz, dbg_lbo, dbg_sbo;  // operand layout knobs (test hook spc_debug_set)
+  int dbg_skip_mma, dbg_skip_gather, dbg_skip;  // timing experiments only (results are wrong when set)
   int n_work;
 };
 
@@ -409,6 +424,13 @@ __device__ __forceinline__ uint32_t wg_swz(int j, int r, int mode) {
   if (mode == 0) return (uint32_t)((j ^ (r & 7)) << 4);  // SWIZZLE_128B (16-byte base)
   return (uint32_t)((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4));
 }
+
+#define WG_TIMED_WAIT(slot, call)                         \
+  do {                                                    \
+    long long _t0 = clock64();                            \
+    call;                                                 \
+    wg_cnt[slot] += clock64() - _t0;                      \
+  } while (0)
 
 // offsets (bitmask) that the chunks of M block `mb` (global index) belong to
 __device__ __forceinline__ uint32_t mblock_taps(int mb, int ncc, int nq) {
@@ -437,6 +459,12 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
   const uint32_t t_full = bar_base + 8u * (2 * kWgMaxAStages + 2 * kWgBStages);
   const uint32_t t_empty = t_full + 8u;
   const uint32_t tmem_slot = t_full + 16u;
+  const uint32_t idx_base = bar_base + 256u;
+  // lookup tables (no integer division inside the per-step loops: every role is a single warp per
+  // scheduler, so long dependent instruction chains cost their full latency)
+  uint32_t* s_mbtaps = reinterpret_cast<uint32_t*>(smem_raw + (idx_base + kWgIdxBytes - smem_u32(smem_raw)));
+  uint8_t* s_qk = reinterpret_cast<uint8_t*>(s_mbtaps + kWgMaxMb);
+  uint8_t* s_qcc = s_qk + kWgMaxMb * 4;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -448,162 +476,171 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     mbar_init(t_empty, kNumEpilogueThreads);
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
+  for (int mb = threadIdx.x; mb < p.n_mb; mb += blockDim.x) s_mbtaps[mb] = mblock_taps(mb, p.ncc, p.nq);
+  for (int q = threadIdx.x; q < p.n_mb * 4; q += blockDim.x) {
+    s_qk[q] = (uint8_t)(q < p.nq ? q / p.ncc : 255);
+    s_qcc[q] = (uint8_t)(q % p.ncc);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t all_taps = p.K >= 32 ? 0xFFFFFFFFu : ((1u << p.K) - 1u);
+  long long wg_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long wg_t0 = clock64();
 
   // (row block -> offset mask); tile masks are per 128 rows = 2 row blocks
   auto rb_mask = [&](int rb) -> uint32_t {
     return p.tile_mask ? (p.tile_mask[rb >> 1] & all_taps) : all_taps;
   };
 
-  if (warp < 4) {
+  if (warp < kNumProducerWarps) {
     // ============================ producers ============================
-    int a_stage = 0, b_stage = 0, arr_a = 0, arr_b = 0, outstanding = 0;
-    uint32_t a_phase = 0, b_phase = 0, hasb_fifo = 0;  // bit i = i-th oldest outstanding group carries B
-    auto arrive_oldest = [&]() {
-      if (hasb_fifo & 1u) { mbar_arrive(b_full(arr_b)); if (++arr_b == kWgBStages) arr_b = 0; }
-      mbar_arrive(a_full(arr_a));
-      if (++arr_a == p.a_stages) arr_a = 0;
-      hasb_fifo >>= 1;
-      --outstanding;
+    // The neighbour indices of a step are fetched into a per-warp shared-memory ring kWgIdxDist
+    // steps ahead with 4-byte cp.async, so their (DRAM) latency never sits on the issue path.
+    // "full" barriers are signalled by the hardware when a thread's copies have landed
+    // (cp.async.mbarrier.arrive.noinc), so the producer never blocks on its own loads — only on
+    // free slots — and the pipeline is as deep as the rings.
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    const int slot_w = warp >> 1;                        // chunk slot (0..3) this warp pair fills
+    const int row0 = (warp & 1) * 32;                    // this warp's half of the 64-row block
+    const int g8 = (lane >> 3) * 8;                      // lane group -> rows [row0+g8, row0+g8+8)
+    const int j = lane & 7;                              // 16-byte piece of the 128-byte line
+
+    // flat iterator over the active (work item, row block, M block) steps of this CTA
+    // (`mask_next` is loaded one row block ahead so that the dependent global load of the tile mask
+    // never sits on the critical path)
+    struct Step { int w, rb, mb, rb1, mb0, mb1; uint32_t mask, mask_next; bool ok; };
+    auto begin_work = [&](Step& s) {
+      const int split = s.w / p.n_pass, pass = s.w - split * p.n_pass;
+      s.mb0 = pass * p.n_mb / p.n_pass;
+      s.mb1 = (pass + 1) * p.n_mb / p.n_pass;
+      s.rb = split * p.rb_per_split - 1;
+      s.rb1 = min((split + 1) * p.rb_per_split, p.n_rb);
+      s.mb = s.mb1;  // forces the first next() onto (rb0, mb0)
+      s.mask = 0;
+      s.mask_next = s.rb + 1 < s.rb1 ? rb_mask(s.rb + 1) : 0u;
     };
-    // Wait for a free slot WITHOUT starving the consumer: the B ring is shallower than the look-ahead
-    // window, so the MMA warp may need groups this thread has issued but not yet published.  While
-    // the slot is busy, publish the oldest outstanding group (its copies are the next to land
-    // anyway); once nothing is outstanding, block.
-    auto wait_oldest = [&]() {
-      switch (outstanding) {
-        case 1: cp_async_wait<0>(); break;
-        case 2: cp_async_wait<1>(); break;
-        case 3: cp_async_wait<2>(); break;
-        case 4: cp_async_wait<3>(); break;
-        case 5: cp_async_wait<4>(); break;
-        default: cp_async_wait<5>(); break;
-      }
-      fence_proxy_async_smem();
-    };
-    auto wait_empty = [&](uint32_t bar, uint32_t parity) {
-      while (!mbar_test_wait(bar, parity)) {
-        if (outstanding == 0) { mbar_wait(bar, parity); return; }
-        wait_oldest();
-        arrive_oldest();
+    auto next = [&](Step& s) {
+      for (;;) {
+        if (++s.mb >= s.mb1) {
+          s.mb = s.mb0;
+          if (++s.rb >= s.rb1) {
+            s.w += gridDim.x;
+            if (s.w >= p.n_work) { s.ok = false; return; }
+            begin_work(s);
+            continue;
+          }
+          s.mask = s.mask_next;
+          s.mask_next = s.rb + 1 < s.rb1 ? rb_mask(s.rb + 1) : 0u;
+        }
+        if (s_mbtaps[s.mb] & s.mask) return;
       }
     };
-    const int g16 = (lane >> 3) * 16;  // this lane group gathers rows [g16, g16+16) of the row block
-    const int j = lane & 7;            // 16-byte piece of the 128-byte line
-    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-      const int split = w / p.n_pass, pass = w - split * p.n_pass;
-      const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
-      const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
-      // iterator over the active (row block, M block) steps of this work item
-      auto advance = [&](int& rb, int& mb, uint32_t& mask) -> bool {
-        for (;;) {
-          if (++mb >= mb1) {
-            mb = mb0;
-            if (++rb >= rb1) return false;
-            mask = rb_mask(rb);
-          }
-          if (mblock_taps(mb, p.ncc, p.nq) & mask) return true;
+    // ring slot of this warp for step number `seq`: 64 int32 row indices
+    auto idx_slot = [&](uint32_t seq) { return idx_base + (uint32_t)((warp * kWgIdxRing + (seq % kWgIdxRing)) * 32 * 4); };
+    auto fetch_idx = [&](const Step& s, uint32_t seq) {
+      const int q = s.mb * 4 + slot_w;
+      if (q >= p.nq || (p.dbg_skip & 1)) return;
+      const int k = s_qk[q];
+      const uint32_t dst = idx_slot(seq);
+      const int o = s.rb * kWgR + row0 + lane;
+      if (o < p.m_out) cp_async_4(dst + lane * 4, p.nbr + (size_t)k * p.m_out + o);
+      else st_shared_s32(dst + lane * 4, -1);
+    };
+
+    Step cur, pf;
+    cur.w = blockIdx.x; cur.ok = cur.w < p.n_work;
+    if (cur.ok) { begin_work(cur); next(cur); }
+    pf = cur;
+    uint32_t seq = 0, pf_seq = 0;
+    // prologue: indices of the first kWgIdxDist steps
+    for (int d = 0; d < kWgIdxDist && pf.ok; ++d) { fetch_idx(pf, pf_seq++); next(pf); }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    int b_rb = -1, b_w = -1;
+    while (cur.ok) {
+      if (pf.ok) { fetch_idx(pf, pf_seq++); next(pf); }  // joins this step's commit group
+      const int o0 = cur.rb * kWgR;
+      bool with_b = false;
+      if (b_rb != cur.rb || b_w != cur.w) {  // first active M block of a row block brings the dout rows
+        b_rb = cur.rb; b_w = cur.w;
+        with_b = true;
+        WG_TIMED_WAIT(1, mbar_wait(b_empty(b_stage), b_phase ^ 1u));
+        const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
+        const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
+        for (int e = threadIdx.x; e < n16 && !(p.dbg_skip & 2); e += kNumProducerThreads) {
+          const int jj = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
+          const int o = o0 + r;
+          const bool ok = o < p.m_out;
+          const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + jj * 4;
+          cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(jj, r, p.dbg_swz), src, ok ? 16u : 0u);
         }
-      };
-      // neighbour rows of this warp's chunk (offset k of chunk mb*4+warp) for the lane's 16 rows
-      auto load_idx = [&](int rb, int mb, int* idx) {
-        const int q = mb * 4 + warp;
-        const int k = q < p.nq ? q / p.ncc : -1;
-        const int o = rb * kWgR + g16;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          idx[i] = (k >= 0 && o + i < p.m_out) ? __ldg(p.nbr + (size_t)k * p.m_out + o + i) : -1;
-      };
-      int rb = rb0 - 1, mb = mb1;  // so that the first advance() lands on (rb0, mb0)
-      uint32_t mask = 0;
-      bool have = advance(rb, mb, mask);
-      int idx_cur[16], idx_next[16];
-      if (have) load_idx(rb, mb, idx_cur);
-      int b_rb = -1;
-      while (have) {
-        int nrb = rb, nmb = mb;
-        uint32_t nmask = mask;
-        const bool have_next = advance(nrb, nmb, nmask);
-        if (have_next) load_idx(nrb, nmb, idx_next);  // prefetch: hides the index-load latency
-        const int o0 = rb * kWgR;
-        bool with_b = false;
-        if (b_rb != rb) {  // first active M block of this row block brings the dout rows along
-          b_rb = rb;
-          with_b = true;
-          wait_empty(b_empty(b_stage), b_phase ^ 1u);
-          const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
-          const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
-          for (int e = threadIdx.x; e < n16; e += kNumProducerThreads) {
-            const int jj = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
-            const int o = o0 + r;
-            const bool ok = o < p.m_out;
-            const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + jj * 4;
-            cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(jj, r, p.dbg_swz), src, ok ? 16u : 0u);
-          }
-        }
-        wait_empty(a_empty(a_stage), a_phase ^ 1u);
-        {
-          // warp w gathers chunk slot w of this M block: 64 rows x 128 B
-          const int q = mb * 4 + warp;
-          if (q < p.nq) {
-            const int cc = q % p.ncc;
-            const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + warp * kWgChunkBlock + g16 * kChunkBytes;
-            const float* srcb = p.in + cc * 32 + j * 4;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int src_row = idx_cur[i];
-              const float* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin;
-              cp_async_16(dsta + i * kChunkBytes + wg_swz(j, i, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
-            }
-          }
-        }
-        cp_async_commit();
-        hasb_fifo |= (with_b ? 1u : 0u) << outstanding;
-        ++outstanding;
-        if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
-        if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
-        if (outstanding > LOOKAHEAD) {
-          cp_async_wait<LOOKAHEAD>();
-          fence_proxy_async_smem();
-          arrive_oldest();
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) idx_cur[i] = idx_next[i];
-        rb = nrb; mb = nmb; mask = nmask; have = have_next;
+        cp_async_mbar_arrive_noinc(b_full(b_stage));
       }
+      WG_TIMED_WAIT(0, mbar_wait(a_empty(a_stage), a_phase ^ 1u));
+      {
+        // a warp pair gathers chunk slot `slot_w` of this M block (64 rows x 128 B), 32 rows each
+        const int q = cur.mb * 4 + slot_w;
+        if (q < p.nq && !p.dbg_skip_gather) {
+          const int cc = s_qcc[q];
+          const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + slot_w * kWgChunkBlock + (row0 + g8) * kChunkBytes;
+          const float* srcb = p.in + cc * 32 + j * 4;
+          int idx[8];
+          const uint32_t slot = idx_slot(seq) + g8 * 4;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) ld_shared_v4(slot + v * 16, idx[4 * v], idx[4 * v + 1], idx[4 * v + 2], idx[4 * v + 3]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int src_row = idx[i];
+            const float* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin;
+            cp_async_16(dsta + i * kChunkBytes + wg_swz(j, i, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
+          }
+        }
+      }
+      cp_async_mbar_arrive_noinc(a_full(a_stage));
+      cp_async_commit();
+      if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
+      if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
+      // the index copies of step seq+1 were committed kWgIdxDist-1 groups ago: this never blocks in
+      // steady state (at most a_stages < kWgIdxDist-1 groups can be pending) and guarantees they landed
+      WG_TIMED_WAIT(2, cp_async_wait<kWgIdxDist - 2>());
+      __syncwarp();
+      ++seq;
+      next(cur);
     }
     cp_async_wait<0>();
-    fence_proxy_async_smem();
-    while (outstanding > 0) arrive_oldest();
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0, t_phase = 0;
     const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
+    const uint64_t desc_hi = make_desc(0, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int split = w / p.n_pass, pass = w - split * p.n_pass;
       const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
       const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
-      mbar_wait(t_empty, t_phase ^ 1u);  // epilogue drained the accumulators of the previous item
+      WG_TIMED_WAIT(5, mbar_wait(t_empty, t_phase ^ 1u));  // epilogue drained the accumulators of the previous item
       tc_fence_after();
       uint32_t touched = 0;
+      uint32_t mask_next = rb0 < rb1 ? rb_mask(rb0) : 0u;
       for (int rb = rb0; rb < rb1; ++rb) {
-        const uint32_t mask = rb_mask(rb);
+        const uint32_t mask = mask_next;
+        mask_next = rb + 1 < rb1 ? rb_mask(rb + 1) : 0u;  // prefetched: hidden behind this row block
         bool b_ready = false;
         int b_used = -1;
         for (int mb = mb0; mb < mb1; ++mb) {
-          if (!(mblock_taps(mb, p.ncc, p.nq) & mask)) continue;
+          if (!(s_mbtaps[mb] & mask)) continue;
           if (!b_ready) {
-            mbar_wait(b_full(b_stage), b_phase);
+            WG_TIMED_WAIT(4, mbar_wait(b_full(b_stage), b_phase));
             b_ready = true;
             b_used = b_stage;
           }
-          mbar_wait(a_full(a_stage), a_phase);
+          WG_TIMED_WAIT(3, mbar_wait(a_full(a_stage), a_phase));
+          fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = a_base + (uint32_t)a_stage * kWgAStage;
@@ -612,9 +649,10 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
             const uint32_t was = (touched >> (mb - mb0)) & 1u;
 #pragma unroll
             for (int r8 = 0; r8 < kWgR / 8; ++r8) {
-              const uint64_t adesc = make_desc(a_addr + r8 * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-              const uint64_t bdesc = make_desc(b_addr + r8 * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
-              mma_tf32(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
+              // descriptors differ only in the start address field: 1024 B (8 rows) per step = 64 units
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr >> 4) + 64u * r8) & 0x3FFFu);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr >> 4) + 64u * r8) & 0x3FFFu);
+              if (!p.dbg_skip_mma) mma_tf32(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
             }
             mma_commit(a_empty(a_stage));
           }
@@ -645,19 +683,20 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       for (int rb = rb0 + lane; rb < rb1; rb += 32) seen |= rb_mask(rb);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
-      mbar_wait(t_full, t_phase);
+      mbar_wait_sleep(t_full, t_phase);
       tc_fence_after();
       for (int mb = mb0; mb < mb1; ++mb) {
-        if (!(mblock_taps(mb, p.ncc, p.nq) & seen)) continue;
+        if (!(s_mbtaps[mb] & seen)) continue;
         const int q = mb * 4 + ew;
         if (q >= p.nq) continue;  // padding chunk of the last M block (warp-uniform)
-        const int k = q / p.ncc, cc = q - k * p.ncc;
+        const int k = s_qk[q], cc = s_qcc[q];
         if (!((seen >> k) & 1u)) continue;  // this offset has no pair in the row range: stays zero
         float* dst = p.dw + ((size_t)k * p.Cin + cc * 32 + lane) * p.Cout;
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((mb - mb0) * p.Cout);
         for (int c0 = 0; c0 < p.Cout; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
+          if (p.dbg_skip & 4) continue;
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(v[i]),
@@ -670,9 +709,14 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       t_phase ^= 1u;
     }
   }
+  if (blockIdx.x < kNumSMs && (threadIdx.x == 0 || threadIdx.x == kMmaWarp * 32)) {
+    const int base = threadIdx.x == 0 ? 0 : 3, n = 3;
+    for (int i = 0; i < n; ++i) g_wg_counters[blockIdx.x * 8 + base + i] = wg_cnt[base + i];
+    g_wg_counters[blockIdx.x * 8 + (threadIdx.x == 0 ? 6 : 7)] = clock64() - wg_t0;
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -712,7 +756,7 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
   p.n_pass = (p.n_mb + cap - 1) / cap;
   p.mb_per_pass = (p.n_mb + p.n_pass - 1) / p.n_pass;
   p.n_rb = (int)ceil_div(m_out, kWgR);
-  int want_split = (2 * kNumSMs + p.n_pass - 1) / p.n_pass;
+  int want_split = (2 * kNumSMs) / p.n_pass;  // <= 2 work items per CTA (static round-robin)
   if (want_split > p.n_rb) want_split = p.n_rb;
   if (want_split < 1) want_split = 1;
   p.rb_per_split = (p.n_rb + want_split - 1) / want_split;
@@ -720,7 +764,7 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
   p.n_split = (p.n_rb + p.rb_per_split - 1) / p.rb_per_split;
   p.n_work = p.n_split * p.n_pass;
   const int b_stage_bytes = (c_out / 32) * kWgChunkBlock;
-  int a_stages = (kSmemLimit - 1024 - 256 - kWgBStages * b_stage_bytes) / kWgAStage;
+  int a_stages = (kSmemLimit - 1024 - 256 - kWgIdxBytes - kWgTabBytes - kWgBStages * b_stage_bytes) / kWgAStage;
   if (a_stages > kWgMaxAStages) a_stages = kWgMaxAStages;
   SPC_REQUIRE(a_stages >= 2, "wgrad tile does not fit in shared memory");
   p.a_stages = a_stages;
@@ -729,7 +773,11 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
   p.dbg_swz = g_dbg[1] ? g_dbg[1] - 1 : 1;
   p.dbg_lbo = g_dbg[2] ? g_dbg[2] : kWgChunkBlock;
   p.dbg_sbo = g_dbg[3] ? g_dbg[3] : 512;
-  const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256;
+  p.dbg_skip_mma = g_dbg[4];
+  p.dbg_skip_gather = g_dbg[5];
+  p.dbg_skip = g_dbg[6];
+  const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256 + kWgIdxBytes + kWgTabBytes;
+  SPC_REQUIRE(p.n_mb <= kWgMaxMb, "too many M blocks");
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
   const int la = a_stages >= 6 ? 5 : (a_stages >= 4 ? 3 : 1);
   switch (la) {

@@ -51,15 +51,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// long waits (an epilogue warp waiting for a whole tile): back off between probes so the spinning
+// warp does not compete with the producer / MMA warps for issue slots and the barrier unit
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+}
+
 // ---- cp.async (LDGSTS) ----------------------------------------------------------
 // 16-byte copy, zero-filled when src_bytes == 0
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 4-byte copy (no alignment requirement beyond 4)
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_shared_s32(uint32_t dst, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t src, int& a, int& b, int& c, int& d) {
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// mbarrier arrive that fires when all cp.async issued so far by this thread have landed; .noinc: the
+// arrival is part of the barrier's expected count (no explicit wait_group / arrive needed)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 // generic-proxy writes -> visible to the async proxy (UMMA / TMA reads of shared memory)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -39,6 +39,7 @@ SIGNATURES = {
     "spc_scatter_add_rows": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "spc_debug_force_mt": (None, [c_int]),
     "spc_debug_set": (None, [c_int, c_int]),
+    "spc_debug_read": (c_int, [_P, c_int]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),

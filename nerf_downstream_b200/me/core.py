@@ -393,17 +393,30 @@ class Tensor:
     _manager: CoordinateManager
     quantization_mode: SparseTensorQuantizationMode
 
+    # Lazily evaluated features: MinkowskiBatchNorm defers its "apply" pass so that a following
+    # `+= residual` and / or ReLU run in the SAME kernel (one read + one write instead of three of
+    # each).  `_lazy(relu, residual)` produces the feature rows; it is resolved by the first reader.
+    _lazy = None
+    _lazy_res = None
+
+    def _materialize(self, relu: bool = False) -> None:
+        fn, res = self._lazy, self._lazy_res
+        self._lazy = self._lazy_res = None
+        self._F = fn(relu, res)
+
     @property
     def F(self) -> torch.Tensor:
+        if self._F is None and self._lazy is not None:
+            self._materialize()
         return self._F
 
     @property
     def features(self) -> torch.Tensor:
-        return self._F
+        return self.F
 
     @property
     def feats(self) -> torch.Tensor:
-        return self._F
+        return self.F
 
     @property
     def coordinate_manager(self) -> CoordinateManager:
@@ -419,29 +432,29 @@ class Tensor:
 
     @property
     def device(self):
-        return self._F.device
+        return self.F.device
 
     @property
     def dtype(self):
-        return self._F.dtype
+        return self.F.dtype
 
     @property
     def shape(self):
-        return self._F.shape
+        return self.F.shape
 
     @property
     def requires_grad(self):
-        return self._F.requires_grad
+        return self.F.requires_grad
 
     def requires_grad_(self, requires_grad: bool = True):
-        self._F.requires_grad_(requires_grad)
+        self.F.requires_grad_(requires_grad)
         return self
 
     def size(self, *args):
-        return self._F.size(*args)
+        return self.F.size(*args)
 
     def __len__(self):
-        return self._F.shape[0]
+        return self.F.shape[0]
 
 
 class SparseTensor(Tensor):
@@ -502,6 +515,20 @@ class SparseTensor(Tensor):
         if requires_grad is not None:
             self._F.requires_grad_(requires_grad)
 
+    @classmethod
+    def _deferred(cls, fn, coordinate_map_key, coordinate_manager) -> "SparseTensor":
+        """A tensor whose feature rows are produced on first use by `fn(relu, residual)`."""
+        t = object.__new__(cls)
+        t.quantization_mode = SparseTensorQuantizationMode.RANDOM_SUBSAMPLE
+        t.unique_index = None
+        t.inverse_mapping = None
+        t._manager = coordinate_manager
+        t.coordinate_map_key = coordinate_map_key
+        t._F = None
+        t._lazy = fn
+        t._lazy_res = None
+        return t
+
     def _insert(self, coordinates, tensor_stride):
         mgr = self._manager
         ts = _to_list(tensor_stride, mgr.D, "tensor_stride")
@@ -535,36 +562,39 @@ class SparseTensor(Tensor):
     def __iadd__(self, other):
         if isinstance(other, SparseTensor):
             self._same_map(other)
-            self._F = ops.AddFn.apply(self._F, other._F)
+            if self._F is None and self._lazy is not None and self._lazy_res is None:
+                self._lazy_res = other.F  # folded into the deferred BatchNorm apply (resnet_block.py:66)
+            else:
+                self._F = ops.AddFn.apply(self.F, other.F)
         else:
-            self._F = self._F + other
+            self._F = self.F + other
         return self
 
     def __add__(self, other):
         if isinstance(other, SparseTensor):
             self._same_map(other)
-            return SparseTensor(ops.AddFn.apply(self._F, other._F), coordinate_map_key=self.coordinate_map_key,
+            return SparseTensor(ops.AddFn.apply(self.F, other.F), coordinate_map_key=self.coordinate_map_key,
                                 coordinate_manager=self._manager)
-        return SparseTensor(self._F + other, coordinate_map_key=self.coordinate_map_key,
+        return SparseTensor(self.F + other, coordinate_map_key=self.coordinate_map_key,
                             coordinate_manager=self._manager)
 
     def __mul__(self, other):
         if isinstance(other, SparseTensor):
             self._same_map(other)
-            other = other._F
-        return SparseTensor(self._F * other, coordinate_map_key=self.coordinate_map_key,
+            other = other.F
+        return SparseTensor(self.F * other, coordinate_map_key=self.coordinate_map_key,
                             coordinate_manager=self._manager)
 
     def slice(self, X: "TensorField") -> "TensorField":
         """Features of this sparse tensor at the original points of `X` (res16unet.py:435)."""
         assert isinstance(X, TensorField), "slice expects a TensorField"
         inv = X.inverse_mapping(self.coordinate_map_key)
-        return TensorField(ops.GatherRowsFn.apply(self._F, inv),
+        return TensorField(ops.GatherRowsFn.apply(self.F, inv),
                            coordinate_field_map_key=X.coordinate_field_map_key,
                            coordinate_manager=X.coordinate_manager, quantization_mode=X.quantization_mode)
 
     def features_at(self, batch_index: int) -> torch.Tensor:
-        return self._F[self.C[:, 0] == batch_index]
+        return self.F[self.C[:, 0] == batch_index]
 
     def coordinates_at(self, batch_index: int) -> torch.Tensor:
         C = self.C
@@ -581,11 +611,11 @@ class SparseTensor(Tensor):
         return [self.coordinates_at(b) for b in range(nb)]
 
     def detach(self):
-        return SparseTensor(self._F.detach(), coordinate_map_key=self.coordinate_map_key,
+        return SparseTensor(self.F.detach(), coordinate_map_key=self.coordinate_map_key,
                             coordinate_manager=self._manager)
 
     def __repr__(self):
-        return (f"SparseTensor(\n  coordinates={self.C}\n  features={self._F}\n  "
+        return (f"SparseTensor(\n  coordinates={self.C}\n  features={self.F}\n  "
                 f"coordinate_map_key={self.coordinate_map_key}\n)")
 
 

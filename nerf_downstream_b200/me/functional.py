@@ -2,7 +2,7 @@
 import torch.nn.functional as F
 
 from .. import ops
-from .modules import _wrap_like
+from .modules import _fused_relu, _wrap_like
 
 
 def _wrap_fn(fn):
@@ -14,7 +14,7 @@ def _wrap_fn(fn):
 
 def relu(input, *args, **kwargs):
     """ReLU on the feature rows through the sm_100a elementwise kernel."""
-    return _wrap_like(input, ops.ReLUFn.apply(input.F))
+    return _fused_relu(input)
 
 
 leaky_relu = _wrap_fn(F.leaky_relu)

@@ -170,6 +170,11 @@ class MinkowskiBatchNorm(nn.Module):
                                      0.0 if momentum is None else momentum, bn.eps, relu, residual)
 
     def forward(self, input):
+        if isinstance(input, SparseTensor):
+            # defer the apply pass: a following `+= residual` / ReLU is fused into it (_fused_relu)
+            x = input.F
+            return SparseTensor._deferred(lambda relu, res: self._run(x, relu, res), input.coordinate_map_key,
+                                          input.coordinate_manager)
         return _wrap_like(input, self._run(input.F))
 
     def __repr__(self):
@@ -242,11 +247,27 @@ class MinkowskiNonlinearityBase(MinkowskiModuleBase):
         return self.__class__.__name__ + "()"
 
 
+def _fused_relu(input):
+    """ReLU; when `input` is a BatchNorm output whose apply pass is still pending, BN (+ residual add)
+    + ReLU run as ONE kernel.  The pre-activation rows of `input` are then never produced."""
+    if isinstance(input, SparseTensor) and input._F is None and input._lazy is not None:
+        input._materialize(relu=True)
+        out = SparseTensor(input._F, coordinate_map_key=input.coordinate_map_key,
+                           coordinate_manager=input.coordinate_manager)
+
+        def _gone(relu, res):
+            raise RuntimeError("the pre-activation features of this BatchNorm output were fused into the "
+                               "following ReLU; read .F before applying the ReLU if you need them")
+        input._F, input._lazy = None, _gone
+        return out
+    return _wrap_like(input, ops.ReLUFn.apply(input.F))
+
+
 class MinkowskiReLU(MinkowskiNonlinearityBase):
     MODULE = nn.ReLU
 
     def forward(self, input):
-        return _wrap_like(input, ops.ReLUFn.apply(input.F))
+        return _fused_relu(input)
 
 
 class MinkowskiPReLU(MinkowskiNonlinearityBase):

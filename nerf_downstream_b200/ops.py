@@ -406,27 +406,49 @@ class SparseConvFn(torch.autograd.Function):
         if x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
             raise RuntimeError(f"conv input {tuple(x.shape)} does not match map rows {km.m_in} / kernel {tuple(w3.shape)}")
         b = bias.contiguous().view(-1) if bias is not None else None
+        K, c_in, c_out = w3.shape
+        # The tensor-core kernels take channel counts that are multiples of 32; on large maps zero-pad
+        # odd widths (27 SH channels, 20 classes) instead of dropping to the CUDA-core kernels.
+        pad_in = pad_out = 0
+        if precision == L.PREC_TF32 and K <= 32 and max(km.m_in, km.m_out) >= 4096:
+            pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
+        if pad_in:
+            x = torch.nn.functional.pad(x, (0, pad_in))
+        if pad_in or pad_out:
+            w3 = torch.nn.functional.pad(w3, (0, pad_out, 0, pad_in))
+            if b is not None and pad_out:
+                b = torch.nn.functional.pad(b, (0, pad_out))
         out = conv_fwd_raw(x, w3, b, km, precision)
+        if pad_out:
+            out = out[:, :c_out].contiguous()
         ctx.save_for_backward(x, w3)
         ctx.km = km
         ctx.precision = precision
         ctx.has_bias = bias is not None
         ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (c_in, c_out, pad_in, pad_out)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, w3 = ctx.saved_tensors
         km, prec = ctx.km, ctx.precision
+        c_in, c_out, pad_in, pad_out = ctx.dims
         g = _feat(g)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(g, w3, km, prec)
-        if ctx.needs_input_grad[1]:
-            K, c_in, c_out = w3.shape
-            dw = conv_wgrad_raw(x, g, km, K, c_in, c_out, prec)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0).view(ctx.bias_shape)
+        if pad_out:
+            g = torch.nn.functional.pad(g, (0, pad_out))
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad_raw(g, w3, km, prec)
+            if pad_in:
+                dx = dx[:, :c_in].contiguous()
+        if ctx.needs_input_grad[1]:
+            K, ci, co = w3.shape
+            dw = conv_wgrad_raw(x, g, km, K, ci, co, prec)
+            if pad_in or pad_out:
+                dw = dw[:, :c_in, :c_out].contiguous()
         return dx, dw, db, None, None
 
 
