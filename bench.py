@@ -186,7 +186,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L.load()
     ops.set_default_precision(args.precision)
 
@@ -262,13 +263,13 @@ def run_ours(args):
     # ---- per-kernel-class device times inside a (separately) timed region -> roofline -------------
     roofline = None
     classes = {}
+    prof = ops.KernelProfiler() if rank == 0 else None
+    ops.set_profiler(prof)
+    for _ in range(2):  # every rank steps (the gradient all-reduce is collective); rank 0 records
+        step(d_coords, d_feats, d_labels)
+    torch.cuda.synchronize()
+    ops.set_profiler(None)
     if rank == 0:
-        prof = ops.KernelProfiler()
-        ops.set_profiler(prof)
-        for _ in range(2):
-            step(d_coords, d_feats, d_labels)
-        torch.cuda.synchronize()
-        ops.set_profiler(None)
         classes = prof.summary()
         if args.detail:
             det = prof.summary_detail()
