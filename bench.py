@@ -310,7 +310,7 @@ def run_ours(args):
         cpu = cpu_baseline(args.cpu_voxels) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"MinkUNet34C (Res16UNet34C 27->20) fwd+bwd+SGD, synthetic ScanNet-shaped "
                                        f"plenoxel scenes, {args.voxels} voxels/scene, {args.scenes} scene(s)/GPU, "
@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--voxels", type=int, default=1_000_000, help="voxels per scene")
     ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU per step")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")

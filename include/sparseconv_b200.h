@@ -45,6 +45,7 @@ extern "C" {
 /* precision modes of the convolution kernels */
 #define SPC_PREC_FP32 0   /* CUDA-core FP32 FMA, fp32-faithful             */
 #define SPC_PREC_TF32 1   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+#define SPC_PREC_BF16 2   /* tcgen05.mma kind::f16 on bf16 copies of the rows (spc_to_bf16), fp32 accumulate */
 
 int spc_abi_version(void);
 const char* spc_last_error(void);
@@ -140,13 +141,16 @@ void spc_debug_force_mt(int mt);
 void spc_debug_set(int idx, int val); /* test hook: wgrad operand-layout knobs, 0 = default */
 int spc_debug_read(long long* host, int n); /* test hook: wgrad role cycle counters -> host buffer */
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
-int spc_conv_fwd(const float* in, const float* w, const float* bias, const int32_t* nbr,
+/* fp32 -> bf16 (round to nearest even) copy of n values; feeds the SPC_PREC_BF16 convolutions. */
+int spc_to_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
+/* `in` / `dout` point to fp32 rows, or to bf16 rows when precision == SPC_PREC_BF16. */
+int spc_conv_fwd(const void* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                  float* out, void* workspace, int64_t workspace_bytes, void* stream);
-int spc_conv_dgrad(const float* dout, const float* w, const int32_t* nbr_t,
+int spc_conv_dgrad(const void* dout, const float* w, const int32_t* nbr_t,
                    const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* din, void* workspace, int64_t workspace_bytes, void* stream);
-int spc_conv_wgrad(const float* in, const float* dout, const int32_t* nbr,
+int spc_conv_wgrad(const void* in, const void* dout, const int32_t* nbr,
                    const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* dw, void* workspace, int64_t workspace_bytes, void* stream);
 

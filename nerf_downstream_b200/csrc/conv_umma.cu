@@ -1,37 +1,42 @@
-// conv_umma.cu — sparse convolution forward / dgrad as an output-stationary implicit GEMM on
-// the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// conv_umma.cu — sparse convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators
+// in TMEM): forward / dgrad as an output-stationary implicit GEMM, wgrad as a reduction GEMM.
 //
-//   out[o, :] = sum_k  A[nbr[k, o], :] @ B_k          A: [*, Ck] fp32 rows, B_k: [Ck, Cn]
+//   fwd / dgrad:  out[o, :] = sum_k  A[nbr[k, o], :] @ B_k        A: [*, Ck] rows, B_k: [Ck, Cn]
+//   wgrad      :  dW[k]     = sum_o  in[nbr[k, o], :]^T  dout[o, :]
 //
-// One persistent CTA per SM, warp-specialised:
-//   warps 0-3  producers : gather A rows with 16-byte cp.async (LDGSTS, zero-fill for missing
-//                          neighbours) straight into the 128B-swizzled K-major UMMA layout; one
-//                          elected thread also streams the pre-swizzled weight slab of the stage
-//                          with a single bulk copy on the TMA engine (UBLKCP);
-//   warp  8    MMA       : one elected lane issues tcgen05.mma (M=128, N=cn_tile, K=8 per
-//                          instruction) for every pipeline stage and commits stage release /
-//                          accumulator completion to mbarriers;
-//   warps 4-7  epilogue  : tcgen05.ld the fp32 accumulator (32 lanes per warp), add bias, store.
-// A CTA tile is MT x 128 output rows (MT accumulators share every weight slab, halving weight
-// traffic at MT=2); accumulators are double-buffered in TMEM when they fit in 512 columns so the
-// epilogue of tile i overlaps the main loop of tile i+1.  A pipeline stage is one (offset k,
-// 32-channel chunk) pair: MT*16 KB of gathered rows + cn_tile*128 B of weights.
-// Offsets with no neighbour inside a tile are skipped using the per-tile offset mask built
-// with the kernel map (spc_tile_mask).  Output rows are owned by one CTA: no atomics.
+// Two operand precisions share the code (template BF16):
+//   false  kind::tf32 — fp32 rows in shared memory (the tensor core uses the upper 19 bits),
+//          32 channels = 128-byte swizzle rows, 4 MMAs (K=8) per row chunk;
+//   true   kind::f16 with bf16 operands — rows converted once per layer (spc_to_bf16), 32 channels =
+//          64-byte rows (SWIZZLE_64B), 2 MMAs (K=16) per row chunk: half the gather bytes and twice
+//          the MMA rate.  Accumulation is fp32 in TMEM in both.
 //
-// The same kernel computes dgrad (A = dOut gathered by the transposed map, B_k = W[k]^T).
+// One persistent CTA per SM, warp-specialised (every role is latency-bound on instruction issue when
+// it is alone on its scheduler, so the gather runs on two producer warps per scheduler):
+//   warps 0-7   producers : gather rows with 16-byte cp.async (LDGSTS, zero-fill for missing
+//                           neighbours) straight into the swizzled UMMA layout; forward weights arrive
+//                           as ONE TMA bulk copy (UBLKCP) of a pre-swizzled slab per stage.  "Full"
+//                           barriers are signalled by the hardware (cp.async.mbarrier.arrive.noinc):
+//                           no wait_group / proxy fence on the producer side, it only waits for slots;
+//   warps 8-11  epilogue  : tcgen05.ld the fp32 accumulator (32 TMEM lanes per warp), bias, store
+//                           (wgrad: fp32 red.global.add.v4 of the partial dW);
+//   warp  12    MMA       : one elected lane issues tcgen05.mma and commits stage release /
+//                           accumulator completion to mbarriers.
+// Forward: a CTA tile is MT x 128 output rows (MT accumulators share every weight slab); accumulators
+// are double-buffered in TMEM when they fit in 512 columns so the epilogue of tile i overlaps the main
+// loop of tile i+1.  A pipeline stage is one (offset k, 32-channel chunk) pair.  Offsets with no
+// neighbour inside a tile are skipped using the per-tile offset mask (spc_tile_mask).  Output rows are
+// owned by one CTA: no atomics in forward / dgrad.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace spc {
 using namespace ptx;
 
-constexpr int kTileM = 128;          // rows per accumulator (UMMA M)
-constexpr int kChunkBytes = 128;     // one swizzle row = 32 fp32 channels
-constexpr int kAStageBytes = kTileM * kChunkBytes;  // 16 KB per sub-tile per stage
+constexpr int kTileM = 128;  // rows per accumulator (UMMA M)
 constexpr int kMaxStages = 8;
-// Every role is latency-bound on instruction issue when it is the only warp on its scheduler, so
-// the gather runs on TWO producer warps per scheduler.
 constexpr int kNumProducerWarps = 8;
 constexpr int kNumProducerThreads = kNumProducerWarps * 32;
 constexpr int kNumEpilogueThreads = 128;
@@ -42,9 +47,39 @@ constexpr int kSmemLimit = 227 * 1024;
 // cycle counters of the wgrad roles (test hook spc_debug_read): per CTA 8 x int64
 __device__ long long g_wg_counters[kNumSMs * 8];
 
+template <bool BF16>
+struct Prec {
+  static constexpr int kElt = BF16 ? 2 : 4;             // bytes per element
+  static constexpr int kRowBytes = 32 * kElt;           // one 32-channel chunk of a row
+  static constexpr int kLanesPerRow = kRowBytes / 16;   // 16-byte cp.async pieces per row chunk
+  static constexpr int kRowsPerInstr = 32 / kLanesPerRow;
+  static constexpr int kMmaPerRow = BF16 ? 2 : 4;       // K = 16 bf16 / 8 tf32 = 32 bytes each
+  // K-major operand (forward): SWIZZLE_64B for 64-byte rows, SWIZZLE_128B for 128-byte rows
+  static constexpr uint32_t kLayoutK = BF16 ? 4u : 2u;
+  static constexpr uint32_t kSboK = 8 * kRowBytes;
+  // MN-major operand (wgrad): 32-bit types must use SWIZZLE_128B_BASE32B, bf16 uses SWIZZLE_64B
+  static constexpr uint32_t kLayoutMN = BF16 ? 4u : 1u;
+  // byte offset of 16-byte piece j of row r inside its row chunk (K-major forward layout)
+  __device__ static __forceinline__ uint32_t swz_k(int j, int r) {
+    return BF16 ? (uint32_t)((j ^ ((r >> 1) & 3)) << 4) : (uint32_t)((j ^ (r & 7)) << 4);
+  }
+  // same for the MN-major wgrad layout (tf32: 32-byte chunks XOR row&3)
+  __device__ static __forceinline__ uint32_t swz_mn(int j, int r) {
+    return BF16 ? (uint32_t)((j ^ ((r >> 1) & 3)) << 4)
+                : (uint32_t)((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4));
+  }
+  __device__ static __forceinline__ uint32_t idesc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return BF16 ? make_idesc_bf16(M, N, a_mn, b_mn) : make_idesc_tf32(M, N, a_mn, b_mn);
+  }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    if (BF16) mma_bf16(d, a, b, id, acc);
+    else mma_tf32(d, a, b, id, acc);
+  }
+};
+
 struct UmmaConvParams {
-  const float* A;            // [*, Ck]
-  const float* Bp;           // packed weights [K][kc][nt][cn_tile][32] (swizzled rows)
+  const void* A;             // [*, Ck] fp32 or bf16
+  const void* Bp;            // packed weights [K][kc][nt][cn_tile][32] (swizzled rows)
   const float* bias;         // [Cn] or null
   const int* nbr;            // [K, m_out]
   const uint32_t* tile_mask; // [ceil(m_out/128)] or null (all offsets active)
@@ -69,10 +104,11 @@ int64_t umma_fwd_workspace(int K, int c_in, int c_out) {
 }
 
 // W [K][Ck][Cn] (or [K][Cn][Ck] when transposed) -> per (k, chunk, n-tile) slab of cn_tile rows x
-// 128 B, 16-byte chunks XOR-swizzled with (row & 7): the exact shared-memory image UMMA expects
-// for a K-major SWIZZLE_128B B operand, so a stage's weights arrive with ONE bulk copy.
+// one row chunk, 16-byte pieces XOR-swizzled: the exact shared-memory image UMMA expects for a
+// K-major swizzled B operand, so a stage's weights arrive with ONE bulk copy.
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Wp, int K, int Ck, int Cn,
+pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, int Ck, int Cn,
                     int cn_tile, int transpose) {
   const long long total = (long long)K * Ck * Cn;
   const int n_ntiles = Cn / cn_tile, kc_count = Ck / 32;
@@ -86,20 +122,53 @@ pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Wp, int K, 
     int k = (int)(t / kc_count);
     int c = kc * 32 + jj, col = nt * cn_tile + n;
     float v = transpose ? W[((long long)k * Cn + col) * Ck + c] : W[((long long)k * Ck + c) * Cn + col];
-    int j = jj >> 2, w = jj & 3;
     long long slab = (((long long)k * kc_count + kc) * n_ntiles + nt) * cn_tile * 32;
-    Wp[slab + n * 32 + ((j ^ (n & 7)) << 2) + w] = v;
+    if (BF16) {
+      int j = jj >> 3, w = jj & 7;  // 8 bf16 per 16-byte piece
+      reinterpret_cast<__nv_bfloat16*>(Wp_)[slab + n * 32 + ((j ^ ((n >> 1) & 3)) << 3) + w] = __float2bfloat16_rn(v);
+    } else {
+      int j = jj >> 2, w = jj & 3;  // 4 fp32 per 16-byte piece
+      reinterpret_cast<float*>(Wp_)[slab + n * 32 + ((j ^ (n & 7)) << 2) + w] = v;
+    }
   }
 }
 
-template <int MT, int LOOKAHEAD>
+__global__ void __launch_bounds__(256)
+to_bf16_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ dst, int vec_ok) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = vec_ok ? n / 4 : 0;
+  for (long long q = i0; q < n4; q += stride) {
+    float4 v = reinterpret_cast<const float4*>(src)[q];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[q] = o;
+  }
+  for (long long q = n4 * 4 + i0; q < n; q += stride) dst[q] = __float2bfloat16_rn(src[q]);
+}
+
+int to_bf16(const float* src, int64_t n, void* dst, cudaStream_t stream) {
+  if (n == 0) return 0;
+  int vec_ok = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0);
+  int64_t want = ceil_div(ceil_div(n, 4), 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  to_bf16_kernel<<<grid, 256, 0, stream>>>(src, n, (__nv_bfloat16*)dst, vec_ok);
+  SPC_LAUNCHED("to_bf16_kernel");
+  return 0;
+}
+
+template <int MT, bool BF16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const UmmaConvParams p) {
+  using PR = Prec<BF16>;
+  constexpr int kAStage = kTileM * PR::kRowBytes;  // one sub-tile of one stage
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte alignment
+  // swizzled operands need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_stage_bytes = p.cn_tile * kChunkBytes;
-  const int stage_bytes = MT * kAStageBytes + b_stage_bytes;
+  const int b_stage_bytes = p.cn_tile * PR::kRowBytes;
+  const int stage_bytes = MT * kAStage + b_stage_bytes;
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -113,7 +182,7 @@ conv_umma_kernel(const UmmaConvParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), kNumProducerThreads + 1);  // 128 gather threads + 1 expect_tx
+      mbar_init(full_bar(s), kNumProducerThreads + 1);  // gather threads + 1 expect_tx
       mbar_init(empty_bar(s), 1);                       // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -132,30 +201,37 @@ conv_umma_kernel(const UmmaConvParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int rows_per_work = kTileM * MT;
+  auto work_mask = [&](int mtile) -> uint32_t {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      int t = mtile * MT + mt;
+      if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
+    }
+    if (p.K < 32) mask &= (1u << p.K) - 1u;
+    return mask;
+  };
 
   if (warp < kNumProducerWarps) {
     // ============================ producers ============================
     int stage = 0;
     uint32_t phase = 0;
-    const int sub = lane >> 3;  // row within a group of 4
-    const int j = lane & 7;     // 16-byte chunk within the 128-byte row
+    const int sub = lane / PR::kLanesPerRow;  // row within the rows one instruction covers
+    const int j = lane % PR::kLanesPerRow;    // 16-byte piece within the row chunk
+    const char* Abase = reinterpret_cast<const char*>(p.A);
+    const char* Bbase = reinterpret_cast<const char*>(p.Bp);
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int mtile = w / p.n_ntiles, ntile = w - mtile * p.n_ntiles;
       const int o0 = mtile * rows_per_work;
-      uint32_t mask = 0;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        int t = mtile * MT + mt;
-        if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
-      }
-      if (p.K < 32) mask &= (1u << p.K) - 1u;
-      // prefetch the first active offset's indices
+      const uint32_t mask = work_mask(mtile);
+      // each warp owns 16 rows of every sub-tile; lanes 0-15 hold their indices for the current
+      // offset and prefetch the next active offset's
       int idx_next[MT];
       int k = mask ? __ffs(mask) - 1 : -1;
       auto load_idx = [&](int kk, int* idx) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          int o = o0 + mt * kTileM + warp * 16 + lane;  // lanes 0-15 hold this warp's 16 rows
+          int o = o0 + mt * kTileM + warp * 16 + lane;
           idx[mt] = (lane < 16 && kk >= 0 && o < p.m_out) ? __ldg(p.nbr + (size_t)kk * p.m_out + o) : -1;
         }
       };
@@ -172,23 +248,23 @@ conv_umma_kernel(const UmmaConvParams p) {
           const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
           if (threadIdx.x == 0) {
             mbar_arrive_expect_tx(full_bar(stage), (uint32_t)b_stage_bytes);
-            const float* src = p.Bp + (((size_t)k * p.kc_count + kc) * p.n_ntiles + ntile) * (size_t)p.cn_tile * 32;
-            bulk_g2s(stage_addr + MT * kAStageBytes, src, (uint32_t)b_stage_bytes, full_bar(stage));
+            const char* src = Bbase + (((size_t)k * p.kc_count + kc) * p.n_ntiles + ntile) * (size_t)b_stage_bytes;
+            bulk_g2s(stage_addr + MT * kAStage, src, (uint32_t)b_stage_bytes, full_bar(stage));
           }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int rl = q * 4 + sub;            // row within this warp's 16 rows
-              const int r = warp * 16 + rl;          // row within the 128-row sub-tile
+            for (int q = 0; q < 16 / PR::kRowsPerInstr; ++q) {
+              const int rl = q * PR::kRowsPerInstr + sub;  // row within this warp's 16 rows
+              const int r = warp * 16 + rl;                // row within the 128-row sub-tile
               const int src_row = __shfl_sync(0xffffffffu, idx[mt], rl);
-              const float* src = p.A + (size_t)(src_row >= 0 ? src_row : 0) * p.Ck + kc * 32 + j * 4;
-              const uint32_t dst = stage_addr + mt * kAStageBytes + r * kChunkBytes + ((j ^ (r & 7)) << 4);
+              const char* src = Abase + ((size_t)(src_row >= 0 ? src_row : 0) * p.Ck + kc * 32) * PR::kElt + j * 16;
+              const uint32_t dst = stage_addr + mt * kAStage + r * PR::kRowBytes + PR::swz_k(j, r);
               cp_async_16(dst, src, src_row >= 0 ? 16u : 0u);
             }
           }
           // the stage's "full" barrier is signalled by the hardware when this thread's copies have
-          // landed (cp.async.mbarrier.arrive.noinc): no wait_group, no fence, nothing blocks here
+          // landed: no wait_group, no fence, nothing blocks here
           cp_async_mbar_arrive_noinc(full_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -201,16 +277,10 @@ conv_umma_kernel(const UmmaConvParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)p.cn_tile, 0, 0);
+    const uint32_t idesc = PR::idesc(kTileM, (uint32_t)p.cn_tile, 0, 0);
+    const uint64_t desc_hi = make_desc(0, 16, PR::kSboK, PR::kLayoutK);
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-      const int mtile = w / p.n_ntiles;
-      uint32_t mask = 0;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        int t = mtile * MT + mt;
-        if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
-      }
-      if (p.K < 32) mask &= (1u << p.K) - 1u;
+      const uint32_t mask = work_mask(w / p.n_ntiles);
       const int n_iters = __popc(mask) * p.kc_count;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -220,14 +290,14 @@ conv_umma_kernel(const UmmaConvParams p) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
-          const uint64_t bdesc = make_desc_sw128(stage_addr + MT * kAStageBytes, 16, 1024);
+          const uint64_t bdesc = desc_hi | (uint64_t)(((stage_addr + MT * kAStage) >> 4) & 0x3FFFu);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t adesc = make_desc_sw128(stage_addr + mt * kAStageBytes, 16, 1024);
+            const uint64_t adesc = desc_hi | (uint64_t)(((stage_addr + mt * kAStage) >> 4) & 0x3FFFu);
             const uint32_t d = tmem_base + (uint32_t)((acc * MT + mt) * p.cn_tile);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
-              mma_tf32(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || q > 0) ? 1u : 0u);
+            for (int q = 0; q < PR::kMmaPerRow; ++q)  // 32 bytes of K per MMA
+              PR::mma(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || q > 0) ? 1u : 0u);
           }
           mma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
         }
@@ -246,13 +316,7 @@ conv_umma_kernel(const UmmaConvParams p) {
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int mtile = w / p.n_ntiles, ntile = w - mtile * p.n_ntiles;
       const int o0 = mtile * rows_per_work;
-      uint32_t mask = 0;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        int t = mtile * MT + mt;
-        if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
-      }
-      if (p.K < 32) mask &= (1u << p.K) - 1u;
+      const uint32_t mask = work_mask(mtile);
       mbar_wait_sleep(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll
@@ -293,9 +357,9 @@ conv_umma_kernel(const UmmaConvParams p) {
   }
 }
 
-template <int MT, int LOOKAHEAD>
+template <int MT, bool BF16>
 static int launch_conv_umma(const UmmaConvParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = conv_umma_kernel<MT, LOOKAHEAD>;
+  auto kern = conv_umma_kernel<MT, BF16>;
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kNumThreads, smem, stream>>>(p);
   SPC_LAUNCHED("conv_umma_kernel");
@@ -305,16 +369,19 @@ static int launch_conv_umma(const UmmaConvParams& p, int grid, size_t smem, cuda
 static int g_umma_force_mt = 0;  // test hook: 0 = auto
 static int g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // test hook spc_debug_set: 0 = default
 
-int conv_fwd_umma(const float* in, const float* w, const float* bias, const int* nbr,
+// `in` is fp32 (bf16 == false) or bf16 (bf16 == true) rows; weights are always fp32 and packed here.
+int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
-                  bool transpose_w, float* out, void* workspace, int64_t workspace_bytes,
+                  bool transpose_w, bool bf16, float* out, void* workspace, int64_t workspace_bytes,
                   cudaStream_t stream) {
   if (m_out == 0) return 0;
   SPC_REQUIRE(umma_fwd_supported(c_in, c_out), "shape not supported by the tcgen05 path");
   SPC_REQUIRE(K <= 32, "tcgen05 path supports kernel volume <= 32");
   SPC_REQUIRE(workspace && workspace_bytes >= umma_fwd_workspace(K, c_in, c_out), "workspace too small");
   SPC_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0, "feature rows must be 16-byte aligned");
-  float* Wp = (float*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  void* Wp = (void*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  const int row_bytes = bf16 ? 64 : 128;
+  const int a_stage = kTileM * row_bytes;
 
   UmmaConvParams p;
   p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
@@ -324,10 +391,10 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
   // channels over more CTAs when that shortens the critical path = waves x bytes per stage.
   {
     const int64_t m_tiles = ceil_div(m_out, kTileM);
-    int64_t best = ceil_div(m_tiles * (c_out / p.cn_tile), kNumSMs) * (kAStageBytes + p.cn_tile * kChunkBytes);
+    int64_t best = ceil_div(m_tiles * (c_out / p.cn_tile), kNumSMs) * (a_stage + p.cn_tile * row_bytes);
     for (int t = p.cn_tile - 16; t >= 32; t -= 16) {
       if (c_out % t) continue;
-      int64_t cost = ceil_div(m_tiles * (c_out / t), kNumSMs) * (kAStageBytes + t * kChunkBytes);
+      int64_t cost = ceil_div(m_tiles * (c_out / t), kNumSMs) * (a_stage + t * row_bytes);
       if (cost < best) { best = cost; p.cn_tile = t; }
     }
   }
@@ -337,7 +404,8 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
   {
     long long total = (long long)K * c_in * c_out;
     int grid = (int)std::min<long long>(ceil_div(total, 256), kNumSMs * 8);
-    pack_weights_kernel<<<grid, 256, 0, stream>>>(w, Wp, K, c_in, c_out, p.cn_tile, transpose_w ? 1 : 0);
+    if (bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(w, Wp, K, c_in, c_out, p.cn_tile, transpose_w ? 1 : 0);
+    else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(w, Wp, K, c_in, c_out, p.cn_tile, transpose_w ? 1 : 0);
     SPC_LAUNCHED("pack_weights_kernel");
   }
 
@@ -351,24 +419,15 @@ int conv_fwd_umma(const float* in, const float* w, const float* bias, const int*
   int cols = p.acc_bufs * mt * p.cn_tile;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
-  const int stage_bytes = mt * kAStageBytes + p.cn_tile * kChunkBytes;
+  const int stage_bytes = mt * a_stage + p.cn_tile * row_bytes;
   int stages = (kSmemLimit - 1024 - 256) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   SPC_REQUIRE(stages >= 2, "tile does not fit in shared memory");
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
-  // LOOKAHEAD < stages
-  const int la = stages >= 8 ? 7 : (stages >= 6 ? 5 : (stages >= 4 ? 3 : 1));
-#define SPC_LAUNCH_UMMA(MTV)                                                          \
-  switch (la) {                                                                       \
-    case 7: return launch_conv_umma<MTV, 7>(p, grid, smem, stream);                   \
-    case 5: return launch_conv_umma<MTV, 5>(p, grid, smem, stream);                   \
-    case 3: return launch_conv_umma<MTV, 3>(p, grid, smem, stream);                   \
-    default: return launch_conv_umma<MTV, 1>(p, grid, smem, stream);                  \
-  }
-  if (mt == 2) { SPC_LAUNCH_UMMA(2) } else { SPC_LAUNCH_UMMA(1) }
-#undef SPC_LAUNCH_UMMA
+  if (bf16) return mt == 2 ? launch_conv_umma<2, true>(p, grid, smem, stream) : launch_conv_umma<1, true>(p, grid, smem, stream);
+  return mt == 2 ? launch_conv_umma<2, false>(p, grid, smem, stream) : launch_conv_umma<1, false>(p, grid, smem, stream);
 }
 
 void umma_set_force_mt(int mt) { g_umma_force_mt = mt; }
@@ -384,27 +443,27 @@ void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_dbg[idx] = va
 // GEMM view: D[M x N] += A[M x Kred] * B[Kred x N] with the REDUCTION over out rows o:
 //   M = 128 = four 32-channel "chunks", each chunk = (kernel offset k, channel group cc) — so for
 //       Cin = 32 four different offsets share one MMA, for Cin = 128 one offset fills it;
-//   N = Cout;  Kred = 8 rows per tcgen05.mma (tf32).
+//   N = Cout;  Kred = 8 (tf32) / 16 (bf16) rows per tcgen05.mma.
 // Both operands are MN-major: a gathered input row IS 32 consecutive M elements, a dout row IS
-// Cout consecutive N elements, so rows are laid down as [rows x 128 B] blocks like in the forward
-// kernel; MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3),
-// LBO = distance between 32-element column groups, SBO = distance between 4-row groups.
-// TMEM holds `mb_per_pass` accumulators (512 columns); a work item = (row range, pass) and ends
-// with an fp32 red.global.add of its partial dW — the only atomics of the convolution path.
-constexpr int kWgR = 64;                         // reduction rows per pipeline step
-constexpr int kWgChunkBlock = kWgR * kChunkBytes;  // 8 KB: [64 rows x 128 B]
+// Cout consecutive N elements, so rows are laid down as [rows x row-chunk] blocks like in the forward
+// kernel.  MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (32-byte chunks XOR row & 3), bf16
+// uses SWIZZLE_64B; LBO = distance between 32-element column groups, SBO = distance between 4- (tf32)
+// / 8-row (bf16) groups = 512 B either way.
+// A pipeline step covers kRows = 64 (tf32) / 128 (bf16) out rows of ONE M block: 4 chunk blocks of
+// 8 KB.  TMEM holds floor(512 / Cout) accumulators; a work item = (row range, pass over a group of
+// M blocks) and ends with an fp32 red.global.add of its partial dW — the only atomics of the
+// convolution path.
+constexpr int kWgChunkBlock = 8192;              // [kRows x row chunk]
 constexpr int kWgAStage = 4 * kWgChunkBlock;     // 32 KB: four chunks = one 128-row M block
 constexpr int kWgMaxAStages = 6;
 constexpr int kWgBStages = 2;
-constexpr int kWgIdxRing = 16;   // per-warp ring of index rows (64 int32 each)
-constexpr int kWgIdxDist = 8;    // steps of index prefetch distance (> max LOOKAHEAD + 1)
-constexpr int kWgIdxBytes = kNumProducerWarps * kWgIdxRing * 32 * 4;  // 16 KB: 32 rows per warp and slot
+constexpr int kWgIdxBytes = 16 * 1024;           // per-warp rings of neighbour indices
 constexpr int kWgMaxMb = 128;    // M blocks (K * Cin / 128): 27 offsets x 512 channels = 108
 constexpr int kWgTabBytes = kWgMaxMb * 4 + kWgMaxMb * 4 * 2;  // per-M-block offset masks, per-chunk (k, cc)
 
 struct UmmaWgradParams {
-  const float* in;            // [m_in, Cin]
-  const float* dout;          // [m_out, Cout]
+  const void* in;             // [m_in, Cin] fp32 or bf16
+  const void* dout;           // [m_out, Cout] fp32 or bf16
   const int* nbr;             // [K, m_out]
   const uint32_t* tile_mask;  // [ceil(m_out/128)] or null
   float* dw;                  // [K, Cin, Cout], zeroed
@@ -413,17 +472,9 @@ struct UmmaWgradParams {
   int n_mb, mb_per_pass, n_pass;
   int n_rb, rb_per_split, n_split;
   int a_stages;
-  int dbg_layout, dbg_swz, dbg_lbo, dbg_sbo;  // operand layout knobs (test hook spc_debug_set)
   int dbg_skip_mma, dbg_skip_gather, dbg_skip;  // timing experiments only (results are wrong when set)
   int n_work;
 };
-
-// byte offset of 16-byte piece j (0..7) of row r inside its 128-byte line under
-// SWIZZLE_128B_BASE32B = Swizzle<2,5,2>: the 32-byte chunk index is XORed with (row & 3)
-__device__ __forceinline__ uint32_t wg_swz(int j, int r, int mode) {
-  if (mode == 0) return (uint32_t)((j ^ (r & 7)) << 4);  // SWIZZLE_128B (16-byte base)
-  return (uint32_t)((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4));
-}
 
 #define WG_TIMED_WAIT(slot, call)                         \
   do {                                                    \
@@ -443,9 +494,16 @@ __device__ __forceinline__ uint32_t mblock_taps(int mb, int ncc, int nq) {
   return t;
 }
 
-template <int LOOKAHEAD>
+template <bool BF16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_wgrad_umma_kernel(const UmmaWgradParams p) {
+  using PR = Prec<BF16>;
+  constexpr int kRows = kWgChunkBlock / PR::kRowBytes;      // 64 (tf32) / 128 (bf16) rows per step
+  constexpr int kWarpRows = kRows / 2;                      // rows one producer warp gathers
+  constexpr int kIdxRing = BF16 ? 8 : 16;                   // ring slots of kWarpRows int32 per warp
+  constexpr int kIdxDist = BF16 ? 6 : 8;                    // index prefetch distance in steps
+  constexpr int kMmaPerStep = kRows / (BF16 ? 16 : 8);      // 8 either way, 1024 B of rows each
+  static_assert(kNumProducerWarps * kIdxRing * kWarpRows * 4 == kWgIdxBytes, "index ring size");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = (p.Cout / 32) * kWgChunkBlock;
@@ -490,24 +548,23 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
   long long wg_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long wg_t0 = clock64();
 
-  // (row block -> offset mask); tile masks are per 128 rows = 2 row blocks
+  // (row block -> offset mask); tile masks are per 128 rows
   auto rb_mask = [&](int rb) -> uint32_t {
-    return p.tile_mask ? (p.tile_mask[rb >> 1] & all_taps) : all_taps;
+    return p.tile_mask ? (p.tile_mask[(rb * kRows) >> 7] & all_taps) : all_taps;
   };
 
   if (warp < kNumProducerWarps) {
     // ============================ producers ============================
-    // The neighbour indices of a step are fetched into a per-warp shared-memory ring kWgIdxDist
+    // The neighbour indices of a step are fetched into a per-warp shared-memory ring kIdxDist
     // steps ahead with 4-byte cp.async, so their (DRAM) latency never sits on the issue path.
-    // "full" barriers are signalled by the hardware when a thread's copies have landed
-    // (cp.async.mbarrier.arrive.noinc), so the producer never blocks on its own loads — only on
-    // free slots — and the pipeline is as deep as the rings.
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0;
-    const int slot_w = warp >> 1;                        // chunk slot (0..3) this warp pair fills
-    const int row0 = (warp & 1) * 32;                    // this warp's half of the 64-row block
-    const int g8 = (lane >> 3) * 8;                      // lane group -> rows [row0+g8, row0+g8+8)
-    const int j = lane & 7;                              // 16-byte piece of the 128-byte line
+    const int slot_w = warp >> 1;                                   // chunk slot (0..3) of this warp pair
+    const int row0 = (warp & 1) * kWarpRows;                        // this warp's half of the row block
+    const int g8 = (lane / PR::kLanesPerRow) * 8;                   // lane group -> rows [row0+g8, +8)
+    const int j = lane % PR::kLanesPerRow;                          // 16-byte piece of the row chunk
+    const char* in_base = reinterpret_cast<const char*>(p.in);
+    const char* dout_base = reinterpret_cast<const char*>(p.dout);
 
     // flat iterator over the active (work item, row block, M block) steps of this CTA
     // (`mask_next` is loaded one row block ahead so that the dependent global load of the tile mask
@@ -539,16 +596,20 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
         if (s_mbtaps[s.mb] & s.mask) return;
       }
     };
-    // ring slot of this warp for step number `seq`: 64 int32 row indices
-    auto idx_slot = [&](uint32_t seq) { return idx_base + (uint32_t)((warp * kWgIdxRing + (seq % kWgIdxRing)) * 32 * 4); };
+    // ring slot of this warp for step number `seq`: kWarpRows int32 row indices
+    auto idx_slot = [&](uint32_t seq) { return idx_base + (uint32_t)((warp * kIdxRing + (seq % kIdxRing)) * kWarpRows * 4); };
     auto fetch_idx = [&](const Step& s, uint32_t seq) {
       const int q = s.mb * 4 + slot_w;
       if (q >= p.nq || (p.dbg_skip & 1)) return;
       const int k = s_qk[q];
       const uint32_t dst = idx_slot(seq);
-      const int o = s.rb * kWgR + row0 + lane;
-      if (o < p.m_out) cp_async_4(dst + lane * 4, p.nbr + (size_t)k * p.m_out + o);
-      else st_shared_s32(dst + lane * 4, -1);
+#pragma unroll
+      for (int h = 0; h < kWarpRows / 32; ++h) {
+        const int r = lane + 32 * h;
+        const int o = s.rb * kRows + row0 + r;
+        if (o < p.m_out) cp_async_4(dst + r * 4, p.nbr + (size_t)k * p.m_out + o);
+        else st_shared_s32(dst + r * 4, -1);
+      }
     };
 
     Step cur, pf;
@@ -556,39 +617,39 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     if (cur.ok) { begin_work(cur); next(cur); }
     pf = cur;
     uint32_t seq = 0, pf_seq = 0;
-    // prologue: indices of the first kWgIdxDist steps
-    for (int d = 0; d < kWgIdxDist && pf.ok; ++d) { fetch_idx(pf, pf_seq++); next(pf); }
+    // prologue: indices of the first kIdxDist steps
+    for (int d = 0; d < kIdxDist && pf.ok; ++d) { fetch_idx(pf, pf_seq++); next(pf); }
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
     int b_rb = -1, b_w = -1;
     while (cur.ok) {
       if (pf.ok) { fetch_idx(pf, pf_seq++); next(pf); }  // joins this step's commit group
-      const int o0 = cur.rb * kWgR;
+      const int o0 = cur.rb * kRows;
       bool with_b = false;
       if (b_rb != cur.rb || b_w != cur.w) {  // first active M block of a row block brings the dout rows
         b_rb = cur.rb; b_w = cur.w;
         with_b = true;
         WG_TIMED_WAIT(1, mbar_wait(b_empty(b_stage), b_phase ^ 1u));
         const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
-        const int n16 = (p.Cout / 32) * kWgR * 8;  // 16-byte pieces of the dout block
+        const int n16 = (p.Cout / 32) * kRows * PR::kLanesPerRow;  // 16-byte pieces of the dout block
         for (int e = threadIdx.x; e < n16 && !(p.dbg_skip & 2); e += kNumProducerThreads) {
-          const int jj = e & 7, r = (e >> 3) & (kWgR - 1), cbk = e >> 9;
+          const int jj = e % PR::kLanesPerRow, r = (e / PR::kLanesPerRow) % kRows, cbk = e / (PR::kLanesPerRow * kRows);
           const int o = o0 + r;
           const bool ok = o < p.m_out;
-          const float* src = p.dout + (size_t)(ok ? o : 0) * p.Cout + cbk * 32 + jj * 4;
-          cp_async_16(dstb + cbk * kWgChunkBlock + r * kChunkBytes + wg_swz(jj, r, p.dbg_swz), src, ok ? 16u : 0u);
+          const char* src = dout_base + ((size_t)(ok ? o : 0) * p.Cout + cbk * 32) * PR::kElt + jj * 16;
+          cp_async_16(dstb + cbk * kWgChunkBlock + r * PR::kRowBytes + PR::swz_mn(jj, r), src, ok ? 16u : 0u);
         }
         cp_async_mbar_arrive_noinc(b_full(b_stage));
       }
       WG_TIMED_WAIT(0, mbar_wait(a_empty(a_stage), a_phase ^ 1u));
       {
-        // a warp pair gathers chunk slot `slot_w` of this M block (64 rows x 128 B), 32 rows each
+        // a warp pair gathers chunk slot `slot_w` of this M block, half of the rows each
         const int q = cur.mb * 4 + slot_w;
         if (q < p.nq && !p.dbg_skip_gather) {
           const int cc = s_qcc[q];
-          const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + slot_w * kWgChunkBlock + (row0 + g8) * kChunkBytes;
-          const float* srcb = p.in + cc * 32 + j * 4;
+          const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + slot_w * kWgChunkBlock + (row0 + g8) * PR::kRowBytes;
+          const char* srcb = in_base + (size_t)cc * 32 * PR::kElt + j * 16;
           int idx[8];
           const uint32_t slot = idx_slot(seq) + g8 * 4;
 #pragma unroll
@@ -596,8 +657,8 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int src_row = idx[i];
-            const float* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin;
-            cp_async_16(dsta + i * kChunkBytes + wg_swz(j, i, p.dbg_swz), src, src_row >= 0 ? 16u : 0u);
+            const char* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin * PR::kElt;
+            cp_async_16(dsta + i * PR::kRowBytes + PR::swz_mn(j, i), src, src_row >= 0 ? 16u : 0u);
           }
         }
       }
@@ -605,9 +666,9 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       cp_async_commit();
       if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
       if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
-      // the index copies of step seq+1 were committed kWgIdxDist-1 groups ago: this never blocks in
-      // steady state (at most a_stages < kWgIdxDist-1 groups can be pending) and guarantees they landed
-      WG_TIMED_WAIT(2, cp_async_wait<kWgIdxDist - 2>());
+      // the index copies of step seq+1 were committed kIdxDist-1 groups ago: this never blocks in
+      // steady state (at most a_stages <= kIdxDist-2 groups can be pending) and guarantees they landed
+      WG_TIMED_WAIT(2, cp_async_wait<kIdxDist - 2>());
       __syncwarp();
       ++seq;
       next(cur);
@@ -617,13 +678,13 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     // ============================ MMA issuer ============================
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0, t_phase = 0;
-    const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
-    const uint64_t desc_hi = make_desc(0, p.dbg_lbo, p.dbg_sbo, p.dbg_layout);
+    const uint32_t idesc = PR::idesc(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
+    const uint64_t desc_hi = make_desc(0, kWgChunkBlock, 512, PR::kLayoutMN);
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int split = w / p.n_pass, pass = w - split * p.n_pass;
       const int mb0 = pass * p.n_mb / p.n_pass, mb1 = (pass + 1) * p.n_mb / p.n_pass;  // balanced
       const int rb0 = split * p.rb_per_split, rb1 = min(rb0 + p.rb_per_split, p.n_rb);
-      WG_TIMED_WAIT(5, mbar_wait(t_empty, t_phase ^ 1u));  // epilogue drained the accumulators of the previous item
+      WG_TIMED_WAIT(5, mbar_wait(t_empty, t_phase ^ 1u));  // epilogue drained the previous item's accumulators
       tc_fence_after();
       uint32_t touched = 0;
       uint32_t mask_next = rb0 < rb1 ? rb_mask(rb0) : 0u;
@@ -648,11 +709,11 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
             const uint32_t d = tmem_base + (uint32_t)((mb - mb0) * p.Cout);
             const uint32_t was = (touched >> (mb - mb0)) & 1u;
 #pragma unroll
-            for (int r8 = 0; r8 < kWgR / 8; ++r8) {
-              // descriptors differ only in the start address field: 1024 B (8 rows) per step = 64 units
+            for (int r8 = 0; r8 < kMmaPerStep; ++r8) {
+              // descriptors differ only in the start address field: 1024 B of rows per MMA = 64 units
               const uint64_t adesc = desc_hi | (uint64_t)(((a_addr >> 4) + 64u * r8) & 0x3FFFu);
               const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr >> 4) + 64u * r8) & 0x3FFFu);
-              if (!p.dbg_skip_mma) mma_tf32(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
+              if (!p.dbg_skip_mma) PR::mma(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
             }
             mma_commit(a_empty(a_stage));
           }
@@ -727,17 +788,17 @@ bool umma_wgrad_supported(int c_in, int c_out) {
 }
 int64_t umma_wgrad_workspace(int, int, int) { return 256; }
 
-template <int LOOKAHEAD>
+template <bool BF16>
 static int launch_wgrad_umma(const UmmaWgradParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = conv_wgrad_umma_kernel<LOOKAHEAD>;
+  auto kern = conv_wgrad_umma_kernel<BF16>;
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kNumThreads, smem, stream>>>(p);
   SPC_LAUNCHED("conv_wgrad_umma_kernel");
   return 0;
 }
 
-int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const uint32_t* tile_mask,
-                    int64_t m_out, int c_in, int c_out, int K, float* dw, void* workspace,
+int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
+                    int64_t m_out, int c_in, int c_out, int K, bool bf16, float* dw, void* workspace,
                     int64_t workspace_bytes, cudaStream_t stream) {
   (void)workspace; (void)workspace_bytes;
   SPC_REQUIRE(umma_wgrad_supported(c_in, c_out), "shape not supported by the tcgen05 wgrad path");
@@ -746,45 +807,37 @@ int conv_wgrad_umma(const float* in, const float* dout, const int* nbr, const ui
               "rows must be 16-byte aligned");
   SPC_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (m_out == 0) return 0;
+  const int rows = bf16 ? 128 : 64;  // out rows per pipeline step
   UmmaWgradParams p;
   p.in = in; p.dout = dout; p.nbr = nbr; p.tile_mask = tile_mask; p.dw = dw;
   p.m_out = (int)m_out; p.Cin = c_in; p.Cout = c_out; p.K = K;
   p.ncc = c_in / 32;
   p.nq = K * p.ncc;
   p.n_mb = (p.nq + 3) / 4;
+  SPC_REQUIRE(p.n_mb <= kWgMaxMb, "too many M blocks");
   int cap = 512 / c_out;                       // accumulators that fit in TMEM
   p.n_pass = (p.n_mb + cap - 1) / cap;
   p.mb_per_pass = (p.n_mb + p.n_pass - 1) / p.n_pass;
-  p.n_rb = (int)ceil_div(m_out, kWgR);
+  p.n_rb = (int)ceil_div(m_out, rows);
   int want_split = (2 * kNumSMs) / p.n_pass;  // <= 2 work items per CTA (static round-robin)
   if (want_split > p.n_rb) want_split = p.n_rb;
   if (want_split < 1) want_split = 1;
   p.rb_per_split = (p.n_rb + want_split - 1) / want_split;
-  if (p.rb_per_split & 1) ++p.rb_per_split;    // keep splits aligned to 128-row mask tiles
+  if (!bf16 && (p.rb_per_split & 1)) ++p.rb_per_split;  // keep splits aligned to 128-row mask tiles
   p.n_split = (p.n_rb + p.rb_per_split - 1) / p.rb_per_split;
   p.n_work = p.n_split * p.n_pass;
   const int b_stage_bytes = (c_out / 32) * kWgChunkBlock;
   int a_stages = (kSmemLimit - 1024 - 256 - kWgIdxBytes - kWgTabBytes - kWgBStages * b_stage_bytes) / kWgAStage;
-  if (a_stages > kWgMaxAStages) a_stages = kWgMaxAStages;
+  const int max_a = bf16 ? 4 : kWgMaxAStages;  // pending groups must stay <= index prefetch distance - 2
+  if (a_stages > max_a) a_stages = max_a;
   SPC_REQUIRE(a_stages >= 2, "wgrad tile does not fit in shared memory");
   p.a_stages = a_stages;
-  // MN-major 32-bit operands: SWIZZLE_128B_BASE32B, LBO = chunk-block pitch, SBO = 4-row group pitch
-  p.dbg_layout = g_dbg[0] ? g_dbg[0] : 1;
-  p.dbg_swz = g_dbg[1] ? g_dbg[1] - 1 : 1;
-  p.dbg_lbo = g_dbg[2] ? g_dbg[2] : kWgChunkBlock;
-  p.dbg_sbo = g_dbg[3] ? g_dbg[3] : 512;
   p.dbg_skip_mma = g_dbg[4];
   p.dbg_skip_gather = g_dbg[5];
   p.dbg_skip = g_dbg[6];
   const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256 + kWgIdxBytes + kWgTabBytes;
-  SPC_REQUIRE(p.n_mb <= kWgMaxMb, "too many M blocks");
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
-  const int la = a_stages >= 6 ? 5 : (a_stages >= 4 ? 3 : 1);
-  switch (la) {
-    case 5: return launch_wgrad_umma<5>(p, grid, smem, stream);
-    case 3: return launch_wgrad_umma<3>(p, grid, smem, stream);
-    default: return launch_wgrad_umma<1>(p, grid, smem, stream);
-  }
+  return bf16 ? launch_wgrad_umma<true>(p, grid, smem, stream) : launch_wgrad_umma<false>(p, grid, smem, stream);
 }
 
 }  // namespace spc

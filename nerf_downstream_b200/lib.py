@@ -17,6 +17,7 @@ LIB_PATH = PKG_DIR / "libsparseconv_b200.so"
 
 PREC_FP32 = 0
 PREC_TF32 = 1
+PREC_BF16 = 2
 SRC_FLOAT, SRC_INT, SRC_STRIDE = 0, 1, 2
 SLOT_BYTES = 16
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "spc_debug_set": (None, [c_int, c_int]),
     "spc_debug_read": (c_int, [_P, c_int]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
+    "spc_to_bf16": (c_int, [_P, c_int64, _P, _P]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_wgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),

@@ -61,7 +61,7 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
         self.dimension = dimension
         self.use_mm = False  # kernel_volume == 1 and all strides 1 -> plain matrix product
         self.convolution_mode = convolution_mode
-        # 'tf32' / 'fp32' / None (= ops.default_precision())
+        # 'tf32' / 'bf16' / 'fp32' / None (= ops.default_precision())
         self.precision: Optional[str] = None
         Tensor = torch.FloatTensor
         if self.kernel_generator.kernel_volume == 1 and self.kernel_generator.requires_strided_coordinates:
@@ -85,7 +85,7 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
     def _precision(self) -> int:
         if self.precision is None:
             return ops.default_precision()
-        return {"tf32": L.PREC_TF32, "fp32": L.PREC_FP32}[self.precision]
+        return ops.PRECISIONS[self.precision]
 
     def forward(self, input: SparseTensor, coordinates=None):
         assert isinstance(input, SparseTensor), "MinkowskiConvolution expects a SparseTensor"

@@ -16,13 +16,15 @@ from . import lib as L
 _I3 = ctypes.c_int32 * 3
 
 # precision used by convolution layers unless a layer overrides it
+PRECISIONS = {"tf32": L.PREC_TF32, "fp32": L.PREC_FP32, "bf16": L.PREC_BF16}
 _default_precision = L.PREC_TF32
 
 
 def set_default_precision(mode: str) -> None:
-    """'tf32' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FFMA, fp32-faithful)."""
+    """'tf32' (tcgen05 kind::tf32 on the fp32 rows, default), 'bf16' (tcgen05 kind::f16 on bf16 copies of
+    the rows: half the gather bytes, twice the MMA rate, fp32 accumulation) or 'fp32' (CUDA-core FFMA)."""
     global _default_precision
-    _default_precision = {"tf32": L.PREC_TF32, "fp32": L.PREC_FP32}[mode]
+    _default_precision = PRECISIONS[mode]
 
 
 def default_precision() -> int:
@@ -346,13 +348,25 @@ def _conv_bytes(km, K, c_in, c_out) -> float:
     return 4.0 * km.m_in * c_in + 4.0 * km.m_out * c_out + 4.0 * K * c_in * c_out + 4.0 * K * km.m_out
 
 
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 rows -> bf16 copy (round to nearest even) for the SPC_PREC_BF16 kernels."""
+    lib = L.load()
+    x = _feat(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_to_bf16(L.ptr(x), x.numel(), L.ptr(out), L.stream()), "spc_to_bf16")
+    if e0 is not None:
+        _profiler.end("to_bf16", e0, 0, 6.0 * x.numel())
+    return out
+
+
 def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
     ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
     ws = _empty(ws_bytes, torch.uint8, x.device)
-    mask = km.mask if precision == L.PREC_TF32 else None
+    mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
     L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
                              c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
@@ -369,7 +383,7 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision):
     din = _empty((km.m_in, c_in), torch.float32, g.device)
     ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
     ws = _empty(ws_bytes, torch.uint8, g.device)
-    mask_t = km.mask_t if precision == L.PREC_TF32 else None
+    mask_t = km.mask_t if precision != L.PREC_FP32 else None
     nbr_t = km.nbr_t
     e0 = _profiler.begin() if _profiler else None
     L.check(lib.spc_conv_dgrad(L.ptr(g), L.ptr(w), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out, c_in,
@@ -386,7 +400,7 @@ def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision):
     dw = _empty((K, c_in, c_out), torch.float32, x.device)
     ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
     ws = _empty(ws_bytes, torch.uint8, x.device)
-    mask = km.mask if precision == L.PREC_TF32 else None
+    mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
     L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out, K,
                                precision, L.ptr(dw), L.ptr(ws), ws_bytes, L.stream()), "spc_conv_wgrad")
@@ -410,7 +424,10 @@ class SparseConvFn(torch.autograd.Function):
         # The tensor-core kernels take channel counts that are multiples of 32; on large maps zero-pad
         # odd widths (27 SH channels, 20 classes) instead of dropping to the CUDA-core kernels.
         pad_in = pad_out = 0
-        if precision == L.PREC_TF32 and K <= 32 and max(km.m_in, km.m_out) >= 4096:
+        if precision == L.PREC_BF16 and (K > 32 or max(km.m_in, km.m_out) < 4096 or c_out > 256
+                                         or K * (c_in + (-c_in) % 32) > 128 * 128):
+            precision = L.PREC_TF32  # small maps / wide layers: not worth (or not built for) bf16 copies
+        if precision != L.PREC_FP32 and K <= 32 and max(km.m_in, km.m_out) >= 4096:
             pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
         if pad_in:
             x = torch.nn.functional.pad(x, (0, pad_in))
@@ -418,6 +435,8 @@ class SparseConvFn(torch.autograd.Function):
             w3 = torch.nn.functional.pad(w3, (0, pad_out, 0, pad_in))
             if b is not None and pad_out:
                 b = torch.nn.functional.pad(b, (0, pad_out))
+        if precision == L.PREC_BF16:
+            x = to_bf16(x)  # the bf16 copy is what backward needs too (half the saved bytes)
         out = conv_fwd_raw(x, w3, b, km, precision)
         if pad_out:
             out = out[:, :c_out].contiguous()
@@ -440,6 +459,8 @@ class SparseConvFn(torch.autograd.Function):
             db = g.sum(0).view(ctx.bias_shape)
         if pad_out:
             g = torch.nn.functional.pad(g, (0, pad_out))
+        if prec == L.PREC_BF16:
+            g = to_bf16(g)
         if ctx.needs_input_grad[0]:
             dx = conv_dgrad_raw(g, w3, km, prec)
             if pad_in:

@@ -26,7 +26,7 @@ dev = torch.device("cuda:0")
 for kv in filter(None, args.dbg.split(",")):
     i, v = kv.split("=")
     L.load().spc_debug_set(int(i), int(v))
-prec = L.PREC_TF32 if args.prec == "tf32" else L.PREC_FP32
+prec = ops.PRECISIONS[args.prec]
 c, _, _ = synth.room_batch(777, 1, args.voxels, channels=1, shuffle=args.shuffle)
 cmap, _, _, _ = ops.coords_insert(torch.from_numpy(c).to(dev), L.SRC_FLOAT, (1, 1, 1))
 out_map = cmap
@@ -41,9 +41,11 @@ go = torch.randn(km.m_out, args.cout, generator=g).to(dev)
 _ = km.mask, km.nbr_t, km.mask_t
 P = km.n_pairs
 flops = 2.0 * P * args.cin * args.cout
-fns = {"fwd": lambda: ops.conv_fwd_raw(x, w, None, km, prec),
-       "dgrad": lambda: ops.conv_dgrad_raw(go, w, km, prec),
-       "wgrad": lambda: ops.conv_wgrad_raw(x, go, km, K, args.cin, args.cout, prec)}
+xin, gin = (ops.to_bf16(x), ops.to_bf16(go)) if args.prec == "bf16" else (x, go)
+fns = {"fwd": lambda: ops.conv_fwd_raw(xin, w, None, km, prec),
+       "dgrad": lambda: ops.conv_dgrad_raw(gin, w, km, prec),
+       "wgrad": lambda: ops.conv_wgrad_raw(xin, gin, km, K, args.cin, args.cout, prec),
+       "cvt": lambda: ops.to_bf16(x)}
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > L2
 for name in args.only.split(","):
     fn = fns[name]
@@ -62,7 +64,7 @@ for name in args.only.split(","):
     print(f"{name:6s} M_in={km.m_in} M_out={km.m_out} K={K} {args.cin}->{args.cout} P={P} {args.prec}: "
           f"{t:.3f} ms  {flops / t / 1e9:.1f} TFLOP/s  gather {P * args.cin * 4 / t / 1e6:.0f} GB/s", flush=True)
 
-if "wgrad" in args.only and args.prec == "tf32":
+if "wgrad" in args.only and args.prec != "fp32":
     import ctypes
     import numpy as np
     buf = np.zeros(148 * 8, np.int64)

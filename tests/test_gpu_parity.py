@@ -224,6 +224,33 @@ def test_conv_tf32_tensor_core(cuda_device, ks, stride, cin, cout, transpose, fo
         lib.spc_debug_force_mt(0)
 
 
+BF16_TOL = 2e-2
+BF16_CONV_CASES = [((3, 3, 3), 1, 32, 32, False), ((3, 3, 3), 1, 64, 96, False), ((3, 3, 3), 1, 128, 96, False),
+                   ((3, 3, 3), 1, 96, 96, False), ((3, 3, 3), 1, 256, 256, False), ((3, 3, 3), 2, 64, 128, False),
+                   ((2, 2, 2), 2, 96, 96, False), ((2, 2, 2), 2, 256, 128, True), ((1, 1, 1), 2, 128, 256, False)]
+
+
+@pytest.mark.parametrize("ks,stride,cin,cout,transpose", BF16_CONV_CASES)
+def test_conv_bf16_tensor_core(cuda_device, ks, stride, cin, cout, transpose):
+    """kind::f16 path on bf16 copies of the rows; stated bound |d| <= 2e-2 * max|ref| vs the fp64 oracle."""
+    km, nbr, x, w, b, go = _conv_case(cuda_device, 43, 9000, 11, ks, stride, cin, cout, transpose)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    ref = R.conv_forward(xr, wr, nbr, b)
+    ref.backward(go)
+    d = cuda_device
+    xb, gb = ops.to_bf16(x.float().to(d)), ops.to_bf16(go.float().to(d))
+    wg, bg = w.float().to(d), b.float().to(d).view(-1)
+    K = wg.shape[0]
+
+    def check(got, want, what):
+        err = (got.double().cpu() - want.detach()).abs().max().item()
+        scale = want.detach().abs().max().item()
+        assert err <= BF16_TOL * scale, f"{what}: max err {err:.3e} vs {BF16_TOL} * {scale:.3e}"
+    check(ops.conv_fwd_raw(xb, wg, bg, km, L.PREC_BF16), ref, "forward")
+    check(ops.conv_dgrad_raw(gb, wg, km, L.PREC_BF16), xr.grad, "dgrad")
+    check(ops.conv_wgrad_raw(xb, gb, km, K, cin, cout, L.PREC_BF16), wr.grad, "wgrad")
+
+
 def test_conv_tf32_matches_fp32_kernels_large(cuda_device):
     # on-device cross-check at a size the CPU oracle would not finish quickly (~150 K voxels)
     c, _, _ = synth.room_batch(5, 1, 150_000, channels=1)
