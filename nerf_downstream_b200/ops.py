@@ -134,7 +134,7 @@ def coords_insert(src: torch.Tensor, kind: int, ts: Sequence[int]):
                                   n_slots, L.ptr(coords), L.ptr(first), L.ptr(inverse), L.ptr(count),
                                   L.ptr(status), L.ptr(ws), ws_bytes, L.stream()), "spc_coords_insert")
     if e0 is not None:
-        _profiler.end("coords_insert(hash)", e0, 0, 20.0 * n + 36.0 * n)
+        _profiler.end("coords_insert(hash)", e0, 0, 20.0 * n + 36.0 * n, f"N{n}")
     m, err = status.tolist()  # host sync
     if err:
         raise RuntimeError("coordinate out of the supported range: batch index must be in [0,1022] and "
@@ -259,7 +259,8 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
                                ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
                                L.stream()), "spc_kernel_map")
     if e0 is not None:
-        _profiler.end("kernel_map", e0, 0, (16.0 + 8.0 * K + 4.0 * K) * out_map.size)
+        _profiler.end("kernel_map", e0, 0, (16.0 + 8.0 * K + 4.0 * K) * out_map.size,
+                      f"K{K} M{out_map.size} ts{in_map.tensor_stride[0]}")
     return KernelMap(nbr, tap_count, K, in_map.size, out_map.size)
 
 
@@ -506,7 +507,7 @@ class BatchNormFn(torch.autograd.Function):
         L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res), m, C,
                                  float(eps), int(relu), L.ptr(y), L.stream()), "spc_bn_apply")
         if e0 is not None:
-            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)) * m * C)
+            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)) * m * C, f"C{C} M{m}")
         ctx.save_for_backward(x, y if relu else None, mean, var, gamma)
         ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
         return y
@@ -530,7 +531,8 @@ class BatchNormFn(torch.autograd.Function):
                                relu, use_batch, L.ptr(dx), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
                                ws_bytes, L.stream()), "spc_bn_bwd")
         if e0 is not None:
-            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)) * m * C)
+            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)) * m * C,
+                          f"C{C} M{m}")
         return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,
                 dres)
 

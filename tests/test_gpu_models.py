@@ -5,6 +5,8 @@ functional CPU oracle (oracle/nets.py) with identical weights.
 Tolerances (stated, end to end through 14 / 50+ layers with batch-norm in between):
   fp32 mode : logits  |d| <= 2e-3 * max|ref| ; parameter gradients  cosine >= 0.999
   tf32 mode : logits  cosine >= 0.9999, |d| <= 3e-2 * max|ref| ; gradients cosine >= 0.9
+  bf16 mode : logits  cosine >= 0.999, |d| <= 1e-1 * max|ref| ; gradients cosine >= 0.7 (bf16 operands carry 8
+              mantissa bits against TF32's 10: four times the rounding step, fp32 accumulation in both)
 Every individual op inside these backward passes agrees with an fp64 recomputation to <= 1e-6 relative
 (scripts/diag_ops_in_model.py); the looser end-to-end gradient bars reflect how fp32 / tf32 rounding is
 amplified through 50 layers of batch-norm over a few dozen rows at the deepest level of a SMALL test scene
@@ -45,25 +47,26 @@ def _compare(model, fwd, coords, feats, target_fn, mode, dev):
         if mode == "fp32":
             assert err <= 2e-3 * scale, (err, scale)
             assert cos >= 0.99999
-        else:
+        elif mode == "tf32":
             assert cos >= 0.9999, cos
             assert err <= 3e-2 * scale, (err, scale)
+        else:
+            assert cos >= 0.999, cos
+            assert err <= 1e-1 * scale, (err, scale)
         worst = 1.0
         for name, p in model.named_parameters():
             g_ref = params[name].grad
             assert p.grad is not None and g_ref is not None, name
             c = _cos(p.grad, g_ref)
             worst = min(worst, c)
-            if mode == "fp32":
-                assert c >= 0.999, (name, c)
-            else:
-                assert c >= 0.9, (name, c)
+            assert c >= {"fp32": 0.999, "tf32": 0.9, "bf16": 0.7}[mode], (name, c)
+        print(f"[{mode}] logits cos={cos:.6f} max err={err:.3e} (scale {scale:.3e}) worst grad cos={worst:.4f}")
         return cos, worst
     finally:
         ops.set_default_precision("tf32")
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_resnet14_matches_oracle(cuda_device, mode):
     torch.manual_seed(0)
     coords, feats, labels = synth.co3d_batch(777, 3, lattice=64)
@@ -75,7 +78,7 @@ def test_resnet14_matches_oracle(cuda_device, mode):
     _compare(model, nets.resnet_forward, coords, feats, target, mode, cuda_device)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_res16unet34c_matches_oracle(cuda_device, mode):
     torch.manual_seed(1)
     coords, feats, labels = synth.room_batch(777, 2, 40_000)
