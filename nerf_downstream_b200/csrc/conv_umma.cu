@@ -182,7 +182,7 @@ conv_umma_kernel(const UmmaConvParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), kNumProducerThreads + 1);  // gather threads + 1 expect_tx
+      mbar_init(full_bar(s), 32 + 1);                   // the 32 lanes of the owning warp + 1 expect_tx
       mbar_init(empty_bar(s), 1);                       // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -214,81 +214,131 @@ conv_umma_kernel(const UmmaConvParams p) {
 
   if (warp < kNumProducerWarps) {
     // ============================ producers ============================
-    int stage = 0;
-    uint32_t phase = 0;
+    // Stage n of this CTA's stage sequence (work item, active offset k, channel chunk kc) is filled
+    // entirely by warp n % nprod: a warp waits for ITS ring slot, issues every gather copy of the
+    // stage (and the weight slab) and moves on, so the address arithmetic of up to eight stages runs
+    // concurrently on the four schedulers instead of all warps marching through one stage in
+    // lock-step.  nprod <= ring slots: a warp is then never two ring revolutions ahead of the MMA
+    // warp, which the one-bit phase parity of the "empty" barriers could not tell apart.
+    const int nprod = p.stages < kNumProducerWarps ? p.stages : kNumProducerWarps;
+    constexpr int R = PR::kRowsPerInstr;  // rows one LDGSTS instruction covers
+    constexpr int NQ = kTileM / R;        // instructions per 128-row sub-tile
     const int sub = lane / PR::kLanesPerRow;  // row within the rows one instruction covers
     const int j = lane % PR::kLanesPerRow;    // 16-byte piece within the row chunk
-    const char* Abase = reinterpret_cast<const char*>(p.A);
+    const char* Abase = reinterpret_cast<const char*>(p.A) + j * 16;
     const char* Bbase = reinterpret_cast<const char*>(p.Bp);
-    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-      const int mtile = w / p.n_ntiles, ntile = w - mtile * p.n_ntiles;
-      const int o0 = mtile * rows_per_work;
-      const uint32_t mask = work_mask(mtile);
-      // each warp owns 16 rows of every sub-tile; lanes 0-15 hold their indices for the current
-      // offset and prefetch the next active offset's
-      int idx_next[MT];
-      int k = mask ? __ffs(mask) - 1 : -1;
-      auto load_idx = [&](int kk, int* idx) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          int o = o0 + mt * kTileM + warp * 16 + lane;
-          idx[mt] = (lane < 16 && kk >= 0 && o < p.m_out) ? __ldg(p.nbr + (size_t)kk * p.m_out + o) : -1;
-        }
-      };
-      load_idx(k, idx_next);
-      while (k >= 0) {
-        int idx[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) idx[mt] = idx_next[mt];
-        uint32_t rest = mask & ~((2u << k) - 1u);
-        const int k_next = rest ? __ffs(rest) - 1 : -1;
-        load_idx(k_next, idx_next);
-        for (int kc = 0; kc < p.kc_count; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
-          if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)b_stage_bytes);
-            const char* src = Bbase + (((size_t)k * p.kc_count + kc) * p.n_ntiles + ntile) * (size_t)b_stage_bytes;
-            bulk_g2s(stage_addr + MT * kAStage, src, (uint32_t)b_stage_bytes, full_bar(stage));
-          }
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-            for (int q = 0; q < 16 / PR::kRowsPerInstr; ++q) {
-              const int rl = q * PR::kRowsPerInstr + sub;  // row within this warp's 16 rows
-              const int r = warp * 16 + rl;                // row within the 128-row sub-tile
-              const int src_row = __shfl_sync(0xffffffffu, idx[mt], rl);
-              const char* src = Abase + ((size_t)(src_row >= 0 ? src_row : 0) * p.Ck + kc * 32) * PR::kElt + j * 16;
-              const uint32_t dst = stage_addr + mt * kAStage + r * PR::kRowBytes + PR::swz_k(j, r);
-              cp_async_16(dst, src, src_row >= 0 ? 16u : 0u);
-            }
-          }
-          // the stage's "full" barrier is signalled by the hardware when this thread's copies have
-          // landed: no wait_group, no fence, nothing blocks here
-          cp_async_mbar_arrive_noinc(full_bar(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        }
-        k = k_next;
+    const size_t row_pitch = (size_t)p.Ck * PR::kElt;
+    const bool leader = elect_one();
+
+    // iterator over the stages this warp owns
+    struct It { int w, s, S, ord, n0; uint32_t mask, rest; bool ok; };  // n0 = (first stage of item) % nprod
+    auto open_item = [&](It& it) {  // first owned stage of item it.w or of a later item
+      for (;;) {
+        if (it.w >= p.n_work || warp >= nprod) { it.ok = false; return; }
+        it.mask = work_mask(it.w / p.n_ntiles);
+        it.S = __popc(it.mask) * p.kc_count;
+        it.s = warp - it.n0;
+        if (it.s < 0) it.s += nprod;
+        if (it.s < it.S) { it.rest = it.mask; it.ord = 0; return; }
+        it.n0 = (it.n0 + it.S) % nprod;
+        it.w += gridDim.x;
       }
+    };
+    auto advance = [&](It& it) {
+      it.s += nprod;
+      if (it.s >= it.S) {
+        it.n0 = (it.n0 + it.S) % nprod;
+        it.w += gridDim.x;
+        open_item(it);
+      }
+    };
+    // (k, kc) of the current stage; `rest` / `ord` walk the set bits of the offset mask
+    auto locate = [&](It& it, int& k, int& kc) {
+      const int ord = it.s / p.kc_count;
+      kc = it.s - ord * p.kc_count;
+      while (it.ord < ord) { it.rest &= it.rest - 1u; ++it.ord; }
+      k = __ffs(it.rest) - 1;
+    };
+    // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 of every sub-tile
+    auto load_idx = [&](const It& it, int k, int* idx) {
+      const int o0 = (it.w / p.n_ntiles) * rows_per_work;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = o0 + mt * kTileM + i * 32 + lane;
+          idx[mt * 4 + i] = o < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + o) : -1;
+        }
+      }
+    };
+
+    It cur;
+    cur.w = blockIdx.x; cur.n0 = 0; cur.ok = true;
+    open_item(cur);
+    int k = 0, kc = 0;
+    int idx[MT * 4];
+    if (cur.ok) { locate(cur, k, kc); load_idx(cur, k, idx); }
+    int slot = warp;  // ring slot / phase of sequence number warp + nprod * i
+    uint32_t phase = 0;
+    while (cur.ok) {
+      // indices of the NEXT owned stage: their latency hides behind this stage's slot wait
+      It nxt = cur;
+      advance(nxt);
+      int k_n = 0, kc_n = 0;
+      int idx_n[MT * 4];
+      if (nxt.ok) { locate(nxt, k_n, kc_n); load_idx(nxt, k_n, idx_n); }
+
+      const int ntile = cur.w % p.n_ntiles;
+      mbar_wait(empty_bar(slot), phase ^ 1u);
+      const uint32_t stage_addr = smem_base + (uint32_t)slot * stage_bytes;
+      if (leader) {
+        mbar_arrive_expect_tx(full_bar(slot), (uint32_t)b_stage_bytes);
+        const char* src = Bbase + (((size_t)k * p.kc_count + kc) * p.n_ntiles + ntile) * (size_t)b_stage_bytes;
+        bulk_g2s(stage_addr + MT * kAStage, src, (uint32_t)b_stage_bytes, full_bar(slot));
+      }
+      __syncwarp();
+      const char* Akc = Abase + (size_t)kc * PR::kRowBytes;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int r = q * R + sub;  // row within the 128-row sub-tile
+          const int src_row = __shfl_sync(0xffffffffu, idx[mt * 4 + ((q * R) >> 5)], r & 31);
+          const char* src = Akc + (size_t)(src_row >= 0 ? src_row : 0) * row_pitch;
+          const uint32_t dst = stage_addr + mt * kAStage + r * PR::kRowBytes + PR::swz_k(j, r);
+          cp_async_16(dst, src, src_row >= 0 ? 16u : 0u);
+        }
+      }
+      // the stage's "full" barrier is signalled by the hardware when this lane's copies have landed:
+      // no wait_group, no fence, nothing blocks here
+      cp_async_mbar_arrive_noinc(full_bar(slot));
+      slot += nprod;
+      if (slot >= p.stages) { slot -= p.stages; phase ^= 1u; }
+      cur = nxt; k = k_n; kc = kc_n;
+#pragma unroll
+      for (int i = 0; i < MT * 4; ++i) idx[i] = idx_n[i];
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t idesc = PR::idesc(kTileM, (uint32_t)p.cn_tile, 0, 0);
-    const uint64_t desc_hi = make_desc(0, 16, PR::kSboK, PR::kLayoutK);
-    for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-      const uint32_t mask = work_mask(w / p.n_ntiles);
-      const int n_iters = __popc(mask) * p.kc_count;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(full_bar(stage), phase);
-        fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+    // ONE elected thread runs the whole loop: under elect.sync the compiler keeps descriptors in
+    // uniform registers and emits back-to-back UTCHMMA (a `lane == 0` branch costs an ELECT /
+    // BRA.U.ANY waterfall around every tcgen05 instruction).
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = PR::idesc(kTileM, (uint32_t)p.cn_tile, 0, 0);
+      const uint64_t desc_hi = make_desc(0, 16, PR::kSboK, PR::kLayoutK);
+      for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+        const uint32_t mask = work_mask(w / p.n_ntiles);
+        const int n_iters = __popc(mask) * p.kc_count;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) {
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          tc_fence_after();
           const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
           const uint64_t bdesc = desc_hi | (uint64_t)(((stage_addr + MT * kAStage) >> 4) & 0x3FFFu);
 #pragma unroll
@@ -300,14 +350,13 @@ conv_umma_kernel(const UmmaConvParams p) {
               PR::mma(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || q > 0) ? 1u : 0u);
           }
           mma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        mma_commit(tfull_bar(acc));
+        if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
       }
-      if (lane == 0) mma_commit(tfull_bar(acc));
-      __syncwarp();
-      if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
     }
+    __syncwarp();
   } else {
     // ============================ epilogue ============================
     const int ew = warp & 3;  // TMEM lane group this warp may access
