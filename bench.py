@@ -205,7 +205,7 @@ def run_ours(args):
     def step(c, f, y):
         field = ME.TensorField(coordinates=c, features=f)
         logits = model(field)
-        loss = F.cross_entropy(logits, y, ignore_index=255)
+        loss = ops.cross_entropy(logits, y, ignore_index=255)
         tr.backward_and_step(loss)
         key = field.coordinate_manager.get_unique_coordinate_map_key(1)
         voxels_per_step[0] = field.coordinate_manager.size(key)

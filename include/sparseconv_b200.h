@@ -200,6 +200,18 @@ int spc_global_pool_fwd(const float* in, const int32_t* coords, int64_t m, int C
 int spc_global_pool_bwd(const float* dout, const int32_t* coords, const int32_t* cnt, int64_t m,
                         int C, int n_batch, int avg, float* din, void* stream);
 
+/* Softmax cross-entropy with ignore_index over rows [n, C] (C <= 64), mean over the non-ignored rows
+ * (classification_training.py:33, segmentation_training.py:27-44: nn.CrossEntropyLoss(ignore_index=)).
+ * fwd: stats[0] = sum of -log p[target], stats[1] = number of non-ignored rows (doubles, device),
+ *      grad_raw[i, c] = p[i, c] - [c == target[i]] (0 for ignored rows); *bad_target = 1 if a target
+ *      is outside [0, C) and is not ignore_index.  loss = stats[0] / stats[1].
+ * bwd: dlogits = grad_raw * grad_out[0] / stats[1]. */
+int spc_ce_fwd(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_index,
+               float* grad_raw, double* stats, int32_t* bad_target, void* stream);
+int spc_ce_bwd(const float* grad_raw, const double* stats, const float* grad_out, int64_t n, int C,
+               float* dlogits, void* stream);
+
+
 /* Fused SGD step on a flat arena (co3d_cls.gin:33-39; optim.py:60-69):
  * g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf. */
 int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,

@@ -87,7 +87,8 @@ struct UmmaConvParams {
   int m_out, Ck, Cn, K;
   int cn_tile, n_ntiles, kc_count;
   int stages, acc_bufs, tmem_cols;
-  int n_work;                // m_tiles * n_ntiles
+  int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
+  int n_work;                // m_tiles * n_ntiles * ksplit
 };
 
 static inline int pick_cn_tile(int Cn) {
@@ -201,7 +202,11 @@ conv_umma_kernel(const UmmaConvParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int rows_per_work = kTileM * MT;
-  auto work_mask = [&](int mtile) -> uint32_t {
+  // work item w -> (m tile, n tile, offset group); w = (mtile * n_ntiles + ntile) * ksplit + kg
+  const int items_per_mtile = p.n_ntiles * p.ksplit;
+  auto work_mask = [&](int w) -> uint32_t {
+    const int mtile = w / items_per_mtile;
+    const int kg = w % p.ksplit;
     uint32_t mask = 0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -209,6 +214,11 @@ conv_umma_kernel(const UmmaConvParams p) {
       if ((long long)t * kTileM < p.m_out) mask |= p.tile_mask ? p.tile_mask[t] : 0xFFFFFFFFu;
     }
     if (p.K < 32) mask &= (1u << p.K) - 1u;
+    if (p.ksplit > 1) {  // this item's share of the offsets
+      const int k0 = kg * p.k_per, k1 = min(k0 + p.k_per, p.K);
+      const uint32_t hi = k1 >= 32 ? 0xFFFFFFFFu : ((1u << k1) - 1u);
+      mask &= hi & ~((1u << k0) - 1u);
+    }
     return mask;
   };
 
@@ -235,7 +245,7 @@ conv_umma_kernel(const UmmaConvParams p) {
     auto open_item = [&](It& it) {  // first owned stage of item it.w or of a later item
       for (;;) {
         if (it.w >= p.n_work || warp >= nprod) { it.ok = false; return; }
-        it.mask = work_mask(it.w / p.n_ntiles);
+        it.mask = work_mask(it.w);
         it.S = __popc(it.mask) * p.kc_count;
         it.s = warp - it.n0;
         if (it.s < 0) it.s += nprod;
@@ -261,7 +271,7 @@ conv_umma_kernel(const UmmaConvParams p) {
     };
     // lane l holds the neighbour rows of tile rows l, l+32, l+64, l+96 of every sub-tile
     auto load_idx = [&](const It& it, int k, int* idx) {
-      const int o0 = (it.w / p.n_ntiles) * rows_per_work;
+      const int o0 = (it.w / items_per_mtile) * rows_per_work;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -288,7 +298,7 @@ conv_umma_kernel(const UmmaConvParams p) {
       int idx_n[MT * 4];
       if (nxt.ok) { locate(nxt, k_n, kc_n); load_idx(nxt, k_n, idx_n); }
 
-      const int ntile = cur.w % p.n_ntiles;
+      const int ntile = (cur.w / p.ksplit) % p.n_ntiles;
       mbar_wait(empty_bar(slot), phase ^ 1u);
       const uint32_t stage_addr = smem_base + (uint32_t)slot * stage_bytes;
       if (leader) {
@@ -331,7 +341,7 @@ conv_umma_kernel(const UmmaConvParams p) {
       const uint32_t idesc = PR::idesc(kTileM, (uint32_t)p.cn_tile, 0, 0);
       const uint64_t desc_hi = make_desc(0, 16, PR::kSboK, PR::kLayoutK);
       for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-        const uint32_t mask = work_mask(w / p.n_ntiles);
+        const uint32_t mask = work_mask(w);
         const int n_iters = __popc(mask) * p.kc_count;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -363,9 +373,10 @@ conv_umma_kernel(const UmmaConvParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-      const int mtile = w / p.n_ntiles, ntile = w - mtile * p.n_ntiles;
+      const int mtile = w / items_per_mtile, ntile = (w / p.ksplit) % p.n_ntiles, kg = w % p.ksplit;
       const int o0 = mtile * rows_per_work;
-      const uint32_t mask = work_mask(mtile);
+      const uint32_t mask = work_mask(w);
+      const bool add_bias = p.bias != nullptr && kg == 0;
       mbar_wait_sleep(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll
@@ -381,14 +392,24 @@ conv_umma_kernel(const UmmaConvParams p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.f;
           }
-          if (p.bias) {
+          if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ntile * p.cn_tile + c0 + i);
           }
           if (row_ok) {
+            if (p.ksplit > 1) {  // partial sums of several offset groups meet in the (zeroed) output
+              if (mask != 0 || add_bias) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(v[i]),
+                               "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
+                               : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
           }
         }
       }
@@ -435,20 +456,42 @@ int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* 
   UmmaConvParams p;
   p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
   p.m_out = (int)m_out; p.Ck = c_in; p.Cn = c_out; p.K = K;
-  p.cn_tile = pick_cn_tile(c_out);
-  // Small maps (deep UNet levels): too few 128-row tiles to fill 148 SMs, so split the output
-  // channels over more CTAs when that shortens the critical path = waves x bytes per stage.
-  {
-    const int64_t m_tiles = ceil_div(m_out, kTileM);
-    int64_t best = ceil_div(m_tiles * (c_out / p.cn_tile), kNumSMs) * (a_stage + p.cn_tile * row_bytes);
-    for (int t = p.cn_tile - 16; t >= 32; t -= 16) {
-      if (c_out % t) continue;
-      int64_t cost = ceil_div(m_tiles * (c_out / t), kNumSMs) * (a_stage + t * row_bytes);
-      if (cost < best) { best = cost; p.cn_tile = t; }
-    }
-  }
-  p.n_ntiles = c_out / p.cn_tile;
   p.kc_count = c_in / 32;
+  // Tile shape: MT sub-tiles of 128 rows x cn_tile output channels per work item, and on small maps
+  // (deep UNet levels: too few row tiles for 148 SMs) the K offsets split over `ksplit` items whose
+  // partial sums meet in the zeroed output through fp32 red.global.add.  Chosen to minimise the
+  // critical path = waves x bytes a CTA stages per item (gather + weight slabs, what bounds the
+  // kernel); large maps always come out as ksplit = 1 (atomic-free, one owner per output row).
+  int mt = 1;
+  p.cn_tile = pick_cn_tile(c_out);
+  p.ksplit = 1;
+  {
+    double best = 1e300;
+    const int cn_max = p.cn_tile;
+    for (int cand_mt = 1; cand_mt <= 2; ++cand_mt) {
+      if (g_umma_force_mt && cand_mt != g_umma_force_mt) continue;
+      for (int cn = cn_max; cn >= 16; cn -= 16) {
+        if (c_out % cn || cand_mt * cn > 512) continue;
+        const int64_t stage_b = (int64_t)cand_mt * a_stage + (int64_t)cn * row_bytes;
+        if ((kSmemLimit - 1024 - 256) / stage_b < 2) continue;
+        const int64_t items1 = ceil_div(m_out, kTileM * cand_mt) * (c_out / cn);
+        const int ks_max = items1 >= kNumSMs ? 1 : K;
+        for (int ks = 1; ks <= ks_max; ++ks) {
+          const int k_per = (int)ceil_div(K, ks);
+          if (ceil_div(K, k_per) != ks) continue;  // same split as a smaller ks
+          const int64_t items = items1 * ks;
+          double per_item = (double)k_per * p.kc_count * stage_b;
+          if (ks > 1) per_item += 3.0 * cand_mt * kTileM * cn * 4;  // zero-fill + atomic epilogue
+          per_item += 20000.0;                                       // fixed per-item latency
+          const double cost = (double)ceil_div(items, kNumSMs) * per_item + 1e-6 * items * per_item;
+          if (cost < best) { best = cost; mt = cand_mt; p.cn_tile = cn; p.ksplit = ks; }
+        }
+      }
+    }
+    SPC_REQUIRE(best < 1e300, "tile does not fit in shared memory");
+  }
+  p.k_per = (int)ceil_div(K, p.ksplit);
+  p.n_ntiles = c_out / p.cn_tile;
 
   {
     long long total = (long long)K * c_in * c_out;
@@ -457,13 +500,10 @@ int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* 
     else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(w, Wp, K, c_in, c_out, p.cn_tile, transpose_w ? 1 : 0);
     SPC_LAUNCHED("pack_weights_kernel");
   }
+  if (p.ksplit > 1) SPC_CUDA(cudaMemsetAsync(out, 0, (size_t)m_out * c_out * sizeof(float), stream));
 
-  // MT = 2 halves weight traffic; only worth it when there are enough tiles to fill the GPU.
-  int mt = (2 * p.cn_tile <= 512 && ceil_div(m_out, 256) * p.n_ntiles >= 2 * kNumSMs) ? 2 : 1;
-  if (g_umma_force_mt == 1 || g_umma_force_mt == 2) mt = g_umma_force_mt;
-  if (mt * p.cn_tile > 512) mt = 1;
   const int rows_per_work = kTileM * mt;
-  p.n_work = (int)ceil_div(m_out, rows_per_work) * p.n_ntiles;
+  p.n_work = (int)ceil_div(m_out, rows_per_work) * p.n_ntiles * p.ksplit;
   p.acc_bufs = (2 * mt * p.cn_tile <= 512) ? 2 : 1;
   int cols = p.acc_bufs * mt * p.cn_tile;
   p.tmem_cols = 32;
@@ -725,6 +765,8 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
     cp_async_wait<0>();
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
+    // one elected thread runs the whole loop (see conv_umma_kernel)
+    if (elect_one()) {
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0, t_phase = 0;
     const uint32_t idesc = PR::idesc(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
@@ -752,7 +794,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
           WG_TIMED_WAIT(3, mbar_wait(a_full(a_stage), a_phase));
           fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t a_addr = a_base + (uint32_t)a_stage * kWgAStage;
             const uint32_t b_addr = b_base + (uint32_t)b_used * b_stage_bytes;
             const uint32_t d = tmem_base + (uint32_t)((mb - mb0) * p.Cout);
@@ -766,20 +808,19 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
             }
             mma_commit(a_empty(a_stage));
           }
-          __syncwarp();
           touched |= 1u << (mb - mb0);
           if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
         }
         if (b_ready) {
-          if (lane == 0) mma_commit(b_empty(b_used));
-          __syncwarp();
+          mma_commit(b_empty(b_used));
           if (++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
         }
       }
-      if (lane == 0) mma_commit(t_full);
-      __syncwarp();
+      mma_commit(t_full);
       t_phase ^= 1u;
     }
+    }
+    __syncwarp();
   } else {
     // ============================ epilogue ============================
     const int ew = warp & 3;
@@ -818,6 +859,15 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       mbar_arrive(t_empty);
       t_phase ^= 1u;
     }
+  }
+  if (warp == kMmaWarp) {  // the counters live in the elected lane: make them visible to lane 0
+#pragma unroll
+    for (int i = 3; i < 6; ++i)
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, wg_cnt[i], d);
+        wg_cnt[i] = o > wg_cnt[i] ? o : wg_cnt[i];
+      }
   }
   if (blockIdx.x < kNumSMs && (threadIdx.x == 0 || threadIdx.x == kMmaWarp * 32)) {
     const int base = threadIdx.x == 0 ? 0 : 3, n = 3;

@@ -340,6 +340,78 @@ global_pool_bwd_kernel(const float* __restrict__ dout, const int4* __restrict__ 
   din[e] = v;
 }
 
+// ---------------------------------------------------------------------------
+// softmax cross-entropy over rows [n, C] with ignore_index (segmentation_training.py:27-44,
+// classification_training.py:33): one thread per row, rows stay in registers (C <= 64).
+// Writes stats[0] += sum_i -log p_i[y_i], stats[1] += #non-ignored rows, and the raw gradient
+// graw[i, c] = p_i[c] - [c == y_i] (zero for ignored rows); backward scales by gout / count.
+// ---------------------------------------------------------------------------
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, long long n,
+              int C, long long ignore_index, float* __restrict__ graw, double* __restrict__ stats,
+              int* __restrict__ bad_target) {
+  float loss = 0.f;
+  int cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long y = target[i];
+    float* g = graw + i * C;
+    if (y == ignore_index) {
+      for (int c = 0; c < C; ++c) g[c] = 0.f;
+      continue;
+    }
+    if (y < 0 || y >= C) { *bad_target = 1; continue; }
+    float v[CMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { v[c] = logits[i * C + c]; mx = fmaxf(mx, v[c]); }
+    float sum = 0.f, vy = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        if (c == (int)y) vy = v[c];
+        v[c] = __expf(v[c] - mx);
+        sum += v[c];
+      }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) g[c] = v[c] * inv - (c == (int)y ? 1.f : 0.f);
+    loss += (mx - vy) + __logf(sum);
+    ++cnt;
+  }
+  // block reduction -> one double atomic per block
+  __shared__ float s_loss[8];
+  __shared__ int s_cnt[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, d);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  }
+  if ((threadIdx.x & 31) == 0) { s_loss[threadIdx.x >> 5] = loss; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0;
+    long long k = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { l += (double)s_loss[w]; k += s_cnt[w]; }
+    atomicAdd(stats, l);
+    atomicAdd(stats + 1, (double)k);
+  }
+}
+
+// dlogits = graw * (gout / count)
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const float* __restrict__ graw, const double* __restrict__ stats,
+              const float* __restrict__ gout, long long total, float* __restrict__ dlogits) {
+  const double cnt = stats[1];
+  const float sc = cnt > 0.0 ? (float)((double)gout[0] / cnt) : 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x)
+    dlogits[e] = graw[e] * sc;
+}
+
 }  // namespace spc
 
 using namespace spc;
@@ -511,4 +583,34 @@ int spc_global_pool_bwd(const float* dout, const int32_t* coords, const int32_t*
   return 0;
 }
 
+int spc_ce_fwd(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_index,
+               float* grad_raw, double* stats, int32_t* bad_target, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && C <= 64, "cross entropy supports 1..64 classes");
+  SPC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), stream));
+  SPC_CUDA(cudaMemsetAsync(bad_target, 0, sizeof(int32_t), stream));
+  if (n == 0) return 0;
+  int64_t want = ceil_div(n, 256);
+  int grid = (int)(want < kNumSMs * 8 ? want : kNumSMs * 8);
+  if (C <= 32)
+    ce_fwd_kernel<32><<<grid, 256, 0, stream>>>(logits, (const long long*)target, n, C, ignore_index, grad_raw, stats, bad_target);
+  else
+    ce_fwd_kernel<64><<<grid, 256, 0, stream>>>(logits, (const long long*)target, n, C, ignore_index, grad_raw, stats, bad_target);
+  SPC_LAUNCHED("ce_fwd_kernel");
+  return 0;
+}
+
+int spc_ce_bwd(const float* grad_raw, const double* stats, const float* grad_out, int64_t n, int C,
+               float* dlogits, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n == 0) return 0;
+  long long total = (long long)n * C;
+  int64_t want = ceil_div(total, 256 * 4);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  ce_bwd_kernel<<<grid, 256, 0, stream>>>(grad_raw, stats, grad_out, total, dlogits);
+  SPC_LAUNCHED("ce_bwd_kernel");
+  return 0;
+}
+
 }  // extern "C"
+

@@ -425,10 +425,11 @@ class SparseConvFn(torch.autograd.Function):
         # The tensor-core kernels take channel counts that are multiples of 32; on large maps zero-pad
         # odd widths (27 SH channels, 20 classes) instead of dropping to the CUDA-core kernels.
         pad_in = pad_out = 0
-        if precision == L.PREC_BF16 and (K > 32 or max(km.m_in, km.m_out) < 4096 or c_out > 256
-                                         or K * (c_in + (-c_in) % 32) > 128 * 128):
-            precision = L.PREC_TF32  # small maps / wide layers: not worth (or not built for) bf16 copies
-        if precision != L.PREC_FP32 and K <= 32 and max(km.m_in, km.m_out) >= 4096:
+        big = max(km.m_in, km.m_out) >= 4096
+        if precision == L.PREC_BF16 and (K > 32 or c_out > 256 or K * (c_in + (-c_in) % 32) > 128 * 128
+                                         or (not big and (c_in % 32 or c_out % 32))):
+            precision = L.PREC_TF32  # shapes the bf16 kernels are not built for
+        if precision != L.PREC_FP32 and K <= 32 and big:
             pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
         if pad_in:
             x = torch.nn.functional.pad(x, (0, pad_in))
@@ -641,6 +642,49 @@ class GlobalPoolFn(torch.autograd.Function):
         L.check(lib.spc_global_pool_bwd(L.ptr(g), L.ptr(coords), L.ptr(cnt), m, C, n_batch, avg, L.ptr(din),
                                         L.stream()), "spc_global_pool_bwd")
         return din, None, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """mean softmax cross-entropy with ignore_index (nn.CrossEntropyLoss semantics) in one pass."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        lib = L.load()
+        logits = _feat(logits)
+        if target.dtype != torch.int64:
+            raise RuntimeError(f"targets must be int64, got {target.dtype}")
+        target = target.contiguous()
+        n, C = logits.shape
+        if target.shape != (n,):
+            raise RuntimeError(f"target shape {tuple(target.shape)} does not match logits {tuple(logits.shape)}")
+        graw = _empty((n, C), torch.float32, logits.device)
+        stats = _empty(2, torch.float64, logits.device)
+        bad = _empty(1, torch.int32, logits.device)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_ce_fwd(L.ptr(logits), L.ptr(target), n, C, int(ignore_index), L.ptr(graw), L.ptr(stats),
+                               L.ptr(bad), L.stream()), "spc_ce_fwd")
+        if e0 is not None:
+            _profiler.end("cross_entropy", e0, 0, (8.0 * C + 8.0) * n, f"C{C} N{n}")
+        ctx.save_for_backward(graw, stats)
+        ctx.bad = bad
+        return (stats[0] / stats[1]).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        graw, stats = ctx.saved_tensors
+        n, C = graw.shape
+        gout = gout.to(torch.float32).contiguous().view(1)
+        dlogits = torch.empty_like(graw)
+        L.check(lib.spc_ce_bwd(L.ptr(graw), L.ptr(stats), L.ptr(gout), n, C, L.ptr(dlogits), L.stream()),
+                "spc_ce_bwd")
+        return dlogits, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """F.cross_entropy(logits, target, ignore_index=...) (mean reduction) on the fused kernel.  Targets
+    outside [0, C) that are not ignore_index make `check_targets` raise (no host sync here)."""
+    return CrossEntropyFn.apply(logits, target, ignore_index)
 
 
 def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):

@@ -390,3 +390,23 @@ def test_full_size_round_trips(cuda_device):
     assert bool((m2.coords[parent.long()] == want).all())
     m2b, _, parent_b, _ = ops.coords_insert(m2.coords, L.SRC_STRIDE, (2, 2, 2))
     assert m2b.size == m2.size and bool((parent_b == torch.arange(m2.size, device=cuda_device)).all())
+
+
+@pytest.mark.parametrize("n,C", [(1, 20), (777, 20), (50_000, 20), (4096, 51), (100, 3)])
+def test_cross_entropy_matches_torch(cuda_device, n, C):
+    """fused CE (mean over non-ignored rows) vs torch's fp64 cross_entropy; |d| <= 1e-5 * (1 + |ref|)."""
+    g = torch.Generator().manual_seed(n + C)
+    logits = (torch.randn(n, C, generator=g) * 3).requires_grad_()
+    y = torch.randint(0, C, (n,), generator=g)
+    y[torch.rand(n, generator=g) < 0.1] = 255
+    if n == 1:
+        y[0] = 3
+    ref_in = logits.detach().double().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(ref_in, y, ignore_index=255)
+    ref.backward()
+    x = logits.detach().to(cuda_device).requires_grad_()
+    loss = ops.cross_entropy(x, y.to(cuda_device), ignore_index=255)
+    (loss * 2.5).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * (1 + abs(ref.item()))
+    err = (x.grad.double().cpu() - 2.5 * ref_in.grad).abs().max().item()
+    assert err <= 1e-6 * (1 + (2.5 * ref_in.grad).abs().max().item()), err
