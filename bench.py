@@ -263,6 +263,7 @@ def run_ours(args):
     # ---- per-kernel-class device times inside a (separately) timed region -> roofline -------------
     roofline = None
     kmap_ms = None
+    others = None
     classes = {}
     prof = ops.KernelProfiler() if rank == 0 else None
     ops.set_profiler(prof)
@@ -290,8 +291,11 @@ def run_ours(args):
                        "algorithmic_gbs": v["bytes"] / v["n"] / (v["ms"] / v["n"] * 1e-3) / 1e9}
         step_ms_prof = sum(v["ms"] for v in classes.values()) / 2
         if det:
-            # dominant kernel = the (kernel, layer shape) entry with the largest device time in the step
-            (name, detail), s = max(det.items(), key=lambda kv: kv[1]["ms"])
+            # dominant kernel = the kernel class with the largest device time in the step, reported on the
+            # layer shape that takes most of that time
+            top_class = max(classes.items(), key=lambda kv: kv[1]["ms"])[0]
+            (name, detail), s = max(((k, v) for k, v in det.items() if k[0] == top_class),
+                                    key=lambda kv: kv[1]["ms"])
             t = s["ms"] * 1e-3
             shape = detail.split(" P")[0]
             traffic = None
@@ -317,6 +321,20 @@ def run_ours(args):
                 roofline = {**common, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": ach / peaks["hbm_gbs"], "peak_note": peaks["source"]}
 
+        if det:
+            # context: the five largest (kernel, shape) entries with their own roofline fractions
+            others = []
+            for (n_, d_), v in sorted(det.items(), key=lambda kv: -kv[1]["ms"])[:5]:
+                t_ = v["ms"] * 1e-3
+                if n_.startswith("conv") and v["flops"] > 0:
+                    pk = peaks["bf16_sustained"] if args.precision == "bf16" else peaks["bf16_sustained"] / 2.0
+                    others.append({"kernel": f"{n_} {d_.split(' P')[0]}", "ms_per_step": round(v["ms"] / 2, 3),
+                                   "tflops": round(v["flops"] / t_ / 1e12, 1), "frac": round(v["flops"] / t_ / 1e12 / pk, 3)})
+                else:
+                    others.append({"kernel": f"{n_} {d_}".strip(), "ms_per_step": round(v["ms"] / 2, 3),
+                                   "gbs": round(v["bytes"] / t_ / 1e9, 0),
+                                   "frac": round(v["bytes"] / t_ / 1e9 / peaks["hbm_gbs"], 3)})
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -338,6 +356,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "kernel_map_build_ms": kmap_ms,
+                "other_kernels": others,
                 "cpu_baseline": cpu,
                 "kernel_classes_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in
                                                sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}}

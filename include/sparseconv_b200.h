@@ -168,10 +168,11 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
                  void* workspace, int64_t workspace_bytes, void* stream);
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,
-                 int relu, float* y, void* stream);
+                 int relu, float* y, void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);
 int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mean,
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
-               int training, float* dx, float* dresidual, float* dgamma, float* dbeta,
+               int training, float* dx, void* dx_bf16 /* optional bf16 copy of dx, or NULL */,
+               float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* y = relu(x) ; dx = dy * (y > 0) ; y = a + b  (MinkowskiReLU, SparseTensor +=). */

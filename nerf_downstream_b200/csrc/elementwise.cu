@@ -7,6 +7,8 @@
 //   - per-channel parameters (scale/shift) live in registers,
 //   - a warp always touches one contiguous span of memory (rows are contiguous),
 //   - the grid is a multiple of the SM count and strides over row groups.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace spc {
@@ -35,6 +37,20 @@ static inline int pick_grid(int64_t m, int rows_per_iter, int blocks_per_sm) {
 }
 
 template <int VEC> struct Vec;
+// round-to-nearest-even bf16 copy of VEC values (the operand format of the SPC_PREC_BF16 convolutions)
+template <int VEC>
+__device__ __forceinline__ void store_bf16(__nv_bfloat16* p, const float* v) {
+  if (VEC == 4) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = o;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) p[j] = __float2bfloat16_rn(v[j]);
+  }
+}
 template <> struct Vec<1> {
   float v[1];
   __device__ static Vec load(const float* p) { Vec r; r.v[0] = *p; return r; }
@@ -145,7 +161,8 @@ __global__ void __launch_bounds__(1024)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                 const float* __restrict__ var, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ res, long long m, int C,
-                int lanes, int rows, float eps, int relu, float* __restrict__ y) {
+                int lanes, int rows, float eps, int relu, float* __restrict__ y,
+                __nv_bfloat16* __restrict__ yb) {
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
   const int c0 = lane * VEC;
   float sc[VEC], sh[VEC];
@@ -170,6 +187,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
       for (int j = 0; j < VEC; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
     }
     o.store(y + off);
+    if (yb) store_bf16<VEC>(yb + off, o.v);
   }
 }
 
@@ -181,7 +199,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
                     const float* __restrict__ var, const float* __restrict__ gamma,
                     const float* __restrict__ sums /* [2C]: sum dy', sum dy'(x-mean) */,
                     long long m, int C, int lanes, int rows, float eps, int relu, int training,
-                    float* __restrict__ dx, float* __restrict__ dres) {
+                    float* __restrict__ dx, float* __restrict__ dres, __nv_bfloat16* __restrict__ dxb) {
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
   const int c0 = lane * VEC;
   float sc[VEC], mu[VEC], k0[VEC], k1[VEC];
@@ -207,6 +225,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
 #pragma unroll
     for (int j = 0; j < VEC; ++j) o.v[j] = sc[j] * (g.v[j] - k0[j] - (xv.v[j] - mu[j]) * k1[j]);
     o.store(dx + off);
+    if (dxb) store_bf16<VEC>(dxb + off, o.v);
   }
 }
 
@@ -474,23 +493,24 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
 
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps, int relu,
-                 float* y, void* stream_) {
+                 float* y, void* y_bf16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(C >= 1, "bad C");
   if (m == 0) return 0;
   int vec = pick_vec(C, x, residual, y);
+  if (y_bf16 && ((uintptr_t)y_bf16 % 8)) vec = 1;
   RowMap rm = make_row_map(C, vec);
   SPC_REQUIRE(rm.threads <= 1024, "C too large");
   int grid = pick_grid(m, rm.rows, 8);
   DISPATCH_VEC(vec, bn_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
-      x, mean, var, gamma, beta, residual, m, C, rm.lanes, rm.rows, eps, relu, y));
+      x, mean, var, gamma, beta, residual, m, C, rm.lanes, rm.rows, eps, relu, y, (__nv_bfloat16*)y_bf16));
   SPC_LAUNCHED("bn_apply_kernel");
   return 0;
 }
 
 int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mean,
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
-               int training, float* dx, float* dresidual, float* dgamma, float* dbeta,
+               int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
@@ -505,11 +525,12 @@ int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mea
   if (rc) return rc;
   int vec = pick_vec(C, x, y, dy, dx);
   if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;
+  if (dx_bf16 && ((uintptr_t)dx_bf16 % 8)) vec = 1;
   RowMap rm = make_row_map(C, vec);
   SPC_REQUIRE(rm.threads <= 1024, "C too large");
   int grid = pick_grid(m, rm.rows, 8);
   DISPATCH_VEC(vec, bn_bwd_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
-      x, y, dy, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx, dresidual));
+      x, y, dy, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx, dresidual, (__nv_bfloat16*)dx_bf16));
   SPC_LAUNCHED("bn_bwd_apply_kernel");
   return 0;
 }

@@ -7,6 +7,7 @@ for the reference's call sites.  All arithmetic happens in
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -349,9 +350,43 @@ def _conv_bytes(km, K, c_in, c_out) -> float:
     return 4.0 * km.m_in * c_in + 4.0 * km.m_out * c_out + 4.0 * K * c_in * c_out + 4.0 * K * km.m_out
 
 
+# bf16 copies written as a side output by the kernel that produced the fp32 rows (BatchNorm apply /
+# backward): data_ptr -> (weakref to the fp32 tensor, its version, bf16 tensor).  A convolution in
+# bf16 mode takes the copy instead of running a conversion pass over the rows.
+_bf16_side: dict = {}
+
+
+def _remember_bf16(t: torch.Tensor, tb: torch.Tensor) -> None:
+    key = t.data_ptr()
+
+    def _drop(ref, key=key):
+        e = _bf16_side.get(key)
+        if e is not None and e[0] is ref:
+            del _bf16_side[key]
+    _bf16_side[key] = (weakref.ref(t, _drop), t._version, tb)
+
+
+def _lookup_bf16(t: torch.Tensor):
+    e = _bf16_side.get(t.data_ptr())
+    if e is None:
+        return None
+    ref, version, tb = e
+    o = ref()
+    if o is None or o.shape != t.shape or tb.shape != t.shape or t._version != version or not t.is_contiguous():
+        return None
+    return tb
+
+
+def _want_bf16_side(m: int, C: int) -> bool:
+    return _default_precision == L.PREC_BF16 and C % 32 == 0 and C <= 512 and m > 0
+
+
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 rows -> bf16 copy (round to nearest even) for the SPC_PREC_BF16 kernels."""
     lib = L.load()
+    side = _lookup_bf16(x)
+    if side is not None:
+        return side
     x = _feat(x)
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     e0 = _profiler.begin() if _profiler else None
@@ -505,10 +540,14 @@ class BatchNormFn(torch.autograd.Function):
             mean, var = running_mean, running_var
         res = _feat(residual) if residual is not None else None
         y = _empty((m, C), torch.float32, dev)
+        yb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
         L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res), m, C,
-                                 float(eps), int(relu), L.ptr(y), L.stream()), "spc_bn_apply")
+                                 float(eps), int(relu), L.ptr(y), L.ptr(yb), L.stream()), "spc_bn_apply")
+        if yb is not None:
+            _remember_bf16(y, yb)
         if e0 is not None:
-            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)) * m * C, f"C{C} M{m}")
+            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)
+                                            + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
         ctx.save_for_backward(x, y if relu else None, mean, var, gamma)
         ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
         return y
@@ -524,15 +563,19 @@ class BatchNormFn(torch.autograd.Function):
         ws_bytes = int(lib.spc_bn_workspace(m, C))
         ws = _empty(ws_bytes, torch.uint8, dev)
         dx = _empty((m, C), torch.float32, dev)
+        dxb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
         dres = _empty((m, C), torch.float32, dev) if has_res else None
         dgamma = _empty(C, torch.float32, dev)
         dbeta = _empty(C, torch.float32, dev)
         e0 = _profiler.begin() if _profiler else None
         L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y), L.ptr(dy), L.ptr(mean), L.ptr(var), L.ptr(gamma), m, C, eps,
-                               relu, use_batch, L.ptr(dx), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
-                               ws_bytes, L.stream()), "spc_bn_bwd")
+                               relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
+                               L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
+        if dxb is not None:
+            _remember_bf16(dx, dxb)
         if e0 is not None:
-            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)) * m * C,
+            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)
+                                            + (2.0 if dxb is not None else 0.0)) * m * C,
                           f"C{C} M{m}")
         return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,
                 dres)
