@@ -236,7 +236,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = L.launch_count()
-    ms = timed(args.steps, lambda: step(d_coords, d_feats, d_labels))
+    host_s = [0.0]
+
+    def host_timed_step():
+        t0 = time.perf_counter()
+        step(d_coords, d_feats, d_labels)
+        host_s[0] += time.perf_counter() - t0  # host time to ISSUE the step (no device sync inside the timer)
+
+    ms = timed(args.steps, host_timed_step)
     launches = L.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     vox = torch.tensor([float(voxels_per_step[0])], device=dev)
@@ -244,6 +251,19 @@ def run_ours(args):
         dist.all_reduce(vox, op=dist.ReduceOp.SUM)
     total_voxels = float(vox.item())
     value = total_voxels * args.steps / (ms * 1e-3)
+
+    if args.host_profile and rank == 0:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step(d_coords, d_feats, d_labels)
+        pr.disable()
+        torch.cuda.synchronize()
+        st = pstats.Stats(pr, stream=sys.stderr)
+        st.sort_stats("tottime").print_stats(45)
+        st.sort_stats("cumulative").print_stats(45)
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
     def e2e_step():
@@ -354,6 +374,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps},
                 "gpu_launches": int(launches),
+                "host_issue_ms_per_step": 1e3 * host_s[0] / args.steps,
                 "roofline": roofline,
                 "kernel_map_build_ms": kmap_ms,
                 "other_kernels": others,
@@ -377,6 +398,7 @@ def main():
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
+    ap.add_argument("--host-profile", action="store_true", help="cProfile of 3 steps on stderr (host overhead)")
     ap.add_argument("--shuffle", action="store_true",
                     help="deliver voxels in random order instead of the loaders' raster order (adversarial locality)")
     args = ap.parse_args()

@@ -74,6 +74,14 @@ int spc_coords_insert(const void* src, int64_t n, int src_kind, const int32_t* t
                       int32_t* out_coords, int32_t* out_first, int32_t* out_inverse,
                       int32_t* out_count, int32_t* status,
                       void* workspace, int64_t workspace_bytes, void* stream);
+/* Same, with the number of valid source rows read on the DEVICE: rows = min(n, *n_dev) when n_dev is
+ * not NULL (`n` is then an upper bound that sizes the launch and every buffer).  Lets a pyramid of
+ * stride maps (status[0] of one level = n_dev of the next) be enqueued without a host round trip
+ * per level. */
+int spc_coords_insert_dev(const void* src, int64_t n, const int32_t* n_dev, int src_kind, const int32_t* ts,
+                          void* slots, int64_t n_slots, int32_t* out_coords, int32_t* out_first,
+                          int32_t* out_inverse, int32_t* out_count, int32_t* status, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /*
  * Kernel-map construction (CoordinateManager.kernel_map, sparse_conv.py:90-96,

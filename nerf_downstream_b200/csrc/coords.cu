@@ -32,9 +32,10 @@ constexpr int kScanThreads = 1024;
 // ---------------------------------------------------------------------------
 template <int SRC>
 __global__ void __launch_bounds__(256)
-insert_kernel(const void* __restrict__ src, int n, int3 ts, Slot* slots,
+insert_kernel(const void* __restrict__ src, int n, const int* __restrict__ n_dev, int3 ts, Slot* slots,
               unsigned long long bucket_mask, int* __restrict__ slot_of, int* status) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);  // row count produced on the device by the previous level
   if (i >= n) return;
   int b, x, y, z;
   if (SRC == SPC_SRC_FLOAT) {
@@ -97,8 +98,9 @@ __device__ __forceinline__ bool is_first(const Slot* slots, const int* slot_of, 
 // 2. per-block number of first occurrences
 __global__ void __launch_bounds__(kScanThreads)
 count_first_kernel(const Slot* __restrict__ slots, const int* __restrict__ slot_of, int n,
-                   int* __restrict__ block_count) {
+                   const int* __restrict__ n_dev, int* __restrict__ block_count) {
   int i = blockIdx.x * kScanThreads + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   int c = __syncthreads_count(is_first(slots, slot_of, i, n));
   if (threadIdx.x == 0) block_count[blockIdx.x] = c;
 }
@@ -161,11 +163,12 @@ __device__ __forceinline__ int block_ballot_prefix(bool flag, int* warp_sum /*[3
 
 // 4. give every first occurrence its row; emit coordinates and unique_index
 __global__ void __launch_bounds__(kScanThreads)
-assign_rows_kernel(Slot* slots, const int* __restrict__ slot_of, int n,
+assign_rows_kernel(Slot* slots, const int* __restrict__ slot_of, int n, const int* __restrict__ n_dev,
                    const int* __restrict__ block_offset, int4* __restrict__ out_coords,
                    int* __restrict__ out_first) {
   __shared__ int warp_sum[32];
   int i = blockIdx.x * kScanThreads + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   bool flag = is_first(slots, slot_of, i, n);
   int row = block_offset[blockIdx.x] + block_ballot_prefix(flag, warp_sum);
   if (flag) {
@@ -179,8 +182,9 @@ assign_rows_kernel(Slot* slots, const int* __restrict__ slot_of, int n,
 // 5. inverse map and per-voxel multiplicity
 __global__ void __launch_bounds__(256)
 inverse_kernel(const Slot* __restrict__ slots, const int* __restrict__ slot_of, int n,
-               int* __restrict__ inverse, int* __restrict__ count) {
+               const int* __restrict__ n_dev, int* __restrict__ inverse, int* __restrict__ count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int s = slot_of[i];
   int row = -1;
@@ -385,6 +389,14 @@ int spc_coords_insert(const void* src, int64_t n, int src_kind, const int32_t* t
                       int64_t n_slots, int32_t* out_coords, int32_t* out_first,
                       int32_t* out_inverse, int32_t* out_count, int32_t* status, void* workspace,
                       int64_t workspace_bytes, void* stream_) {
+  return spc_coords_insert_dev(src, n, nullptr, src_kind, ts, slots, n_slots, out_coords, out_first, out_inverse,
+                               out_count, status, workspace, workspace_bytes, stream_);
+}
+
+int spc_coords_insert_dev(const void* src, int64_t n, const int32_t* n_dev, int src_kind, const int32_t* ts,
+                          void* slots, int64_t n_slots, int32_t* out_coords, int32_t* out_first,
+                          int32_t* out_inverse, int32_t* out_count, int32_t* status, void* workspace,
+                          int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(n >= 0 && n < (1ll << 31) - kScanThreads, "n out of range");
   SPC_REQUIRE(n_slots >= 64 && (n_slots & (n_slots - 1)) == 0 && n_slots >= 2 * n,
@@ -405,20 +417,20 @@ int spc_coords_insert(const void* src, int64_t n, int src_kind, const int32_t* t
   const int grid256 = (int)ceil_div(n, 256);
   Slot* sl = (Slot*)slots;
   if (src_kind == SPC_SRC_FLOAT)
-    insert_kernel<SPC_SRC_FLOAT><<<grid256, 256, 0, stream>>>(src, (int)n, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_FLOAT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
   else if (src_kind == SPC_SRC_INT)
-    insert_kernel<SPC_SRC_INT><<<grid256, 256, 0, stream>>>(src, (int)n, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_INT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
   else
-    insert_kernel<SPC_SRC_STRIDE><<<grid256, 256, 0, stream>>>(src, (int)n, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_STRIDE><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
   SPC_LAUNCHED("insert_kernel");
-  count_first_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, block_off);
+  count_first_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, n_dev, block_off);
   SPC_LAUNCHED("count_first_kernel");
   scan_blocks_kernel<<<1, kScanThreads, 0, stream>>>(block_off, nb, status);
   SPC_LAUNCHED("scan_blocks_kernel");
-  assign_rows_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, block_off,
+  assign_rows_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, n_dev, block_off,
                                                       (int4*)out_coords, out_first);
   SPC_LAUNCHED("assign_rows_kernel");
-  inverse_kernel<<<grid256, 256, 0, stream>>>(sl, slot_of, (int)n, out_inverse, out_count);
+  inverse_kernel<<<grid256, 256, 0, stream>>>(sl, slot_of, (int)n, n_dev, out_inverse, out_count);
   SPC_LAUNCHED("inverse_kernel");
   return 0;
 }

@@ -30,6 +30,7 @@ SIGNATURES = {
     "spc_table_slots": (c_int64, [c_int64]),
     "spc_coords_insert_workspace": (c_int64, [c_int64]),
     "spc_coords_insert": (c_int, [_P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "spc_coords_insert_dev": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "spc_kernel_map": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, _P, _P, _P]),
     "spc_tile_mask": (c_int, [_P, c_int64, c_int, _P, _P]),
     "spc_kernel_map_transpose": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
@@ -109,7 +110,14 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle: this is called
+    once per kernel launch, torch.cuda.current_stream() costs several microseconds of Python)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch._C._cuda_getDevice())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -186,6 +186,8 @@ class _FieldMap:
 class CoordinateManager:
     """Registry of coordinate maps and cached kernel maps of one forward pass."""
 
+    default_prefetch_depth = 4  # stride-2 maps built ahead per stride() miss (1 = only the requested map)
+
     def __init__(self, D: int = 3, coordinate_map_type=None, allocator_type=None, minkowski_algorithm=None,
                  num_threads: int = -1):
         if D != 3:
@@ -202,6 +204,7 @@ class CoordinateManager:
         self._identity_maps: Dict[CoordinateMapKey, ops.KernelMap] = {}
         self._n_batch: Optional[int] = None
         self._field_counter = 0
+        self.prefetch_depth = CoordinateManager.default_prefetch_depth
 
     # ---- creation -----------------------------------------------------------
     def _unique_key(self, ts, string_id, table) -> CoordinateMapKey:
@@ -306,11 +309,28 @@ class CoordinateManager:
         out_key = CoordinateMapKey(out_ts, string_id)
         if out_key in self._maps:
             return out_key
-        cmap, first, inverse, count = ops.coords_insert(in_map.coords, L.SRC_STRIDE, out_ts)
-        cmap.tensor_stride = tuple(out_ts)
-        self._maps[out_key] = cmap
-        self._insert_aux[out_key] = (first, inverse, count)
-        self._stride_parent[out_key] = (in_key, inverse, count)
+        # A stride-2 request is (in every network of the reference) the first of a pyramid 2,4,8,16:
+        # build `prefetch_depth` levels now with ONE host synchronisation, so that the host can enqueue
+        # the whole encoder without stopping at every level to learn its row count.
+        chain = [out_ts]
+        if string_id == "" and all(v == 2 for v in s):
+            while len(chain) < self.prefetch_depth:
+                nxt = [2 * t for t in chain[-1]]
+                if CoordinateMapKey(nxt, "") in self._maps or max(nxt) > 4096:
+                    break
+                chain.append(nxt)
+        if len(chain) == 1:
+            built = [ops.coords_insert(in_map.coords, L.SRC_STRIDE, out_ts)]
+        else:
+            built = ops.coords_insert_pyramid(in_map, chain)
+        parent = in_key
+        for ts_l, (cmap, first, inverse, count) in zip(chain, built):
+            key = CoordinateMapKey(ts_l, string_id)
+            cmap.tensor_stride = tuple(ts_l)
+            self._maps[key] = cmap
+            self._insert_aux[key] = (first, inverse, count)
+            self._stride_parent[key] = (parent, inverse, count)
+            parent = key
         return out_key
 
     def origin(self) -> CoordinateMapKey:

@@ -36,6 +36,21 @@ def _empty(shape, dtype, device):
     return torch.empty(shape, dtype=dtype, device=device)
 
 
+# Scratch for the kernels (packed weight slabs, BN partial sums): one grow-only buffer per (device,
+# stream).  Kernels on one stream run in order, so the next call may overwrite it; nothing in it is
+# read after the call that filled it.
+_workspaces: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, L.stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 # ---------------------------------------------------------------------------
 # optional per-kernel-class timing (bench.py roofline); off unless a profiler is installed
 # ---------------------------------------------------------------------------
@@ -142,6 +157,47 @@ def coords_insert(src: torch.Tensor, kind: int, ts: Sequence[int]):
                            "x,y,z in [-131072,131071] (and finite)")
     cmap = CoordMap(coords[:m], table, n_slots, m, ts)
     return cmap, first[:m], inverse, count[:m]
+
+
+def coords_insert_pyramid(in_map: CoordMap, ts_list):
+    """Stride maps ts_list[0] <- in_map, ts_list[1] <- ts_list[0], ... enqueued back to back with
+    upper-bound allocations (a strided map never has more rows than its parent) and device-side row
+    counts, then ONE host synchronisation for all levels instead of one per level.
+    Returns [(CoordMap, first_idx, inverse, count), ...] exactly as coords_insert would."""
+    lib = L.load()
+    dev = in_map.coords.device
+    n_up = in_map.size
+    src, n_dev = in_map.coords, None
+    pend = []
+    e0 = _profiler.begin() if _profiler else None
+    for ts in ts_list:
+        n_slots = int(lib.spc_table_slots(n_up))
+        table = _empty(n_slots * L.SLOT_BYTES, torch.uint8, dev)
+        coords = _empty((n_up, 4), torch.int32, dev)
+        first = _empty(n_up, torch.int32, dev)
+        inverse = _empty(n_up, torch.int32, dev)
+        count = _empty(n_up, torch.int32, dev)
+        status = _empty(2, torch.int32, dev)
+        ws_bytes = int(lib.spc_coords_insert_workspace(n_up))
+        ws = _empty(ws_bytes, torch.uint8, dev)
+        ts_arr = _I3(*[int(t) for t in ts])
+        L.check(lib.spc_coords_insert_dev(L.ptr(src), n_up, L.ptr(n_dev), L.SRC_STRIDE,
+                                          ctypes.cast(ts_arr, ctypes.c_void_p), L.ptr(table), n_slots, L.ptr(coords),
+                                          L.ptr(first), L.ptr(inverse), L.ptr(count), L.ptr(status), L.ptr(ws),
+                                          ws_bytes, L.stream()), "spc_coords_insert_dev")
+        pend.append((ts, table, n_slots, coords, first, inverse, count, status))
+        src, n_dev = coords, status
+    if e0 is not None:
+        _profiler.end("coords_insert(hash)", e0, 0, (20.0 + 36.0) * n_up * len(ts_list), f"pyramid x{len(ts_list)} N{n_up}")
+    sizes = torch.stack([p[7] for p in pend]).tolist()  # the one host sync
+    out, n_prev = [], in_map.size
+    for (ts, table, n_slots, coords, first, inverse, count, _), (m, err) in zip(pend, sizes):
+        if err:
+            raise RuntimeError("coordinate out of the supported range: batch index must be in [0,1022] and "
+                               "x,y,z in [-131072,131071]")
+        out.append((CoordMap(coords[:m], table, n_slots, m, ts), first[:m], inverse[:n_prev], count[:m]))
+        n_prev = m
+    return out
 
 
 def kernel_offsets(kernel_size: Sequence[int], tensor_stride: Sequence[int], dilation: Sequence[int]):
@@ -345,6 +401,17 @@ class GatherRowsFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 # convolution
 # ---------------------------------------------------------------------------
+_ws_bytes_cache: dict = {}
+
+
+def _conv_ws_bytes(lib, K, c_in, c_out, precision) -> int:
+    key = (K, c_in, c_out, precision)
+    v = _ws_bytes_cache.get(key)
+    if v is None:
+        v = _ws_bytes_cache[key] = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
+    return v
+
+
 def _conv_bytes(km, K, c_in, c_out) -> float:
     """Algorithmic bytes of one conv pass: every feature row once, weights once, dense map once."""
     return 4.0 * km.m_in * c_in + 4.0 * km.m_out * c_out + 4.0 * K * c_in * c_out + 4.0 * K * km.m_out
@@ -400,8 +467,8 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
-    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
-    ws = _empty(ws_bytes, torch.uint8, x.device)
+    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
+    ws = _workspace(ws_bytes, x.device)
     mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
     L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
@@ -417,8 +484,8 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision):
     lib = L.load()
     K, c_in, c_out = w.shape
     din = _empty((km.m_in, c_in), torch.float32, g.device)
-    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
-    ws = _empty(ws_bytes, torch.uint8, g.device)
+    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
+    ws = _workspace(ws_bytes, g.device)
     mask_t = km.mask_t if precision != L.PREC_FP32 else None
     nbr_t = km.nbr_t
     e0 = _profiler.begin() if _profiler else None
@@ -434,8 +501,8 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision):
 def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision):
     lib = L.load()
     dw = _empty((K, c_in, c_out), torch.float32, x.device)
-    ws_bytes = int(lib.spc_conv_workspace(K, c_in, c_out, precision))
-    ws = _empty(ws_bytes, torch.uint8, x.device)
+    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
+    ws = _workspace(ws_bytes, x.device)
     mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
     L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out, K,
@@ -523,7 +590,7 @@ class BatchNormFn(torch.autograd.Function):
         m, C = x.shape
         dev = x.device
         ws_bytes = int(lib.spc_bn_workspace(m, C))
-        ws = _empty(ws_bytes, torch.uint8, dev)
+        ws = _workspace(ws_bytes, dev)
         use_batch = training or running_mean is None
         e0 = _profiler.begin() if _profiler else None
         if use_batch:
@@ -561,7 +628,7 @@ class BatchNormFn(torch.autograd.Function):
         m, C = x.shape
         dev = x.device
         ws_bytes = int(lib.spc_bn_workspace(m, C))
-        ws = _empty(ws_bytes, torch.uint8, dev)
+        ws = _workspace(ws_bytes, dev)
         dx = _empty((m, C), torch.float32, dev)
         dxb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
         dres = _empty((m, C), torch.float32, dev) if has_res else None

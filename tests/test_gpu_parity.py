@@ -99,6 +99,26 @@ def test_stride_map_exact(cuda_device, stride):
     assert (R.unique_first_c(R.stride_coords_c(uc, ts))[0] == suc).all()
 
 
+def test_stride_pyramid_matches_level_by_level(cuda_device):
+    """coords_insert_pyramid (device-side row counts, one host sync) == one coords_insert per level, and
+    its hash tables answer kernel-map probes exactly like the oracle."""
+    _, _, cmap, uc, _, _ = _maps(cuda_device, 13, 60000, 40)
+    chain = [(2, 2, 2), (4, 4, 4), (8, 8, 8), (16, 16, 16)]
+    built = ops.coords_insert_pyramid(cmap, chain)
+    src, src_np = cmap, uc
+    for ts, (pm, pfirst, pinv, pcount) in zip(chain, built):
+        sm, first, inv, count = ops.coords_insert(src.coords, L.SRC_STRIDE, ts)
+        assert pm.size == sm.size and (pm.coords == sm.coords).all()
+        assert (pfirst == first).all() and (pinv == inv).all() and (pcount == count).all()
+        ref_np = R.unique_first_np(R.stride_coords_np(src_np, ts))[0]
+        assert (pm.coords.cpu().numpy() == ref_np).all()
+        pm.tensor_stride = ts
+        offs = ops.kernel_offsets((3, 3, 3), ts, (1, 1, 1))
+        km = ops.build_kernel_map(pm, pm, offs)
+        assert (km.nbr.cpu().numpy() == R.kernel_map_np(ref_np, ref_np, offs)).all()
+        src, src_np = pm, ref_np
+
+
 KMAP_CASES = [((3, 3, 3), 1), ((3, 3, 3), 2), ((2, 2, 2), 2), ((1, 1, 1), 2), ((5, 5, 5), 1), ((3, 1, 3), 1)]
 
 
