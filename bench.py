@@ -393,8 +393,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--voxels", type=int, default=1_000_000, help="voxels per scene")
-    ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU per step")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--scenes", type=int, default=2,
+                    help="scenes per GPU per step (SURVEY.md §8d config 2: B = 1 and B = 2; the reference trains at 8)")
+    ap.add_argument("--precision", default="bf16", choices=["tf32", "bf16", "fp32"],
+                    help="conv operand precision: bf16 (default; fp32 accumulate), tf32, or fp32 CUDA cores")
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
