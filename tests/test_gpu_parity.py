@@ -291,6 +291,17 @@ def test_conv_tf32_matches_fp32_kernels_large(cuda_device):
     assert_fp32(lhs, rhs, "linearity")
     # 3^3 stride-1 maps are symmetric: nbr[k][o] = i  <=>  nbr[26-k][i] = o
     assert bool((km.nbr_t == km.nbr.flip(0)).all())
+    # bf16 operands on the same large map (MT = 2 tiles) against the fp32 CUDA-core kernels
+    xb, gb = ops.to_bf16(x), ops.to_bf16(go)
+    db = ops.conv_dgrad_raw(go, w, km, L.PREC_FP32)
+
+    def close_bf16(got, want, what):
+        err = (got - want).abs().max().item()
+        assert err <= BF16_TOL * want.abs().max().item(), f"{what}: {err:.3e}"
+    close_bf16(ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16), b, "bf16 fwd")
+    close_bf16(ops.conv_dgrad_raw(gb, w, km, L.PREC_BF16), db, "bf16 dgrad")
+    dw32 = ops.conv_wgrad_raw(x, go, km, 27, 64, 96, L.PREC_FP32)
+    close_bf16(ops.conv_wgrad_raw(xb, gb, km, 27, 64, 96, L.PREC_BF16), dw32, "bf16 wgrad")
 
 
 # ---------------------------------------------------------------------------
