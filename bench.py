@@ -320,8 +320,10 @@ def run_ours(args):
             shape = detail.split(" P")[0]
             traffic = None
             tfile = ROOT / "profiles" / "roofline_traffic.json"
-            if tfile.exists():
-                traffic = json.loads(tfile.read_text()).get(f"{args.precision} {name} {shape}")
+            if tfile.exists():  # ncu DRAM bytes per row of this kernel shape x rows of the reported launch
+                ent = json.loads(tfile.read_text()).get(f"{args.precision} {name} {shape.split(' M')[0]}")
+                if ent and " M" in shape:
+                    traffic = ent["dram_bytes_per_row"] * int(shape.split(" M")[1].split()[0])
             common = {"kernel": f"{name} {shape}".strip(), "traffic": traffic, "launches": s["n"],
                       "avg_launch_ms": s["ms"] / s["n"], "share_of_step": s["ms"] / 2 / step_ms_prof,
                       "class_share_of_step": classes[name]["ms"] / 2 / step_ms_prof}
