@@ -266,13 +266,32 @@ def run_ours(args):
         st.sort_stats("cumulative").print_stats(45)
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
+    # Every step's inputs travel host -> device from pinned memory inside the timed region and the
+    # loss is read back every step.  As a training input pipeline does (pin_memory + non_blocking),
+    # the copy of batch i+1 is enqueued on a copy stream while step i computes (two device buffers);
+    # batch i+1 is never touched before its copy event, and buffer reuse is safe because loss.item()
+    # of step i-1 has synchronised the device.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [tuple(torch.empty_like(t, device=dev) for t in (h_coords, h_feats, h_labels)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    turn = [0]
+
+    def enqueue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(bufs[slot], (h_coords, h_feats, h_labels)):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def e2e_step():
-        c = h_coords.to(dev, non_blocking=True)
-        f = h_feats.to(dev, non_blocking=True)
-        y = h_labels.to(dev, non_blocking=True)
+        slot = turn[0] & 1
+        turn[0] += 1
+        torch.cuda.current_stream().wait_event(ready[slot])
+        enqueue_copy(slot ^ 1)  # next step's batch, overlapped with this step
+        c, f, y = bufs[slot]
         loss = step(c, f, y)
         return loss.item()  # device -> host read of the step's result
 
+    enqueue_copy(0)
     e2e_step()
     e2e_steps = max(3, args.steps // 2)
     ms_e2e = timed(e2e_steps, e2e_step)
