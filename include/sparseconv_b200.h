@@ -177,7 +177,8 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,
                  int relu, float* y, void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);
-int spc_bn_bwd(const float* x, const float* y, const float* dy, const float* mean,
+int spc_bn_bwd(const float* x, const float* y, const void* y_bf16 /* ReLU mask from the bf16 copy of y instead of y, or NULL */,
+               const float* dy, const float* mean,
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
                int training, float* dx, void* dx_bf16 /* optional bf16 copy of dx, or NULL */,
                float* dresidual, float* dgamma, float* dbeta,

@@ -615,7 +615,8 @@ class BatchNormFn(torch.autograd.Function):
         if e0 is not None:
             _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)
                                             + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
-        ctx.save_for_backward(x, y if relu else None, mean, var, gamma)
+        # the ReLU mask of backward comes from the bf16 copy when there is one (2 instead of 4 bytes per value)
+        ctx.save_for_backward(x, (yb if yb is not None else y) if relu else None, mean, var, gamma)
         ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
         return y
 
@@ -635,13 +636,14 @@ class BatchNormFn(torch.autograd.Function):
         dgamma = _empty(C, torch.float32, dev)
         dbeta = _empty(C, torch.float32, dev)
         e0 = _profiler.begin() if _profiler else None
-        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y), L.ptr(dy), L.ptr(mean), L.ptr(var), L.ptr(gamma), m, C, eps,
+        y32, y16 = (None, y) if (y is not None and y.dtype == torch.bfloat16) else (y, None)
+        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y32), L.ptr(y16), L.ptr(dy), L.ptr(mean), L.ptr(var), L.ptr(gamma), m, C, eps,
                                relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
                                L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
         if dxb is not None:
             _remember_bf16(dx, dxb)
         if e0 is not None:
-            _profiler.end("bn_bwd", e0, 0, (20.0 + (8.0 if relu else 0.0) + (4.0 if has_res else 0.0)
+            _profiler.end("bn_bwd", e0, 0, (20.0 + ((4.0 if y16 is not None else 8.0) if relu else 0.0) + (4.0 if has_res else 0.0)
                                             + (2.0 if dxb is not None else 0.0)) * m * C,
                           f"C{C} M{m}")
         return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,

@@ -344,6 +344,41 @@ def test_batchnorm_matches_torch(cuda_device, m, C, relu, res):
     assert_fp32(ev, torch.nn.functional.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-5), "bn eval")
 
 
+@pytest.mark.parametrize("m,C,relu,res", [(3000, 96, True, True), (50000, 128, True, False), (777, 32, False, True)])
+def test_batchnorm_bf16_side_outputs(cuda_device, m, C, relu, res):
+    """bf16 operand mode: BatchNorm apply / backward also write the bf16 copy of y / dx that the next
+    convolution consumes, and the backward ReLU mask is read from the bf16 copy.  The fp32 results must equal
+    the plain-mode results bit for bit; the side copies must be the RNE rounding of the fp32 rows."""
+    g = torch.Generator().manual_seed(m * 3 + C)
+    d = cuda_device
+    x = (torch.randn(m, C, generator=g) * 2 + 0.5).to(d)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(d), torch.randn(C, generator=g).to(d)
+    r = torch.randn(m, C, generator=g).to(d) if res else None
+    go = torch.randn(m, C, generator=g).to(d)
+
+    def run():
+        xg, gg, bg = x.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+        rg = r.clone().requires_grad_() if res else None
+        out = ops.BatchNormFn.apply(xg, gg, bg, torch.zeros(C, device=d), torch.ones(C, device=d), True, 0.1, 1e-5,
+                                    relu, rg)
+        grads = torch.autograd.grad(out, [xg, gg, bg] + ([rg] if res else []), go)
+        return out, grads
+
+    out_ref, grads_ref = run()
+    ops.set_default_precision("bf16")
+    try:
+        out, grads = run()
+        yb = ops._lookup_bf16(out)
+        dxb = ops._lookup_bf16(grads[0])
+    finally:
+        ops.set_default_precision("tf32")
+    assert bool((out == out_ref).all())
+    for a, b in zip(grads, grads_ref):
+        assert bool((a == b).all())
+    assert yb is not None and bool((yb == out.to(torch.bfloat16)).all())
+    assert dxb is not None and bool((dxb == grads[0].to(torch.bfloat16)).all())
+
+
 def test_relu_add(cuda_device):
     x = torch.randn(1001, 37, device=cuda_device, requires_grad=True)
     y = ops.ReLUFn.apply(x)
