@@ -546,7 +546,7 @@ constexpr int kWgChunkBlock = 8192;              // [kRows x row chunk]
 constexpr int kWgAStage = 4 * kWgChunkBlock;     // 32 KB: four chunks = one 128-row M block
 constexpr int kWgMaxAStages = 6;
 constexpr int kWgBStages = 2;
-constexpr int kWgIdxBytes = 16 * 1024;           // per-warp rings of neighbour indices
+constexpr int kWgIdxBytes = 0;                   // (the per-warp neighbour-index rings of the lock-step producer are gone)
 constexpr int kWgMaxMb = 128;    // M blocks (K * Cin / 128): 27 offsets x 512 channels = 108
 constexpr int kWgTabBytes = kWgMaxMb * 4 + kWgMaxMb * 4 * 2;  // per-M-block offset masks, per-chunk (k, cc)
 
@@ -560,7 +560,7 @@ struct UmmaWgradParams {
   int ncc, nq;                // chunks per offset, total chunks
   int n_mb, mb_per_pass, n_pass;
   int n_rb, rb_per_split, n_split;
-  int a_stages;
+  int a_stages, b_warps;      // A ring slots (= A producer warps), warps per B ring slot
   int dbg_skip_mma, dbg_skip_gather, dbg_skip;  // timing experiments only (results are wrong when set)
   int n_work;
 };
@@ -588,11 +588,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 conv_wgrad_umma_kernel(const UmmaWgradParams p) {
   using PR = Prec<BF16>;
   constexpr int kRows = kWgChunkBlock / PR::kRowBytes;      // 64 (tf32) / 128 (bf16) rows per step
-  constexpr int kWarpRows = kRows / 2;                      // rows one producer warp gathers
-  constexpr int kIdxRing = BF16 ? 8 : 16;                   // ring slots of kWarpRows int32 per warp
-  constexpr int kIdxDist = BF16 ? 6 : 8;                    // index prefetch distance in steps
   constexpr int kMmaPerStep = kRows / (BF16 ? 16 : 8);      // 8 either way, 1024 B of rows each
-  static_assert(kNumProducerWarps * kIdxRing * kWarpRows * 4 == kWgIdxBytes, "index ring size");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = (p.Cout / 32) * kWgChunkBlock;
@@ -617,8 +613,9 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), kNumProducerThreads); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), kNumProducerThreads); mbar_init(b_empty(s), 1); }
+    // full barriers: the 32 lanes of the one warp that fills the stage (cp.async ... arrive.noinc)
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 32); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), 32 * p.b_warps); mbar_init(b_empty(s), 1); }
     mbar_init(t_full, 1);
     mbar_init(t_empty, kNumEpilogueThreads);
     fence_mbar_init();
@@ -644,21 +641,22 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
 
   if (warp < kNumProducerWarps) {
     // ============================ producers ============================
-    // The neighbour indices of a step are fetched into a per-warp shared-memory ring kIdxDist
-    // steps ahead with 4-byte cp.async, so their (DRAM) latency never sits on the issue path.
-    int a_stage = 0, b_stage = 0;
-    uint32_t a_phase = 0, b_phase = 0;
-    const int slot_w = warp >> 1;                                   // chunk slot (0..3) of this warp pair
-    const int row0 = (warp & 1) * kWarpRows;                        // this warp's half of the row block
-    const int g8 = (lane / PR::kLanesPerRow) * 8;                   // lane group -> rows [row0+g8, +8)
-    const int j = lane % PR::kLanesPerRow;                          // 16-byte piece of the row chunk
-    const char* in_base = reinterpret_cast<const char*>(p.in);
+    // One warp per pipeline stage (see conv_umma_kernel): A stage number n (the n-th active (work item,
+    // row block, M block) step of this CTA) is gathered entirely by warp n mod a_stages, which always
+    // fills ring slot = its own rank; the dout rows of the m-th active row block are loaded by B warp
+    // m mod 2 (warps a_stages, a_stages + 1).  Every warp walks the same step sequence and acts on its own.
+    constexpr int R = PR::kRowsPerInstr;       // rows one LDGSTS instruction covers
+    constexpr int NQ = kRows / R;              // instructions per [kRows x 32-channel] chunk block (16)
+    constexpr int NI = kRows / 32;             // neighbour indices per lane and chunk (rows lane + 32 i)
+    const int sub = lane / PR::kLanesPerRow;   // row within the rows one instruction covers
+    const int j = lane % PR::kLanesPerRow;     // 16-byte piece within the row chunk
+    const char* in_base = reinterpret_cast<const char*>(p.in) + j * 16;
     const char* dout_base = reinterpret_cast<const char*>(p.dout);
+    const size_t in_pitch = (size_t)p.Cin * PR::kElt;
 
-    // flat iterator over the active (work item, row block, M block) steps of this CTA
-    // (`mask_next` is loaded one row block ahead so that the dependent global load of the tile mask
-    // never sits on the critical path)
-    struct Step { int w, rb, mb, rb1, mb0, mb1; uint32_t mask, mask_next; bool ok; };
+    // flat iterator over the active (work item, row block, M block) steps of this CTA; `first` marks the
+    // first active M block of a row block (= one B stage)
+    struct Step { int w, rb, mb, rb1, mb0, mb1; uint32_t mask; bool ok, first; };
     auto begin_work = [&](Step& s) {
       const int split = s.w / p.n_pass, pass = s.w - split * p.n_pass;
       s.mb0 = pass * p.n_mb / p.n_pass;
@@ -667,9 +665,9 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       s.rb1 = min((split + 1) * p.rb_per_split, p.n_rb);
       s.mb = s.mb1;  // forces the first next() onto (rb0, mb0)
       s.mask = 0;
-      s.mask_next = s.rb + 1 < s.rb1 ? rb_mask(s.rb + 1) : 0u;
     };
     auto next = [&](Step& s) {
+      s.first = false;
       for (;;) {
         if (++s.mb >= s.mb1) {
           s.mb = s.mb0;
@@ -679,88 +677,96 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
             begin_work(s);
             continue;
           }
-          s.mask = s.mask_next;
-          s.mask_next = s.rb + 1 < s.rb1 ? rb_mask(s.rb + 1) : 0u;
+          s.mask = rb_mask(s.rb);
+          s.first = true;  // stays set until an active M block of this row block is found
         }
         if (s_mbtaps[s.mb] & s.mask) return;
       }
     };
-    // ring slot of this warp for step number `seq`: kWarpRows int32 row indices
-    auto idx_slot = [&](uint32_t seq) { return idx_base + (uint32_t)((warp * kIdxRing + (seq % kIdxRing)) * kWarpRows * 4); };
-    auto fetch_idx = [&](const Step& s, uint32_t seq) {
-      const int q = s.mb * 4 + slot_w;
-      if (q >= p.nq || (p.dbg_skip & 1)) return;
-      const int k = s_qk[q];
-      const uint32_t dst = idx_slot(seq);
-#pragma unroll
-      for (int h = 0; h < kWarpRows / 32; ++h) {
-        const int r = lane + 32 * h;
-        const int o = s.rb * kRows + row0 + r;
-        if (o < p.m_out) cp_async_4(dst + r * 4, p.nbr + (size_t)k * p.m_out + o);
-        else st_shared_s32(dst + r * 4, -1);
-      }
-    };
+    Step cur;
+    cur.w = blockIdx.x; cur.ok = cur.w < p.n_work; cur.first = false;
+    if (cur.ok) {
+      begin_work(cur);
+      // first step: `first` must survive skipped M blocks, which next() guarantees (it only clears it on entry)
+      next(cur);
+    }
 
-    Step cur, pf;
-    cur.w = blockIdx.x; cur.ok = cur.w < p.n_work;
-    if (cur.ok) { begin_work(cur); next(cur); }
-    pf = cur;
-    uint32_t seq = 0, pf_seq = 0;
-    // prologue: indices of the first kIdxDist steps
-    for (int d = 0; d < kIdxDist && pf.ok; ++d) { fetch_idx(pf, pf_seq++); next(pf); }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    int b_rb = -1, b_w = -1;
-    while (cur.ok) {
-      if (pf.ok) { fetch_idx(pf, pf_seq++); next(pf); }  // joins this step's commit group
-      const int o0 = cur.rb * kRows;
-      bool with_b = false;
-      if (b_rb != cur.rb || b_w != cur.w) {  // first active M block of a row block brings the dout rows
-        b_rb = cur.rb; b_w = cur.w;
-        with_b = true;
-        WG_TIMED_WAIT(1, mbar_wait(b_empty(b_stage), b_phase ^ 1u));
-        const uint32_t dstb = b_base + (uint32_t)b_stage * b_stage_bytes;
-        const int n16 = (p.Cout / 32) * kRows * PR::kLanesPerRow;  // 16-byte pieces of the dout block
-        for (int e = threadIdx.x; e < n16 && !(p.dbg_skip & 2); e += kNumProducerThreads) {
-          const int jj = e % PR::kLanesPerRow, r = (e / PR::kLanesPerRow) % kRows, cbk = e / (PR::kLanesPerRow * kRows);
-          const int o = o0 + r;
-          const bool ok = o < p.m_out;
-          const char* src = dout_base + ((size_t)(ok ? o : 0) * p.Cout + cbk * 32) * PR::kElt + jj * 16;
-          cp_async_16(dstb + cbk * kWgChunkBlock + r * PR::kRowBytes + PR::swz_mn(jj, r), src, ok ? 16u : 0u);
-        }
-        cp_async_mbar_arrive_noinc(b_full(b_stage));
-      }
-      WG_TIMED_WAIT(0, mbar_wait(a_empty(a_stage), a_phase ^ 1u));
-      {
-        // a warp pair gathers chunk slot `slot_w` of this M block, half of the rows each
-        const int q = cur.mb * 4 + slot_w;
-        if (q < p.nq && !p.dbg_skip_gather) {
-          const int cc = s_qcc[q];
-          const uint32_t dsta = a_base + (uint32_t)a_stage * kWgAStage + slot_w * kWgChunkBlock + (row0 + g8) * PR::kRowBytes;
-          const char* srcb = in_base + (size_t)cc * 32 * PR::kElt + j * 16;
-          int idx[8];
-          const uint32_t slot = idx_slot(seq) + g8 * 4;
+    if (warp < p.a_stages) {
+      // ---- A stages: gathered input rows of the four (offset, channel group) chunks of one M block ----
+      auto load_idx = [&](const Step& st, int* idx) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) ld_shared_v4(slot + v * 16, idx[4 * v], idx[4 * v + 1], idx[4 * v + 2], idx[4 * v + 3]);
+        for (int sl = 0; sl < 4; ++sl) {
+          const int q = st.mb * 4 + sl;
+          const int k = q < p.nq ? (int)s_qk[q] : -1;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int src_row = idx[i];
-            const char* src = srcb + (size_t)(src_row >= 0 ? src_row : 0) * p.Cin * PR::kElt;
-            cp_async_16(dsta + i * PR::kRowBytes + PR::swz_mn(j, i), src, src_row >= 0 ? 16u : 0u);
+          for (int i = 0; i < NI; ++i) {
+            const int o = st.rb * kRows + i * 32 + lane;
+            idx[sl * NI + i] = (k >= 0 && o < p.m_out) ? __ldg(p.nbr + (size_t)k * p.m_out + o) : -1;
           }
         }
+      };
+      // advance to this warp's first owned step (step number == warp)
+      for (int skip = 0; skip < warp && cur.ok; ++skip) next(cur);
+      int idx[4 * NI];
+      if (cur.ok) load_idx(cur, idx);
+      uint32_t a_phase = 0;
+      const uint32_t stage_addr = a_base + (uint32_t)warp * kWgAStage;
+      while (cur.ok) {
+        Step nxt = cur;
+        for (int skip = 0; skip < p.a_stages && nxt.ok; ++skip) next(nxt);
+        int idx_n[4 * NI];
+        if (nxt.ok) load_idx(nxt, idx_n);  // latency hides behind this stage's slot wait
+
+        WG_TIMED_WAIT(0, mbar_wait(a_empty(warp), a_phase ^ 1u));
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int q = cur.mb * 4 + sl;
+          if (q < p.nq && !p.dbg_skip_gather) {  // (padding chunk of the last M block: rows stay as they are)
+            const char* src_c = in_base + (size_t)s_qcc[q] * PR::kRowBytes;
+            const uint32_t dst_c = stage_addr + sl * kWgChunkBlock;
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+              const int r = qi * R + sub;  // row within the row block
+              const int src_row = __shfl_sync(0xffffffffu, idx[sl * NI + ((qi * R) >> 5)], r & 31);
+              const char* src = src_c + (size_t)(src_row >= 0 ? src_row : 0) * in_pitch;
+              cp_async_16(dst_c + r * PR::kRowBytes + PR::swz_mn(j, r), src, src_row >= 0 ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_mbar_arrive_noinc(a_full(warp));
+        a_phase ^= 1u;
+        cur = nxt;
+#pragma unroll
+        for (int i = 0; i < 4 * NI; ++i) idx[i] = idx_n[i];
       }
-      cp_async_mbar_arrive_noinc(a_full(a_stage));
-      cp_async_commit();
-      if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1u; }
-      if (with_b && ++b_stage == kWgBStages) { b_stage = 0; b_phase ^= 1u; }
-      // the index copies of step seq+1 were committed kIdxDist-1 groups ago: this never blocks in
-      // steady state (at most a_stages <= kIdxDist-2 groups can be pending) and guarantees they landed
-      WG_TIMED_WAIT(2, cp_async_wait<kIdxDist - 2>());
-      __syncwarp();
-      ++seq;
-      next(cur);
+    } else if (warp < p.a_stages + kWgBStages * p.b_warps) {
+      // ---- B stages: the dout rows of one row block (contiguous rows, all Cout channels), b_warps warps
+      // per ring slot (wide Cout: a B stage is as large as two A stages) ----
+      const int bi = warp - p.a_stages;
+      const int bw = bi / p.b_warps, part = bi - bw * p.b_warps;  // ring slot / share of its pieces
+      uint32_t b_phase = 0;
+      int m = 0;  // number of the active row block
+      while (cur.ok) {
+        if (cur.first) {
+          if ((m & 1) == bw) {
+            WG_TIMED_WAIT(1, mbar_wait(b_empty(bw), b_phase ^ 1u));
+            const uint32_t dstb = b_base + (uint32_t)bw * b_stage_bytes;
+            const int o0 = cur.rb * kRows;
+            const int n16 = (p.Cout / 32) * kRows * PR::kLanesPerRow;  // 16-byte pieces of the dout block
+            for (int e = part * 32 + lane; e < n16 && !(p.dbg_skip & 2); e += 32 * p.b_warps) {
+              const int jj = e % PR::kLanesPerRow, r = (e / PR::kLanesPerRow) % kRows, cbk = e / (PR::kLanesPerRow * kRows);
+              const int o = o0 + r;
+              const bool ok = o < p.m_out;
+              const char* src = dout_base + ((size_t)(ok ? o : 0) * p.Cout + cbk * 32) * PR::kElt + jj * 16;
+              cp_async_16(dstb + cbk * kWgChunkBlock + r * PR::kRowBytes + PR::swz_mn(jj, r), src, ok ? 16u : 0u);
+            }
+            cp_async_mbar_arrive_noinc(b_full(bw));
+            b_phase ^= 1u;
+          }
+          ++m;
+        }
+        next(cur);
+      }
     }
     cp_async_wait<0>();
   } else if (warp == kMmaWarp) {
@@ -927,10 +933,10 @@ int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint
   p.n_work = p.n_split * p.n_pass;
   const int b_stage_bytes = (c_out / 32) * kWgChunkBlock;
   int a_stages = (kSmemLimit - 1024 - 256 - kWgIdxBytes - kWgTabBytes - kWgBStages * b_stage_bytes) / kWgAStage;
-  const int max_a = bf16 ? 4 : kWgMaxAStages;  // pending groups must stay <= index prefetch distance - 2
-  if (a_stages > max_a) a_stages = max_a;
+  if (a_stages > kWgMaxAStages) a_stages = kWgMaxAStages;  // one producer warp per A stage + two B warps <= 8 warps
   SPC_REQUIRE(a_stages >= 2, "wgrad tile does not fit in shared memory");
   p.a_stages = a_stages;
+  p.b_warps = (kNumProducerWarps - a_stages) / kWgBStages >= 2 && c_out >= 128 ? 2 : 1;
   p.dbg_skip_mma = g_dbg[4];
   p.dbg_skip_gather = g_dbg[5];
   p.dbg_skip = g_dbg[6];
