@@ -155,6 +155,14 @@ int spc_to_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
 int spc_conv_fwd(const void* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                  float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* spc_conv_fwd that also accumulates, in its epilogue, the per-channel sum and sum of squares of the output
+ * rows into bn_stats[2 * c_out] (doubles, zeroed here) for the BatchNorm that follows (spc_bn_finalize), saving
+ * that layer's statistics pass over the rows.  Done only when the launch has one output-channel tile and no
+ * offset split (large maps, c_out <= 256): *stats_fused (HOST int, may be NULL) says whether bn_stats is valid. */
+int spc_conv_fwd_stats(const void* in, const float* w, const float* bias, const int32_t* nbr,
+                       const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                       int precision, float* out, double* bn_stats, int32_t* stats_fused, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 int spc_conv_dgrad(const void* dout, const float* w, const int32_t* nbr_t,
                    const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* din, void* workspace, int64_t workspace_bytes, void* stream);
@@ -174,6 +182,9 @@ int64_t spc_bn_workspace(int64_t m, int C);
 int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
                  float* running_mean, float* running_var, float momentum, /* nullable */
                  void* workspace, int64_t workspace_bytes, void* stream);
+/* mean / biased variance (+ running statistics) from the sums written by spc_conv_fwd_stats. */
+int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
+                    float* running_var, float momentum, void* stream);
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,
                  int relu, float* y, void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);

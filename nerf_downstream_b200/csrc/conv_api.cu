@@ -16,8 +16,8 @@ bool umma_fwd_supported(int c_in, int c_out);
 int64_t umma_fwd_workspace(int K, int c_in, int c_out);
 int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
-                  bool transpose_w, bool bf16, float* out, void* workspace, int64_t workspace_bytes,
-                  cudaStream_t stream);
+                  bool transpose_w, bool bf16, float* out, double* stats, int* stats_fused, void* workspace,
+                  int64_t workspace_bytes, cudaStream_t stream);
 bool umma_wgrad_supported(int c_in, int c_out);
 int64_t umma_wgrad_workspace(int K, int c_in, int c_out);
 int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
@@ -58,17 +58,26 @@ int spc_to_bf16(const float* src, int64_t n, void* dst, void* stream) {
 int spc_conv_fwd(const void* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                  float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return spc_conv_fwd_stats(in, w, bias, nbr, tile_mask, m_in, m_out, c_in, c_out, K, precision, out, nullptr, nullptr,
+                            workspace, workspace_bytes, stream);
+}
+
+int spc_conv_fwd_stats(const void* in, const float* w, const float* bias, const int32_t* nbr,
+                       const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                       int precision, float* out, double* bn_stats, int32_t* stats_fused, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  if (stats_fused) *stats_fused = 0;
   (void)m_in;
   SPC_REQUIRE(c_in >= 1 && c_out >= 1 && K >= 1, "bad shape");
   SPC_REQUIRE(prec_ok(precision), "bad precision mode");
   const bool umma = K <= 32 && umma_fwd_supported(c_in, c_out);
   if (precision == SPC_PREC_BF16) {
     SPC_REQUIRE(umma, "bf16 mode needs a tensor-core shape (Cin % 32 == 0, Cout % 16 == 0, K <= 32)");
-    return conv_fwd_umma(in, w, bias, nbr, tile_mask, m_out, c_in, c_out, K, false, true, out, workspace,
+    return conv_fwd_umma(in, w, bias, nbr, tile_mask, m_out, c_in, c_out, K, false, true, out, bn_stats, stats_fused, workspace,
                          workspace_bytes, (cudaStream_t)stream);
   }
   if (precision == SPC_PREC_TF32 && umma)
-    return conv_fwd_umma(in, w, bias, nbr, tile_mask, m_out, c_in, c_out, K, false, false, out, workspace,
+    return conv_fwd_umma(in, w, bias, nbr, tile_mask, m_out, c_in, c_out, K, false, false, out, bn_stats, stats_fused, workspace,
                          workspace_bytes, (cudaStream_t)stream);
   return conv_fwd_simt((const float*)in, w, bias, nbr, m_out, c_in, c_out, K, false, out, (cudaStream_t)stream);
 }
@@ -84,11 +93,11 @@ int spc_conv_dgrad(const void* dout, const float* w, const int32_t* nbr_t,
   const bool umma = K <= 32 && umma_fwd_supported(c_out, c_in);
   if (precision == SPC_PREC_BF16) {
     SPC_REQUIRE(umma, "bf16 mode needs a tensor-core shape (Cout % 32 == 0, Cin % 16 == 0, K <= 32)");
-    return conv_fwd_umma(dout, w, nullptr, nbr_t, tile_mask_t, m_in, c_out, c_in, K, true, true, din, workspace,
+    return conv_fwd_umma(dout, w, nullptr, nbr_t, tile_mask_t, m_in, c_out, c_in, K, true, true, din, nullptr, nullptr, workspace,
                          workspace_bytes, (cudaStream_t)stream);
   }
   if (precision == SPC_PREC_TF32 && umma)
-    return conv_fwd_umma(dout, w, nullptr, nbr_t, tile_mask_t, m_in, c_out, c_in, K, true, false, din, workspace,
+    return conv_fwd_umma(dout, w, nullptr, nbr_t, tile_mask_t, m_in, c_out, c_in, K, true, false, din, nullptr, nullptr, workspace,
                          workspace_bytes, (cudaStream_t)stream);
   return conv_fwd_simt((const float*)dout, w, nullptr, nbr_t, m_in, c_out, c_in, K, true, din, (cudaStream_t)stream);
 }

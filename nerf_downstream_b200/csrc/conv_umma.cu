@@ -84,6 +84,7 @@ struct UmmaConvParams {
   const int* nbr;            // [K, m_out]
   const uint32_t* tile_mask; // [ceil(m_out/128)] or null (all offsets active)
   float* out;                // [m_out, Cn]
+  double* stats;             // optional [2][Cn]: per-channel sum and sum of squares of `out` (BatchNorm fusion)
   int m_out, Ck, Cn, K;
   int cn_tile, n_ntiles, kc_count;
   int stages, acc_bufs, tmem_cols;
@@ -178,6 +179,9 @@ conv_umma_kernel(const UmmaConvParams p) {
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // BatchNorm-statistics fusion (p.stats): per epilogue warp a [16][33] transposition scratch and
+  // double accumulators [2][Cn] behind the barrier block
+  uint8_t* stats_smem = smem_raw + (bar_base + 256u - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -372,6 +376,14 @@ conv_umma_kernel(const UmmaConvParams p) {
     const int ew = warp & 3;  // TMEM lane group this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    // statistics fusion: this warp's scratch; lanes 0-15 own the sums, lanes 16-31 the sums of squares of
+    // 16 columns at a time (host guarantees n_ntiles == 1 and ksplit == 1 when p.stats is set)
+    float* s_tr = reinterpret_cast<float*>(stats_smem) + ew * (16 * 33);
+    double* s_dacc = reinterpret_cast<double*>(stats_smem + 4 * 16 * 33 * sizeof(float)) + ew * 2 * p.Cn;
+    if (p.stats) {
+      for (int c = lane; c < 2 * p.Cn; c += 32) s_dacc[c] = 0.0;
+      __syncwarp();
+    }
     for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
       const int mtile = w / items_per_mtile, ntile = (w / p.ksplit) % p.n_ntiles, kg = w % p.ksplit;
       const int o0 = mtile * rows_per_work;
@@ -411,11 +423,32 @@ conv_umma_kernel(const UmmaConvParams p) {
                 *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
           }
+          if (p.stats) {
+            // column sums over this warp's 32 rows: transpose through shared memory (conflict-free, pitch 33),
+            // one lane per (column, sum | sum of squares), fp32 over 32 rows, double across tiles
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s_tr[i * 33 + lane] = row_ok ? v[i] : 0.f;
+            __syncwarp();
+            const int col = lane & 15;
+            float a = 0.f;
+            if (lane < 16) {
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) a += s_tr[col * 33 + r];
+            } else {
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) { const float x = s_tr[col * 33 + r]; a = fmaf(x, x, a); }
+            }
+            s_dacc[(lane >> 4) * p.Cn + c0 + col] += (double)a;
+            __syncwarp();
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (p.stats) {  // one double atomic per (warp, channel, moment) and CTA
+      for (int c = lane; c < 2 * p.Cn; c += 32) atomicAdd(p.stats + c, s_dacc[c]);
     }
   }
 
@@ -440,10 +473,13 @@ static int g_umma_force_mt = 0;  // test hook: 0 = auto
 static int g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // test hook spc_debug_set: 0 = default
 
 // `in` is fp32 (bf16 == false) or bf16 (bf16 == true) rows; weights are always fp32 and packed here.
+// `stats` (optional, [2][c_out] doubles): per-channel sum / sum of squares of the output rows, accumulated
+// in the epilogue when the launch has one n tile and no offset split; *stats_fused says whether it was.
 int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
-                  bool transpose_w, bool bf16, float* out, void* workspace, int64_t workspace_bytes,
-                  cudaStream_t stream) {
+                  bool transpose_w, bool bf16, float* out, double* stats, int* stats_fused, void* workspace,
+                  int64_t workspace_bytes, cudaStream_t stream) {
+  if (stats_fused) *stats_fused = 0;
   if (m_out == 0) return 0;
   SPC_REQUIRE(umma_fwd_supported(c_in, c_out), "shape not supported by the tcgen05 path");
   SPC_REQUIRE(K <= 32, "tcgen05 path supports kernel volume <= 32");
@@ -454,7 +490,7 @@ int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* 
   const int a_stage = kTileM * row_bytes;
 
   UmmaConvParams p;
-  p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
+  p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out; p.stats = nullptr;
   p.m_out = (int)m_out; p.Ck = c_in; p.Cn = c_out; p.K = K;
   p.kc_count = c_in / 32;
   // Tile shape: MT sub-tiles of 128 rows x cn_tile output channels per work item, and on small maps
@@ -509,11 +545,23 @@ int conv_fwd_umma(const void* in, const float* w, const float* bias, const int* 
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   const int stage_bytes = mt * a_stage + p.cn_tile * row_bytes;
-  int stages = (kSmemLimit - 1024 - 256) / stage_bytes;
+  // BatchNorm-statistics fusion: one n tile, no offset split (every output value is final in the epilogue)
+  int extra = 0;
+  if (stats && p.n_ntiles == 1 && p.ksplit == 1) {
+    extra = 4 * 16 * 33 * (int)sizeof(float) + 4 * 2 * c_out * (int)sizeof(double) + 16;
+    if ((kSmemLimit - 1024 - 256 - extra) / stage_bytes >= 4) {
+      p.stats = stats;
+      SPC_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * c_out * sizeof(double), stream));
+      if (stats_fused) *stats_fused = 1;
+    } else {
+      extra = 0;
+    }
+  }
+  int stages = (kSmemLimit - 1024 - 256 - extra) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   SPC_REQUIRE(stages >= 2, "tile does not fit in shared memory");
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + extra;
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
   if (bf16) return mt == 2 ? launch_conv_umma<2, true>(p, grid, smem, stream) : launch_conv_umma<1, true>(p, grid, smem, stream);
   return mt == 2 ? launch_conv_umma<2, false>(p, grid, smem, stream) : launch_conv_umma<1, false>(p, grid, smem, stream);

@@ -450,6 +450,25 @@ ce_bwd_kernel(const float* __restrict__ graw, const double* __restrict__ stats,
     dlogits[e] = graw[e] * sc;
 }
 
+// mean / biased variance (+ running statistics) from per-channel sums gsum[0..C) = sum x, gsum[C..2C) = sum x^2
+// accumulated in double by the convolution epilogue (spc_conv_fwd_stats)
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ gsum, long long m, int C, float* __restrict__ mean,
+                   float* __restrict__ var, float* run_mean, float* run_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = gsum[c] / (double)m;
+  double v = gsum[C + c] / (double)m - mu * mu;
+  v = v > 0.0 ? v : 0.0;
+  mean[c] = (float)mu;
+  var[c] = (float)v;
+  if (run_mean) {  // nn.BatchNorm1d: running_var tracks the UNBIASED variance
+    const double unb = m > 1 ? v * (double)m / (double)(m - 1) : v;
+    run_mean[c] = (float)((1.0 - momentum) * run_mean[c] + momentum * mu);
+    run_var[c] = (float)((1.0 - momentum) * run_var[c] + momentum * unb);
+  }
+}
+
 }  // namespace spc
 
 using namespace spc;
@@ -510,6 +529,15 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
   fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
   fin.momentum = momentum; fin.eps = 0.f;
   return col_reduce_launch(0, x, nullptr, nullptr, nullptr, nullptr, m, C, 0, fin, stream);
+}
+
+int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
+                    float* running_var, float momentum, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(m >= 1 && C >= 1 && sums, "empty input");
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, stream>>>(sums, m, C, mean, var, running_mean, running_var, momentum);
+  SPC_LAUNCHED("bn_finalize_kernel");
+  return 0;
 }
 
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,

@@ -463,7 +463,40 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
+# per-channel (sum, sum of squares) of a convolution output, accumulated by its epilogue for the BatchNorm that
+# follows: data_ptr of the output rows -> (weakref, version, float64 [2 C])
+_stats_side: dict = {}
+
+
+def _remember_stats(t: torch.Tensor, sums: torch.Tensor) -> None:
+    key = t.data_ptr()
+
+    def _drop(ref, key=key):
+        e = _stats_side.get(key)
+        if e is not None and e[0] is ref:
+            del _stats_side[key]
+    _stats_side[key] = (weakref.ref(t, _drop), t._version, sums)
+
+
+def _lookup_stats(t: torch.Tensor):
+    e = _stats_side.get(t.data_ptr())
+    if e is None:
+        return None
+    ref, version, sums = e
+    o = ref()
+    if o is None or o.shape != t.shape or t._version != version or sums.numel() != 2 * t.shape[1]:
+        return None
+    return sums
+
+
+# Convolution epilogues can accumulate the statistics of a following BatchNorm (spc_conv_fwd_stats).  Measured on
+# the 2 x 1 M-voxel UNet step: BatchNorm forward -1.3 ms, convolution forward +1.6 ms — the transposition of the
+# accumulator tile goes through the same LSU / shared-memory pipe that bounds the row gather — so it is OFF by
+# default; `ops.fuse_bn_stats = True` turns it on (tests/test_gpu_parity.py covers it).
+fuse_bn_stats = False
+
+
+def conv_fwd_raw(x, w, bias, km: KernelMap, precision, want_stats: bool = False):
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
@@ -471,9 +504,18 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision):
     ws = _workspace(ws_bytes, x.device)
     mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
-                             c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
-            "spc_conv_fwd")
+    if want_stats and fuse_bn_stats and precision != L.PREC_FP32 and c_out <= 256 and km.m_out >= 16384:
+        sums = _empty(2 * c_out, torch.float64, x.device)
+        fused = ctypes.c_int32(0)
+        L.check(lib.spc_conv_fwd_stats(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
+                                       c_in, c_out, K, precision, L.ptr(out), L.ptr(sums), ctypes.addressof(fused),
+                                       L.ptr(ws), ws_bytes, L.stream()), "spc_conv_fwd_stats")
+        if fused.value:
+            _remember_stats(out, sums)
+    else:
+        L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
+                                 c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
+                "spc_conv_fwd")
     if e0 is not None:
         _profiler.end("conv_fwd", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
                       f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
@@ -541,7 +583,7 @@ class SparseConvFn(torch.autograd.Function):
                 b = torch.nn.functional.pad(b, (0, pad_out))
         if precision == L.PREC_BF16:
             x = to_bf16(x)  # the bf16 copy is what backward needs too (half the saved bytes)
-        out = conv_fwd_raw(x, w3, b, km, precision)
+        out = conv_fwd_raw(x, w3, b, km, precision, want_stats=not pad_out)
         if pad_out:
             out = out[:, :c_out].contiguous()
         ctx.save_for_backward(x, w3)
@@ -599,10 +641,17 @@ class BatchNormFn(torch.autograd.Function):
             mean = _empty(C, torch.float32, dev)
             var = _empty(C, torch.float32, dev)
             upd = training and running_mean is not None
-            L.check(lib.spc_bn_stats(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
-                                     L.ptr(running_mean) if upd else None,
-                                     L.ptr(running_var) if upd else None, float(momentum), L.ptr(ws), ws_bytes,
-                                     L.stream()), "spc_bn_stats")
+            sums = _lookup_stats(x)
+            if sums is not None:  # accumulated by the producing convolution's epilogue: no pass over x
+                L.check(lib.spc_bn_finalize(L.ptr(sums), m, C, L.ptr(mean), L.ptr(var),
+                                            L.ptr(running_mean) if upd else None,
+                                            L.ptr(running_var) if upd else None, float(momentum), L.stream()),
+                        "spc_bn_finalize")
+            else:
+                L.check(lib.spc_bn_stats(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
+                                         L.ptr(running_mean) if upd else None,
+                                         L.ptr(running_var) if upd else None, float(momentum), L.ptr(ws), ws_bytes,
+                                         L.stream()), "spc_bn_stats")
         else:
             mean, var = running_mean, running_var
         res = _feat(residual) if residual is not None else None
@@ -613,7 +662,8 @@ class BatchNormFn(torch.autograd.Function):
         if yb is not None:
             _remember_bf16(y, yb)
         if e0 is not None:
-            _profiler.end("bn_fwd", e0, 0, (12.0 + (4.0 if res is not None else 0.0)
+            _profiler.end("bn_fwd", e0, 0, ((8.0 if (use_batch and sums is not None) else 12.0)
+                                            + (4.0 if res is not None else 0.0)
                                             + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
         # the ReLU mask of backward comes from the bf16 copy when there is one (2 instead of 4 bytes per value)
         ctx.save_for_backward(x, (yb if yb is not None else y) if relu else None, mean, var, gamma)
