@@ -712,6 +712,7 @@ struct UmmaWgradParams {
   int n_mb, mb_per_pass, n_pass;
   int n_rb, rb_per_split, n_split;
   int a_stages, b_warps;      // A ring slots (= A producer warps), warps per B ring slot
+  int b_tma;                  // dout row blocks arrive by TMA tile loads (no LSU work)
   int dbg_skip_mma, dbg_skip_gather, dbg_skip;  // timing experiments only (results are wrong when set)
   int n_work;
 };
@@ -736,7 +737,7 @@ __device__ __forceinline__ uint32_t mblock_taps(int mb, int ncc, int nq) {
 
 template <bool BF16>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_wgrad_umma_kernel(const UmmaWgradParams p) {
+conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensorMap tmap_dout) {
   using PR = Prec<BF16>;
   constexpr int kRows = kWgChunkBlock / PR::kRowBytes;      // 64 (tf32) / 128 (bf16) rows per step
   constexpr int kMmaPerStep = kRows / (BF16 ? 16 : 8);      // 8 either way, 1024 B of rows each
@@ -766,7 +767,8 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
   if (threadIdx.x == 0) {
     // full barriers: the 32 lanes of the one warp that fills the stage (cp.async ... arrive.noinc)
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 32); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), 32 * p.b_warps); mbar_init(b_empty(s), 1); }
+    // b_full: one expect_tx arrival (TMA tile loads of the dout rows), or the lanes of the B warps (LDGSTS)
+    for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), p.b_tma ? 1 : 32 * p.b_warps); mbar_init(b_empty(s), 1); }
     mbar_init(t_full, 1);
     mbar_init(t_empty, kNumEpilogueThreads);
     fence_mbar_init();
@@ -900,18 +902,30 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p) {
       while (cur.ok) {
         if (cur.first) {
           if ((m & 1) == bw) {
-            WG_TIMED_WAIT(1, mbar_wait(b_empty(bw), b_phase ^ 1u));
             const uint32_t dstb = b_base + (uint32_t)bw * b_stage_bytes;
             const int o0 = cur.rb * kRows;
-            const int n16 = (p.Cout / 32) * kRows * PR::kLanesPerRow;  // 16-byte pieces of the dout block
-            for (int e = part * 32 + lane; e < n16 && !(p.dbg_skip & 2); e += 32 * p.b_warps) {
-              const int jj = e % PR::kLanesPerRow, r = (e / PR::kLanesPerRow) % kRows, cbk = e / (PR::kLanesPerRow * kRows);
-              const int o = o0 + r;
-              const bool ok = o < p.m_out;
-              const char* src = dout_base + ((size_t)(ok ? o : 0) * p.Cout + cbk * 32) * PR::kElt + jj * 16;
-              cp_async_16(dstb + cbk * kWgChunkBlock + r * PR::kRowBytes + PR::swz_mn(jj, r), src, ok ? 16u : 0u);
+            if (p.b_tma) {
+              // contiguous rows: Cout / 32 tile loads (32 channels x kRows rows, hardware swizzle = the MN-major
+              // UMMA layout) issued by one lane; rows past m_out are zero-filled by the TMA unit
+              if (lane == 0) {
+                WG_TIMED_WAIT(1, mbar_wait(b_empty(bw), b_phase ^ 1u));
+                mbar_arrive_expect_tx(b_full(bw), (uint32_t)b_stage_bytes);
+                for (int cbk = 0; cbk < p.Cout / 32 && !(p.dbg_skip & 2); ++cbk)
+                  tma_load_2d(dstb + cbk * kWgChunkBlock, &tmap_dout, b_full(bw), cbk * 32, o0);
+              }
+              __syncwarp();
+            } else {
+              WG_TIMED_WAIT(1, mbar_wait(b_empty(bw), b_phase ^ 1u));
+              const int n16 = (p.Cout / 32) * kRows * PR::kLanesPerRow;  // 16-byte pieces of the dout block
+              for (int e = part * 32 + lane; e < n16 && !(p.dbg_skip & 2); e += 32 * p.b_warps) {
+                const int jj = e % PR::kLanesPerRow, r = (e / PR::kLanesPerRow) % kRows, cbk = e / (PR::kLanesPerRow * kRows);
+                const int o = o0 + r;
+                const bool ok = o < p.m_out;
+                const char* src = dout_base + ((size_t)(ok ? o : 0) * p.Cout + cbk * 32) * PR::kElt + jj * 16;
+                cp_async_16(dstb + cbk * kWgChunkBlock + r * PR::kRowBytes + PR::swz_mn(jj, r), src, ok ? 16u : 0u);
+              }
+              cp_async_mbar_arrive_noinc(b_full(bw));
             }
-            cp_async_mbar_arrive_noinc(b_full(bw));
             b_phase ^= 1u;
           }
           ++m;
@@ -1044,11 +1058,27 @@ bool umma_wgrad_supported(int c_in, int c_out) {
 }
 int64_t umma_wgrad_workspace(int, int, int) { return 256; }
 
+// [rows, C] row-major tensor, box = 32 channels x box_rows rows, written in the MN-major UMMA layout of the
+// wgrad operands: bf16 SWIZZLE_64B, fp32 SWIZZLE_128B with 32-byte atoms
+static bool make_rows_tile_map(CUtensorMap* map, const void* base, int64_t rows, int C, int box_rows, bool bf16) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)C * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+             const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <bool BF16>
-static int launch_wgrad_umma(const UmmaWgradParams& p, int grid, size_t smem, cudaStream_t stream) {
+static int launch_wgrad_umma(const UmmaWgradParams& p, const CUtensorMap& tmap, int grid, size_t smem,
+                             cudaStream_t stream) {
   auto kern = conv_wgrad_umma_kernel<BF16>;
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kNumThreads, smem, stream>>>(p);
+  kern<<<grid, kNumThreads, smem, stream>>>(p, tmap);
   SPC_LAUNCHED("conv_wgrad_umma_kernel");
   return 0;
 }
@@ -1093,7 +1123,11 @@ int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint
   p.dbg_skip = g_dbg[6];
   const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256 + kWgIdxBytes + kWgTabBytes;
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
-  return bf16 ? launch_wgrad_umma<true>(p, grid, smem, stream) : launch_wgrad_umma<false>(p, grid, smem, stream);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  p.b_tma = (g_dbg[1] != 1 && make_rows_tile_map(&tmap, dout, m_out, c_out, rows, bf16)) ? 1 : 0;
+  if (p.b_tma) p.b_warps = 1;  // one issuing lane per B ring slot
+  return bf16 ? launch_wgrad_umma<true>(p, tmap, grid, smem, stream) : launch_wgrad_umma<false>(p, tmap, grid, smem, stream);
 }
 
 }  // namespace spc

@@ -104,6 +104,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
+// TMA tile load (cp.async.bulk.tensor.2d): box of the tensor map at element coordinates (c0, c1) ->
+// shared memory in the map's swizzle, complete_tx on `bar`.  Out-of-bounds elements are zero-filled.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // TMA tensor stores shared -> global (bulk async-group): one box of the tensor map at element coordinates
 // (c0, c1); rows / columns outside the tensor are clipped.  The reduce form adds (fp32) into global memory.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
