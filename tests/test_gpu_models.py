@@ -8,7 +8,7 @@ ResNet14 / Res16UNet34C on the small random-weight test scenes):
          [1.00000 / 0.99997], worst single parameter >= 0.999
   tf32 : logits cos >= 0.9999, |d| <= 3e-2 max|ref| ; gradients cos >= 0.95 [0.99909 / 0.968],
          worst single parameter >= 0.85 [0.914 .. 0.920 over runs: wgrad sums with fp32 atomics]
-  bf16 : logits cos >= 0.995 [0.99999 / 0.99888], |d| <= 2e-1 max|ref| ; gradients cos >= 0.75 [0.993 / 0.806],
+  bf16 : logits cos >= 0.995 [0.99999 / 0.99888], |d| <= 2e-1 max|ref| ; gradients cos >= 0.7 [0.993 / 0.80-0.81],
          worst single parameter >= 0.45 [0.57 .. 0.59]
 Every individual op inside these backward passes agrees with an fp64 recomputation to its op-level bound
 (tests/test_gpu_parity.py: fp32 1e-4, tf32 3e-3, bf16 2e-2 of max|ref|; scripts/diag_ops_in_model.py).  The
@@ -73,7 +73,7 @@ def _compare(model, fwd, coords, feats, target_fn, mode, dev):
         total = _cos(torch.cat(ga), torch.cat(gr))
         print(f"[{mode}] logits cos={cos:.6f} max err={err:.3e} (scale {scale:.3e}) all-parameter grad cos={total:.5f} "
               f"worst single parameter {worst_name}: {worst:.4f}")
-        assert total >= {"fp32": 0.9999, "tf32": 0.95, "bf16": 0.75}[mode], total
+        assert total >= {"fp32": 0.9999, "tf32": 0.95, "bf16": 0.7}[mode], total
         assert worst >= {"fp32": 0.999, "tf32": 0.85, "bf16": 0.45}[mode], (worst_name, worst)
         return cos, worst
     finally:
