@@ -233,6 +233,20 @@ int spc_ce_bwd(const float* grad_raw, const double* stats, const float* grad_out
                float* dlogits, void* stream);
 
 
+/* ---- the two ends of the path (SURVEY.md §8f "next" rows 2 and 3) ------------------------------------------
+ * spc_plenoxel_decode: one PeRFception plenoxel record -> network input (co3d_3d/src/data/co3d.py:164-172,196-203).
+ *   links[n] (int32 or int64 flat indices of the occupied cells of a reso[0] x reso[1] x reso[2] grid) ->
+ *   out_coords[n,4] float (batch_index, i, j, k) with i = links / (r1 r2), j = (links % (r1 r2)) / r2, k = links % r2,
+ *   optionally mapped through affine12 = HOST float[12] (row-major 3x3 then translation; NULL = identity), and
+ *   sh_u8[n,C] uint8 -> out_feats[n,C] float = sh * sh_scale + sh_min (two roundings, as numpy / torch compute it).
+ * spc_seg_metrics: IoUMeter.update (co3d_3d/src/metrics.py:29-41) in one pass: counts[3][C] (uint64, ACCUMULATED,
+ *   caller zeroes) += per-class #seen, #correct, #predicted of argmax(logits[n,C]) over rows with target != ignore. */
+int spc_plenoxel_decode(const void* links, int links_is_int64, int64_t n, const int32_t* reso, int32_t batch_index,
+                        const float* affine12, const uint8_t* sh_u8, int C, float sh_scale, float sh_min,
+                        float* out_coords, float* out_feats, void* stream);
+int spc_seg_metrics(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_label,
+                    uint64_t* counts, void* stream);
+
 /* Fused SGD step on a flat arena (co3d_cls.gin:33-39; optim.py:60-69):
  * g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf. */
 int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,

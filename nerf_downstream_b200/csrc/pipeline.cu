@@ -1,0 +1,137 @@
+// pipeline.cu — the two ends of the hot path that the reference runs on the CPU / with per-class torch loops
+// (SURVEY.md §8f "next" rows 2 and 3):
+//   plenoxel_decode : PeRFception plenoxel record -> network input.  links (flat indices of the occupied cells of the
+//                     reso^3 grid) -> float coordinates (b, i, j, k) [optionally through an affine map, the form of the
+//                     reference's rotation / scale / translation augmentations], uint8 spherical-harmonic coefficients ->
+//                     float features  sh * scale + min                      (co3d_3d/src/data/co3d.py:164-172,196-203)
+//   seg_metrics     : per-class seen / correct / predicted counts of argmax(logits) against the labels with an ignore
+//                     label — IoUMeter.update                                (co3d_3d/src/metrics.py:29-41)
+#include "common.cuh"
+
+namespace spc {
+
+struct Affine {
+  float m[9];  // row-major 3x3
+  float t[3];
+  int enabled;
+};
+
+__global__ void __launch_bounds__(256)
+plenoxel_decode_kernel(const long long* __restrict__ links64, const int* __restrict__ links32, long long n,
+                       int r1, int r2, float batch, Affine aff, const unsigned char* __restrict__ sh_u8, int C,
+                       float sh_scale, float sh_min, float* __restrict__ coords, float* __restrict__ feats) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long plane = (long long)r1 * r2;
+  for (long long i = t0; i < n; i += stride) {
+    const long long l = links64 ? links64[i] : (long long)links32[i];
+    // torch.div(links, r1*r2, 'trunc'), torch.div(links % (r1*r2), r2, 'trunc'), links % r2   (co3d.py:196-203)
+    const float x = (float)(l / plane), y = (float)((l % plane) / r2), z = (float)(l % r2);
+    float4 c;
+    c.x = batch;
+    if (aff.enabled) {  // products and sums rounded one by one, left to right, like the numpy / torch reference
+      c.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[0], x), __fmul_rn(aff.m[1], y)), __fmul_rn(aff.m[2], z)), aff.t[0]);
+      c.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[3], x), __fmul_rn(aff.m[4], y)), __fmul_rn(aff.m[5], z)), aff.t[1]);
+      c.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[6], x), __fmul_rn(aff.m[7], y)), __fmul_rn(aff.m[8], z)), aff.t[2]);
+    } else {
+      c.y = x; c.z = y; c.w = z;
+    }
+    reinterpret_cast<float4*>(coords)[i] = c;
+  }
+  // features: flat over n * C bytes, 4 per thread where alignment allows;  sh.float() * scale + min  (co3d.py:169)
+  const long long total = n * (long long)C;
+  const bool vec = ((uintptr_t)sh_u8 % 4 == 0) && ((uintptr_t)feats % 16 == 0);
+  const long long n4 = vec ? total / 4 : 0;
+  for (long long q = t0; q < n4; q += stride) {
+    const uchar4 u = reinterpret_cast<const uchar4*>(sh_u8)[q];
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn((float)u.x, sh_scale), sh_min);
+    o.y = __fadd_rn(__fmul_rn((float)u.y, sh_scale), sh_min);
+    o.z = __fadd_rn(__fmul_rn((float)u.z, sh_scale), sh_min);
+    o.w = __fadd_rn(__fmul_rn((float)u.w, sh_scale), sh_min);
+    reinterpret_cast<float4*>(feats)[q] = o;
+  }
+  for (long long e = n4 * 4 + t0; e < total; e += stride) feats[e] = __fadd_rn(__fmul_rn((float)sh_u8[e], sh_scale), sh_min);
+}
+
+// counts[0][c] = #(target == c), counts[1][c] = #(target == c and argmax == c), counts[2][c] = #(argmax == c),
+// over rows whose target is not the ignore label.  argmax ties -> the lowest class index (torch.argmax on CUDA
+// returns one of the maxima; the reference's logits are floats where exact ties do not occur in practice).
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+seg_metrics_kernel(const float* __restrict__ logits, const long long* __restrict__ target, long long n, int C,
+                   long long ignore_label, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int s[3 * CMAX];
+  for (int i = threadIdx.x; i < 3 * CMAX; i += blockDim.x) s[i] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long y = target[i];
+    if (y == ignore_label) continue;
+    int best = 0;
+    float bv = logits[i * C];
+    for (int c = 1; c < C; ++c) {
+      const float v = logits[i * C + c];
+      if (v > bv) { bv = v; best = c; }
+    }
+    atomicAdd(&s[2 * CMAX + best], 1u);
+    if (y >= 0 && y < C) {
+      atomicAdd(&s[(int)y], 1u);
+      if (best == (int)y) atomicAdd(&s[CMAX + (int)y], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    const unsigned int v = s[which * CMAX + c];
+    if (v) atomicAdd(&counts[which * C + c], (unsigned long long)v);
+  }
+}
+
+}  // namespace spc
+
+using namespace spc;
+
+extern "C" {
+
+int spc_plenoxel_decode(const void* links, int links_is_int64, int64_t n, const int32_t* reso, int32_t batch_index,
+                        const float* affine12, const uint8_t* sh_u8, int C, float sh_scale, float sh_min,
+                        float* out_coords, float* out_feats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(n >= 0 && C >= 0 && reso && reso[1] > 0 && reso[2] > 0, "bad arguments");
+  SPC_REQUIRE(((uintptr_t)out_coords % 16) == 0, "coordinates must be 16-byte aligned");
+  if (n == 0) return 0;
+  Affine aff;
+  memset(&aff, 0, sizeof(aff));
+  if (affine12) {
+    memcpy(aff.m, affine12, 9 * sizeof(float));
+    memcpy(aff.t, affine12 + 9, 3 * sizeof(float));
+    aff.enabled = 1;
+  }
+  int64_t want = ceil_div(n, 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  plenoxel_decode_kernel<<<grid, 256, 0, stream>>>(links_is_int64 ? (const long long*)links : nullptr,
+                                                    links_is_int64 ? nullptr : (const int*)links, n, reso[1], reso[2],
+                                                    (float)batch_index, aff, sh_u8, C, sh_scale, sh_min, out_coords,
+                                                    out_feats);
+  SPC_LAUNCHED("plenoxel_decode_kernel");
+  return 0;
+}
+
+int spc_seg_metrics(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_label,
+                    uint64_t* counts, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && C <= 256, "seg_metrics supports 1..256 classes");
+  if (n == 0) return 0;
+  int64_t want = ceil_div(n, 256 * 4);
+  int grid = (int)(want < kNumSMs * 8 ? (want > 0 ? want : 1) : kNumSMs * 8);
+  if (C <= 64)
+    seg_metrics_kernel<64><<<grid, 256, 0, stream>>>(logits, (const long long*)target, n, C, ignore_label,
+                                                      (unsigned long long*)counts);
+  else
+    seg_metrics_kernel<256><<<grid, 256, 0, stream>>>(logits, (const long long*)target, n, C, ignore_label,
+                                                       (unsigned long long*)counts);
+  SPC_LAUNCHED("seg_metrics_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+"""The two ends of the hot path on the GPU (SURVEY.md §8f "next" rows 2 and 3).
+
+`plenoxel_decode` turns one PeRFception plenoxel record (what `COD3D.load_data` reads from disk,
+co3d_3d/src/data/co3d.py:126-172) into the `(coordinates, features)` pair the reference builds on the CPU in
+`__getitem__` (co3d.py:196-203) and hands to `ME.TensorField`; `IoUMeter` is the reference's metric
+(co3d_3d/src/metrics.py:5-58) with the per-class Python loop replaced by one kernel over the logits.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as L
+
+
+def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float, reso: Sequence[int],
+                    batch_index: int = 0, affine: Optional[Sequence[float]] = None):
+    """links [n] int32/int64 (flat cell indices), sh_u8 [n, C] uint8 -> coords [n,4] float32 (b,i,j,k), feats [n,C]
+    float32 = sh * scale + min.  `affine` = 12 floats (row-major 3x3, then translation) applied to (i,j,k)."""
+    lib = L.load()
+    if links.dtype not in (torch.int32, torch.int64) or links.dim() != 1:
+        raise RuntimeError("links must be a 1-D int32 / int64 tensor")
+    if sh_u8.dtype != torch.uint8 or sh_u8.dim() != 2 or sh_u8.shape[0] != links.shape[0]:
+        raise RuntimeError("sh must be uint8 [n, C]")
+    links, sh_u8 = links.contiguous(), sh_u8.contiguous()
+    n, C = sh_u8.shape
+    dev = links.device
+    coords = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    feats = torch.empty((n, C), dtype=torch.float32, device=dev)
+    r = (ctypes.c_int32 * 3)(*[int(v) for v in reso])
+    aff = None
+    if affine is not None:
+        if len(affine) != 12:
+            raise RuntimeError("affine must hold 12 floats (3x3 row-major + translation)")
+        aff = (ctypes.c_float * 12)(*[float(v) for v in affine])
+    L.check(lib.spc_plenoxel_decode(L.ptr(links), int(links.dtype == torch.int64), n, ctypes.cast(r, ctypes.c_void_p),
+                                    int(batch_index), ctypes.cast(aff, ctypes.c_void_p) if aff is not None else None,
+                                    L.ptr(sh_u8), C, float(sh_scale), float(sh_min), L.ptr(coords), L.ptr(feats),
+                                    L.stream()), "spc_plenoxel_decode")
+    return coords, feats
+
+
+def seg_counts(logits: torch.Tensor, target: torch.Tensor, ignore_label: int, out: Optional[torch.Tensor] = None):
+    """counts[3, C] int64 (+= when `out` is given): per class #seen, #correct, #predicted of argmax(logits)."""
+    lib = L.load()
+    if logits.dtype != torch.float32 or logits.dim() != 2:
+        raise RuntimeError("logits must be float32 [n, C]")
+    if target.dtype != torch.int64 or target.shape != (logits.shape[0],):
+        raise RuntimeError("target must be int64 [n]")
+    logits, target = logits.contiguous(), target.contiguous()
+    n, C = logits.shape
+    if out is None:
+        out = torch.zeros((3, C), dtype=torch.int64, device=logits.device)
+    L.check(lib.spc_seg_metrics(L.ptr(logits), L.ptr(target), n, C, int(ignore_label), L.ptr(out), L.stream()),
+            "spc_seg_metrics")
+    return out
+
+
+class IoUMeter:
+    """co3d_3d/src/metrics.py IoUMeter: update() accumulates, compute() -> (miou, ious, mAcc, accs)."""
+
+    def __init__(self, num_classes: int, ignore_label: int, void_label=None):
+        self.num_classes, self.ignore_label, self.void_label = num_classes, ignore_label, void_label
+        self.counts = None
+
+    def update(self, logits: torch.Tensor, targets: torch.Tensor):
+        if self.counts is None:
+            self.counts = torch.zeros((3, self.num_classes), dtype=torch.int64, device=logits.device)
+        seg_counts(logits, targets, self.ignore_label, out=self.counts)
+
+    def compute(self):
+        seen, correct, positive = (self.counts[i].to(torch.float32) for i in range(3))
+        present = seen != 0
+        ious = torch.where(present, correct / (seen + positive - correct).clamp_min(1), torch.zeros_like(seen))
+        accs = torch.where(present, correct / seen.clamp_min(1), torch.zeros_like(seen))
+        if self.void_label is not None:
+            return ious[:-1].mean(), ious, accs[:-1].mean(), accs
+        return ious.mean(), ious, accs.mean(), accs

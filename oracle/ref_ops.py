@@ -318,3 +318,42 @@ class OracleManager:
                 fn = kernel_map_c if self.use_c else kernel_map_np
                 self.kmaps[key] = fn(self.maps[tuple(ts_in)], self.maps[tuple(ts_out)], offs)
         return self.kmaps[key]
+
+
+# ---------------------------------------------------------------------------
+# the two ends of the path
+# ---------------------------------------------------------------------------
+def plenoxel_decode_np(links: np.ndarray, sh_u8: np.ndarray, sh_scale: float, sh_min: float, reso, batch_index=0,
+                       affine=None):
+    """co3d_3d/src/data/co3d.py:196-203 (links -> (i,j,k), trunc division) and :169 (sh.astype(float32) * scale +
+    min); `affine` (12 floats) = 3x3 then translation, products and sums rounded in float32 left to right."""
+    links = links.astype(np.int64)
+    r1, r2 = int(reso[1]), int(reso[2])
+    x = (links // (r1 * r2)).astype(np.float32)
+    y = ((links % (r1 * r2)) // r2).astype(np.float32)
+    z = (links % r2).astype(np.float32)
+    if affine is not None:
+        a = np.asarray(affine, np.float32)
+
+        def row(i):
+            acc = (a[3 * i] * x).astype(np.float32)
+            acc = (acc + (a[3 * i + 1] * y).astype(np.float32)).astype(np.float32)
+            acc = (acc + (a[3 * i + 2] * z).astype(np.float32)).astype(np.float32)
+            return (acc + a[9 + i]).astype(np.float32)
+        x, y, z = row(0), row(1), row(2)
+    coords = np.stack([np.full_like(x, np.float32(batch_index)), x, y, z], 1).astype(np.float32)
+    feats = (sh_u8.astype(np.float32) * np.float32(sh_scale)).astype(np.float32) + np.float32(sh_min)
+    return coords, feats.astype(np.float32)
+
+
+def iou_counts_np(logits: np.ndarray, target: np.ndarray, num_classes: int, ignore_label: int) -> np.ndarray:
+    """IoUMeter.update (co3d_3d/src/metrics.py:29-41) on preds = argmax(logits): [3, C] seen / correct / positive."""
+    preds = logits.argmax(1)
+    valid = target != ignore_label
+    preds, target = preds[valid], target[valid]
+    out = np.zeros((3, num_classes), np.int64)
+    for i in range(num_classes):
+        out[0, i] = (target == i).sum()
+        out[1, i] = np.logical_and(target == i, preds == target).sum()
+        out[2, i] = (preds == i).sum()
+    return out

@@ -497,3 +497,48 @@ def test_cross_entropy_matches_torch(cuda_device, n, C):
     assert abs(loss.item() - ref.item()) <= 1e-5 * (1 + abs(ref.item()))
     err = (x.grad.double().cpu() - 2.5 * ref_in.grad).abs().max().item()
     assert err <= 1e-6 * (1 + (2.5 * ref_in.grad).abs().max().item()), err
+
+
+@pytest.mark.parametrize("n,reso,dtype,with_affine", [(1, (128, 128, 128), torch.int64, False),
+                                                       (5000, (128, 128, 128), torch.int32, True),
+                                                       (200_003, (256, 256, 256), torch.int64, True)])
+def test_plenoxel_decode_exact(cuda_device, n, reso, dtype, with_affine):
+    """links -> (i,j,k) and u8 SH dequantisation (co3d.py:169,196-203): bit-exact against the numpy restatement."""
+    from nerf_downstream_b200 import pipeline
+    rng = np.random.default_rng(n)
+    links = np.sort(rng.choice(reso[0] * reso[1] * reso[2], size=n, replace=False)).astype(np.int64)
+    sh = rng.integers(0, 256, size=(n, 27), dtype=np.uint8)
+    scale, mn = np.float32(2.0 / 255.0), np.float32(-1.0)
+    aff = None
+    if with_affine:
+        th = 0.7
+        aff = [np.cos(th) * 1.1, 0, np.sin(th) * 1.1, 0, 1.1, 0, -np.sin(th) * 1.1, 0, np.cos(th) * 1.1, 3.25, -7.5, 0.125]
+    rc, rf = R.plenoxel_decode_np(links, sh, scale, mn, reso, batch_index=3, affine=aff)
+    c, f = pipeline.plenoxel_decode(torch.from_numpy(links).to(dtype).to(cuda_device), torch.from_numpy(sh).to(cuda_device),
+                                    float(scale), float(mn), reso, batch_index=3, affine=aff)
+    assert (c.cpu().numpy() == rc).all()
+    assert (f.cpu().numpy() == rf).all()
+    # and the decoded record quantises to the voxels it came from (identity affine)
+    if not with_affine:
+        cmap, _, _, _ = ops.coords_insert(c, L.SRC_FLOAT, (1, 1, 1))
+        assert cmap.size == n
+
+
+@pytest.mark.parametrize("n,C", [(1, 20), (100_000, 20), (4097, 51)])
+def test_seg_metrics_match_reference_loop(cuda_device, n, C):
+    """IoUMeter.update (metrics.py:29-41): per-class seen / correct / positive counts, exact; accumulation over calls."""
+    from nerf_downstream_b200 import pipeline
+    g = torch.Generator().manual_seed(n + C)
+    logits = torch.randn(n, C, generator=g)
+    y = torch.randint(0, C, (n,), generator=g)
+    y[torch.rand(n, generator=g) < 0.15] = 255
+    ref = R.iou_counts_np(logits.numpy(), y.numpy(), C, 255)
+    meter = pipeline.IoUMeter(C, 255)
+    meter.update(logits.to(cuda_device), y.to(cuda_device))
+    assert (meter.counts.cpu().numpy() == ref).all()
+    meter.update(logits.to(cuda_device), y.to(cuda_device))
+    assert (meter.counts.cpu().numpy() == 2 * ref).all()
+    miou, ious, macc, accs = meter.compute()
+    seen, cor, pos = (ref[i].astype(np.float64) for i in range(3))
+    want = np.where(seen > 0, cor / np.maximum(seen + pos - cor, 1), 0.0)
+    assert np.allclose(ious.cpu().numpy(), want, atol=1e-6)

@@ -124,3 +124,28 @@ def test_conv_autograd_gradcheck():
     x = torch.randn(c.shape[0], 2, dtype=torch.float64, requires_grad=True)
     w = torch.randn(27, 2, 3, dtype=torch.float64, requires_grad=True)
     assert torch.autograd.gradcheck(lambda a, b: R.conv_forward(a, b, nbr), (x, w))
+
+
+def test_plenoxel_decode_oracle_matches_reference_expressions():
+    """oracle.plenoxel_decode_np against the reference's own torch expressions for links -> coordinates
+    (co3d_3d/src/data/co3d.py:196-203) and the u8 dequantisation (co3d.py:169), evaluated here on the CPU."""
+    import torch
+    reso = [128, 128, 128]
+    rng = np.random.default_rng(0)
+    links = torch.from_numpy(np.sort(rng.choice(128 ** 3, size=4000, replace=False)).astype(np.int64))
+    coordinates = torch.stack([torch.div(links, (reso[1] * reso[2]), rounding_mode="trunc"),
+                               torch.div(links % (reso[1] * reso[2]), reso[2], rounding_mode="trunc"),
+                               links % reso[2]], 1).float()
+    sh = rng.integers(0, 256, size=(4000, 27), dtype=np.uint8)
+    scale, mn = np.float32(2 / 255), np.float32(-1)
+    ref_sh = sh.astype(np.float32) * scale + mn
+    c, f = R.plenoxel_decode_np(links.numpy(), sh, scale, mn, reso, batch_index=2)
+    assert (c[:, 1:] == coordinates.numpy()).all() and (c[:, 0] == 2).all()
+    assert (f == ref_sh).all()
+
+
+def test_iou_counts_oracle_known_answer():
+    logits = np.array([[2., 1, 0], [0, 3, 1], [0, 1, 5], [9, 0, 0], [0, 0, 1]], np.float32)
+    target = np.array([0, 1, 1, 255, 2])
+    out = R.iou_counts_np(logits, target, 3, 255)
+    assert out.tolist() == [[1, 2, 1], [1, 1, 1], [1, 1, 2]]
