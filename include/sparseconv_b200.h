@@ -149,8 +149,10 @@ void spc_debug_force_mt(int mt);
 void spc_debug_set(int idx, int val); /* test hook: wgrad operand-layout knobs, 0 = default */
 int spc_debug_read(long long* host, int n); /* test hook: wgrad role cycle counters -> host buffer */
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
-/* fp32 -> bf16 (round to nearest even) copy of n values; feeds the SPC_PREC_BF16 convolutions. */
-int spc_to_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
+/* fp32 rows -> dense bf16 rows (round to nearest even) for the SPC_PREC_BF16 convolutions: src has `rows` rows of
+ * c_src valid columns at a pitch of src_pitch elements (a column slice of a wider tensor is read in place); dst
+ * is [rows, c_dst] with c_dst >= c_src, columns past c_src zero (channel padding to the tensor-core widths). */
+int spc_to_bf16(const float* src, int64_t rows, int c_src, int64_t src_pitch, int c_dst, void* dst_bf16, void* stream);
 /* `in` / `dout` point to fp32 rows, or to bf16 rows when precision == SPC_PREC_BF16. */
 int spc_conv_fwd(const void* in, const float* w, const float* bias, const int32_t* nbr,
                  const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
@@ -189,8 +191,8 @@ int spc_bn_apply(const float* x, const float* mean, const float* var, const floa
                  const float* beta, const float* residual, int64_t m, int C, float eps,
                  int relu, float* y, void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);
 int spc_bn_bwd(const float* x, const float* y, const void* y_bf16 /* ReLU mask from the bf16 copy of y instead of y, or NULL */,
-               const float* dy, const float* mean,
-               const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+               const float* dy, int64_t dy_pitch /* elements between rows of dy (>= C; a column slice is read in place) */,
+               const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
                int training, float* dx, void* dx_bf16 /* optional bf16 copy of dx, or NULL */,
                float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream);

@@ -23,7 +23,7 @@ int64_t umma_wgrad_workspace(int K, int c_in, int c_out);
 int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
                     int64_t m_out, int c_in, int c_out, int K, bool bf16, float* dw, void* workspace,
                     int64_t workspace_bytes, cudaStream_t stream);
-int to_bf16(const float* src, int64_t n, void* dst, cudaStream_t stream);
+int to_bf16(const float* src, int64_t rows, int c_src, int64_t src_pitch, int c_dst, void* dst, cudaStream_t stream);
 void umma_set_force_mt(int mt);
 void umma_debug_set(int idx, int val);
 int umma_debug_read(long long* host, int n);
@@ -51,8 +51,9 @@ int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision) {
 
 static bool prec_ok(int p) { return p == SPC_PREC_FP32 || p == SPC_PREC_TF32 || p == SPC_PREC_BF16; }
 
-int spc_to_bf16(const float* src, int64_t n, void* dst, void* stream) {
-  return to_bf16(src, n, dst, (cudaStream_t)stream);
+int spc_to_bf16(const float* src, int64_t rows, int c_src, int64_t src_pitch, int c_dst, void* dst, void* stream) {
+  SPC_REQUIRE(rows >= 0 && c_src >= 0 && c_dst >= c_src && src_pitch >= c_src, "bad shape");
+  return to_bf16(src, rows, c_src, src_pitch, c_dst, dst, (cudaStream_t)stream);
 }
 
 int spc_conv_fwd(const void* in, const float* w, const float* bias, const int32_t* nbr,

@@ -137,28 +137,45 @@ pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, 
   }
 }
 
+// fp32 rows (row pitch `src_pitch` elements, c_src valid columns) -> dense bf16 rows of c_dst >= c_src columns
+// (columns past c_src are zero): conversion, de-striding of a column slice and channel padding in one pass.
 __global__ void __launch_bounds__(256)
-to_bf16_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ dst, int vec_ok) {
+to_bf16_kernel(const float* __restrict__ src, long long rows, int c_src, long long src_pitch, int c_dst,
+               __nv_bfloat16* __restrict__ dst, int vec_ok) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n4 = vec_ok ? n / 4 : 0;
-  for (long long q = i0; q < n4; q += stride) {
-    float4 v = reinterpret_cast<const float4*>(src)[q];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(dst)[q] = o;
+  if (vec_ok) {  // 4 columns per thread: c_src, c_dst, src_pitch multiples of 4, pointers aligned
+    const int q_per_row = c_dst / 4;
+    const long long nq = rows * q_per_row;
+    for (long long q = i0; q < nq; q += stride) {
+      const long long r = q / q_per_row;
+      const int c = (int)(q - r * q_per_row) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < c_src) v = *reinterpret_cast<const float4*>(src + r * src_pitch + c);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst + r * c_dst + c) = o;
+    }
+  } else {
+    const long long n = rows * c_dst;
+    for (long long e = i0; e < n; e += stride) {
+      const long long r = e / c_dst;
+      const int c = (int)(e - r * c_dst);
+      dst[e] = __float2bfloat16_rn(c < c_src ? src[r * src_pitch + c] : 0.f);
+    }
   }
-  for (long long q = n4 * 4 + i0; q < n; q += stride) dst[q] = __float2bfloat16_rn(src[q]);
 }
 
-int to_bf16(const float* src, int64_t n, void* dst, cudaStream_t stream) {
-  if (n == 0) return 0;
-  int vec_ok = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0);
-  int64_t want = ceil_div(ceil_div(n, 4), 256);
+int to_bf16(const float* src, int64_t rows, int c_src, int64_t src_pitch, int c_dst, void* dst, cudaStream_t stream) {
+  if (rows == 0 || c_dst == 0) return 0;
+  const int vec_ok = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0) && c_src % 4 == 0 && c_dst % 4 == 0 &&
+                     src_pitch % 4 == 0;
+  const int64_t n = rows * c_dst;
+  int64_t want = ceil_div(vec_ok ? ceil_div(n, 4) : n, 256);
   int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
-  to_bf16_kernel<<<grid, 256, 0, stream>>>(src, n, (__nv_bfloat16*)dst, vec_ok);
+  to_bf16_kernel<<<grid, 256, 0, stream>>>(src, rows, c_src, src_pitch, c_dst, (__nv_bfloat16*)dst, vec_ok);
   SPC_LAUNCHED("to_bf16_kernel");
   return 0;
 }

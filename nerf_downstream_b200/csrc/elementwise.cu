@@ -108,8 +108,8 @@ struct ColFinal {
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(1024)
 col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                  const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, const float* __restrict__ mean, long long m, int C,
-                  int lanes, int rows, int relu, ColFinal fin) {
+                  const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, long long dy_pitch,
+                  const float* __restrict__ mean, long long m, int C, int lanes, int rows, int relu, ColFinal fin) {
   extern __shared__ float sm[];  // [rows][2*C]
   __shared__ bool s_last;
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
@@ -125,7 +125,7 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { float d = xv.v[j] - mu[j]; s0[j] += d; s1[j] += d * d; }
     } else {
-      Vec<VEC> g = Vec<VEC>::load(dy + off);
+      Vec<VEC> g = Vec<VEC>::load(dy + r * dy_pitch + c0);
       if (relu) {
         Vec<VEC> yv = load_mask_rows<VEC>(y, yb, off);
 #pragma unroll
@@ -214,7 +214,8 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 template <int VEC>
 __global__ void __launch_bounds__(1024)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, const float* __restrict__ mean,
+                    const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, long long dy_pitch,
+                    const float* __restrict__ mean,
                     const float* __restrict__ var, const float* __restrict__ gamma,
                     const float* __restrict__ sums /* [2C]: sum dy', sum dy'(x-mean) */,
                     long long m, int C, int lanes, int rows, float eps, int relu, int training,
@@ -233,7 +234,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
   }
   for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
     const long long off = r * C + c0;
-    Vec<VEC> g = Vec<VEC>::load(dy + off);
+    Vec<VEC> g = Vec<VEC>::load(dy + r * dy_pitch + c0);
     if (relu) {
       Vec<VEC> yv = load_mask_rows<VEC>(y, yb, off);
 #pragma unroll
@@ -499,10 +500,11 @@ static BnWs bn_ws(void* workspace, int C) {
 }
 
 static int col_reduce_launch(int mode, const float* x, const float* y, const void* y_bf16, const float* dy,
-                             const float* mean, int64_t m, int C, int relu, ColFinal fin,
+                             int64_t dy_pitch, const float* mean, int64_t m, int C, int relu, ColFinal fin,
                              cudaStream_t stream) {
   int vec = pick_vec(C, x, y, dy);
   if (y_bf16 && ((uintptr_t)y_bf16 % 8)) vec = 1;
+  if (dy && dy_pitch % 4) vec = 1;
   const __nv_bfloat16* yb = (const __nv_bfloat16*)y_bf16;
   RowMap rm = make_row_map(C, vec);
   if (rm.threads > 1024) return fail("col_reduce", "C too large (max 1024 scalar / 4096 vec4)");
@@ -511,8 +513,8 @@ static int col_reduce_launch(int mode, const float* x, const float* y, const voi
   if (smem > 40 * 1024) return fail("col_reduce", "shared memory");
   SPC_CUDA(cudaMemsetAsync(fin.gsum, 0, (size_t)2 * C * 8 + 64, stream));  // sums + ticket counter
   DISPATCH_VEC(vec,
-    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, mean, m, C, rm.lanes, rm.rows, relu, fin);
-    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, mean, m, C, rm.lanes, rm.rows, relu, fin));
+    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, m, C, rm.lanes, rm.rows, relu, fin);
+    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, m, C, rm.lanes, rm.rows, relu, fin));
   SPC_LAUNCHED("col_reduce_kernel");
   return 0;
 }
@@ -528,7 +530,7 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
   fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
   fin.momentum = momentum; fin.eps = 0.f;
-  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, nullptr, m, C, 0, fin, stream);
+  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, m, C, 0, fin, stream);
 }
 
 int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
@@ -557,7 +559,7 @@ int spc_bn_apply(const float* x, const float* mean, const float* var, const floa
   return 0;
 }
 
-int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* dy, const float* mean,
+int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* dy, int64_t dy_pitch, const float* mean,
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
                int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream_) {
@@ -565,22 +567,24 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* 
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
   SPC_REQUIRE(!relu || y || y_bf16, "relu backward needs y (fp32 rows or their bf16 copy)");
+  SPC_REQUIRE(dy_pitch >= C, "dy pitch smaller than C");
   BnWs w = bn_ws(workspace, C);
   float* sums = w.raw;
   ColFinal fin;
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = dbeta; fin.out1 = dgamma; fin.raw = sums;
   fin.run_mean = nullptr; fin.run_var = nullptr; fin.var = var; fin.momentum = 0.f; fin.eps = eps;
-  int rc = col_reduce_launch(1, x, y, y_bf16, dy, mean, m, C, relu, fin, stream);
+  int rc = col_reduce_launch(1, x, y, y_bf16, dy, dy_pitch, mean, m, C, relu, fin, stream);
   if (rc) return rc;
   int vec = pick_vec(C, x, y, dy, dx);
   if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;
   if (dx_bf16 && ((uintptr_t)dx_bf16 % 8)) vec = 1;
   if (y_bf16 && ((uintptr_t)y_bf16 % 8)) vec = 1;
+  if (dy_pitch % 4) vec = 1;
   RowMap rm = make_row_map(C, vec);
   SPC_REQUIRE(rm.threads <= 1024, "C too large");
   int grid = pick_grid(m, rm.rows, 8);
   DISPATCH_VEC(vec, bn_bwd_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
-      x, y, (const __nv_bfloat16*)y_bf16, dy, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx,
+      x, y, (const __nv_bfloat16*)y_bf16, dy, dy_pitch, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx,
       dresidual, (__nv_bfloat16*)dx_bf16));
   SPC_LAUNCHED("bn_bwd_apply_kernel");
   return 0;

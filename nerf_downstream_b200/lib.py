@@ -43,7 +43,7 @@ SIGNATURES = {
     "spc_debug_set": (None, [c_int, c_int]),
     "spc_debug_read": (c_int, [_P, c_int]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
-    "spc_to_bf16": (c_int, [_P, c_int64, _P, _P]),
+    "spc_to_bf16": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_fwd_stats": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
     "spc_bn_finalize": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P]),
@@ -52,7 +52,7 @@ SIGNATURES = {
     "spc_bn_workspace": (c_int64, [c_int64, c_int]),
     "spc_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "spc_bn_apply": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P, _P, _P]),
-    "spc_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "spc_bn_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "spc_relu_fwd": (c_int, [_P, c_int64, _P, _P]),
     "spc_relu_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "spc_add": (c_int, [_P, _P, c_int64, _P, _P]),

@@ -324,6 +324,24 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
 # ---------------------------------------------------------------------------
 # feature-row ops
 # ---------------------------------------------------------------------------
+def _rows_view(x: torch.Tensor):
+    """(tensor, row pitch in elements) for kernels that take a row pitch: a column slice of a wider row-major tensor
+    (what torch.cat's backward hands out) is read in place instead of being copied to a dense tensor first."""
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"features must be float32, got {x.dtype}")
+    if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1] and x.shape[0] > 1:
+        return x, x.stride(0)
+    x = x.contiguous()
+    return x, (x.shape[1] if x.dim() == 2 else 0)
+
+
+def _ptr_rows(x: torch.Tensor):
+    """device pointer of a row-strided CUDA tensor (L.ptr insists on dense tensors)"""
+    if not x.is_cuda:
+        raise RuntimeError("sparseconv_b200 kernels need CUDA tensors (no CPU fallback)")
+    return x.data_ptr()
+
+
 def _feat(x: torch.Tensor) -> torch.Tensor:
     if x.dtype != torch.float32:
         raise RuntimeError(f"features must be float32, got {x.dtype}")
@@ -448,18 +466,23 @@ def _want_bf16_side(m: int, C: int) -> bool:
     return _default_precision == L.PREC_BF16 and C % 32 == 0 and C <= 512 and m > 0
 
 
-def to_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 rows -> bf16 copy (round to nearest even) for the SPC_PREC_BF16 kernels."""
+def to_bf16(x: torch.Tensor, pad_to: int = 0) -> torch.Tensor:
+    """fp32 rows -> dense bf16 copy (round to nearest even) for the SPC_PREC_BF16 kernels, optionally zero-padded
+    to `pad_to` columns; a column slice of a wider tensor is converted in place (no dense fp32 copy first)."""
     lib = L.load()
-    side = _lookup_bf16(x)
+    side = _lookup_bf16(x) if not pad_to or pad_to == x.shape[1] else None
     if side is not None:
         return side
-    x = _feat(x)
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.dim() != 2:
+        raise RuntimeError("to_bf16 expects [rows, C] features")
+    x, pitch = _rows_view(x)
+    m, C = x.shape
+    c_dst = max(C, int(pad_to))
+    out = torch.empty((m, c_dst), dtype=torch.bfloat16, device=x.device)
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_to_bf16(L.ptr(x), x.numel(), L.ptr(out), L.stream()), "spc_to_bf16")
+    L.check(lib.spc_to_bf16(_ptr_rows(x), m, C, pitch, c_dst, L.ptr(out), L.stream()), "spc_to_bf16")
     if e0 is not None:
-        _profiler.end("to_bf16", e0, 0, 6.0 * x.numel())
+        _profiler.end("to_bf16", e0, 0, 4.0 * m * C + 2.0 * m * c_dst)
     return out
 
 
@@ -575,14 +598,15 @@ class SparseConvFn(torch.autograd.Function):
             precision = L.PREC_TF32  # shapes the bf16 kernels are not built for
         if precision != L.PREC_FP32 and K <= 32 and big:
             pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
-        if pad_in:
+        if pad_in and precision != L.PREC_BF16:
             x = torch.nn.functional.pad(x, (0, pad_in))
         if pad_in or pad_out:
             w3 = torch.nn.functional.pad(w3, (0, pad_out, 0, pad_in))
             if b is not None and pad_out:
                 b = torch.nn.functional.pad(b, (0, pad_out))
         if precision == L.PREC_BF16:
-            x = to_bf16(x)  # the bf16 copy is what backward needs too (half the saved bytes)
+            # conversion and channel padding in one pass; the bf16 copy is what backward needs too
+            x = to_bf16(x, pad_to=c_in + pad_in)
         out = conv_fwd_raw(x, w3, b, km, precision, want_stats=not pad_out)
         if pad_out:
             out = out[:, :c_out].contiguous()
@@ -599,14 +623,15 @@ class SparseConvFn(torch.autograd.Function):
         x, w3 = ctx.saved_tensors
         km, prec = ctx.km, ctx.precision
         c_in, c_out, pad_in, pad_out = ctx.dims
-        g = _feat(g)
         dx = dw = db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0).view(ctx.bias_shape)
-        if pad_out:
-            g = torch.nn.functional.pad(g, (0, pad_out))
         if prec == L.PREC_BF16:
-            g = to_bf16(g)
+            g = to_bf16(g, pad_to=c_out + pad_out)  # converts, de-strides and pads in one pass
+        else:
+            g = _feat(g)
+            if pad_out:
+                g = torch.nn.functional.pad(g, (0, pad_out))
         if ctx.needs_input_grad[0]:
             dx = conv_dgrad_raw(g, w3, km, prec)
             if pad_in:
@@ -675,7 +700,7 @@ class BatchNormFn(torch.autograd.Function):
         lib = L.load()
         x, y, mean, var, gamma = ctx.saved_tensors
         eps, relu, use_batch, has_res, affine = ctx.cfg
-        dy = _feat(dy)
+        dy, dy_pitch = _rows_view(dy)
         m, C = x.shape
         dev = x.device
         ws_bytes = int(lib.spc_bn_workspace(m, C))
@@ -687,7 +712,8 @@ class BatchNormFn(torch.autograd.Function):
         dbeta = _empty(C, torch.float32, dev)
         e0 = _profiler.begin() if _profiler else None
         y32, y16 = (None, y) if (y is not None and y.dtype == torch.bfloat16) else (y, None)
-        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y32), L.ptr(y16), L.ptr(dy), L.ptr(mean), L.ptr(var), L.ptr(gamma), m, C, eps,
+        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y32), L.ptr(y16), _ptr_rows(dy), dy_pitch, L.ptr(mean), L.ptr(var),
+                               L.ptr(gamma), m, C, eps,
                                relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
                                L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
         if dxb is not None:

@@ -542,3 +542,25 @@ def test_seg_metrics_match_reference_loop(cuda_device, n, C):
     seen, cor, pos = (ref[i].astype(np.float64) for i in range(3))
     want = np.where(seen > 0, cor / np.maximum(seen + pos - cor, 1), 0.0)
     assert np.allclose(ious.cpu().numpy(), want, atol=1e-6)
+
+
+def test_row_pitch_inputs(cuda_device):
+    """Kernels that take a row pitch read a column slice of a wider tensor in place (what torch.cat's backward hands
+    out): bf16 conversion (+ channel padding) and BatchNorm backward must equal the dense-copy results bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    wide = torch.randn(5000, 128, generator=g).to(cuda_device)
+    sl = wide[:, 32:128]  # 96 of 128 columns, pitch 128
+    assert not sl.is_contiguous()
+    assert bool((ops.to_bf16(sl) == sl.contiguous().to(torch.bfloat16)).all())
+    x27 = torch.randn(4097, 27, generator=g).to(cuda_device)
+    p = ops.to_bf16(x27, pad_to=32)
+    assert p.shape == (4097, 32) and bool((p[:, :27] == x27.to(torch.bfloat16)).all()) and bool((p[:, 27:] == 0).all())
+    x = torch.randn(5000, 96, generator=g).to(cuda_device)
+    gam, bet = torch.rand(96, generator=g).to(cuda_device) + 0.5, torch.randn(96, generator=g).to(cuda_device)
+
+    def bn_grads(dy):
+        xg = x.clone().requires_grad_()
+        out = ops.BatchNormFn.apply(xg, gam, bet, torch.zeros(96, device=cuda_device), torch.ones(96, device=cuda_device),
+                                    True, 0.1, 1e-5, True, None)
+        return torch.autograd.grad(out, xg, dy)[0]
+    assert bool((bn_grads(sl) == bn_grads(sl.contiguous())).all())
