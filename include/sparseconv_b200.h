@@ -146,7 +146,9 @@ int spc_scatter_add_rows(const float* src, const int32_t* index, int64_t n, int6
  *   workspace: spc_conv_workspace(...) bytes (packed weights for the TF32 path).
  */
 void spc_debug_force_mt(int mt);
-void spc_debug_set(int idx, int val); /* test hook: wgrad operand-layout knobs, 0 = default */
+void spc_debug_set(int idx, int val); /* test / measurement hook, every knob 0 = default: 1 wgrad dout by LDGSTS instead of
+                                        * TMA, 2 no TMA-store epilogue, 3 epilogue writes nothing (timing only, wrong results),
+                                        * 4-6 wgrad skip-MMA / skip-gather / skip-parts (timing only, wrong results) */
 int spc_debug_read(long long* host, int n); /* test hook: wgrad role cycle counters -> host buffer */
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
 /* fp32 rows -> dense bf16 rows (round to nearest even) for the SPC_PREC_BF16 convolutions: src has `rows` rows of
