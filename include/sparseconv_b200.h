@@ -237,6 +237,17 @@ int spc_ce_bwd(const float* grad_raw, const double* stats, const float* grad_out
                float* dlogits, void* stream);
 
 
+/* ---- max pooling (ME.MinkowskiMaxPooling / MinkowskiGlobalMaxPooling) --------------------
+ * local: out[o, c] = max over present neighbours of the kernel map, arg[o, c] = winning input row (-1: none);
+ * backward routes dout to the winning rows (din zeroed inside).  global: per batch index, rows found through
+ * coords[:, 0]; arg[b, c] = first row attaining the maximum; backward = spc_pool_max_bwd with m_out = n_batch. */
+int spc_pool_max_fwd(const float* in, const int32_t* nbr, int64_t m_out, int C, int K, float* out, int32_t* arg,
+                     void* stream);
+int spc_pool_max_bwd(const float* dout, const int32_t* arg, int64_t m_out, int64_t m_in, int C, float* din,
+                     void* stream);
+int spc_global_max_fwd(const float* in, const int32_t* coords, int64_t m, int C, int n_batch, float* out,
+                       int32_t* arg, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- the two ends of the path (SURVEY.md §8f "next" rows 2 and 3) ------------------------------------------
  * spc_plenoxel_decode: one PeRFception plenoxel record -> network input (co3d_3d/src/data/co3d.py:164-172,196-203).
  *   links[n] (int32 or int64 flat indices of the occupied cells of a reso[0] x reso[1] x reso[2] grid) ->

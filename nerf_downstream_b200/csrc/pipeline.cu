@@ -87,6 +87,77 @@ seg_metrics_kernel(const float* __restrict__ logits, const long long* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------
+// max pooling (ME.MinkowskiMaxPooling / MinkowskiGlobalMaxPooling of the other backbones)
+// ---------------------------------------------------------------------------
+// out[o, c] = max over the present neighbours nbr[k, o] of in[., c]; arg[o, c] = the input row that won (lowest k on
+// ties, -1 / 0 when the output row has no neighbour).  One thread per (output row, channel).
+__global__ void __launch_bounds__(256)
+pool_max_fwd_kernel(const float* __restrict__ in, const int* __restrict__ nbr, long long m_out, int C, int K,
+                    float* __restrict__ out, int* __restrict__ arg) {
+  const long long total = m_out * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long o = e / C;
+    const int c = (int)(e - o * C);
+    float best = 0.f;
+    int who = -1;
+    for (int k = 0; k < K; ++k) {
+      const int i = nbr[(long long)k * m_out + o];
+      if (i < 0) continue;
+      const float v = in[(long long)i * C + c];
+      if (who < 0 || v > best) { best = v; who = i; }
+    }
+    out[e] = best;
+    arg[e] = who;
+  }
+}
+
+// din[arg[o, c], c] += dout[o, c]   (din zeroed by the wrapper; regions may overlap when kernel > stride)
+__global__ void __launch_bounds__(256)
+pool_max_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, long long total, int C,
+                    float* __restrict__ din) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = arg[e];
+    if (i >= 0) atomicAdd(din + (long long)i * C + (e % C), dout[e]);
+  }
+}
+
+// order-preserving float <-> unsigned encoding for atomicMax
+__device__ __forceinline__ unsigned enc_f(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__global__ void __launch_bounds__(256)
+global_max_pass1_kernel(const float* __restrict__ in, const int4* __restrict__ coords, long long total, int C,
+                        int n_batch, unsigned* __restrict__ best) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / C;
+    const int b = coords[r].x;
+    if (b >= 0 && b < n_batch) atomicMax(best + (long long)b * C + (e - r * C), enc_f(in[e]));
+  }
+}
+__global__ void __launch_bounds__(256)
+global_max_pass2_kernel(const float* __restrict__ in, const int4* __restrict__ coords, long long total, int C,
+                        int n_batch, const unsigned* __restrict__ best, int* __restrict__ arg) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / C;
+    const int b = coords[r].x;
+    if (b >= 0 && b < n_batch && enc_f(in[e]) == best[(long long)b * C + (e - r * C)])
+      atomicMin(arg + (long long)b * C + (e - r * C), (int)r);  // first row attaining the maximum
+  }
+}
+__global__ void __launch_bounds__(256)
+global_max_finish_kernel(const unsigned* __restrict__ best, int* __restrict__ arg, int n, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const bool any = arg[e] != 0x7F7F7F7F;
+  out[e] = any ? dec_f(best[e]) : 0.f;
+  if (!any) arg[e] = -1;
+}
+
 }  // namespace spc
 
 using namespace spc;
@@ -134,4 +205,51 @@ int spc_seg_metrics(const float* logits, const int64_t* target, int64_t n, int C
   return 0;
 }
 
+int spc_pool_max_fwd(const float* in, const int32_t* nbr, int64_t m_out, int C, int K, float* out, int32_t* arg,
+                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && K >= 1, "bad shape");
+  if (m_out == 0) return 0;
+  int64_t want = ceil_div(m_out * C, 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  pool_max_fwd_kernel<<<grid, 256, 0, stream>>>(in, nbr, m_out, C, K, out, arg);
+  SPC_LAUNCHED("pool_max_fwd_kernel");
+  return 0;
+}
+
+int spc_pool_max_bwd(const float* dout, const int32_t* arg, int64_t m_out, int64_t m_in, int C, float* din,
+                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_CUDA(cudaMemsetAsync(din, 0, (size_t)m_in * C * sizeof(float), stream));
+  if (m_out == 0) return 0;
+  int64_t want = ceil_div(m_out * C, 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  pool_max_bwd_kernel<<<grid, 256, 0, stream>>>(dout, arg, m_out * C, C, din);
+  SPC_LAUNCHED("pool_max_bwd_kernel");
+  return 0;
+}
+
+int spc_global_max_fwd(const float* in, const int32_t* coords, int64_t m, int C, int n_batch, float* out,
+                       int32_t* arg, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(C >= 1 && n_batch >= 1, "bad shape");
+  SPC_REQUIRE(workspace && workspace_bytes >= (int64_t)n_batch * C * 4, "workspace too small (n_batch * C * 4 bytes)");
+  unsigned* best = (unsigned*)workspace;
+  SPC_CUDA(cudaMemsetAsync(best, 0, (size_t)n_batch * C * 4, stream));      // below every encoded float
+  SPC_CUDA(cudaMemsetAsync(arg, 0x7F, (size_t)n_batch * C * 4, stream));    // 0x7F7F7F7F > any row index
+  const int64_t total = m * C;
+  int64_t want = ceil_div(total > 0 ? total : 1, 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  if (total > 0) {
+    global_max_pass1_kernel<<<grid, 256, 0, stream>>>(in, (const int4*)coords, total, C, n_batch, best);
+    SPC_LAUNCHED("global_max_pass1_kernel");
+    global_max_pass2_kernel<<<grid, 256, 0, stream>>>(in, (const int4*)coords, total, C, n_batch, best, arg);
+    SPC_LAUNCHED("global_max_pass2_kernel");
+  }
+  global_max_finish_kernel<<<(n_batch * C + 255) / 256, 256, 0, stream>>>(best, arg, n_batch * C, out);
+  SPC_LAUNCHED("global_max_finish_kernel");
+  return 0;
+}
+
 }  // extern "C"
+

@@ -361,8 +361,16 @@ class MinkowskiAvgPooling(MinkowskiLocalPoolingBase):
 
 
 class MinkowskiMaxPooling(MinkowskiLocalPoolingBase):
-    def forward(self, input, coordinates=None):
-        raise NotImplementedError("MinkowskiMaxPooling is outside the built hot path (SURVEY.md §8f rank 4)")
+    """Max over the kernel region (the existing neighbours of every output voxel), gradient to the arg-max rows."""
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        in_key = input.coordinate_map_key
+        out_key = mgr.stride(in_key, self.kernel_generator.kernel_stride)
+        km = mgr.get_kernel_map(in_key, out_key, self.kernel_generator, is_pool=True)
+        out = ops.LocalMaxPoolFn.apply(input.F, km)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
 
 
 class MinkowskiGlobalPooling(MinkowskiModuleBase):
@@ -395,9 +403,18 @@ class MinkowskiGlobalSumPooling(MinkowskiGlobalPooling):
 class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
     def __init__(self, mode=None):
         super().__init__()
+        self.pooling_mode = mode
 
-    def forward(self, input):
-        raise NotImplementedError("MinkowskiGlobalMaxPooling is outside the built hot path (SURVEY.md §8f rank 4)")
+    def forward(self, input: SparseTensor):
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        out_key = mgr.origin()
+        nb = mgr.size(out_key)
+        out = ops.GlobalMaxPoolFn.apply(input.F, input.C, nb)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "()"
 
 
 # ---------------------------------------------------------------------------

@@ -806,6 +806,63 @@ class LocalPoolFn(torch.autograd.Function):
         return din, None, None
 
 
+class LocalMaxPoolFn(torch.autograd.Function):
+    """Max pooling over a kernel-map region (ME.MinkowskiMaxPooling); backward routes to the arg-max rows."""
+
+    @staticmethod
+    def forward(ctx, x, km):
+        lib = L.load()
+        x = _feat(x)
+        C = x.shape[1]
+        out = _empty((km.m_out, C), torch.float32, x.device)
+        arg = _empty((km.m_out, C), torch.int32, x.device)
+        L.check(lib.spc_pool_max_fwd(L.ptr(x), L.ptr(km.nbr), km.m_out, C, km.K, L.ptr(out), L.ptr(arg), L.stream()),
+                "spc_pool_max_fwd")
+        ctx.save_for_backward(arg)
+        ctx.m_in = km.m_in
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        (arg,) = ctx.saved_tensors
+        g = _feat(g)
+        m_out, C = g.shape
+        din = _empty((ctx.m_in, C), torch.float32, g.device)
+        L.check(lib.spc_pool_max_bwd(L.ptr(g), L.ptr(arg), m_out, ctx.m_in, C, L.ptr(din), L.stream()),
+                "spc_pool_max_bwd")
+        return din, None
+
+
+class GlobalMaxPoolFn(torch.autograd.Function):
+    """Per-batch-index maximum over all rows (ME.MinkowskiGlobalMaxPooling)."""
+
+    @staticmethod
+    def forward(ctx, x, coords, n_batch):
+        lib = L.load()
+        x = _feat(x)
+        m, C = x.shape
+        out = _empty((n_batch, C), torch.float32, x.device)
+        arg = _empty((n_batch, C), torch.int32, x.device)
+        ws_bytes = n_batch * C * 4
+        ws = _workspace(ws_bytes, x.device)
+        L.check(lib.spc_global_max_fwd(L.ptr(x), L.ptr(coords), m, C, n_batch, L.ptr(out), L.ptr(arg), L.ptr(ws),
+                                       ws_bytes, L.stream()), "spc_global_max_fwd")
+        ctx.save_for_backward(arg)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        (arg,) = ctx.saved_tensors
+        g = _feat(g)
+        nb, C = g.shape
+        din = _empty((ctx.m, C), torch.float32, g.device)
+        L.check(lib.spc_pool_max_bwd(L.ptr(g), L.ptr(arg), nb, ctx.m, C, L.ptr(din), L.stream()), "spc_pool_max_bwd")
+        return din, None, None
+
+
 class GlobalPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, coords, n_batch, avg):

@@ -357,3 +357,34 @@ def iou_counts_np(logits: np.ndarray, target: np.ndarray, num_classes: int, igno
         out[1, i] = np.logical_and(target == i, preds == target).sum()
         out[2, i] = (preds == i).sum()
     return out
+
+
+def pool_max_np(x: np.ndarray, nbr: np.ndarray):
+    """Max pooling over a kernel-map region (ME.MinkowskiMaxPooling semantics: maximum over the EXISTING neighbours
+    of each output voxel): returns (out [M_out, C], arg [M_out, C] = winning input row, -1 when there is none)."""
+    K, m_out = nbr.shape
+    C = x.shape[1]
+    out = np.zeros((m_out, C), x.dtype)
+    arg = np.full((m_out, C), -1, np.int64)
+    for o in range(m_out):
+        rows = nbr[:, o][nbr[:, o] >= 0]
+        if rows.size:
+            vals = x[rows]                      # [n, C], in offset order
+            w = vals.argmax(0)                  # first maximum = lowest offset index
+            out[o] = vals[w, np.arange(C)]
+            arg[o] = rows[w]
+    return out, arg
+
+
+def global_max_np(x: np.ndarray, batch: np.ndarray, n_batch: int):
+    """Per-batch-index maximum (ME.MinkowskiGlobalMaxPooling): (out [B, C], arg [B, C] = first row attaining it)."""
+    C = x.shape[1]
+    out = np.zeros((n_batch, C), x.dtype)
+    arg = np.full((n_batch, C), -1, np.int64)
+    for b in range(n_batch):
+        rows = np.nonzero(batch == b)[0]
+        if rows.size:
+            w = x[rows].argmax(0)
+            out[b] = x[rows][w, np.arange(C)]
+            arg[b] = rows[w]
+    return out, arg

@@ -564,3 +564,37 @@ def test_row_pitch_inputs(cuda_device):
                                     True, 0.1, 1e-5, True, None)
         return torch.autograd.grad(out, xg, dy)[0]
     assert bool((bn_grads(sl) == bn_grads(sl.contiguous())).all())
+
+
+def test_max_pooling_matches_oracle(cuda_device):
+    """MinkowskiMaxPooling (k = 2 and 3, stride 2) and MinkowskiGlobalMaxPooling: values exact, gradient routed to the
+    arg-max rows (numpy restatement)."""
+    from nerf_downstream_b200 import me as ME
+    coords, feats = synth.random_cloud(9, 6000, extent=14, n_batch=3, channels=16)
+    x = ME.TensorField(coordinates=gpu(coords, cuda_device), features=gpu(feats, cuda_device)).sparse()
+    xf = x.F.detach().cpu().numpy()
+    xc = x.C.cpu().numpy()
+    for ks in (2, 3):
+        xin = ME.SparseTensor(x.F.detach().clone().requires_grad_(), coordinate_map_key=x.coordinate_map_key,
+                              coordinate_manager=x.coordinate_manager)
+        y = ME.MinkowskiMaxPooling(kernel_size=ks, stride=2, dimension=3)(xin)
+        out_c = y.C.cpu().numpy()
+        offs = R.kernel_offsets((ks,) * 3, (1, 1, 1))
+        nbr = R.kernel_map_np(xc, out_c, offs)
+        ref, arg = R.pool_max_np(xf, nbr)
+        assert (y.F.detach().cpu().numpy() == ref).all()
+        go = torch.randn(y.F.shape, generator=torch.Generator().manual_seed(ks))
+        y.F.backward(go.to(cuda_device))
+        want = np.zeros_like(xf)
+        np.add.at(want, (arg[arg >= 0], np.nonzero(arg >= 0)[1]), go.numpy()[arg >= 0])
+        assert np.allclose(xin.F.grad.cpu().numpy(), want, atol=1e-6)
+    xin = ME.SparseTensor(x.F.detach().clone().requires_grad_(), coordinate_map_key=x.coordinate_map_key,
+                          coordinate_manager=x.coordinate_manager)
+    g = ME.MinkowskiGlobalMaxPooling()(xin)
+    ref, arg = R.global_max_np(xf, xc[:, 0], 3)
+    assert (g.F.detach().cpu().numpy() == ref).all()
+    go = torch.randn(3, 16, generator=torch.Generator().manual_seed(1))
+    g.F.backward(go.to(cuda_device))
+    want = np.zeros_like(xf)
+    want[arg, np.arange(16)[None, :].repeat(3, 0)] = go.numpy()
+    assert np.allclose(xin.F.grad.cpu().numpy(), want, atol=1e-6)
