@@ -60,10 +60,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// long waits (an epilogue warp waiting for a whole tile): back off between probes so the spinning
-// warp does not compete with the producer / MMA warps for issue slots and the barrier unit
+// long waits (an epilogue warp waiting for a whole tile): try_wait with a suspend-time hint, so that the
+// hardware parks the warp instead of letting it re-issue the probe every few cycles (the spinning
+// epilogue warps were a third of all instructions the forward kernel issued) and does not compete with
+// the producer / MMA warps of its scheduler for issue slots
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
 }
 
 // ---- cp.async (LDGSTS) ----------------------------------------------------------
