@@ -11,22 +11,29 @@
 //          64-byte rows (SWIZZLE_64B), 2 MMAs (K=16) per row chunk: half the gather bytes and twice
 //          the MMA rate.  Accumulation is fp32 in TMEM in both.
 //
-// One persistent CTA per SM, warp-specialised (every role is latency-bound on instruction issue when
-// it is alone on its scheduler, so the gather runs on two producer warps per scheduler):
-//   warps 0-7   producers : gather rows with 16-byte cp.async (LDGSTS, zero-fill for missing
-//                           neighbours) straight into the swizzled UMMA layout; forward weights arrive
-//                           as ONE TMA bulk copy (UBLKCP) of a pre-swizzled slab per stage.  "Full"
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-7   producers : ONE WARP PER PIPELINE STAGE.  Stage n is filled entirely by producer warp
+//                           n mod 8: it prefetches the stage's neighbour indices, waits for its ring slot,
+//                           gathers the rows with 16-byte cp.async (LDGSTS, zero-fill for missing
+//                           neighbours) straight into the swizzled UMMA layout and brings the stage's
+//                           weights as ONE TMA bulk copy (UBLKCP) of a pre-swizzled slab.  "Full"
 //                           barriers are signalled by the hardware (cp.async.mbarrier.arrive.noinc):
-//                           no wait_group / proxy fence on the producer side, it only waits for slots;
-//   warps 8-11  epilogue  : tcgen05.ld the fp32 accumulator (32 TMEM lanes per warp), bias, store
-//                           (wgrad: fp32 red.global.add.v4 of the partial dW);
-//   warp  12    MMA       : one elected lane issues tcgen05.mma and commits stage release /
-//                           accumulator completion to mbarriers.
-// Forward: a CTA tile is MT x 128 output rows (MT accumulators share every weight slab); accumulators
-// are double-buffered in TMEM when they fit in 512 columns so the epilogue of tile i overlaps the main
-// loop of tile i+1.  A pipeline stage is one (offset k, 32-channel chunk) pair.  Offsets with no
-// neighbour inside a tile are skipped using the per-tile offset mask (spc_tile_mask).  Output rows are
-// owned by one CTA: no atomics in forward / dgrad.
+//                           no wait_group / proxy fence on the producer side, it only waits for slots.
+//                           (wgrad: one warp per A stage + dedicated warps that bring the contiguous
+//                           dout row blocks with TMA tile loads.)
+//   warps 8-11  epilogue  : tcgen05.ld the fp32 accumulator (32 TMEM lanes per warp), bias, 16-byte
+//                           conflict-free stores into a 128B-swizzled shared-memory tile, TMA tensor
+//                           store (reduce-add on offset-split items) — no st.global, the LSU belongs to
+//                           the gather (wgrad: fp32 red.global.add.v4 of the partial dW);
+//   warp  12    MMA       : one ELECTED thread (elect.sync) runs the whole issue loop: tcgen05.mma from
+//                           uniform registers, tcgen05.commit for stage release / accumulator completion.
+// Forward: a work item is MT x 128 output rows x cn_tile channels (MT accumulators share every weight
+// slab), on small maps x one group of kernel offsets; accumulators are double-buffered in TMEM when they
+// fit in 512 columns so the epilogue of tile i overlaps the main loop of tile i+1.  A pipeline stage is
+// one (offset k, 32-channel chunk) pair.  Offsets with no neighbour inside a tile are skipped using the
+// per-tile offset mask (spc_tile_mask).  On large maps output rows are owned by one CTA: no atomics in
+// forward / dgrad.  What bounds it (profiles/): the LSU / shared-memory pipe shared by the LDGSTS gather,
+// any epilogue stores and even UTCHMMA issue — which is why everything except the gather stays off it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -707,7 +714,7 @@ void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_dbg[idx] = va
 // uses SWIZZLE_64B; LBO = distance between 32-element column groups, SBO = distance between 4- (tf32)
 // / 8-row (bf16) groups = 512 B either way.
 // A pipeline step covers kRows = 64 (tf32) / 128 (bf16) out rows of ONE M block: 4 chunk blocks of
-// 8 KB.  TMEM holds floor(512 / Cout) accumulators; a work item = (row range, pass over a group of
+// 8 KB (halving the bf16 step to 64 rows was measured 27 % slower: the per-step costs dominate).  TMEM holds floor(512 / Cout) accumulators; a work item = (row range, pass over a group of
 // M blocks) and ends with an fp32 red.global.add of its partial dW — the only atomics of the
 // convolution path.
 constexpr int kWgChunkBlock = 8192;              // [kRows x row chunk]
