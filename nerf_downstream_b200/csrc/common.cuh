@@ -85,21 +85,27 @@ __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
   return k;
 }
 
+// One 256-bit read-only load (LDG.E.256, sm_100+): a whole 32-byte bucket = both slots in ONE instruction and
+// one L1 tag look-up.  The probes are fully divergent, so the kernel-map builder is bound by L1 tag throughput
+// (one sector per clock and SM): two LDG.128 per probe cost twice as much.
+__device__ __forceinline__ void ldg256(const void* p, unsigned long long (&v)[4]) {
+  asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
+               : "l"(p));
+}
+
 // Read-only probe of a 2-slot bucket table.  Returns map row or -1.
 __device__ __forceinline__ int table_lookup(const Slot* __restrict__ slots,
                                             unsigned long long bucket_mask,
                                             unsigned long long key) {
   unsigned long long b = hash_key(key) & bucket_mask;
-  const uint4* base = reinterpret_cast<const uint4*>(slots);
   for (;;) {
-    uint4 s0 = __ldg(base + 2 * b);
-    uint4 s1 = __ldg(base + 2 * b + 1);
-    unsigned long long k0 = ((unsigned long long)s0.y << 32) | s0.x;
-    unsigned long long k1 = ((unsigned long long)s1.y << 32) | s1.x;
-    if (k0 == key) return (int)s0.w;
-    if (k1 == key) return (int)s1.w;
+    unsigned long long v[4];  // {key0, first0 | row0 << 32, key1, first1 | row1 << 32}
+    ldg256(slots + 2 * b, v);
+    if (v[0] == key) return (int)(v[1] >> 32);
+    if (v[2] == key) return (int)(v[3] >> 32);
     // slots of a bucket fill in order and nothing is ever deleted
-    if (k0 == kEmptyKey || k1 == kEmptyKey) return -1;
+    if (v[0] == kEmptyKey || v[2] == kEmptyKey) return -1;
     b = (b + 1) & bucket_mask;
   }
 }
