@@ -149,3 +149,35 @@ def test_iou_counts_oracle_known_answer():
     target = np.array([0, 1, 1, 255, 2])
     out = R.iou_counts_np(logits, target, 3, 255)
     assert out.tolist() == [[1, 2, 1], [1, 1, 1], [1, 1, 2]]
+
+
+def test_iou_counts_oracle_matches_reference_update_loop():
+    """oracle.iou_counts_np against the body of IoUMeter.update (co3d_3d/src/metrics.py:29-41) evaluated with torch."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    num_classes, ignore_label = 7, 255
+    logits = torch.randn(5000, num_classes, generator=g)
+    targets = torch.randint(0, num_classes, (5000,), generator=g)
+    targets[torch.rand(5000, generator=g) < 0.2] = ignore_label
+    preds = logits.argmax(1)
+    total_seen, total_correct, total_positive = (torch.zeros(num_classes) for _ in range(3))
+    valid = targets != ignore_label
+    p, t = preds[valid], targets[valid]
+    for i in range(num_classes):
+        total_seen[i] += (t == i).sum()
+        total_correct[i] += torch.logical_and(t == i, p == t).float().sum()
+        total_positive[i] += (p == i).sum()
+    out = R.iou_counts_np(logits.numpy(), targets.numpy(), num_classes, ignore_label)
+    assert (out[0] == total_seen.numpy()).all() and (out[1] == total_correct.numpy()).all()
+    assert (out[2] == total_positive.numpy()).all()
+
+
+def test_max_pool_oracle_known_answers():
+    x = np.array([[1., 5], [3, 2], [0, 9]], np.float32)
+    nbr = np.array([[0, -1], [1, 2]])                     # out row 0 <- rows {0, 1}, out row 1 <- row {2}
+    out, arg = R.pool_max_np(x, nbr)
+    assert out.tolist() == [[3, 5], [0, 9]] and arg.tolist() == [[1, 0], [2, 2]]
+    out, arg = R.pool_max_np(x, np.array([[-1], [-1]]))    # no neighbour at all: zeros, arg -1
+    assert out.tolist() == [[0, 0]] and arg.tolist() == [[-1, -1]]
+    out, arg = R.global_max_np(x, np.array([0, 0, 1]), 3)  # batch 2 is empty
+    assert out.tolist() == [[3, 5], [0, 9], [0, 0]] and arg.tolist() == [[1, 0], [2, 2], [-1, -1]]
