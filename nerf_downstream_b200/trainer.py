@@ -122,11 +122,12 @@ class DataParallelTrainer:
 
 
 def cosine_lr(base_lr: float, step: int, max_steps: int, eta_min: float = 0.0) -> float:
-    """CosineAnnealingLR (co3d_3d/src/modules/optim.py:103-120)."""
-    import math
-    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * min(step, max_steps) / max_steps)) / 2
+    """CosineAnnealingLR (co3d_3d/src/modules/optim.py:103-120); see `schedules.cosine`."""
+    from . import schedules
+    return schedules.cosine(base_lr, max_steps, eta_min).lr(step)
 
 
 def poly_lr(base_lr: float, step: int, max_steps: int, power: float = 0.9) -> float:
-    """PolyLR (co3d_3d/src/modules/optim.py:190-204)."""
-    return base_lr * (1 - min(step, max_steps - 1) / max_steps) ** power
+    """PolyLR = base_lr * (1 - step / (max_steps + 1)) ** power (optim.py:181-204); see `schedules.poly`."""
+    from . import schedules
+    return schedules.poly(base_lr, max_steps, power).lr(step)

@@ -1,0 +1,472 @@
+"""Trainer + config parity for the hot path.
+
+What the reference's Lightning glue computes around the sparse network, restated as a plain loop over the
+data-parallel step of `trainer.DataParallelTrainer` — same configuration names (`train.*` gin bindings,
+co3d_3d/train.py:50-96), same losses, metrics, schedules and checkpoint layout, so that a `*.gin` file of the
+reference drives a run here and a Lightning checkpoint of the reference evaluates here:
+
+  * losses   — `F.cross_entropy` (classification_training.py:33) and `SegLoss` (segmentation_training.py:27-44:
+               class weights all one except an optional `void_weight` on the LAST class, `ignore_index`), with the
+               `use_sync_grad` re-weighting by point counts (segmentation_training.py:112-120);
+  * metrics  — top-1 / top-5 (classification_training.py:82-97 and torchmetrics `Accuracy`), overall accuracy and
+               mIoU of a step (`_eval_metrics`, segmentation_training.py:230-239 with utils/__init__.py:103-130),
+               the epoch `IoUMeter` (metrics.py:5-58; the counting kernel lives in `pipeline.py`);
+  * schedule — `schedules.get_schedule`, stepped once per optimiser step, total steps = max_steps + warm-up
+               (train.py:175);
+  * checkpoints — Lightning layout `{"state_dict": {"model.<key>": ...}, "optimizer_states": [...],
+               "lr_schedulers": [...], "global_step", "epoch"}` (eval.py:47-67, lightning_module_base.py:75-105),
+               incl. `convert_self_supervised_checkpoint` (lightning_module_base.py:62-72).
+
+Datasets, augmentations, loggers and the Lightning runtime itself stay out of scope: batches are
+whatever iterable of `{"coordinates", "features", "labels"}` dicts the caller provides (`data/utils.py:25-50`).
+Nothing here falls back to a CPU model: the network runs through the CUDA library or not at all.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from collections import OrderedDict
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ginlite, schedules
+
+EPS = 1e-10     # utils/__init__.py:7
+
+
+# ---- metrics -------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def accuracy_topk(output: torch.Tensor, target: torch.Tensor, topk: Sequence[int] = (1,)) -> List[float]:
+    """Percent of rows whose target is among the k largest logits (classification_training.py:82-97)."""
+    maxk = min(max(topk), output.shape[1])          # (the reference raises with fewer than max(topk) classes)
+    batch_size = target.size(0)
+    _, pred = output.topk(maxk, 1, True, True)
+    correct = pred.t().eq(target.view(1, -1))
+    return [correct[:k].flatten().float().sum().mul(100.0 / batch_size).item() for k in topk]
+
+
+@torch.no_grad()
+def precision_at_one(pred: torch.Tensor, target: torch.Tensor, ignore_label: int = 255) -> float:
+    """Percent of non-ignored points predicted correctly; NaN when every point is ignored (utils/__init__.py:103-114)."""
+    keep = target.reshape(-1) != ignore_label
+    n = int(keep.sum())
+    if n == 0:
+        return float("nan")
+    return (pred.reshape(-1)[keep] == target.reshape(-1)[keep]).float().sum().mul(100.0 / n).item()
+
+
+@torch.no_grad()
+def fast_hist(pred: torch.Tensor, label: torch.Tensor, n: int) -> np.ndarray:
+    """Confusion matrix hist[label, pred] over points with 0 <= label < n (utils/__init__.py:117-123) — note the
+    reference filters on the label RANGE here, not on the ignore label."""
+    k = (label >= 0) & (label < n)
+    count = torch.bincount(n * label[k].long() + pred[k].long(), minlength=n * n)
+    return count.cpu().numpy().reshape(n, n)
+
+
+def per_class_iu(hist: np.ndarray) -> np.ndarray:
+    """diag / (row sum + column sum - diag + EPS) (utils/__init__.py:126-128)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist) + EPS)
+
+
+@torch.no_grad()
+def eval_metrics(output: torch.Tensor, target: torch.Tensor, num_labels: int, ignore_label: int = 255) -> Dict[str, float]:
+    """`SegmentationTraining._eval_metrics` (segmentation_training.py:230-239): {"OA", "mIoU"} in percent."""
+    pred = output.argmax(1)
+    hist = fast_hist(pred, target, num_labels)
+    return {"OA": precision_at_one(pred, target, ignore_label), "mIoU": float((per_class_iu(hist) * 100).mean())}
+
+
+class AccuracyMeter:
+    """torchmetrics `Accuracy(num_classes, top_k)` as the reference uses it (classification_training.py:12-18,59-60,
+    67-68): accumulates #correct / #seen over `update(logits, labels)` calls, `compute()` returns the fraction."""
+
+    def __init__(self, num_classes: int, top_k: int = 1):
+        self.num_classes, self.top_k = num_classes, top_k
+        self.reset()
+
+    def reset(self):
+        self.correct, self.total = 0, 0
+
+    @torch.no_grad()
+    def update(self, logits: torch.Tensor, labels: torch.Tensor):
+        k = min(self.top_k, logits.shape[1])
+        top = logits.topk(k, 1, True, True).indices
+        self.correct += int((top == labels.view(-1, 1)).any(1).sum())
+        self.total += int(labels.numel())
+
+    __call__ = update
+
+    def compute(self) -> float:
+        return self.correct / self.total if self.total else float("nan")
+
+    def all_reduce(self, group=None):
+        if dist.is_available() and dist.is_initialized():
+            t = torch.tensor([self.correct, self.total], dtype=torch.int64)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, group=group)
+            self.correct, self.total = int(t[0]), int(t[1])
+
+
+# ---- losses --------------------------------------------------------------------------------------------------
+class SegLoss(torch.nn.Module):
+    """segmentation_training.py:27-44.  weight = ones(num_labels), weight[-1] = void_weight when given and > 0.
+    On CUDA logits with unit weights this is the fused `spc_ce_fwd/bwd` kernel; with a void weight the weighted
+    kernel (`spc_ce_fwd_weighted`)."""
+
+    def __init__(self, ignore_index: int, num_labels: int, void_weight: Optional[float] = None):
+        super().__init__()
+        self.ignore_index = ignore_index
+        weight = torch.ones(num_labels)
+        self.weighted = void_weight is not None and void_weight > 0
+        if self.weighted:
+            weight[-1] = void_weight
+        self.register_buffer("weight", weight, persistent=False)
+
+    def forward(self, output: torch.Tensor, batch) -> torch.Tensor:
+        labels = (batch["labels"] if isinstance(batch, dict) else batch).long().to(output.device)
+        if output.is_cuda:
+            from . import ops
+            return ops.cross_entropy(output, labels, self.ignore_index,
+                                     self.weight.to(output.device) if self.weighted else None)
+        return F.cross_entropy(output, labels, weight=self.weight.to(output.device), ignore_index=self.ignore_index)
+
+
+def sync_grad_scale(num_points: int, group=None) -> float:
+    """`training_step_end` with use_sync_grad (segmentation_training.py:112-120): the factor a rank's loss is multiplied
+    with, num_points / sum(all ranks' num_points) * world — so that after DDP's gradient MEAN every point of the global
+    batch weighs the same."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    t = torch.tensor([float(num_points)], dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t, group=group)
+    total = sum(float(g) for g in gathered)
+    return float(num_points) / total * world
+
+
+# ---- checkpoints (Lightning layout) --------------------------------------------------------------------------
+def convert_self_supervised_checkpoint(state_dict) -> "OrderedDict[str, torch.Tensor]":
+    """lightning_module_base.py:62-72: drop `predictor` / `final` entries, `model.encoder` -> `model`."""
+    out = OrderedDict()
+    for k, v in state_dict.items():
+        if "predictor" in k or "final" in k:
+            continue
+        out[k.replace("model.encoder", "model")] = v
+    return out
+
+
+def lightning_state_dict(model: torch.nn.Module) -> "OrderedDict[str, torch.Tensor]":
+    """The module's state dict under the `model.` prefix Lightning gives it (`BaseModule.model`, eval.py:47-67)."""
+    return OrderedDict((f"model.{k}", v.detach().clone()) for k, v in model.state_dict().items())
+
+
+def load_lightning_state_dict(model: torch.nn.Module, state_dict, strict: bool = True):
+    """Load `checkpoint["state_dict"]` of the reference (keys `model.<...>`; entries of the Lightning module itself,
+    e.g. `criterion.weight`, are not the network's and are skipped)."""
+    own = OrderedDict((k[len("model."):], v) for k, v in state_dict.items() if k.startswith("model."))
+    if not own and len(state_dict):
+        raise KeyError("no 'model.'-prefixed entries: not a checkpoint of the reference's training modules")
+    return model.load_state_dict(own, strict=strict)
+
+
+def optimizer_state(trainer) -> dict:
+    """`torch.optim.SGD.state_dict()` layout (what Lightning stores in `optimizer_states`): parameters are numbered in
+    `model.parameters()` order, each with its `momentum_buffer`."""
+    params = [p for p in trainer.model.parameters() if p.requires_grad]
+    slot = {id(p): o for p, o in zip(trainer.arena.order, trainer.arena.offsets)}
+    state = {}
+    if trainer.steps > 0:
+        for i, p in enumerate(params):
+            o = slot[id(p)]
+            state[i] = {"momentum_buffer": trainer.momentum_buf[o:o + p.numel()].view_as(p).detach().clone()}
+    group = {"lr": trainer.lr, "momentum": trainer.momentum, "dampening": 0, "weight_decay": trainer.weight_decay,
+             "nesterov": False, "maximize": False, "foreach": None, "differentiable": False, "fused": None,
+             "initial_lr": getattr(trainer, "initial_lr", trainer.lr), "params": list(range(len(params)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def load_optimizer_state(trainer, opt_state: dict, keep_lr: Optional[float] = None) -> None:
+    """Inverse of `optimizer_state`.  `keep_lr`: start from the configured learning rate instead of the stored one
+    (the intent of lightning_module_base.py:93-101)."""
+    params = [p for p in trainer.model.parameters() if p.requires_grad]
+    slot = {id(p): o for p, o in zip(trainer.arena.order, trainer.arena.offsets)}
+    group = opt_state["param_groups"][0]
+    if len(group["params"]) != len(params):
+        raise ValueError(f"optimizer state holds {len(group['params'])} parameters, the model has {len(params)}")
+    state = opt_state.get("state", {})
+    trainer.momentum_buf.zero_()
+    loaded = 0
+    for i, p in enumerate(params):
+        st = state.get(i, state.get(str(i)))
+        if st is None or st.get("momentum_buffer") is None:
+            continue
+        o = slot[id(p)]
+        trainer.momentum_buf[o:o + p.numel()].view_as(p).copy_(st["momentum_buffer"])
+        loaded += 1
+    trainer.momentum, trainer.weight_decay = group["momentum"], group["weight_decay"]
+    trainer.lr = group["lr"] if keep_lr is None else keep_lr
+    # spc_sgd_step initialises the buffer with the first gradient (torch: buf = grad on the first step)
+    trainer.steps = max(trainer.steps, 1) if loaded else 0
+
+
+def save_checkpoint(path: str, trainer, global_step: int, epoch: int = 0, extra: Optional[dict] = None) -> None:
+    ckpt = {"epoch": epoch, "global_step": global_step, "pytorch-lightning_version": "1.5.10",
+            "state_dict": lightning_state_dict(trainer.model),
+            "optimizer_states": [optimizer_state(trainer)],
+            "lr_schedulers": [{"last_epoch": global_step, "_step_count": global_step + 1,
+                               "_last_lr": [trainer.lr]}]}
+    ckpt.update(extra or {})
+    tmp = f"{path}.tmp"
+    torch.save(ckpt, tmp)
+    os.replace(tmp, path)
+
+
+def load_checkpoint(path: str, trainer=None, model: Optional[torch.nn.Module] = None, load_weights: bool = True,
+                    load_optimizers: bool = False, transfer_self_supervised: bool = False, lr: Optional[float] = None,
+                    map_location="cpu") -> dict:
+    """`configure_optimizers` checkpoint handling (lightning_module_base.py:82-105): weights (optionally converted from
+    a self-supervised run, non-strict) and / or optimizer state."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    model = model if model is not None else trainer.model
+    if load_weights:
+        sd = ckpt["state_dict"]
+        if transfer_self_supervised:
+            load_lightning_state_dict(model, convert_self_supervised_checkpoint(sd), strict=False)
+        else:
+            load_lightning_state_dict(model, sd)
+    if load_optimizers:
+        if trainer is None:
+            raise ValueError("load_optimizers needs the trainer")
+        load_optimizer_state(trainer, ckpt["optimizer_states"][0], keep_lr=lr)
+    return ckpt
+
+
+# ---- the run ---------------------------------------------------------------------------------------------------
+class TrainConfig:
+    """The `train.*` bindings of a gin file with the defaults of `train()` (co3d_3d/train.py:50-96)."""
+    DEFAULTS = dict(max_steps=None, max_epochs=-1, warmup_steps=-1, training_module="SegmentationTraining",
+                    optimizer_name="SGD", scheduler_name="PolyLR", scheduler_interval="step", lr=1e-3,
+                    weight_decay=1e-4, batch_size=8, val_batch_size=6, val_every_n_steps=1000, log_every_n_steps=10,
+                    resume_training=False, checkpoint_path=None, load_weights=False, load_optimizers=False,
+                    transfer_self_supervised=False, use_sync_batchnorm=False, use_sync_grad=False, ignore_label=-100,
+                    monitor_metric="val/mIoU", void_weight=None, gpus=1)
+
+    def __init__(self, **overrides):
+        bound = {k.split(".", 1)[1]: v for k, v in ginlite.config_dict().items() if k.startswith("train.")}
+        unknown = set(overrides) - set(self.DEFAULTS)
+        if unknown:
+            raise TypeError(f"unknown train() arguments: {sorted(unknown)}")
+        for k, v in self.DEFAULTS.items():
+            setattr(self, k, overrides.get(k, bound.get(k, v)))
+        if self.max_steps is None:
+            raise ginlite.GinError("train.max_steps is not bound (required argument of train(), train.py:56)")
+        self.momentum = _bound(f"{self.optimizer_name}.momentum", 0.0)
+        self.scheduler_kwargs = {k.split(".", 1)[1]: v for k, v in ginlite.config_dict().items()
+                                 if k.startswith(f"{self.scheduler_name}.")}
+
+    @property
+    def total_steps(self) -> int:
+        """`max_steps + warmup_steps` optimiser steps (train.py:175)."""
+        return self.max_steps + (self.warmup_steps if self.warmup_steps and self.warmup_steps > 0 else 0)
+
+    def schedule(self) -> Optional[schedules.Schedule]:
+        return schedules.get_schedule(self.scheduler_name, self.lr, self.max_steps, self.warmup_steps, self.max_epochs,
+                                      self.scheduler_interval, **self.scheduler_kwargs)
+
+
+def _bound(key: str, default):
+    try:
+        return ginlite.query_parameter(key)
+    except ValueError:
+        return default
+
+
+def get_model(name: Optional[str] = None, in_channel: Optional[int] = None, out_channel: Optional[int] = None):
+    """`get_model` (src/models/__init__.py:18-20) over the networks of `models.py`, arguments from `get_model.*`."""
+    from . import models
+    name = name if name is not None else ginlite.query_parameter("get_model.name")
+    in_channel = in_channel if in_channel is not None else ginlite.query_parameter("get_model.in_channel")
+    out_channel = out_channel if out_channel is not None else ginlite.query_parameter("get_model.out_channel")
+    if not hasattr(models, name):
+        known = sorted(n for n in dir(models) if n.startswith(("ResNet", "Res16UNet")))
+        raise KeyError(f"model {name!r} is not built here (have {known})")
+    return getattr(models, name)(in_channel, out_channel)
+
+
+class Run:
+    """One training run: `fit()` is `trainer.fit` of train.py:163-186 for a single rank of the data-parallel job.
+
+    model      — a network over the ME-compatible surface (takes a TensorField; `models.py` or the reference's files)
+    make_input — batch dict -> network input (default: `ME.TensorField(coordinates=, features=)`, base_model.py:10-13)
+    """
+
+    def __init__(self, model: torch.nn.Module, cfg: TrainConfig, num_labels: Optional[int] = None,
+                 void_label=None, save_path: Optional[str] = None, make_input: Optional[Callable] = None,
+                 log: Optional[Callable[[dict], None]] = None):
+        from . import trainer as T
+        if cfg.optimizer_name != "SGD":
+            raise NotImplementedError("the fused optimiser step implements SGD (what every reference config selects: "
+                                      "co3d_cls.gin:33, scannet_plenoxel.gin:58)")
+        self.model, self.cfg, self.save_path, self.log = model, cfg, save_path, log or (lambda d: None)
+        self.segmentation = cfg.training_module == "SegmentationTraining"
+        if cfg.training_module not in ("SegmentationTraining", "ClassificationTraining"):
+            raise AssertionError(f"{cfg.training_module} not in ['SegmentationTraining', 'ClassificationTraining']")
+        self.num_labels = num_labels if num_labels is not None else ginlite.query_parameter("get_model.out_channel")
+        self.trainer = T.DataParallelTrainer(model, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+        self.trainer.initial_lr = cfg.lr
+        self.schedule = cfg.schedule()
+        self.global_step = 0
+        self.best = -math.inf
+        self.make_input = make_input or self._tensor_field
+        if self.segmentation:
+            self.criterion = SegLoss(cfg.ignore_label, self.num_labels, cfg.void_weight)
+            from .pipeline import IoUMeter
+            self.iou_meter = IoUMeter(self.num_labels, cfg.ignore_label, void_label)
+        else:
+            self.acc1_meter = AccuracyMeter(self.num_labels, 1)
+            self.acc5_meter = AccuracyMeter(self.num_labels, 5)
+        if cfg.checkpoint_path is not None and (cfg.load_weights or cfg.load_optimizers or cfg.resume_training):
+            ckpt = load_checkpoint(cfg.checkpoint_path, self.trainer, load_weights=cfg.load_weights or cfg.resume_training,
+                                   load_optimizers=cfg.load_optimizers or cfg.resume_training,
+                                   transfer_self_supervised=cfg.transfer_self_supervised,
+                                   lr=None if cfg.resume_training else cfg.lr)
+            if cfg.resume_training:
+                self.global_step = int(ckpt.get("global_step", 0))
+        self._apply_schedule()
+
+    @staticmethod
+    def _tensor_field(batch):
+        from . import me as ME
+        return ME.TensorField(coordinates=batch["coordinates"], features=batch["features"])
+
+    def _apply_schedule(self):
+        if self.schedule is not None:
+            self.trainer.set_lr(self.schedule.lr(self.global_step))
+            m = self.schedule.momentum(self.global_step)
+            if m is not None:
+                self.trainer.momentum = m
+
+    # -- one optimiser step (training_step + backward + optimizer.step + scheduler.step) -------------------------
+    def training_step(self, batch) -> torch.Tensor:
+        self.model.train()
+        logits = self.model(self.make_input(batch))
+        labels = batch["labels"].long()
+        if self.segmentation:
+            loss = self.criterion(logits, batch)
+            if self.cfg.use_sync_grad:
+                loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
+        else:
+            from . import ops
+            loss = ops.cross_entropy(logits, labels) if logits.is_cuda else F.cross_entropy(logits, labels)
+        step = self.global_step
+        if step % self.cfg.log_every_n_steps == 0 and step > 0:
+            loss_float = loss.detach().cpu().item()
+            if not np.isfinite(loss_float):
+                raise ValueError(f"Invalid loss: {loss_float}")
+            out = {"train/loss": loss_float, "train/lr": self.trainer.lr, "global_step": step}
+            if self.segmentation:
+                for k, v in eval_metrics(logits.detach(), labels, logits.shape[1], self.cfg.ignore_label).items():
+                    out[f"train/{k}"] = v
+                out["train/ignore_ratio"] = ((labels == self.cfg.ignore_label).sum() / labels.shape[0] * 100).item()
+            else:
+                out["train/acc1"], out["train/acc5"] = accuracy_topk(logits.detach(), labels, (1, 5))
+            self.log(out)
+        self.trainer.backward_and_step(loss)
+        self.global_step += 1
+        self._apply_schedule()
+        return loss.detach()
+
+    # -- validation epoch ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def validate(self, batches: Iterable[dict]) -> Dict[str, float]:
+        self.model.eval()
+        losses, oas = [], []
+        if self.segmentation:
+            self.iou_meter.counts = None
+        else:
+            self.acc1_meter.reset()
+            self.acc5_meter.reset()
+        for batch in batches:
+            logits = self.model(self.make_input(batch))
+            labels = batch["labels"].long()
+            if self.segmentation:
+                losses.append(self.criterion(logits, batch).item())
+                oas.append(eval_metrics(logits, labels, logits.shape[1], self.cfg.ignore_label)["OA"])
+                self.iou_meter.update(logits, labels)
+            else:
+                losses.append(F.cross_entropy(logits, labels).item())
+                self.acc1_meter(logits, labels)
+                self.acc5_meter(logits, labels)
+        assert len(losses) > 0
+        out = {"val/loss": float(np.mean(losses)), "global_step": self.global_step}
+        if self.segmentation:
+            miou, ious, macc, accs = self.iou_meter.compute()
+            out.update({"val/OA": float(np.mean(oas)), "val/mIoU": float(miou) * 100, "val/mAcc": float(macc) * 100})
+            if out["val/mIoU"] > self.best:
+                self.best = out["val/mIoU"]
+            out["val/best_mIoU"] = self.best
+            if self.save_path:
+                with open(os.path.join(self.save_path, "eval_results.json"), "w") as f:
+                    json.dump({"iou": [*(ious * 100).cpu().tolist(), float(miou)],
+                               "acc": [*(accs * 100).cpu().tolist(), float(macc)]}, f)
+        else:
+            out.update({"val/acc1": self.acc1_meter.compute(), "val/acc5": self.acc5_meter.compute()})
+        self.log(out)
+        return out
+
+    # -- the loop --------------------------------------------------------------------------------------------------
+    def fit(self, train_batches: Callable[[], Iterable[dict]], val_batches: Optional[Callable[[], Iterable[dict]]] = None):
+        """`train_batches()` / `val_batches()` return a fresh iterable per epoch.  Stops after `total_steps` optimiser
+        steps (or `max_epochs` epochs when > 0); validates every `val_every_n_steps`; keeps `last.ckpt` and the best
+        checkpoint by `monitor_metric` (ModelCheckpoint(save_top_k=1, save_last=True, mode="max"), train.py:150-157)."""
+        cfg = self.cfg
+        rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+        if self.save_path and rank0:
+            os.makedirs(self.save_path, exist_ok=True)
+        epoch, best_monitor, last_val = 0, -math.inf, None
+        while self.global_step < cfg.total_steps and (cfg.max_epochs <= 0 or epoch < cfg.max_epochs):
+            seen = 0
+            for batch in train_batches():
+                if self.global_step >= cfg.total_steps:
+                    break
+                self.training_step(batch)
+                seen += 1
+                if val_batches is not None and self.global_step % cfg.val_every_n_steps == 0:
+                    last_val = self.validate(val_batches())
+                    monitor = last_val.get(cfg.monitor_metric)
+                    if self.save_path and rank0:
+                        save_checkpoint(os.path.join(self.save_path, "last.ckpt"), self.trainer, self.global_step, epoch)
+                        if monitor is not None and monitor > best_monitor:
+                            best_monitor = monitor
+                            save_checkpoint(os.path.join(self.save_path, "best.ckpt"), self.trainer, self.global_step,
+                                            epoch, {"monitor": {cfg.monitor_metric: monitor}})
+            if seen == 0:
+                raise RuntimeError("train_batches() produced no batch")
+            epoch += 1
+        if self.save_path and rank0:
+            save_checkpoint(os.path.join(self.save_path, "last.ckpt"), self.trainer, self.global_step, epoch)
+        return last_val
+
+
+def train(config_files: Sequence[str], bindings: Sequence[str], train_batches, val_batches=None, model=None,
+          save_path: Optional[str] = None, device="cuda", log=None, **overrides) -> Run:
+    """`python -m co3d_3d.train --ginc ... --ginb ...` for one rank (train.py:199-263): parse the gin files and
+    bindings, build `get_model()` unless a model is passed, run `fit`."""
+    ginlite.parse_config_files_and_bindings(config_files, bindings)
+    cfg = TrainConfig(**overrides)
+    if model is None:
+        model = get_model().to(device)
+    run = Run(model, cfg, save_path=save_path, void_label=_bound("PlenoxelScannetDataset.void_label", None), log=log)
+    run.fit(train_batches, val_batches)
+    return run

@@ -44,6 +44,14 @@ def _worker(rank, world, port, q):
         (sum(ref(x).pow(2).mean() for x in xs) / world).backward()
         opt.step()
     err = max((a - b).abs().max().item() for a, b in zip(model.parameters(), ref.parameters()))
+    # use_sync_grad loss re-weighting (segmentation_training.py:112-120): n_r / sum(n) * world
+    from nerf_downstream_b200 import training
+    scale = training.sync_grad_scale(100 if rank == 0 else 300)
+    assert abs(scale - (0.5 if rank == 0 else 1.5)) < 1e-12, scale
+    meter = training.AccuracyMeter(4)
+    meter.correct, meter.total = 3 + rank, 10
+    meter.all_reduce()
+    assert (meter.correct, meter.total) == (7, 20)
     q.put((rank, err, [p.data_ptr() for p in model.parameters()][0] == tr.arena.data.data_ptr() + 4 * tr.arena.offsets[-1]))
     dist.destroy_process_group()
 
@@ -68,4 +76,6 @@ def test_schedules():
     from nerf_downstream_b200 import trainer
     assert abs(trainer.cosine_lr(0.1, 0, 100) - 0.1) < 1e-12 and abs(trainer.cosine_lr(0.1, 100, 100)) < 1e-12
     assert abs(trainer.cosine_lr(0.1, 50, 100) - 0.05) < 1e-12
-    assert abs(trainer.poly_lr(0.1, 0, 100) - 0.1) < 1e-12 and trainer.poly_lr(0.1, 99, 100) < 0.002
+    # PolyFunctor: (1 - step / (max_steps + 1)) ** poly_exp  (optim.py:181-188)
+    assert abs(trainer.poly_lr(0.1, 0, 100) - 0.1) < 1e-12
+    assert abs(trainer.poly_lr(0.1, 99, 100) - 0.1 * (1 - 99 / 101) ** 0.9) < 1e-15
