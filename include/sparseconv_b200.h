@@ -262,6 +262,36 @@ int spc_plenoxel_decode(const void* links, int links_is_int64, int64_t n, const 
 int spc_seg_metrics(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_label,
                     uint64_t* counts, void* stream);
 
+/* ---- segmentation head --------------------------------------------------------------------
+ * spc_seg_head_fwd: `out.slice(x).F` (res16unet.py:435) -> `SegLoss` (segmentation_training.py:27-44) ->
+ *   `IoUMeter.update` (metrics.py:29-41) in ONE pass over the n points.
+ *   logits[m, C]      voxel rows of the network output
+ *   inverse[n]        point -> voxel row (ME's inverse_mapping, int32); NULL = identity (then m == n): a plain
+ *                     class-weighted F.cross_entropy over rows
+ *   target[n]         int64 labels; == ignore_index rows contribute nothing
+ *   class_weight[C]   float or NULL (all one) — F.cross_entropy's `weight` (SegLoss: ones, void_weight on the last)
+ *   grad_raw[m, C]    out: sum over the points of a voxel of w[y] * (softmax - onehot)  (= backward of the slice
+ *                     gather already applied); spc_ce_bwd(grad_raw, stats, gout, m, C) turns it into dlogits
+ *   stats[2]          out (double): sum w[y] * nll, sum w[y]  -> loss = stats[0] / stats[1]
+ *   counts[3, C]      uint64, ACCUMULATED (caller zeroes), or NULL: #seen, #correct, #predicted per class
+ *   bad_target[1]     out: 1 = a label outside [0, C) other than ignore_index, 2 = inverse entry outside [0, m) */
+int spc_seg_head_fwd(const float* logits, int64_t m, const int32_t* inverse, const int64_t* target, int64_t n, int C,
+                     int64_t ignore_index, const float* class_weight, float* grad_raw, double* stats,
+                     uint64_t* counts, int32_t* bad_target, void* stream);
+
+/* ---- instance normalisation (ME.MinkowskiInstanceNorm, modules/common.py:25-26) ------------
+ * Per (batch index = coords[r, 0], channel): mean and biased variance over the rows of that instance,
+ *   y = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c]      (gamma / beta may be NULL)
+ * fwd writes mean[n_batch, C], rstd[n_batch, C], cnt[n_batch] for the backward; ws = n_batch * 2 * C doubles.
+ * bwd: dx = gamma * rstd * (dy - mean_b(dy) - xhat * mean_b(dy * xhat)); sums[n_batch, 2, C] (double) returns
+ *   sum dy and sum dy * xhat per instance, from which dgamma = sum_b sums[b, 1], dbeta = sum_b sums[b, 0]. */
+int spc_inst_norm_fwd(const float* x, const int32_t* coords, int64_t m, int C, int n_batch, const float* gamma,
+                      const float* beta, float eps, float* y, float* mean, float* rstd, int32_t* cnt, double* ws,
+                      void* stream);
+int spc_inst_norm_bwd(const float* x, const float* dy, const int32_t* coords, int64_t m, int C, int n_batch,
+                      const float* gamma, const float* mean, const float* rstd, const int32_t* cnt, float* dx,
+                      double* sums, void* stream);
+
 /* Fused SGD step on a flat arena (co3d_cls.gin:33-39; optim.py:60-69):
  * g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf. */
 int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,

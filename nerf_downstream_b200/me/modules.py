@@ -218,7 +218,10 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
 
 
 class MinkowskiInstanceNorm(MinkowskiModuleBase):
-    """Constructed by get_norm('IN') only (common.py:25-26); not on the hot path -> not built."""
+    """Per-instance (batch index) normalisation with a [1, C] affine, built by get_norm('IN') (common.py:25-26).
+    ME computes it as global-average-pool / broadcast passes: mean over the rows of an instance, biased variance,
+    (x - mean) / sqrt(var + 1e-8), then `* weight + bias`; here it is spc_inst_norm_fwd/bwd."""
+    EPS = 1e-8
 
     def __init__(self, num_features):
         super().__init__()
@@ -226,8 +229,20 @@ class MinkowskiInstanceNorm(MinkowskiModuleBase):
         self.weight = Parameter(torch.ones(1, num_features))
         self.bias = Parameter(torch.zeros(1, num_features))
 
+    def reset_parameters(self):
+        with torch.no_grad():
+            self.weight.fill_(1)
+            self.bias.zero_()
+
     def forward(self, input):
-        raise NotImplementedError("MinkowskiInstanceNorm is outside the built hot path (SURVEY.md §8f rank 4)")
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        nb = mgr.size(mgr.origin())
+        out = ops.InstanceNormFn.apply(input.F, input.C, nb, self.weight, self.bias, self.EPS)
+        return SparseTensor(out, coordinate_map_key=input.coordinate_map_key, coordinate_manager=mgr)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(nchannels={self.num_features})"
 
 
 # ---------------------------------------------------------------------------

@@ -74,10 +74,91 @@ class SparseCollation:
         return sparse_collate(coords, feats, labels, dtype=self.dtype, device=self.device)
 
 
-def sparse_quantize(*args, **kwargs):
-    raise NotImplementedError(
-        "ME.utils.sparse_quantize is used only by out-of-scope datasets (SURVEY.md §2.1 row 11); "
-        "use TensorField(...).sparse() for on-device quantisation")
+def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, return_index=False,
+                    return_inverse=False, return_maps_only=False, quantization_size=None, device="cuda"):
+    """ME.utils.sparse_quantize as the reference calls it (co3d_3d/src/data/scannet.py:235-242): voxelise a point
+    cloud — `floor(coordinates / quantization_size)`, one row per occupied voxel.
+
+    Returns, like ME, `discrete_coords[, features][, labels][, unique_index][, inverse_index]` (numpy arrays for numpy
+    input, tensors on the GPU otherwise).  A voxel whose points carry different labels gets `ignore_label`.  Voxels
+    come in the order of their first point (ME's CPU hash map leaves the order unspecified); `unique_index` is that
+    first point.  The hashing runs in the coordinate kernels (`spc_coords_insert`) — there is no CPU path, so this
+    needs a CUDA device even though ME's default is "cpu"."""
+    from .. import lib as L
+    from .. import ops
+    if torch.is_tensor(coordinates) and coordinates.is_cuda:
+        dev = coordinates.device
+    else:
+        if not torch.cuda.is_available():
+            raise RuntimeError("sparse_quantize runs in the CUDA coordinate kernels (no CPU backend)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return _sparse_quantize(coordinates, features, labels, ignore_label, return_index, return_inverse,
+                            return_maps_only, quantization_size, dev,
+                            lambda disc: ops.coords_insert(disc, L.SRC_INT, (1, 1, 1)))
+
+
+def _sparse_quantize(coordinates, features, labels, ignore_label, return_index, return_inverse, return_maps_only,
+                     quantization_size, dev, insert):
+    """Host logic of `sparse_quantize`; `insert(int32 [N,4]) -> (CoordMap, first, inverse, count)` is the hash kernel."""
+    import numpy as np
+    is_np = isinstance(coordinates, np.ndarray)
+
+    def to_dev(a):
+        if a is None:
+            return None
+        return (torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a).to(dev)
+
+    c = to_dev(coordinates)
+    assert c.dim() == 2, "The coordinates must be a 2D matrix. The shape of the input is " + str(tuple(c.shape))
+    if features is not None:
+        assert features.ndim == 2 and coordinates.shape[0] == features.shape[0]
+    if labels is not None:
+        assert coordinates.shape[0] == len(labels)
+    n, D = c.shape
+    if D != 3:
+        raise NotImplementedError("this engine is built for 3 spatial dimensions")
+    if quantization_size is not None:
+        q = quantization_size
+        if isinstance(q, (list, tuple, np.ndarray, torch.Tensor)):
+            assert len(q) == D, "Quantization size and coordinates size mismatch."
+            q = torch.as_tensor(np.asarray(q) if not torch.is_tensor(q) else q, device=dev).to(c.dtype if
+                                                                                              c.is_floating_point() else torch.float64)
+        elif isinstance(q, (int, float)):
+            # a device tensor, not a Python scalar: torch divides by a host scalar as `c * (1 / q)`, numpy as `c / q`
+            q = torch.tensor(q, dtype=c.dtype if c.is_floating_point() else torch.float64, device=dev)
+        else:
+            raise ValueError("Not supported type for quantization_size.")
+        c = torch.floor(c / q)                      # true division in the input's precision, as numpy does
+    elif c.is_floating_point():
+        c = torch.floor(c)
+    disc = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+    disc[:, 1:] = c.to(torch.int32)
+    cmap, first, inverse, _count = insert(disc)
+    unique_index, inverse_index = first.long(), inverse.long()
+
+    def back(t):
+        return t.cpu().numpy() if is_np else t
+
+    if return_maps_only:
+        out = [back(unique_index)]
+        if return_inverse:
+            out.append(back(inverse_index))
+        return out[0] if len(out) == 1 else tuple(out)
+    out = [back(cmap.coords[:, 1:].contiguous())]
+    if features is not None:
+        out.append(back(to_dev(features)[unique_index]))
+    if labels is not None:
+        lab = to_dev(labels).long()
+        vox = lab[unique_index].clone()
+        conflict = lab != vox[inverse_index]
+        vox[inverse_index[conflict]] = ignore_label
+        vox = vox.to(torch.int32)
+        out.append(back(vox))
+    if return_index:
+        out.append(back(unique_index))
+    if return_inverse:
+        out.append(back(inverse_index))
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):

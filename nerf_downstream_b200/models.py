@@ -145,6 +145,11 @@ class SparseResUNet(nn.Module):
         self.final = _conv(c, out_channel, 1, bias=True)
 
     def forward(self, x: ME.TensorField):
+        return self.forward_sparse(x).slice(x).F
+
+    def forward_sparse(self, x: ME.TensorField) -> ME.SparseTensor:
+        """The head's voxel logits before `slice` — what `pipeline.seg_head_loss` consumes (one fused pass instead
+        of slice -> loss -> metrics)."""
         out = x.sparse()
         skips = [self.conv0p1s1(out)]
         out = skips[0]
@@ -155,7 +160,7 @@ class SparseResUNet(nn.Module):
         for i, name in enumerate(["convtr4p16s2", "convtr5p8s2", "convtr6p4s2", "convtr7p2s2"]):
             out = ME.cat(getattr(self, name)(out), skips.pop())
             out = getattr(self, f"block{5 + i}")(out)
-        return self.final(out).slice(x).F
+        return self.final(out)
 
 
 class Res16UNet34C(SparseResUNet):

@@ -926,10 +926,115 @@ class CrossEntropyFn(torch.autograd.Function):
         return dlogits, None, None
 
 
-def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
-    """F.cross_entropy(logits, target, ignore_index=...) (mean reduction) on the fused kernel.  Targets
-    outside [0, C) that are not ignore_index make `check_targets` raise (no host sync here)."""
-    return CrossEntropyFn.apply(logits, target, ignore_index)
+class SegHeadFn(torch.autograd.Function):
+    """`SegLoss(out.slice(x).F, labels)` (+ `IoUMeter.update`) as one pass over the points (spc_seg_head_fwd):
+    inverse-map gather of the voxel logits, class-weighted softmax cross-entropy with ignore index, gradient
+    accumulated on the voxel rows, optional per-class counts.  `inverse=None`: rows are the points themselves."""
+
+    @staticmethod
+    def forward(ctx, logits, inverse, target, ignore_index, weight, counts):
+        lib = L.load()
+        logits = _feat(logits)
+        if target.dtype != torch.int64:
+            raise RuntimeError(f"targets must be int64, got {target.dtype}")
+        target = target.contiguous()
+        m, C = logits.shape
+        n = target.shape[0]
+        if target.dim() != 1 or (inverse is None and n != m):
+            raise RuntimeError(f"target shape {tuple(target.shape)} does not match logits {tuple(logits.shape)}")
+        if inverse is not None:
+            if inverse.dtype != torch.int32 or inverse.shape != (n,):
+                raise RuntimeError("inverse map must be int32 [n]")
+            inverse = inverse.contiguous()
+        if weight is not None:
+            if weight.dtype != torch.float32 or weight.shape != (C,):
+                raise RuntimeError(f"class weights must be float32 [{C}]")
+            weight = weight.contiguous()
+        if counts is not None and (counts.dtype != torch.int64 or counts.shape != (3, C) or not counts.is_contiguous()):
+            raise RuntimeError(f"counts must be a contiguous int64 [3, {C}] tensor")
+        graw = _empty((m, C), torch.float32, logits.device)
+        stats = _empty(2, torch.float64, logits.device)
+        bad = _empty(1, torch.int32, logits.device)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_seg_head_fwd(L.ptr(logits), m, L.ptr(inverse), L.ptr(target), n, C, int(ignore_index),
+                                     L.ptr(weight), L.ptr(graw), L.ptr(stats), L.ptr(counts), L.ptr(bad), L.stream()),
+                "spc_seg_head_fwd")
+        if e0 is not None:
+            _profiler.end("seg_head", e0, 0, 8.0 * C * n + 12.0 * n, f"C{C} N{n}")
+        ctx.save_for_backward(graw, stats)
+        ctx.bad = bad
+        return (stats[0] / stats[1]).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        graw, stats = ctx.saved_tensors
+        m, C = graw.shape
+        gout = gout.to(torch.float32).contiguous().view(1)
+        dlogits = torch.empty_like(graw)
+        L.check(lib.spc_ce_bwd(L.ptr(graw), L.ptr(stats), L.ptr(gout), m, C, L.ptr(dlogits), L.stream()),
+                "spc_ce_bwd")
+        return dlogits, None, None, None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100,
+                  weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.cross_entropy(logits, target, weight=..., ignore_index=...) (mean reduction) on the fused kernels.  Targets
+    outside [0, C) that are not ignore_index set the kernel's `bad_target` flag (no host sync here)."""
+    if weight is None:
+        return CrossEntropyFn.apply(logits, target, ignore_index)
+    return SegHeadFn.apply(logits, None, target, ignore_index, weight, None)
+
+
+def seg_head(logits: torch.Tensor, inverse: Optional[torch.Tensor], target: torch.Tensor, ignore_index: int = -100,
+             weight: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Loss of the voxel logits at the points of the inverse map; `counts` [3, C] int64 accumulates the IoU counts."""
+    return SegHeadFn.apply(logits, inverse, target, ignore_index, weight, counts)
+
+
+class InstanceNormFn(torch.autograd.Function):
+    """MinkowskiInstanceNorm: per (batch index, channel) normalisation + [1, C] affine (spc_inst_norm_fwd/bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, coords, n_batch, gamma, beta, eps):
+        lib = L.load()
+        x = _feat(x)
+        m, C = x.shape
+        dev = x.device
+        y = _empty((m, C), torch.float32, dev)
+        mean = _empty((n_batch, C), torch.float32, dev)
+        rstd = _empty((n_batch, C), torch.float32, dev)
+        cnt = _empty(n_batch, torch.int32, dev)
+        ws = _empty((n_batch, 2, C), torch.float64, dev)
+        g = None if gamma is None else gamma.detach().reshape(-1).contiguous()
+        b = None if beta is None else beta.detach().reshape(-1).contiguous()
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_inst_norm_fwd(L.ptr(x), L.ptr(coords), m, C, n_batch, L.ptr(g), L.ptr(b), float(eps), L.ptr(y),
+                                      L.ptr(mean), L.ptr(rstd), L.ptr(cnt), L.ptr(ws), L.stream()), "spc_inst_norm_fwd")
+        if e0 is not None:
+            _profiler.end("inst_norm_fwd", e0, 0, 12.0 * m * C, f"C{C} M{m}")
+        ctx.save_for_backward(x, coords, g, mean, rstd, cnt)
+        ctx.cfg = (n_batch, gamma is not None and ctx.needs_input_grad[3], beta is not None and ctx.needs_input_grad[4],
+                   None if gamma is None else gamma.shape, None if beta is None else beta.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, coords, g, mean, rstd, cnt = ctx.saved_tensors
+        n_batch, want_g, want_b, gshape, bshape = ctx.cfg
+        dy = _feat(dy)
+        m, C = x.shape
+        dx = _empty((m, C), torch.float32, x.device)
+        sums = _empty((n_batch, 2, C), torch.float64, x.device)
+        e0 = _profiler.begin() if _profiler else None
+        L.check(lib.spc_inst_norm_bwd(L.ptr(x), L.ptr(dy), L.ptr(coords), m, C, n_batch, L.ptr(g), L.ptr(mean),
+                                      L.ptr(rstd), L.ptr(cnt), L.ptr(dx), L.ptr(sums), L.stream()), "spc_inst_norm_bwd")
+        if e0 is not None:
+            _profiler.end("inst_norm_bwd", e0, 0, 20.0 * m * C, f"C{C} M{m}")
+        dgamma = sums[:, 1].sum(0).to(torch.float32).view(gshape) if want_g else None
+        dbeta = sums[:, 0].sum(0).to(torch.float32).view(bshape) if want_b else None
+        return dx, None, None, dgamma, dbeta, None
 
 
 def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):

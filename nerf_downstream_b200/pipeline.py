@@ -58,6 +58,18 @@ def seg_counts(logits: torch.Tensor, target: torch.Tensor, ignore_label: int, ou
     return out
 
 
+def seg_head_loss(out, field, labels: torch.Tensor, ignore_index: int = -100, weight: Optional[torch.Tensor] = None,
+                  counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`SegLoss(out.slice(field).F, labels)` (res16unet.py:435 + segmentation_training.py:27-44) without materialising
+    the sliced logits: one kernel gathers each point's voxel row through the field's inverse map, evaluates the
+    (class-weighted, ignore-aware) cross-entropy, accumulates the gradient on the voxel rows and — when `counts`
+    [3, C] int64 is given — the IoUMeter counts of the same argmax.  `out` is the network's SparseTensor head output
+    (`models.SparseResUNet.forward_sparse`), `field` the TensorField it was computed from."""
+    from . import ops
+    inv = field.inverse_mapping(out.coordinate_map_key)
+    return ops.seg_head(out.F, inv, labels, ignore_index, weight, counts)
+
+
 class IoUMeter:
     """co3d_3d/src/metrics.py IoUMeter: update() accumulates, compute() -> (miou, ious, mAcc, accs)."""
 
@@ -69,6 +81,12 @@ class IoUMeter:
         if self.counts is None:
             self.counts = torch.zeros((3, self.num_classes), dtype=torch.int64, device=logits.device)
         seg_counts(logits, targets, self.ignore_label, out=self.counts)
+
+    def counts_buffer(self, device) -> torch.Tensor:
+        """The [3, C] int64 accumulator, for kernels that add to it directly (`seg_head_loss(counts=...)`)."""
+        if self.counts is None:
+            self.counts = torch.zeros((3, self.num_classes), dtype=torch.int64, device=device)
+        return self.counts
 
     def compute(self):
         seen, correct, positive = (self.counts[i].to(torch.float32) for i in range(3))

@@ -83,6 +83,17 @@ def eval_metrics(output: torch.Tensor, target: torch.Tensor, num_labels: int, ig
     return {"OA": precision_at_one(pred, target, ignore_label), "mIoU": float((per_class_iu(hist) * 100).mean())}
 
 
+def metrics_from_counts(counts: torch.Tensor) -> Dict[str, float]:
+    """{"OA", "mIoU"} of `eval_metrics` from the [3, C] seen / correct / predicted counts the fused segmentation head
+    accumulates (`pipeline.seg_head_loss(counts=...)`): the confusion-matrix row sums, diagonal and column sums."""
+    seen, correct, positive = (counts[i].double().cpu().numpy() for i in range(3))
+    total = seen.sum()
+    oa = float(correct.sum() * 100.0 / total) if total > 0 else float("nan")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iu = correct / (seen + positive - correct + EPS)
+    return {"OA": oa, "mIoU": float((iu * 100).mean())}
+
+
 class AccuracyMeter:
     """torchmetrics `Accuracy(num_classes, top_k)` as the reference uses it (classification_training.py:12-18,59-60,
     67-68): accumulates #correct / #seen over `update(logits, labels)` calls, `compute()` returns the fraction."""
@@ -309,11 +320,13 @@ class Run:
 
     model      — a network over the ME-compatible surface (takes a TensorField; `models.py` or the reference's files)
     make_input — batch dict -> network input (default: `ME.TensorField(coordinates=, features=)`, base_model.py:10-13)
+    fused_head — segmentation only, for models with `forward_sparse` (models.SparseResUNet): slice, SegLoss and the
+                 metric counts run as ONE kernel over the points (`pipeline.seg_head_loss`) instead of three passes
     """
 
     def __init__(self, model: torch.nn.Module, cfg: TrainConfig, num_labels: Optional[int] = None,
                  void_label=None, save_path: Optional[str] = None, make_input: Optional[Callable] = None,
-                 log: Optional[Callable[[dict], None]] = None):
+                 log: Optional[Callable[[dict], None]] = None, fused_head: bool = False):
         from . import trainer as T
         if cfg.optimizer_name != "SGD":
             raise NotImplementedError("the fused optimiser step implements SGD (what every reference config selects: "
@@ -329,6 +342,9 @@ class Run:
         self.global_step = 0
         self.best = -math.inf
         self.make_input = make_input or self._tensor_field
+        self.fused_head = bool(fused_head)
+        if self.fused_head and not (self.segmentation and hasattr(model, "forward_sparse")):
+            raise ValueError("fused_head needs SegmentationTraining and a model with forward_sparse()")
         if self.segmentation:
             self.criterion = SegLoss(cfg.ignore_label, self.num_labels, cfg.void_weight)
             from .pipeline import IoUMeter
@@ -360,9 +376,23 @@ class Run:
     # -- one optimiser step (training_step + backward + optimizer.step + scheduler.step) -------------------------
     def training_step(self, batch) -> torch.Tensor:
         self.model.train()
-        logits = self.model(self.make_input(batch))
         labels = batch["labels"].long()
-        if self.segmentation:
+        step_counts = None
+        if self.fused_head:
+            from . import pipeline
+            field = self.make_input(batch)
+            out = self.model.forward_sparse(field)
+            logits = out.F
+            step_counts = torch.zeros((3, logits.shape[1]), dtype=torch.int64, device=logits.device)
+            crit = self.criterion
+            loss = pipeline.seg_head_loss(out, field, labels.to(logits.device), crit.ignore_index,
+                                          crit.weight.to(logits.device) if crit.weighted else None, step_counts)
+        else:
+            logits = self.model(self.make_input(batch))
+        if self.fused_head:
+            if self.cfg.use_sync_grad:
+                loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
+        elif self.segmentation:
             loss = self.criterion(logits, batch)
             if self.cfg.use_sync_grad:
                 loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
@@ -376,7 +406,9 @@ class Run:
                 raise ValueError(f"Invalid loss: {loss_float}")
             out = {"train/loss": loss_float, "train/lr": self.trainer.lr, "global_step": step}
             if self.segmentation:
-                for k, v in eval_metrics(logits.detach(), labels, logits.shape[1], self.cfg.ignore_label).items():
+                metrics = metrics_from_counts(step_counts) if step_counts is not None else \
+                    eval_metrics(logits.detach(), labels, logits.shape[1], self.cfg.ignore_label)
+                for k, v in metrics.items():
                     out[f"train/{k}"] = v
                 out["train/ignore_ratio"] = ((labels == self.cfg.ignore_label).sum() / labels.shape[0] * 100).item()
             else:
@@ -398,8 +430,20 @@ class Run:
             self.acc1_meter.reset()
             self.acc5_meter.reset()
         for batch in batches:
-            logits = self.model(self.make_input(batch))
             labels = batch["labels"].long()
+            if self.fused_head:
+                from . import pipeline
+                field = self.make_input(batch)
+                sparse_out = self.model.forward_sparse(field)
+                dev = sparse_out.F.device
+                step_counts = torch.zeros((3, self.num_labels), dtype=torch.int64, device=dev)
+                crit = self.criterion
+                losses.append(pipeline.seg_head_loss(sparse_out, field, labels.to(dev), crit.ignore_index,
+                                                     crit.weight.to(dev) if crit.weighted else None, step_counts).item())
+                oas.append(metrics_from_counts(step_counts)["OA"])
+                self.iou_meter.counts_buffer(dev).add_(step_counts)
+                continue
+            logits = self.model(self.make_input(batch))
             if self.segmentation:
                 losses.append(self.criterion(logits, batch).item())
                 oas.append(eval_metrics(logits, labels, logits.shape[1], self.cfg.ignore_label)["OA"])
@@ -460,13 +504,14 @@ class Run:
 
 
 def train(config_files: Sequence[str], bindings: Sequence[str], train_batches, val_batches=None, model=None,
-          save_path: Optional[str] = None, device="cuda", log=None, **overrides) -> Run:
+          save_path: Optional[str] = None, device="cuda", log=None, fused_head: bool = False, **overrides) -> Run:
     """`python -m co3d_3d.train --ginc ... --ginb ...` for one rank (train.py:199-263): parse the gin files and
     bindings, build `get_model()` unless a model is passed, run `fit`."""
     ginlite.parse_config_files_and_bindings(config_files, bindings)
     cfg = TrainConfig(**overrides)
     if model is None:
         model = get_model().to(device)
-    run = Run(model, cfg, save_path=save_path, void_label=_bound("PlenoxelScannetDataset.void_label", None), log=log)
+    run = Run(model, cfg, save_path=save_path, void_label=_bound("PlenoxelScannetDataset.void_label", None), log=log,
+              fused_head=fused_head)
     run.fit(train_batches, val_batches)
     return run

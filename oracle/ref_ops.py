@@ -388,3 +388,73 @@ def global_max_np(x: np.ndarray, batch: np.ndarray, n_batch: int):
             out[b] = x[rows][w, np.arange(C)]
             arg[b] = rows[w]
     return out, arg
+
+
+# ---------------------------------------------------------------------------
+# next rows f3 / f4: segmentation head, instance norm, sparse_quantize
+# ---------------------------------------------------------------------------
+def seg_head(voxel_logits: torch.Tensor, inverse: Optional[np.ndarray], target: np.ndarray, ignore_index: int,
+             weight: Optional[torch.Tensor] = None):
+    """The reference's three separate steps on the CPU, in its own torch expressions:
+      logits = out.slice(x).F                       — voxel rows gathered through the inverse map (res16unet.py:435)
+      loss   = F.cross_entropy(logits, labels, weight=, ignore_index=)       (segmentation_training.py:35-44)
+      counts = IoUMeter.update(logits.argmax(1), labels)                     (metrics.py:29-41)
+    Returns (loss, d loss / d voxel_logits, counts [3, C]) in the dtype of `voxel_logits` (use float64)."""
+    v = voxel_logits.detach().clone().requires_grad_(True)
+    idx = torch.arange(v.shape[0]) if inverse is None else torch.from_numpy(np.asarray(inverse)).long()
+    logits = v[idx]
+    t = torch.from_numpy(np.asarray(target)).long()
+    loss = torch.nn.functional.cross_entropy(logits, t, weight=weight, ignore_index=ignore_index)
+    (grad,) = torch.autograd.grad(loss, v)
+    counts = iou_counts_np(logits.detach().numpy(), t.numpy(), v.shape[1], ignore_index)
+    return loss.detach(), grad, counts
+
+
+def instance_norm(x: torch.Tensor, batch: np.ndarray, n_batch: int, weight: Optional[torch.Tensor] = None,
+                  bias: Optional[torch.Tensor] = None, eps: float = 1e-8) -> torch.Tensor:
+    """ME.MinkowskiInstanceNorm as ME composes it [ME-ext, MinkowskiNormalization.py]: per batch index,
+    mean = avg(x); centered = x - mean; var = avg(centered^2); out = centered / sqrt(var + eps); then the module's
+    `* weight + bias` ([1, C]).  Differentiable torch expressions: autograd of this function is the gradient oracle."""
+    b = torch.from_numpy(np.asarray(batch)).long()
+    out = torch.zeros_like(x)
+    for i in range(n_batch):
+        rows = torch.nonzero(b == i).flatten()
+        if rows.numel() == 0:
+            continue
+        xi = x[rows]
+        centered = xi - xi.mean(0, keepdim=True)
+        var = (centered ** 2).mean(0, keepdim=True)
+        out = out.index_copy(0, rows, centered / torch.sqrt(var + eps))
+    if weight is not None:
+        out = out * weight.reshape(1, -1)
+    if bias is not None:
+        out = out + bias.reshape(1, -1)
+    return out
+
+
+def sparse_quantize_np(coordinates: np.ndarray, features=None, labels=None, ignore_label: int = -100,
+                       quantization_size=None):
+    """ME.utils.sparse_quantize [ME-ext] as the reference calls it (scannet.py:235-242), voxels in first-occurrence
+    order: (discrete coords [M, 3] int32, features[first], voxel labels (ignore_label where the points of a voxel
+    disagree), first index [M], inverse [N])."""
+    c = np.asarray(coordinates)
+    if quantization_size is not None:
+        c = np.floor(c / quantization_size)
+    elif np.issubdtype(c.dtype, np.floating):
+        c = np.floor(c)
+    disc = c.astype(np.int32)
+    _, first, inverse = np.unique(disc, axis=0, return_index=True, return_inverse=True)
+    inverse = np.asarray(inverse).reshape(-1)
+    order = np.argsort(first, kind="stable")            # np.unique sorts lexicographically; we want first occurrence
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    first, inverse = first[order], rank[inverse]
+    out_labels = None
+    if labels is not None:
+        labels = np.asarray(labels).astype(np.int64)
+        out_labels = labels[first].copy()
+        for j in range(labels.shape[0]):                 # sequential, like ME's quantize_label
+            if labels[j] != labels[first[inverse[j]]]:
+                out_labels[inverse[j]] = ignore_label
+        out_labels = out_labels.astype(np.int32)
+    return disc[first], (None if features is None else np.asarray(features)[first]), out_labels, first, inverse

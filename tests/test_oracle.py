@@ -181,3 +181,66 @@ def test_max_pool_oracle_known_answers():
     assert out.tolist() == [[0, 0]] and arg.tolist() == [[-1, -1]]
     out, arg = R.global_max_np(x, np.array([0, 0, 1]), 3)  # batch 2 is empty
     assert out.tolist() == [[3, 5], [0, 9], [0, 0]] and arg.tolist() == [[1, 0], [2, 2], [-1, -1]]
+
+
+# ---- next rows f3 / f4: oracle pins ---------------------------------------------------------------------------
+def test_instance_norm_oracle_matches_torch_instance_norm():
+    """ME composes instance norm from global pooling / broadcast passes; per instance that is exactly
+    torch.nn.functional.instance_norm (biased variance) — pin the oracle on it, values and gradients."""
+    rng = np.random.default_rng(11)
+    batch = np.sort(rng.integers(0, 3, 90))
+    x = torch.randn(90, 7, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(1, 7, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(1, 7, dtype=torch.float64, requires_grad=True)
+    out = R.instance_norm(x, batch, 3, w, b, eps=1e-8)
+    gy = torch.randn(90, 7, dtype=torch.float64)
+    gx, gw, gb = torch.autograd.grad(out, (x, w, b), gy)
+    x2 = x.detach().clone().requires_grad_(True)
+    w2, b2 = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    parts = []
+    for i in range(3):
+        rows = torch.from_numpy(np.nonzero(batch == i)[0])
+        parts.append(torch.nn.functional.instance_norm(x2[rows].T[None], weight=w2.flatten(), bias=b2.flatten(),
+                                                       eps=1e-8)[0].T)
+    ref = torch.cat(parts)
+    hx, hw, hb = torch.autograd.grad(ref, (x2, w2, b2), gy)
+    assert torch.allclose(out, ref, atol=1e-12) and torch.allclose(gx, hx, atol=1e-10)
+    assert torch.allclose(gw.flatten(), hw.flatten(), atol=1e-10) and torch.allclose(gb.flatten(), hb.flatten(), atol=1e-10)
+
+
+def test_seg_head_oracle_known_answer():
+    """Two voxels, three points: point 0 and 2 share voxel 1; uniform logits -> loss = log(C); the gradient of a
+    shared voxel is the sum over its points; counts follow IoUMeter.update."""
+    C = 4
+    logits = torch.zeros(2, C, dtype=torch.float64)
+    logits[0, 2] = 5.0
+    inverse, target = np.array([1, 0, 1]), np.array([0, 2, 3])
+    loss, grad, counts = R.seg_head(logits, inverse, target, -100)
+    p0 = torch.softmax(logits[0], 0)
+    want = (2 * np.log(C) - torch.log(p0[2]).item()) / 3
+    assert abs(loss.item() - want) < 1e-12
+    g1 = torch.full((C,), 2 * 0.25 / 3, dtype=torch.float64)
+    g1[0] -= 1 / 3
+    g1[3] -= 1 / 3
+    assert torch.allclose(grad[1], g1, atol=1e-12)
+    assert counts.tolist() == [[1, 0, 1, 1], [1, 0, 1, 0], [2, 0, 1, 0]]       # argmax of a uniform row = class 0
+    # weights: the void (last) class at 0.5 -> weighted mean
+    w = torch.tensor([1, 1, 1, 0.5], dtype=torch.float64)
+    lw, _, _ = R.seg_head(logits, inverse, target, -100, w)
+    assert abs(lw.item() - (np.log(C) - torch.log(p0[2]).item() + 0.5 * np.log(C)) / 2.5) < 1e-12
+    # ignored points contribute nothing
+    li, gi, ci = R.seg_head(logits, inverse, np.array([0, -100, 3]), -100)
+    assert abs(li.item() - np.log(C)) < 1e-12 and float(gi[0].abs().max()) == 0.0 and ci[0].tolist() == [1, 0, 0, 1]
+
+
+def test_sparse_quantize_oracle_known_answer():
+    xyz = np.array([[0.1, 0.1, 0.1], [0.9, 0.2, 0.3], [-0.1, 0.0, 0.0], [1.2, 0.0, 0.0], [0.4, 0.4, 0.4], [1.9, 0.9, 0.9]])
+    feats = np.arange(6, dtype=np.float32).reshape(6, 1)
+    labels = np.array([3, 3, 1, 2, 5, 2])
+    c, f, l, first, inv = R.sparse_quantize_np(xyz, feats, labels, ignore_label=-100, quantization_size=1.0)
+    assert c.tolist() == [[0, 0, 0], [-1, 0, 0], [1, 0, 0]]                    # first-occurrence order, floor(-0.1) = -1
+    assert first.tolist() == [0, 2, 3] and inv.tolist() == [0, 0, 1, 2, 0, 2]
+    assert f.flatten().tolist() == [0.0, 2.0, 3.0]
+    assert l.tolist() == [-100, 1, 2]                                          # voxel 0 holds labels 3, 3, 5 -> ignore
+    c2, _, _, first2, _ = R.sparse_quantize_np(xyz, quantization_size=0.5)
+    assert c2.shape == (5, 3) and first2.tolist() == [0, 1, 2, 3, 5]          # 0.1 and 0.4 share a 0.5-voxel

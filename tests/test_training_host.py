@@ -449,3 +449,61 @@ def test_train_config_errors():
         training.get_model()
     with pytest.raises(AssertionError, match="not in"):
         training.Run(TinyNet(), training.TrainConfig(max_steps=1, training_module="Foo"), num_labels=4)
+
+
+def test_fused_head_run_equals_three_pass_run(monkeypatch):
+    """`fused_head=True` (one kernel for slice + SegLoss + counts) drives the loop to the same losses, metrics and
+    weights as the three-pass form.  The kernel itself is replaced by its torch restatement here (GPU parity:
+    tests/test_gpu_widen.py); under test are the loop, the counts -> OA / mIoU conversion and the meters."""
+    _cpu_kernels(monkeypatch)
+    from types import SimpleNamespace
+
+    from nerf_downstream_b200 import pipeline
+
+    class SparseTiny(TinyNet):
+        def forward_sparse(self, x):
+            return SimpleNamespace(F=TinyNet.forward(self, x))
+
+    def head_cpu(out, field, labels, ignore_index=-100, weight=None, counts=None):
+        if counts is not None:
+            pipeline.seg_counts(out.F.detach(), labels, ignore_index, out=counts)
+        return torch.nn.functional.cross_entropy(out.F, labels, weight=weight, ignore_index=ignore_index)
+
+    monkeypatch.setattr(pipeline, "seg_head_loss", head_cpu)
+    ginlite.parse_config("train.max_steps = 9\ntrain.scheduler_name = 'PolyLR'\nPolyLR.poly_exp = 0.9\ntrain.lr = 0.1\n"
+                         "train.ignore_label = -255\ntrain.val_every_n_steps = 3\ntrain.log_every_n_steps = 2\n"
+                         "train.void_weight = 0.5\nSGD.momentum = 0.9\nget_model.out_channel = 4")
+    data, val = _batches(30, 3, ignore=-255), _batches(31, 2, ignore=-255)
+    results = []
+    for fused in (False, True):
+        torch.manual_seed(7)
+        logs = []
+        run = training.Run(SparseTiny(), training.TrainConfig(), make_input=lambda b: b["features"], log=logs.append,
+                           fused_head=fused)
+        last = run.fit(lambda: data, lambda: val)
+        results.append((logs, last, [p.detach().clone() for p in run.model.parameters()]))
+    (la, va, pa), (lb, vb, pb) = results
+    assert len(la) == len(lb) and len(la) >= 6
+    for a, b in zip(la, lb):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * (1 + abs(a[k])), (k, a[k], b[k])
+    for k in va:
+        assert abs(va[k] - vb[k]) <= 1e-5 * (1 + abs(va[k])), k
+    for x, y in zip(pa, pb):
+        assert torch.allclose(x, y, atol=1e-6)
+    with pytest.raises(ValueError, match="forward_sparse"):
+        training.Run(TinyNet(), training.TrainConfig(), make_input=lambda b: b["features"], fused_head=True)
+
+
+def test_metrics_from_counts_equals_eval_metrics():
+    golden = json.loads((GOLDEN / "metrics_ref.json").read_text())
+    for name, c in golden.items():
+        counts = torch.tensor([c["seen"], c["correct"], c["positive"]]).long()
+        m = training.metrics_from_counts(counts)
+        if c["precision_at_one"] is None:
+            assert math.isnan(m["OA"])
+            continue
+        assert abs(m["OA"] - c["precision_at_one"]) < 1e-4
+        want = float(np.mean([0.0 if v is None else v for v in c["per_class_iu"]]) * 100)
+        assert abs(m["mIoU"] - want) < 1e-9, name
