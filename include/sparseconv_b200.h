@@ -292,6 +292,20 @@ int spc_inst_norm_bwd(const float* x, const float* dy, const int32_t* coords, in
                       const float* gamma, const float* mean, const float* rstd, const int32_t* cnt, float* dx,
                       double* sums, void* stream);
 
+/* ---- trilinear interpolation / splat (ME.MinkowskiInterpolation, SparseTensor.interpolate,
+ * TensorField.splat; fcnn.py:184-205, transforms.py:472,520-528) ----------------------------------------------------
+ * spc_interp_corners: query[n,4] float (b,x,y,z) -> lower[n,4] int32 = (floor(b), floor(x/ts)*ts, ...) and
+ *   weights[8,n]: corner k = bx + 2 by + 4 bz sits at lower + (bx,by,bz)*ts with weight prod(axis: b ? f : 1 - f),
+ *   f = x/ts - floor(x/ts).  ts = HOST int32[3].  The rows idx[8,n] of the corners in a voxel map are
+ *   spc_kernel_map(table, lower, n, the 8 corner offsets) (interpolate) or the inverse map of inserting them (splat).
+ * spc_interp_fwd: out[j,:] = sum_k weights[k,j] * feats[idx[k,j],:]   (idx < 0: corner not in the map, skipped)
+ * spc_interp_bwd: dfeats[idx[k,j],:] += weights[k,j] * dout[j,:]      (dfeats [m,C] zeroed here) = the splat forward */
+int spc_interp_corners(const float* query, int64_t n, const int32_t* ts, int32_t* lower, float* weights, void* stream);
+int spc_interp_fwd(const float* feats, const int32_t* idx, const float* weights, int64_t n, int C, int K, float* out,
+                   void* stream);
+int spc_interp_bwd(const float* dout, const int32_t* idx, const float* weights, int64_t n, int64_t m, int C, int K,
+                   float* dfeats, void* stream);
+
 /* Fused SGD step on a flat arena (co3d_cls.gin:33-39; optim.py:60-69):
  * g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf. */
 int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,

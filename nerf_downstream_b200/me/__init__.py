@@ -7,7 +7,7 @@ from .core import (ConvolutionMode, CoordinateManager, CoordinateMapKey, Coordin
 from .modules import (MinkowskiAvgPooling, MinkowskiBatchNorm, MinkowskiCELU, MinkowskiConvolution,  # noqa: F401
                       MinkowskiConvolutionBase, MinkowskiConvolutionTranspose, MinkowskiDropout, MinkowskiELU,
                       MinkowskiGELU, MinkowskiGlobalAvgPooling, MinkowskiGlobalMaxPooling, MinkowskiGlobalPooling,
-                      MinkowskiGlobalSumPooling, MinkowskiInstanceNorm, MinkowskiLeakyReLU, MinkowskiLinear,
+                      MinkowskiGlobalSumPooling, MinkowskiInstanceNorm, MinkowskiInterpolation, MinkowskiLeakyReLU, MinkowskiLinear,
                       MinkowskiMaxPooling, MinkowskiModuleBase, MinkowskiNetwork, MinkowskiNonlinearityBase,
                       MinkowskiPReLU, MinkowskiReLU, MinkowskiSELU, MinkowskiSigmoid, MinkowskiSoftmax,
                       MinkowskiSumPooling, MinkowskiSyncBatchNorm, MinkowskiTanh, cat)

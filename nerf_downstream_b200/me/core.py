@@ -202,6 +202,7 @@ class CoordinateManager:
         self._stride_parent: Dict[CoordinateMapKey, tuple] = {}  # out key -> (in key, parent->child rows, count)
         self._kernel_maps: Dict[tuple, ops.KernelMap] = {}
         self._identity_maps: Dict[CoordinateMapKey, ops.KernelMap] = {}
+        self._interp_maps: Dict[tuple, tuple] = {}             # (field key, map key) -> (rows [8,N], weights [8,N])
         self._n_batch: Optional[int] = None
         self._field_counter = 0
         self.prefetch_depth = CoordinateManager.default_prefetch_depth
@@ -613,6 +614,21 @@ class SparseTensor(Tensor):
                            coordinate_field_map_key=X.coordinate_field_map_key,
                            coordinate_manager=X.coordinate_manager, quantization_mode=X.quantization_mode)
 
+    def interpolate(self, X: "TensorField") -> "TensorField":
+        """Trilinear interpolation of this tensor's voxel features at the points of `X` (fcnn.py:200-203): each point
+        reads the 8 voxels of THIS tensor's stride lattice around it; voxels that do not exist contribute zero."""
+        assert isinstance(X, TensorField), "interpolate expects a TensorField"
+        mgr = self._manager
+        ck = (X.coordinate_field_map_key, self.coordinate_map_key)
+        cached = mgr._interp_maps.get(ck)
+        if cached is None:
+            cached = ops.interp_map(mgr._map(self.coordinate_map_key), X.C)
+            mgr._interp_maps[ck] = cached
+        idx, w = cached
+        return TensorField(ops.InterpolateFn.apply(self.F, idx, w),
+                           coordinate_field_map_key=X.coordinate_field_map_key,
+                           coordinate_manager=X.coordinate_manager, quantization_mode=X.quantization_mode)
+
     def features_at(self, batch_index: int) -> torch.Tensor:
         return self.F[self.C[:, 0] == batch_index]
 
@@ -698,6 +714,25 @@ class TensorField(Tensor):
         m = mgr.size(key)
         feats = self._F if self._F.dtype == torch.float32 else self._F.float()
         F = ops.SegmentReduceFn.apply(feats, inverse, count, first, m, code)
+        return SparseTensor(F, coordinate_map_key=key, coordinate_manager=mgr)
+
+    def splat(self) -> SparseTensor:
+        """Spread every point's features over the 8 voxels around it with trilinear weights (fcnn.py:186): the result
+        lives on a new map holding all touched voxels (in order of first touch); `Y.interpolate(X)` is the way back."""
+        mgr = self._manager
+        field_ts = self.coordinate_field_map_key.get_tensor_stride()
+        ts = [max(int(t), 1) for t in field_ts]
+        q = self.C
+        n = q.shape[0]
+        lower, w = ops.interp_corners(q, ts)
+        offs = torch.tensor(ops.corner_offsets(ts), dtype=torch.int32, device=q.device)          # [8, 3]
+        corners = lower[:, None, :].repeat(1, 8, 1)
+        corners[:, :, 1:] += offs[None]
+        key, _ = mgr.insert_and_map(corners.view(-1, 4), tensor_stride=ts)
+        idx = mgr._insert_aux[key][1].view(n, 8).t().contiguous()                                 # rows, [8, N]
+        mgr._interp_maps[(self.coordinate_field_map_key, key)] = (idx, w)
+        feats = self._F if self._F.dtype == torch.float32 else self._F.float()
+        F = ops.SplatFn.apply(feats, idx, w, mgr.size(key))
         return SparseTensor(F, coordinate_map_key=key, coordinate_manager=mgr)
 
     def inverse_mapping(self, sparse_key: CoordinateMapKey) -> torch.Tensor:

@@ -432,6 +432,37 @@ class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
         return self.__class__.__name__ + "()"
 
 
+class MinkowskiInterpolation(MinkowskiModuleBase):
+    """Trilinear sampling of a sparse tensor at continuous coordinates (transforms.py:472,520-528):
+    `forward(input, tfield)` with tfield = float [N, 4] (batch, x, y, z) returns the [N, C] features (a plain tensor,
+    as ME does); `return_kernel_map` / `return_weights` append the (voxel rows, point rows) pairs and their weights."""
+
+    def __init__(self, return_kernel_map=False, return_weights=False):
+        super().__init__()
+        self.return_kernel_map = return_kernel_map
+        self.return_weights = return_weights
+
+    def forward(self, input: SparseTensor, tfield: torch.Tensor):
+        assert isinstance(input, SparseTensor)
+        mgr = input.coordinate_manager
+        query = tfield.to(device=input.F.device, dtype=torch.float32)
+        idx, w = ops.interp_map(mgr._map(input.coordinate_map_key), query)
+        out = ops.InterpolateFn.apply(input.F, idx, w)
+        if not (self.return_kernel_map or self.return_weights):
+            return out
+        valid = idx >= 0
+        points = torch.arange(idx.shape[1], device=idx.device).expand_as(idx)
+        result = [out]
+        if self.return_kernel_map:
+            result.append((idx[valid].long(), points[valid]))
+        if self.return_weights:
+            result.append(w[valid])
+        return tuple(result)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "()"
+
+
 # ---------------------------------------------------------------------------
 # tensor ops
 # ---------------------------------------------------------------------------

@@ -1037,6 +1037,92 @@ class InstanceNormFn(torch.autograd.Function):
         return dx, None, None, dgamma, dbeta, None
 
 
+# ---------------------------------------------------------------------------
+# trilinear interpolation / splat (ME.MinkowskiInterpolation, SparseTensor.interpolate, TensorField.splat)
+# ---------------------------------------------------------------------------
+def corner_offsets(ts: Sequence[int]):
+    """The 8 corners of a lattice cell, k = bx + 2 by + 4 bz (first spatial axis fastest)."""
+    return [((k & 1) * int(ts[0]), ((k >> 1) & 1) * int(ts[1]), ((k >> 2) & 1) * int(ts[2])) for k in range(8)]
+
+
+def interp_corners(query: torch.Tensor, ts: Sequence[int]):
+    """query [N,4] float32 (b,x,y,z) -> (lower corner int32 [N,4], weights float32 [8,N])."""
+    lib = L.load()
+    if query.dtype != torch.float32 or query.dim() != 2 or query.shape[1] != 4:
+        raise RuntimeError(f"query coordinates must be float32 [N,4], got {query.dtype} {tuple(query.shape)}")
+    query = query.contiguous()
+    n = query.shape[0]
+    lower = _empty((n, 4), torch.int32, query.device)
+    w = _empty((8, n), torch.float32, query.device)
+    ts_arr = _I3(*[int(t) for t in ts])
+    L.check(lib.spc_interp_corners(L.ptr(query), n, ctypes.cast(ts_arr, ctypes.c_void_p), L.ptr(lower), L.ptr(w),
+                                   L.stream()), "spc_interp_corners")
+    return lower, w
+
+
+def interp_map(in_map: CoordMap, query: torch.Tensor):
+    """Rows and weights of the 8 voxels of `in_map` around every query point: (idx int32 [8,N], w float32 [8,N])."""
+    lower, w = interp_corners(query, in_map.tensor_stride)
+    km = build_kernel_map(in_map, CoordMap(lower, None, 0, lower.shape[0], in_map.tensor_stride),
+                          corner_offsets(in_map.tensor_stride))
+    return km.nbr, w
+
+
+def _interp_gather(feats, idx, w):
+    lib = L.load()
+    K, n = idx.shape
+    C = feats.shape[1]
+    out = _empty((n, C), torch.float32, feats.device)
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_interp_fwd(L.ptr(feats), L.ptr(idx), L.ptr(w), n, C, K, L.ptr(out), L.stream()), "spc_interp_fwd")
+    if e0 is not None:
+        _profiler.end("interp_gather", e0, 0, 4.0 * C * n * (K + 1) + 8.0 * K * n, f"C{C} N{n}")
+    return out
+
+
+def _interp_scatter(src, idx, w, m):
+    lib = L.load()
+    K, n = idx.shape
+    C = src.shape[1]
+    out = _empty((m, C), torch.float32, src.device)
+    e0 = _profiler.begin() if _profiler else None
+    L.check(lib.spc_interp_bwd(L.ptr(src), L.ptr(idx), L.ptr(w), n, m, C, K, L.ptr(out), L.stream()), "spc_interp_bwd")
+    if e0 is not None:
+        _profiler.end("interp_scatter", e0, 0, 4.0 * C * n * (K + 1) + 8.0 * K * n, f"C{C} N{n}")
+    return out
+
+
+class InterpolateFn(torch.autograd.Function):
+    """out[j] = sum_k w[k,j] * feats[idx[k,j]] — voxel features at the query points."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, w):
+        feats = _feat(feats)
+        ctx.save_for_backward(idx, w)
+        ctx.m = feats.shape[0]
+        return _interp_gather(feats, idx, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, w = ctx.saved_tensors
+        return _interp_scatter(_feat(g), idx, w, ctx.m), None, None
+
+
+class SplatFn(torch.autograd.Function):
+    """out[idx[k,j]] += w[k,j] * feats[j] — point features spread over their 8 voxels (transpose of InterpolateFn)."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, w, m):
+        feats = _feat(feats)
+        ctx.save_for_backward(idx, w)
+        return _interp_scatter(feats, idx, w, m)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, w = ctx.saved_tensors
+        return _interp_gather(_feat(g), idx, w), None, None, None
+
+
 def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):
     lib = L.load()
     L.check(lib.spc_sgd_step(L.ptr(param), L.ptr(grad), L.ptr(buf), param.numel(), float(lr), float(momentum),

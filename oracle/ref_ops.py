@@ -458,3 +458,54 @@ def sparse_quantize_np(coordinates: np.ndarray, features=None, labels=None, igno
                 out_labels[inverse[j]] = ignore_label
         out_labels = out_labels.astype(np.int32)
     return disc[first], (None if features is None else np.asarray(features)[first]), out_labels, first, inverse
+
+
+def interp_map_np(map_coords: np.ndarray, query: np.ndarray, ts: Sequence[int] = (1, 1, 1)):
+    """Trilinear interpolation map of ME.MinkowskiInterpolation / TensorField.splat [ME-ext]: for every query point
+    (b, x, y, z) the 8 lattice voxels around it, corner k = bx + 2 by + 4 bz at floor(x / ts) * ts + bit * ts with
+    weight prod_axis (bit ? f : 1 - f), f = x / ts - floor(x / ts) (float32 arithmetic, like the kernel).
+    Returns (corner coordinates int32 [N, 8, 4], rows in `map_coords` int64 [8, N] (-1 = absent), weights f32 [8, N])."""
+    q = np.asarray(query, np.float32)
+    n = q.shape[0]
+    tsf = np.asarray(ts, np.float32)
+    t = (q[:, 1:] / tsf).astype(np.float32)
+    fl = np.floor(t)
+    frac = (t - fl).astype(np.float32)
+    lower = np.concatenate([np.floor(q[:, :1]).astype(np.int32), fl.astype(np.int32) * np.asarray(ts, np.int32)], 1)
+    corners = np.repeat(lower[:, None, :], 8, 1)
+    w = np.ones((8, n), np.float32)
+    for k in range(8):
+        for a in range(3):
+            bit = (k >> a) & 1
+            corners[:, k, 1 + a] += bit * int(ts[a])
+            w[k] = (w[k] * (frac[:, a] if bit else (np.float32(1) - frac[:, a]))).astype(np.float32)
+    lut = {tuple(c): i for i, c in enumerate(np.asarray(map_coords).tolist())}
+    rows = np.full((8, n), -1, np.int64)
+    for j in range(n):
+        for k in range(8):
+            rows[k, j] = lut.get(tuple(corners[j, k].tolist()), -1)
+    return corners, rows, w
+
+
+def interpolate(feats: torch.Tensor, rows: np.ndarray, w: np.ndarray) -> torch.Tensor:
+    """out[j] = sum_k w[k, j] * feats[rows[k, j]] over the present corners (differentiable torch expression)."""
+    out = torch.zeros((rows.shape[1], feats.shape[1]), dtype=feats.dtype)
+    for k in range(rows.shape[0]):
+        ok = torch.from_numpy(rows[k] >= 0)
+        r = torch.from_numpy(np.where(rows[k] >= 0, rows[k], 0))
+        out = out + torch.where(ok[:, None], feats[r] * torch.from_numpy(w[k]).to(feats.dtype)[:, None],
+                                torch.zeros((), dtype=feats.dtype))
+    return out
+
+
+def splat(feats: torch.Tensor, query: np.ndarray, ts: Sequence[int] = (1, 1, 1)):
+    """TensorField.splat: (voxel coordinates int32 [M, 4] in order of first touch (point-major, corner-minor),
+    voxel features [M, C] = sum over (point, corner) of w * feats[point])."""
+    corners, _, w = interp_map_np(np.zeros((0, 4), np.int32), query, ts)
+    flat = corners.reshape(-1, 4)
+    uc, _, inv = unique_first_np(flat)
+    rows = np.asarray(inv).reshape(-1, 8).T                      # [8, N]
+    out = torch.zeros((uc.shape[0], feats.shape[1]), dtype=feats.dtype)
+    for k in range(8):
+        out = out.index_add(0, torch.from_numpy(rows[k]).long(), feats * torch.from_numpy(w[k]).to(feats.dtype)[:, None])
+    return uc, out, rows, w

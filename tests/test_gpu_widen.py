@@ -268,3 +268,73 @@ SGD.momentum = 0.9
         assert (a - z).abs().max().item() <= 1e-3 * a.abs().max().item()
     finally:
         ginlite.clear_config()
+
+
+# ---- f4: trilinear interpolation / splat ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n_vox,n_query,C,ts", [(3000, 5000, 8, 1), (3000, 4000, 3, 2), (200, 1, 5, 1),
+                                                 (20_000, 60_000, 32, 1)])
+def test_interpolation_matches_oracle(cuda_device, n_vox, n_query, C, ts):
+    rng = np.random.default_rng(n_vox + n_query)
+    c, _ = synth.random_cloud(n_vox, n_vox, extent=10, n_batch=2)
+    cmap, _, _, _ = ops.coords_insert(torch.from_numpy(c).to(cuda_device), 0, (ts, ts, ts))       # 0 = SRC_FLOAT
+    map_coords = cmap.coords.cpu().numpy()
+    q = np.empty((n_query, 4), np.float32)
+    q[:, 0] = rng.integers(0, 2, n_query)
+    q[:, 1:] = rng.uniform(-10.5, 10.5, (n_query, 3))
+    q[: n_query // 10, 1:] = np.round(q[: n_query // 10, 1:])                   # points exactly on the lattice
+    feats = rng.standard_normal((cmap.size, C)).astype(np.float32)
+    gy = rng.standard_normal((n_query, C)).astype(np.float32)
+
+    _, rows, w = R.interp_map_np(map_coords, q, (ts, ts, ts))
+    idx_g, w_g = ops.interp_map(cmap, torch.from_numpy(q).to(cuda_device))
+    assert (idx_g.cpu().numpy() == rows).all()                                   # integer part exact
+    assert np.abs(w_g.cpu().numpy() - w).max() <= 1e-6
+    fr = torch.from_numpy(feats).double().requires_grad_(True)
+    ref = R.interpolate(fr, rows, w)
+    ref.backward(torch.from_numpy(gy).double())
+    fg = torch.from_numpy(feats).to(cuda_device).requires_grad_(True)
+    out = ops.InterpolateFn.apply(fg, idx_g, w_g)
+    out.backward(torch.from_numpy(gy).to(cuda_device))
+    close(out, ref)
+    close(fg.grad, fr.grad)
+
+
+def test_splat_and_interpolate_on_me_surface(cuda_device):
+    rng = np.random.default_rng(3)
+    n, C = 4000, 6
+    q = np.empty((n, 4), np.float32)
+    q[:, 0] = np.sort(rng.integers(0, 2, n))
+    q[:, 1:] = rng.uniform(-6, 6, (n, 3))
+    f = rng.standard_normal((n, C)).astype(np.float32)
+    x = ME.TensorField(coordinates=torch.from_numpy(q).to(cuda_device),
+                       features=torch.from_numpy(f).to(cuda_device).requires_grad_(True))
+    y = x.splat()
+    uc, ref, rows, w = R.splat(torch.from_numpy(f).double(), q)
+    assert (y.C.cpu().numpy() == uc).all() and y.tensor_stride == [1, 1, 1]      # voxels in order of first touch
+    close(y.F, ref)
+    assert abs(y.F.sum().item() - f.sum()) <= 1e-2                               # weights of a point sum to one
+    # back to the points: sum_k w_k * splat[row_k]
+    back = y.interpolate(x)
+    assert back.coordinate_field_map_key == x.coordinate_field_map_key
+    close(back.F, R.interpolate(ref, rows, w), 2e-4)
+    back.F.sum().backward()                                                      # gradient flows through both maps
+    wsum = torch.from_numpy(w).double().sum(0)
+    assert x.F.grad is not None and x.F.grad.shape == (n, C)
+    # d/df_j of sum_i back_i = sum over voxels v touched by j of w_jv * (sum_i w_iv)
+    colsum = torch.zeros(uc.shape[0], dtype=torch.float64)
+    for k in range(8):
+        colsum.index_add_(0, torch.from_numpy(rows[k]).long(), torch.from_numpy(w[k]).double())
+    want = sum(torch.from_numpy(w[k]).double() * colsum[torch.from_numpy(rows[k]).long()] for k in range(8))
+    close(x.F.grad[:, 0], want, 2e-4)
+    # MinkowskiInterpolation on a strided tensor (a linear function on a full lattice is reproduced exactly)
+    g = np.stack(np.meshgrid(*[np.arange(-4, 5, 2)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    bc = np.concatenate([np.zeros((len(g), 1)), g], 1).astype(np.int32)
+    lin = (g @ np.array([[1.0], [-2.0], [0.5]]) + 3.0).astype(np.float32)
+    s = ME.SparseTensor(torch.from_numpy(lin).to(cuda_device), coordinates=torch.from_numpy(bc).to(cuda_device),
+                        tensor_stride=2)
+    pts = np.concatenate([np.zeros((100, 1)), rng.uniform(-4, 3.9, (100, 3))], 1).astype(np.float32)
+    out, (in_rows, out_rows), wts = ME.MinkowskiInterpolation(return_kernel_map=True, return_weights=True)(
+        s, torch.from_numpy(pts).to(cuda_device))
+    want = pts[:, 1:] @ np.array([[1.0], [-2.0], [0.5]]) + 3.0
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-4
+    assert in_rows.shape == out_rows.shape == wts.shape and in_rows.numel() == 800

@@ -244,3 +244,28 @@ def test_sparse_quantize_oracle_known_answer():
     assert l.tolist() == [-100, 1, 2]                                          # voxel 0 holds labels 3, 3, 5 -> ignore
     c2, _, _, first2, _ = R.sparse_quantize_np(xyz, quantization_size=0.5)
     assert c2.shape == (5, 3) and first2.tolist() == [0, 1, 2, 3, 5]          # 0.1 and 0.4 share a 0.5-voxel
+
+
+def test_interpolation_oracle_properties():
+    """Trilinear weights: a point's 8 weights sum to one, a lattice point puts all its weight on its own voxel, and a
+    linear function stored on a full lattice is reproduced exactly; splat conserves the feature mass."""
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(*[np.arange(-3, 3)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    mc = np.concatenate([np.zeros((len(g), 1), np.int64), g], 1).astype(np.int32)
+    A, b = np.array([[1.0, 2.0], [0.5, -1.0], [3.0, 0.25]]), np.array([0.3, -2.0])
+    f = torch.from_numpy(g @ A + b)
+    q = np.concatenate([np.zeros((40, 1)), rng.uniform(-3, 1.99, (40, 3))], 1).astype(np.float32)
+    q[0, 1:] = [1.0, -2.0, 0.0]
+    corners, rows, w = R.interp_map_np(mc, q)
+    assert np.abs(w.sum(0) - 1).max() < 1e-6 and (rows >= 0).all()
+    assert w[0, 0] == 1.0 and (w[1:, 0] == 0).all() and mc[rows[0, 0]].tolist() == [0, 1, -2, 0]
+    assert corners[5, 7].tolist() == (corners[5, 0] + [0, 1, 1, 1]).tolist()       # corner k = bx + 2 by + 4 bz
+    out = R.interpolate(f, rows, w)
+    assert np.abs(out.numpy() - (q[:, 1:].astype(np.float64) @ A + b)).max() < 1e-5
+    # negative coordinates floor towards -inf; a strided lattice scales the cell
+    _, _, w2 = R.interp_map_np(mc, np.array([[0, -0.25, 0, 0]], np.float32))
+    assert abs(w2[0, 0] - 0.25) < 1e-7 and abs(w2[1, 0] - 0.75) < 1e-7
+    c4, _, w4 = R.interp_map_np(mc, np.array([[0, 3.0, 0, 0]], np.float32), (4, 4, 4))
+    assert c4[0, 0].tolist() == [0, 0, 0, 0] and c4[0, 1].tolist() == [0, 4, 0, 0] and abs(w4[1, 0] - 0.75) < 1e-7
+    uc, sf, rows_s, _ = R.splat(torch.ones(40, 2, dtype=torch.float64), q)
+    assert abs(sf.sum().item() - 80) < 1e-4 and rows_s.max() == uc.shape[0] - 1
