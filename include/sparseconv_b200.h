@@ -291,6 +291,9 @@ int spc_inst_norm_fwd(const float* x, const int32_t* coords, int64_t m, int C, i
 int spc_inst_norm_bwd(const float* x, const float* dy, const int32_t* coords, int64_t m, int C, int n_batch,
                       const float* gamma, const float* mean, const float* rstd, const int32_t* cnt, float* dx,
                       double* sums, void* stream);
+/* Debug knob: 1 = always use the scalar kernels (C % 4 == 0 inputs normally take the 16-byte kernels); tests use it
+ * to cross-check the two paths. */
+void spc_inst_norm_force_scalar(int on);
 
 /* ---- trilinear interpolation / splat (ME.MinkowskiInterpolation, SparseTensor.interpolate,
  * TensorField.splat; fcnn.py:184-205, transforms.py:472,520-528) ----------------------------------------------------

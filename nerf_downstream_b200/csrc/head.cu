@@ -8,6 +8,8 @@
 //   instance norm : ME.MinkowskiInstanceNorm (modules/common.py:25-26, resunet.py "IN" variants): per (batch index,
 //                   channel) mean / biased variance over the rows of that instance, (x - mean) / sqrt(var + eps), then
 //                   the [1, C] affine.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace spc {
@@ -215,6 +217,163 @@ inst_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
+// ---- 16-byte versions (C % 4 == 0): a thread owns a channel QUAD, issues four rows' loads before it consumes them, and
+// the per-thread partial sums of a block that lies inside one instance meet in shared memory, so that only `lanes`
+// threads per block touch the double atomics.  lanes = quads per block row (<= 256), rows = 256 / lanes row slots.
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+__device__ __forceinline__ void inst_flush_direct(double* sums, int* cnt, int cur, int n_batch, int C, int cq,
+                                                  const float4& a0, const float4& a1, int k, bool count) {
+  if (cur < 0 || cur >= n_batch || k == 0) return;
+  double* p0 = sums + ((long long)cur * 2 + 0) * C + 4 * cq;
+  double* p1 = sums + ((long long)cur * 2 + 1) * C + 4 * cq;
+  atomicAdd(p0 + 0, (double)a0.x); atomicAdd(p0 + 1, (double)a0.y); atomicAdd(p0 + 2, (double)a0.z); atomicAdd(p0 + 3, (double)a0.w);
+  atomicAdd(p1 + 0, (double)a1.x); atomicAdd(p1 + 1, (double)a1.y); atomicAdd(p1 + 2, (double)a1.z); atomicAdd(p1 + 3, (double)a1.w);
+  if (count && cq == 0) atomicAdd(cnt + cur, k);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+inst_sums4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const int4* __restrict__ coords, long long m, int C, int C4,
+                  int n_batch, int lanes, int rows, int rows_per_block, double* __restrict__ sums,
+                  int* __restrict__ cnt) {
+  __shared__ float4 s0[256], s1[256];
+  __shared__ int s_k[256];
+  __shared__ int s_cur;
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const int cq = blockIdx.y * lanes + lane;
+  const bool active = rl < rows && cq < C4;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < m ? r0 + rows_per_block : m;
+  float4 a0 = f4_zero(), a1 = f4_zero(), mu = f4_zero(), rs = f4_zero();
+  int cur = -1, k = 0;
+  if (active) {
+    for (long long r = r0 + rl; r < r1; r += (long long)rows * 4) {
+      int b[4];
+      float4 v[4], g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * rows;
+        b[u] = INT_MIN;
+        if (rr < r1) {
+          b[u] = coords[rr].x;
+          v[u] = x[rr * C4 + cq];
+          if (BWD) g[u] = dy[rr * C4 + cq];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b[u] == INT_MIN) continue;
+        if (b[u] != cur) {
+          inst_flush_direct(sums, cnt, cur, n_batch, C, cq, a0, a1, k, !BWD);
+          cur = b[u]; a0 = f4_zero(); a1 = f4_zero(); k = 0;
+          if (BWD && cur >= 0 && cur < n_batch) {
+            mu = *reinterpret_cast<const float4*>(mean + (long long)cur * C + 4 * cq);
+            rs = *reinterpret_cast<const float4*>(rstd + (long long)cur * C + 4 * cq);
+          }
+        }
+        if (BWD) {
+          f4_add(a0, g[u]);
+          a1.x += g[u].x * ((v[u].x - mu.x) * rs.x); a1.y += g[u].y * ((v[u].y - mu.y) * rs.y);
+          a1.z += g[u].z * ((v[u].z - mu.z) * rs.z); a1.w += g[u].w * ((v[u].w - mu.w) * rs.w);
+        } else {
+          f4_add(a0, v[u]);
+          a1.x += v[u].x * v[u].x; a1.y += v[u].y * v[u].y; a1.z += v[u].z * v[u].z; a1.w += v[u].w * v[u].w;
+        }
+        ++k;
+      }
+    }
+  }
+  // final flush: through shared memory when every partial sum of the block belongs to the same instance
+  if (threadIdx.x == 0) s_cur = cur;                 // thread 0 always owns row r0 of a launched block
+  __syncthreads();
+  const int bcur = s_cur;
+  const bool mine = active && k > 0;
+  const int uniform = __syncthreads_and(!mine || cur == bcur);
+  if (!uniform || bcur < 0 || bcur >= n_batch) {
+    if (mine) inst_flush_direct(sums, cnt, cur, n_batch, C, cq, a0, a1, k, !BWD);
+    return;
+  }
+  s0[threadIdx.x] = mine ? a0 : f4_zero();
+  s1[threadIdx.x] = mine ? a1 : f4_zero();
+  s_k[threadIdx.x] = mine ? k : 0;
+  __syncthreads();
+  if (rl == 0 && cq < C4) {
+    float4 t0 = f4_zero(), t1 = f4_zero();
+    int kk = 0;
+    for (int sl = 0; sl < rows; ++sl) {
+      f4_add(t0, s0[sl * lanes + lane]);
+      f4_add(t1, s1[sl * lanes + lane]);
+      kk += s_k[sl * lanes + lane];
+    }
+    inst_flush_direct(sums, cnt, bcur, n_batch, C, cq, t0, t1, kk, !BWD);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+inst_apply4_kernel(const float4* __restrict__ x, const int4* __restrict__ coords, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   long long total4, int C, int C4, int n_batch, float4* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += stride) {
+    const long long r = e / C4;
+    const int cq = (int)(e - r * C4);
+    const int b = coords[r].x;
+    const float4 v = x[e];
+    float4 o = f4_zero();
+    if (b >= 0 && b < n_batch) {
+      const float4 mu = *reinterpret_cast<const float4*>(mean + (long long)b * C + 4 * cq);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd + (long long)b * C + 4 * cq);
+      const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 be = beta ? *reinterpret_cast<const float4*>(beta + 4 * cq) : f4_zero();
+      o.x = (v.x - mu.x) * rs.x * ga.x + be.x; o.y = (v.y - mu.y) * rs.y * ga.y + be.y;
+      o.z = (v.z - mu.z) * rs.z * ga.z + be.z; o.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+    }
+    y[e] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+inst_bwd_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const int4* __restrict__ coords,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                       const double* __restrict__ sums, const int* __restrict__ cnt, long long total4, int C, int C4,
+                       int n_batch, float4* __restrict__ dx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += stride) {
+    const long long r = e / C4;
+    const int cq = (int)(e - r * C4);
+    const int b = coords[r].x;
+    const float4 v = x[e], g = dy[e];
+    float4 o = f4_zero();
+    if (b >= 0 && b < n_batch) {
+      const float4 mu = *reinterpret_cast<const float4*>(mean + (long long)b * C + 4 * cq);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd + (long long)b * C + 4 * cq);
+      const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float inv_n = 1.f / (float)cnt[b];
+      const double* p0 = sums + ((long long)b * 2 + 0) * C + 4 * cq;
+      const double* p1 = sums + ((long long)b * 2 + 1) * C + 4 * cq;
+      o.x = ga.x * rs.x * (g.x - (float)p0[0] * inv_n - (v.x - mu.x) * rs.x * ((float)p1[0] * inv_n));
+      o.y = ga.y * rs.y * (g.y - (float)p0[1] * inv_n - (v.y - mu.y) * rs.y * ((float)p1[1] * inv_n));
+      o.z = ga.z * rs.z * (g.z - (float)p0[2] * inv_n - (v.z - mu.z) * rs.z * ((float)p1[2] * inv_n));
+      o.w = ga.w * rs.w * (g.w - (float)p0[3] * inv_n - (v.w - mu.w) * rs.w * ((float)p1[3] * inv_n));
+    }
+    dx[e] = o;
+  }
+}
+
+struct QuadMap { int lanes, rows, ytiles; };
+static QuadMap quad_map(int C4) {
+  QuadMap q;
+  q.lanes = C4 < 256 ? C4 : 256;
+  q.rows = 256 / q.lanes;
+  q.ytiles = (int)ceil_div(C4, q.lanes);
+  return q;
+}
+static bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+static int g_inst_scalar_only = 0;   // debug knob: force the scalar kernels (cross-check of the 16-byte path)
+
 static int flat_grid(long long total) {
   int64_t want = ceil_div(total, 256 * 4);
   return (int)(want < kNumSMs * 16 ? (want > 0 ? want : 1) : kNumSMs * 16);
@@ -248,6 +407,8 @@ int spc_seg_head_fwd(const float* logits, int64_t m, const int32_t* inverse, con
   return 0;
 }
 
+void spc_inst_norm_force_scalar(int on) { g_inst_scalar_only = on; }
+
 int spc_inst_norm_fwd(const float* x, const int32_t* coords, int64_t m, int C, int n_batch, const float* gamma,
                       const float* beta, float eps, float* y, float* mean, float* rstd, int32_t* cnt, double* ws,
                       void* stream_) {
@@ -255,8 +416,16 @@ int spc_inst_norm_fwd(const float* x, const int32_t* coords, int64_t m, int C, i
   SPC_REQUIRE(C >= 1 && n_batch >= 1, "bad shape");
   SPC_CUDA(cudaMemsetAsync(ws, 0, (size_t)n_batch * 2 * C * sizeof(double), stream));
   SPC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_batch * sizeof(int32_t), stream));
-  const int rows_per_block = 512;
-  if (m > 0) {
+  const bool vec = !g_inst_scalar_only && C % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(mean) &&
+                   aligned16(rstd) && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
+  const int rows_per_block = vec ? 1024 : 512;
+  if (m > 0 && vec) {
+    const QuadMap qm = quad_map(C / 4);
+    dim3 grid((unsigned)ceil_div(m, rows_per_block), (unsigned)qm.ytiles);
+    inst_sums4_kernel<false><<<grid, 256, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, (const int4*)coords,
+                                                        m, C, C / 4, n_batch, qm.lanes, qm.rows, rows_per_block, ws, cnt);
+    SPC_LAUNCHED("inst_sums4_kernel");
+  } else if (m > 0) {
     dim3 grid((unsigned)ceil_div(m, rows_per_block), (unsigned)ceil_div(C, 32));
     inst_sums_kernel<false><<<grid, 256, 0, stream>>>(x, nullptr, nullptr, nullptr, (const int4*)coords, m, C, n_batch,
                                                        rows_per_block, ws, cnt);
@@ -266,6 +435,12 @@ int spc_inst_norm_fwd(const float* x, const int32_t* coords, int64_t m, int C, i
   SPC_LAUNCHED("inst_finalize_kernel");
   if (m == 0) return 0;
   const long long total = (long long)m * C;
+  if (vec) {
+    inst_apply4_kernel<<<flat_grid(total), 256, 0, stream>>>((const float4*)x, (const int4*)coords, mean, rstd, gamma,
+                                                              beta, total / 4, C, C / 4, n_batch, (float4*)y);
+    SPC_LAUNCHED("inst_apply4_kernel");
+    return 0;
+  }
   inst_apply_kernel<<<flat_grid(total), 256, 0, stream>>>(x, (const int4*)coords, mean, rstd, gamma, beta, total, C,
                                                            n_batch, y);
   SPC_LAUNCHED("inst_apply_kernel");
@@ -279,12 +454,27 @@ int spc_inst_norm_bwd(const float* x, const float* dy, const int32_t* coords, in
   SPC_REQUIRE(C >= 1 && n_batch >= 1, "bad shape");
   SPC_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_batch * 2 * C * sizeof(double), stream));
   if (m == 0) return 0;
+  const long long total = (long long)m * C;
+  const bool vec = !g_inst_scalar_only && C % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) &&
+                   aligned16(mean) && aligned16(rstd) && (!gamma || aligned16(gamma));
+  if (vec) {
+    const int rpb = 1024;
+    const QuadMap qm = quad_map(C / 4);
+    dim3 grid4((unsigned)ceil_div(m, rpb), (unsigned)qm.ytiles);
+    inst_sums4_kernel<true><<<grid4, 256, 0, stream>>>((const float4*)x, (const float4*)dy, mean, rstd, (const int4*)coords,
+                                                        m, C, C / 4, n_batch, qm.lanes, qm.rows, rpb, sums, nullptr);
+    SPC_LAUNCHED("inst_sums4_kernel");
+    inst_bwd_apply4_kernel<<<flat_grid(total), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const int4*)coords,
+                                                                  mean, rstd, gamma, sums, cnt, total / 4, C, C / 4,
+                                                                  n_batch, (float4*)dx);
+    SPC_LAUNCHED("inst_bwd_apply4_kernel");
+    return 0;
+  }
   const int rows_per_block = 512;
   dim3 grid((unsigned)ceil_div(m, rows_per_block), (unsigned)ceil_div(C, 32));
   inst_sums_kernel<true><<<grid, 256, 0, stream>>>(x, dy, mean, rstd, (const int4*)coords, m, C, n_batch, rows_per_block,
                                                     sums, nullptr);
   SPC_LAUNCHED("inst_sums_kernel");
-  const long long total = (long long)m * C;
   inst_bwd_apply_kernel<<<flat_grid(total), 256, 0, stream>>>(x, dy, (const int4*)coords, mean, rstd, gamma, sums, cnt,
                                                                total, C, n_batch, dx);
   SPC_LAUNCHED("inst_bwd_apply_kernel");

@@ -69,6 +69,7 @@ SIGNATURES = {
     "spc_seg_head_fwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     "spc_inst_norm_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P, _P]),
     "spc_inst_norm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "spc_inst_norm_force_scalar": (None, [c_int]),
     "spc_interp_corners": (c_int, [_P, c_int64, _P, _P, _P, _P]),
     "spc_interp_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P]),
     "spc_interp_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P]),

@@ -38,8 +38,19 @@ def timed(fn, reps=20, warm=5):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     n, C = 1_000_000, 20
     g = torch.Generator(device=dev).manual_seed(0)
+    if only in ("", "head"):
+        bench_head(n, C, g)
+    if only in ("", "inst"):
+        bench_inst(n, g)
+    if only in ("", "interp"):
+        bench_interp(n, g)
+    print(json.dumps({"launches": L.launch_count()}))
+
+
+def bench_head(n, C, g):
     logits = torch.randn(n, C, device=dev, generator=g, requires_grad=True)
     inverse = torch.arange(n, dtype=torch.int32, device=dev)
     target = torch.randint(0, C, (n,), device=dev, generator=g)
@@ -63,6 +74,9 @@ def main():
     print(json.dumps({"kernel": "seg_head fwd+bwd", "n": n, "C": C, "three_pass_ms": round(t3, 4), "fused_ms": round(t1, 4),
                       "speedup": round(t3 / t1, 2), "fused_GBps_algorithmic": round(alg / t1 / 1e6, 1)}))
 
+
+
+def bench_inst(n, g):
     for Cn in (32, 96):
         x = torch.randn(n, Cn, device=dev, generator=g, requires_grad=True)
         coords = torch.zeros(n, 4, dtype=torch.int32, device=dev)
@@ -82,6 +96,9 @@ def main():
                           "bwd_ms": round(tfb - tf, 4), "bwd_GBps": round(bytes_b / max(tfb - tf, 1e-6) / 1e6, 1),
                           "hbm_peak_GBps": peaks.get("hbm_gbs")}))
 
+
+
+def bench_interp(n, g):
     # interpolation of a 1 M-voxel map at 1 M points, 32 channels
     from nerf_downstream_b200 import synth
     c, _, _ = synth.room_batch(777, 1, n, channels=1)
@@ -95,7 +112,6 @@ def main():
     print(json.dumps({"kernel": "interpolate", "m": cmap.size, "n": q.shape[0], "C": 32, "map_ms": round(tm, 4),
                       "gather_ms": round(tg, 4), "corner_hit_rate": round(hit, 3),
                       "gather_GBps_algorithmic": round((4.0 * 32 * (cmap.size + q.shape[0]) + 64.0 * q.shape[0]) / tg / 1e6, 1)}))
-    print(json.dumps({"launches": L.launch_count()}))
 
 
 if __name__ == "__main__":

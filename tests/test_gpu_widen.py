@@ -138,7 +138,8 @@ def test_unet_fused_head_equals_slice_then_loss(cuda_device):
 
 
 # ---- f4: instance norm, sparse_quantize --------------------------------------------------------------------------
-@pytest.mark.parametrize("m,C,n_batch", [(1, 4, 1), (1000, 32, 3), (5003, 96, 4), (20_000, 27, 2), (300, 130, 5)])
+@pytest.mark.parametrize("m,C,n_batch", [(1, 4, 1), (1000, 32, 3), (5003, 96, 4), (20_000, 27, 2), (300, 130, 5),
+                                         (3000, 64, 3), (600, 1028, 2), (100_000, 128, 2)])
 def test_instance_norm_matches_oracle(cuda_device, m, C, n_batch):
     rng = np.random.default_rng(m + C)
     batch = np.sort(rng.integers(0, n_batch, m)).astype(np.int32)
@@ -170,6 +171,31 @@ def test_instance_norm_matches_oracle(cuda_device, m, C, n_batch):
     close(xg.grad, xr.grad, 2e-4)
     close(gg.grad, gr.grad, 2e-4)
     close(bg.grad, br.grad, 2e-4)
+
+
+def test_instance_norm_vector_and_scalar_kernels_agree(cuda_device):
+    from nerf_downstream_b200 import lib as L
+    rng = np.random.default_rng(9)
+    m, C, nb = 7001, 96, 3
+    coords = np.zeros((m, 4), np.int32)
+    coords[:, 0] = np.sort(rng.integers(0, nb, m))
+    x = torch.from_numpy(rng.standard_normal((m, C)).astype(np.float32)).to(cuda_device)
+    gy = torch.from_numpy(rng.standard_normal((m, C)).astype(np.float32)).to(cuda_device)
+    cg = torch.from_numpy(coords).to(cuda_device)
+    res = []
+    try:
+        for scalar in (0, 1):
+            L.load().spc_inst_norm_force_scalar(scalar)
+            xg = x.clone().requires_grad_(True)
+            gam = torch.full((1, C), 1.5, device=cuda_device, requires_grad=True)
+            bet = torch.full((1, C), -0.5, device=cuda_device, requires_grad=True)
+            out = ops.InstanceNormFn.apply(xg, cg, nb, gam, bet, 1e-8)
+            out.backward(gy)
+            res.append((out.detach(), xg.grad, gam.grad, bet.grad))
+    finally:
+        L.load().spc_inst_norm_force_scalar(0)
+    for a, b in zip(*res):
+        close(a, b, 2e-5)
 
 
 def test_instance_norm_module_on_sparse_tensor(cuda_device):
