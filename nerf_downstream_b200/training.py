@@ -515,3 +515,52 @@ def train(config_files: Sequence[str], bindings: Sequence[str], train_batches, v
               fused_head=fused_head)
     run.fit(train_batches, val_batches)
     return run
+
+
+def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] = None, tag: str = "default",
+             ignore_label: Optional[int] = None, training_module: str = "SegmentationTraining", device="cuda",
+             replace: bool = False, fused_head: bool = False, make_input: Optional[Callable] = None):
+    """`python eval.py --ginc ... --load_path <ckpt>` (co3d_3d/eval.py:21-103) for one GPU: build `get_model()` in eval
+    mode, load `checkpoint["state_dict"]` (Lightning layout), run one validation pass and write `<save_path>/<tag>.json`
+    (a list with one result dict, the shape `Trainer.validate` returns).  An existing json is kept unless `replace`
+    (eval.py:42-45).  Checkpoints of pruned networks (`*_mask` / `*_orig` entries, eval.py:51-58) belong to the
+    weight-sparse inference path, which is not built: they raise."""
+    save_path = save_path if save_path is not None else os.path.dirname(load_path)
+    if save_path and not os.path.exists(save_path):
+        os.makedirs(save_path, exist_ok=True)
+    json_path = os.path.join(save_path, f"{tag}.json")
+    if not replace and os.path.isfile(json_path):
+        print("====== skip existing experiment =====")
+        return None
+    if model is None:
+        model = get_model().to(device)
+    model.eval()
+    ckpt = torch.load(load_path, map_location="cpu", weights_only=False)
+    if any("_mask" in k for k in ckpt["state_dict"]):
+        raise NotImplementedError("checkpoint of a pruned network: the weight-sparse inference path is not built")
+    load_lightning_state_dict(model, ckpt["state_dict"])
+    if ignore_label is None:
+        ignore_label = _bound(f"{_bound('get_dataset.dataset_name', 'train')}.ignore_label",
+                              _bound("train.ignore_label", -100))
+    cfg = TrainConfig(max_steps=0, training_module=training_module, ignore_label=ignore_label)
+    # evaluation only: no optimiser state is touched, but the meters / criterion / loop are the trainer's
+    run = Run.__new__(Run)
+    run.model, run.cfg, run.save_path, run.log = model, cfg, save_path, (lambda d: None)
+    run.segmentation = training_module == "SegmentationTraining"
+    run.num_labels = _bound("get_model.out_channel", None)
+    if run.num_labels is None:
+        raise ginlite.GinError("get_model.out_channel is not bound")
+    run.global_step, run.best = int(ckpt.get("global_step", 0)), -math.inf
+    run.make_input = make_input or Run._tensor_field
+    run.fused_head = bool(fused_head)
+    if run.segmentation:
+        from .pipeline import IoUMeter
+        run.criterion = SegLoss(ignore_label, run.num_labels, cfg.void_weight)
+        run.iou_meter = IoUMeter(run.num_labels, ignore_label, _bound("PlenoxelScannetDataset.void_label", None))
+    else:
+        run.acc1_meter, run.acc5_meter = AccuracyMeter(run.num_labels, 1), AccuracyMeter(run.num_labels, 5)
+    results = run.validate(val_batches() if callable(val_batches) else val_batches)
+    results = {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in results.items()}
+    with open(json_path, "w") as f:
+        f.write(json.dumps([results], indent=4))
+    return results

@@ -79,3 +79,70 @@ def test_schedules():
     # PolyFunctor: (1 - step / (max_steps + 1)) ** poly_exp  (optim.py:181-188)
     assert abs(trainer.poly_lr(0.1, 0, 100) - 0.1) < 1e-12
     assert abs(trainer.poly_lr(0.1, 99, 100) - 0.1 * (1 - 99 / 101) ** 0.9) < 1e-15
+
+
+def _fit_worker(rank, world, port, q):
+    """Two ranks run `training.Run.fit` (segmentation, use_sync_grad) on batches of DIFFERENT sizes; with the
+    point-count re-weighting (segmentation_training.py:112-120) and the gradient mean of the data-parallel step, the
+    result must equal single-process SGD on the concatenated batches with the same schedule."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nerf_downstream_b200 import ginlite, ops, schedules, training
+
+    def sgd_cpu(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):
+        d = grad * grad_scale + weight_decay * param
+        buf.copy_(d if first_step else momentum * buf + d)
+        param.sub_(lr * buf)
+
+    ops.sgd_step = sgd_cpu
+    ginlite.parse_config("train.max_steps = 5\ntrain.scheduler_name = 'PolyLR'\nPolyLR.poly_exp = 0.9\ntrain.lr = 0.1\n"
+                         "train.weight_decay = 1e-4\ntrain.use_sync_grad = True\ntrain.log_every_n_steps = 100\n"
+                         "SGD.momentum = 0.9\nget_model.out_channel = 3")
+
+    def make():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.ReLU(), torch.nn.Linear(8, 3))
+
+    def batches(r):
+        g = torch.Generator().manual_seed(50 + r)
+        n = 20 if r == 0 else 44
+        out = []
+        for _ in range(5):
+            x = torch.randn(n, 6, generator=g)
+            out.append({"coordinates": torch.zeros(n, 4), "features": x, "labels": x[:, :3].argmax(1)})
+        return out
+
+    run = training.Run(make(), training.TrainConfig(), make_input=lambda b: b["features"])
+    assert run.trainer.world == world
+    run.fit(lambda: batches(rank))
+    ref = make()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    sched = schedules.poly(0.1, 5, 0.9)
+    all_b = [batches(r) for r in range(world)]
+    for step in range(5):
+        for gr in opt.param_groups:
+            gr["lr"] = sched.lr(step)
+        x = torch.cat([all_b[r][step]["features"] for r in range(world)])
+        y = torch.cat([all_b[r][step]["labels"] for r in range(world)])
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        opt.step()
+    err = max((a - b).abs().max().item() for a, b in zip(run.model.parameters(), ref.parameters()))
+    q.put((rank, err, run.global_step))
+    dist.destroy_process_group()
+
+
+def test_fit_world2_sync_grad_equals_global_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, steps in res:
+        assert steps == 5 and err < 1e-5, (rank, err, steps)

@@ -507,3 +507,32 @@ def test_metrics_from_counts_equals_eval_metrics():
         assert abs(m["OA"] - c["precision_at_one"]) < 1e-4
         want = float(np.mean([0.0 if v is None else v for v in c["per_class_iu"]]) * 100)
         assert abs(m["mIoU"] - want) < 1e-9, name
+
+
+def test_evaluate_from_lightning_checkpoint(tmp_path, monkeypatch):
+    """eval.py: a checkpoint written by the loop evaluates in a fresh model to the numbers of the run's own last
+    validation, the result lands in <tag>.json, and an existing json is kept unless replace=True."""
+    _cpu_kernels(monkeypatch)
+    ginlite.parse_config("train.max_steps = 6\ntrain.scheduler_name = 'none'\ntrain.lr = 0.05\ntrain.ignore_label = -255\n"
+                         "train.val_every_n_steps = 6\nSGD.momentum = 0.9\nget_model.out_channel = 4\n"
+                         "get_dataset.dataset_name = 'PlenoxelScannetDataset'\nPlenoxelScannetDataset.ignore_label = -255")
+    torch.manual_seed(3)
+    data, val = _batches(40, 3, ignore=-255), _batches(41, 2, ignore=-255)
+    run = training.Run(TinyNet(), training.TrainConfig(), save_path=str(tmp_path), make_input=lambda b: b["features"])
+    assert run.schedule is None and run.trainer.lr == 0.05
+    last = run.fit(lambda: data, lambda: val)
+    res = training.evaluate(str(tmp_path / "last.ckpt"), lambda: val, model=TinyNet(), tag="t1",
+                            make_input=lambda b: b["features"])
+    for k in ("val/mIoU", "val/mAcc", "val/OA", "val/loss"):
+        assert abs(res[k] - last[k]) < 1e-6, k
+    stored = json.loads((tmp_path / "t1.json").read_text())
+    assert isinstance(stored, list) and abs(stored[0]["val/mIoU"] - res["val/mIoU"]) < 1e-9
+    assert training.evaluate(str(tmp_path / "last.ckpt"), lambda: val, model=TinyNet(), tag="t1",
+                             make_input=lambda b: b["features"]) is None                       # kept
+    assert training.evaluate(str(tmp_path / "last.ckpt"), val, model=TinyNet(), tag="t1", replace=True,
+                             make_input=lambda b: b["features"]) is not None
+    ckpt = torch.load(tmp_path / "last.ckpt", weights_only=False)
+    ckpt["state_dict"]["model.conv.weight_mask"] = torch.ones(1)
+    torch.save(ckpt, tmp_path / "pruned.ckpt")
+    with pytest.raises(NotImplementedError, match="pruned"):
+        training.evaluate(str(tmp_path / "pruned.ckpt"), val, model=TinyNet(), tag="t2", make_input=lambda b: b["features"])
