@@ -42,6 +42,31 @@ def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, s
     return coords, feats
 
 
+def plenoxel_decode_augmented(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float,
+                              reso: Sequence[int], transformations: Sequence[str], batch_index: int = 0,
+                              params: Optional[dict] = None):
+    """Decode a plenoxel record AND apply the reference's affine-type train transformations (RandomRotation,
+    RandomAffine, RandomHorizontalFlip, RandomTranslation, CoordinateUniformTranslation, RandomScale,
+    DimensionlessCoordinates; co3d_3d/src/data/transforms.py:284-460) in the same kernel pass: the chain is drawn on
+    the host in the reference's RNG order (`augment.sample_chain`), composed into one 3x3 + translation and handed to
+    `spc_plenoxel_decode` as `affine12` — instead of one numpy pass per transform on the CPU.  A horizontal flip
+    mirrors about the data's maximum, which costs one extra coordinates-only decode + a reduction.
+    Returns (coords [n,4] float32, feats [n,C] float32, the AffineChain)."""
+    from . import augment
+    raw = []
+
+    def axis_max(chain, axis):
+        if not raw:
+            raw.append(plenoxel_decode(links, sh_u8[:, :0], 1.0, 0.0, reso, batch_index)[0][:, 1:].double())
+        a = torch.tensor(chain.A[axis], dtype=torch.float64, device=raw[0].device)
+        return float((raw[0] @ a).max().item() + chain.t[axis])
+
+    chain = augment.sample_chain(transformations, axis_max=axis_max, params=params)
+    coords, feats = plenoxel_decode(links, sh_u8, sh_scale, sh_min, reso, batch_index,
+                                    chain.as_affine12() if chain.steps else None)
+    return coords, feats, chain
+
+
 def seg_counts(logits: torch.Tensor, target: torch.Tensor, ignore_label: int, out: Optional[torch.Tensor] = None):
     """counts[3, C] int64 (+= when `out` is given): per class #seen, #correct, #predicted of argmax(logits)."""
     lib = L.load()

@@ -364,3 +364,39 @@ def test_splat_and_interpolate_on_me_surface(cuda_device):
     want = pts[:, 1:] @ np.array([[1.0], [-2.0], [0.5]]) + 3.0
     assert np.abs(out.cpu().numpy() - want).max() <= 1e-4
     assert in_rows.shape == out_rows.shape == wts.shape and in_rows.numel() == 800
+
+
+# ---- f2: decode + the reference's affine augmentations in one pass -----------------------------------------------
+@pytest.mark.parametrize("seed,names", [(0, ["RandomRotation", "RandomAffine", "RandomHorizontalFlip", "RandomTranslation"]),
+                                        (3, ["RandomRotation", "RandomScale", "CoordinateUniformTranslation"]),
+                                        (5, [])])
+def test_plenoxel_decode_augmented(cuda_device, seed, names):
+    """The composed chain runs inside spc_plenoxel_decode: bit-exact against the numpy decode given the same 12 floats,
+    and equal (to float32 rounding) to the float64 chain applied to the decoded lattice indices."""
+    import random
+    rng = np.random.default_rng(seed)
+    reso = (128, 128, 128)
+    n = 20_000
+    links = np.sort(rng.choice(reso[0] * reso[1] * reso[2], size=n, replace=False)).astype(np.int64)
+    sh = rng.integers(0, 256, size=(n, 27), dtype=np.uint8)
+    scale, mn = np.float32(2.0 / 255.0), np.float32(-1.0)
+    params = {"RandomRotation": dict(upright_axis="y", application_ratio=1.0),
+              "RandomAffine": dict(upright_axis="y", application_ratio=1.0),
+              "RandomHorizontalFlip": dict(upright_axis="y", application_ratio=1.0),
+              "RandomTranslation": dict(max_translation=3, application_ratio=1.0),
+              "RandomScale": dict(scale_ratio=0.4, application_ratio=1.0),
+              "CoordinateUniformTranslation": dict(max_translation=0.2)}
+    random.seed(seed)
+    np.random.seed(seed)
+    c, f, chain = pipeline.plenoxel_decode_augmented(torch.from_numpy(links).to(cuda_device),
+                                                     torch.from_numpy(sh).to(cuda_device), float(scale), float(mn), reso,
+                                                     names, batch_index=1, params=params)
+    assert len(chain.steps) >= len(names)
+    rc, rf = R.plenoxel_decode_np(links, sh, scale, mn, reso, batch_index=1,
+                                  affine=chain.as_affine12() if chain.steps else None)
+    assert (c.cpu().numpy() == rc).all() and (f.cpu().numpy() == rf).all()
+    ijk = np.stack([links // (128 * 128), (links % (128 * 128)) // 128, links % 128], 1).astype(np.float64)
+    want = chain.apply(ijk)
+    assert np.abs(c[:, 1:].cpu().numpy() - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+    if "RandomHorizontalFlip" in names:                            # mirrored about the data's own maximum
+        assert abs(float(c[:, 1].min())) <= 1e-3 and abs(float(c[:, 3].min())) <= 1e-3
