@@ -204,8 +204,12 @@ def run_ours(args):
 
     def step(c, f, y):
         field = ME.TensorField(coordinates=c, features=f)
-        logits = model(field)
-        loss = ops.cross_entropy(logits, y, ignore_index=255)
+        if args.fused_head:     # slice + loss (+ gradient of the slice) as one kernel over the points (spc_seg_head_fwd)
+            from nerf_downstream_b200 import pipeline
+            loss = pipeline.seg_head_loss(model.forward_sparse(field), field, y, 255)
+        else:
+            logits = model(field)
+            loss = ops.cross_entropy(logits, y, ignore_index=255)
         tr.backward_and_step(loss)
         key = field.coordinate_manager.get_unique_coordinate_map_key(1)
         voxels_per_step[0] = field.coordinate_manager.size(key)
@@ -422,6 +426,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
     ap.add_argument("--host-profile", action="store_true", help="cProfile of 3 steps on stderr (host overhead)")
+    ap.add_argument("--fused-head", action="store_true",
+                    help="loss through the fused segmentation head (forward_sparse + spc_seg_head_fwd) instead of "
+                         "slice -> cross-entropy; off by default until re-measured inside the step")
     ap.add_argument("--shuffle", action="store_true",
                     help="deliver voxels in random order instead of the loaders' raster order (adversarial locality)")
     args = ap.parse_args()
