@@ -203,6 +203,7 @@ class CoordinateManager:
         self._kernel_maps: Dict[tuple, ops.KernelMap] = {}
         self._identity_maps: Dict[CoordinateMapKey, ops.KernelMap] = {}
         self._interp_maps: Dict[tuple, tuple] = {}             # (field key, map key) -> (rows [8,N], weights [8,N])
+        self._field_batch: Dict[CoordinateMapKey, torch.Tensor] = {}
         self._n_batch: Optional[int] = None
         self._field_counter = 0
         self.prefetch_depth = CoordinateManager.default_prefetch_depth
@@ -296,8 +297,24 @@ class CoordinateManager:
                 if cmap.size:
                     best = max(best, int(cmap.coords[:, 0].max().item()) + 1)  # host sync, once per manager
                     break
+            if best == 0:                       # a pure point network (pointnet.py): only coordinate fields exist
+                for field in self._fields.values():
+                    if field.size:
+                        best = max(best, int(torch.floor(field.coords[:, 0]).max().item()) + 1)
+                        break
             self._n_batch = best
         return self._n_batch
+
+    def field_batch_coordinates(self, field_key: CoordinateMapKey) -> torch.Tensor:
+        """int32 [N,4] rows (floor(batch), 0, 0, 0) of a coordinate field: what the global pooling kernels read to
+        find a point's instance (ME pools a TensorField per batch index too, pointnet.py:90,106)."""
+        cached = self._field_batch.get(field_key)
+        if cached is None:
+            fc = self._fields[field_key].coords
+            cached = torch.zeros((fc.shape[0], 4), dtype=torch.int32, device=fc.device)
+            cached[:, 0] = torch.floor(fc[:, 0]).to(torch.int32)
+            self._field_batch[field_key] = cached
+        return cached
 
     # ---- stride ---------------------------------------------------------------
     def stride(self, in_key: CoordinateMapKey, stride, string_id: str = "") -> CoordinateMapKey:
@@ -339,7 +356,8 @@ class CoordinateManager:
         key = CoordinateMapKey([0] * self.D, "")
         if key not in self._maps:
             nb = self.number_of_unique_batch_indices()
-            dev = next(iter(self._maps.values())).coords.device
+            holders = list(self._maps.values()) or list(self._fields.values())
+            dev = holders[0].coords.device
             coords = torch.zeros((nb, 4), dtype=torch.int32, device=dev)
             coords[:, 0] = torch.arange(nb, dtype=torch.int32, device=dev)
             cmap, _, _, _ = ops.coords_insert(coords, L.SRC_INT, (1, 1, 1))
@@ -736,13 +754,23 @@ class TensorField(Tensor):
         return SparseTensor(F, coordinate_map_key=key, coordinate_manager=mgr)
 
     def inverse_mapping(self, sparse_key: CoordinateMapKey) -> torch.Tensor:
+        """Row of `sparse_key`'s map each point falls into.  For the map this field's `.sparse()` created it is the
+        stored inverse map; for any other map (a strided level: `y2.slice(x)`, fcnn.py:162-165) every point's voxel
+        `floor(c / ts) * ts` is looked up in that map's hash table."""
         inv = self._inverse_mapping.get(sparse_key)
         if inv is None:
             mgr = self._manager
-            if not mgr.exists_field_to_sparse(self.coordinate_field_map_key, sparse_key):
-                raise RuntimeError(f"no field-to-sparse map for {sparse_key}; slice() needs the stride-1 map "
-                                   "created by this field's .sparse()")
-            inv = mgr.field_to_sparse_map(self.coordinate_field_map_key, sparse_key)
+            if mgr.exists_field_to_sparse(self.coordinate_field_map_key, sparse_key):
+                inv = mgr.field_to_sparse_map(self.coordinate_field_map_key, sparse_key)
+            else:
+                cmap = mgr._map(sparse_key)
+                lower, _ = ops.interp_corners(self.C, cmap.tensor_stride)
+                km = ops.build_kernel_map(cmap, ops.CoordMap(lower, None, 0, lower.shape[0], cmap.tensor_stride),
+                                          [(0, 0, 0)])
+                inv = km.nbr[0]
+                if int(km.tap_count[0].item()) != lower.shape[0]:          # host sync, once per (field, map)
+                    raise RuntimeError(f"slice(): some points of the field have no voxel in {sparse_key}")
+                mgr._field_to_sparse[(self.coordinate_field_map_key, sparse_key)] = inv
             self._inverse_mapping[sparse_key] = inv
         return inv
 

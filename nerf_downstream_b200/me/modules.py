@@ -388,6 +388,16 @@ class MinkowskiMaxPooling(MinkowskiLocalPoolingBase):
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
 
 
+def _global_pool_args(input):
+    """(manager, origin key, number of instances, int32 coordinates whose column 0 is the instance of each row)."""
+    assert isinstance(input, (SparseTensor, TensorField))
+    mgr = input.coordinate_manager
+    out_key = mgr.origin()
+    nb = mgr.size(out_key)
+    coords = input.C if isinstance(input, SparseTensor) else mgr.field_batch_coordinates(input.coordinate_field_map_key)
+    return mgr, out_key, nb, coords
+
+
 class MinkowskiGlobalPooling(MinkowskiModuleBase):
     AVG = True
 
@@ -395,12 +405,9 @@ class MinkowskiGlobalPooling(MinkowskiModuleBase):
         super().__init__()
         self.pooling_mode = mode
 
-    def forward(self, input: SparseTensor):
-        assert isinstance(input, SparseTensor)
-        mgr = input.coordinate_manager
-        out_key = mgr.origin()
-        nb = mgr.size(out_key)
-        out = ops.GlobalPoolFn.apply(input.F, input.C, nb, self.AVG)
+    def forward(self, input):
+        mgr, out_key, nb, coords = _global_pool_args(input)
+        out = ops.GlobalPoolFn.apply(input.F, coords, nb, self.AVG)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
 
     def __repr__(self):
@@ -420,12 +427,9 @@ class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
         super().__init__()
         self.pooling_mode = mode
 
-    def forward(self, input: SparseTensor):
-        assert isinstance(input, SparseTensor)
-        mgr = input.coordinate_manager
-        out_key = mgr.origin()
-        nb = mgr.size(out_key)
-        out = ops.GlobalMaxPoolFn.apply(input.F, input.C, nb)
+    def forward(self, input):
+        mgr, out_key, nb, coords = _global_pool_args(input)
+        out = ops.GlobalMaxPoolFn.apply(input.F, coords, nb)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
 
     def __repr__(self):

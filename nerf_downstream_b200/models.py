@@ -175,9 +175,110 @@ class Res16UNet14A(SparseResUNet):
 
 MinkUNet34C = Res16UNet34C
 
+
+# ---- the other in-tree backbones ------------------------------------------------------------
+class GlobalMaxAvgPool(nn.Module):
+    """cat(global max, global average) per batch index (fcnn.py:9-18)."""
+
+    def __init__(self):
+        super().__init__()
+        self.global_max_pool = ME.MinkowskiGlobalMaxPooling()
+        self.global_avg_pool = ME.MinkowskiGlobalAvgPooling()
+
+    def forward(self, tensor):
+        return ME.cat(self.global_max_pool(tensor), self.global_avg_pool(tensor))
+
+
+def _mlp_block(cin, cout):
+    return nn.Sequential(ME.MinkowskiLinear(cin, cout, bias=False), ME.MinkowskiBatchNorm(cout), ME.MinkowskiLeakyReLU())
+
+
+def _conv_block(cin, cout, kernel_size, stride, D=3):
+    return nn.Sequential(ME.MinkowskiConvolution(cin, cout, kernel_size=kernel_size, stride=stride, dimension=D),
+                         ME.MinkowskiBatchNorm(cout), ME.MinkowskiLeakyReLU())
+
+
+class MinkowskiFCNN(ME.MinkowskiNetwork):
+    """Point MLP -> voxel pyramid (conv + max-pool k3 s2, four levels) -> every level sliced back to the points ->
+    cat -> three stride-2 convs -> global max+avg -> MLP classifier (fcnn.py:21-168; same sub-module names)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size=3, embedding_channel=1024,
+                 channels=(32, 48, 64, 96, 128), D=3):
+        super().__init__(D)
+        c = channels
+        self.mlp1 = _mlp_block(in_channel, c[0])
+        self.conv1 = _conv_block(c[0], c[1], kernel_size, 1, D)
+        self.conv2 = _conv_block(c[1], c[2], kernel_size, 2, D)
+        self.conv3 = _conv_block(c[2], c[3], kernel_size, 2, D)
+        self.conv4 = _conv_block(c[3], c[4], kernel_size, 2, D)
+        e = embedding_channel
+        self.conv5 = nn.Sequential(_conv_block(c[1] + c[2] + c[3] + c[4], e // 4, 3, 2, D),
+                                   _conv_block(e // 4, e // 2, 3, 2, D), _conv_block(e // 2, e, 3, 2, D))
+        self.max_pool = ME.MinkowskiMaxPooling(kernel_size=3, stride=2, dimension=D)
+        self.final = nn.Sequential(GlobalMaxAvgPool(), _mlp_block(e * 2, 512), ME.MinkowskiDropout(),
+                                   _mlp_block(512, 512), ME.MinkowskiLinear(512, out_channel, bias=True))
+        for m in self.modules():                                    # weight_initialization (fcnn.py:133-140)
+            if isinstance(m, ME.MinkowskiConvolution):
+                ME.utils.kaiming_normal_(m.kernel, mode="fan_out", nonlinearity="relu")
+            if isinstance(m, ME.MinkowskiBatchNorm):
+                nn.init.constant_(m.bn.weight, 1)
+                nn.init.constant_(m.bn.bias, 0)
+
+    def process_input(self, batch):
+        return ME.TensorField(coordinates=batch["coordinates"], features=batch["features"])
+
+    def _to_voxels(self, x):
+        return x.sparse()
+
+    def _to_points(self, y, x):
+        return y.slice(x)
+
+    def forward(self, x: ME.TensorField):
+        x = self.mlp1(x)
+        y = self._to_voxels(x)
+        y1 = self.max_pool(self.conv1(y))
+        y2 = self.max_pool(self.conv2(y1))
+        y3 = self.max_pool(self.conv3(y2))
+        y4 = self.max_pool(self.conv4(y3))
+        x = ME.cat(*[self._to_points(t, x) for t in (y1, y2, y3, y4)])
+        return self.final(self.conv5(x.sparse())).F
+
+
+class MinkowskiSplatFCNN(MinkowskiFCNN):
+    """The same network with trilinear splat / interpolate between points and voxels (fcnn.py:170-208)."""
+
+    def _to_voxels(self, x):
+        return x.splat()
+
+    def _to_points(self, y, x):
+        return y.interpolate(x)
+
+
+class MinkowskiPointNet(ME.MinkowskiNetwork):
+    """PointNet over a coordinate field: five Linear-BN-ReLU blocks on the points, global max per batch index, MLP head
+    (pointnet.py:56-109; same sub-module names)."""
+
+    def __init__(self, in_channel, out_channel, embedding_channel=1024, dimension=3):
+        super().__init__(dimension)
+
+        def block(cin, cout):
+            return nn.Sequential(ME.MinkowskiLinear(cin, cout, bias=False), ME.MinkowskiBatchNorm(cout), ME.MinkowskiReLU())
+        self.conv1, self.conv2, self.conv3 = block(in_channel, 64), block(64, 64), block(64, 64)
+        self.conv4, self.conv5 = block(64, 128), block(128, embedding_channel)
+        self.max_pool = ME.MinkowskiGlobalMaxPooling()
+        self.linear1 = block(embedding_channel, 512)
+        self.dp1 = ME.MinkowskiDropout()
+        self.linear2 = ME.MinkowskiLinear(512, out_channel, bias=True)
+
+    def process_input(self, batch):
+        return ME.TensorField(coordinates=batch["coordinates"], features=batch["features"])
+
+    def forward(self, x: ME.TensorField):
+        x = self.conv5(self.conv4(self.conv3(self.conv2(self.conv1(x)))))
+        x = self.max_pool(x)
+        return self.linear2(self.dp1(self.linear1(x))).F
+
+
 MODELS = {"ResNet14": ResNet14, "ResNet18": ResNet18, "ResNet34": ResNet34, "Res16UNet34C": Res16UNet34C,
-          "MinkUNet34C": Res16UNet34C, "Res16UNet14A": Res16UNet14A}
-
-
-def get_model(name: str, in_channel: int, out_channel: int):
-    return MODELS[name](in_channel, out_channel)
+          "MinkUNet34C": Res16UNet34C, "Res16UNet14A": Res16UNet14A, "MinkowskiFCNN": MinkowskiFCNN,
+          "MinkowskiSplatFCNN": MinkowskiSplatFCNN, "MinkowskiPointNet": MinkowskiPointNet}
