@@ -322,13 +322,14 @@ class Run:
     make_input — batch dict -> network input (default: `ME.TensorField(coordinates=, features=)`, base_model.py:10-13)
     fused_head — segmentation only, for models with `forward_sparse` (models.SparseResUNet): slice, SegLoss and the
                  metric counts run as ONE kernel over the points (`pipeline.seg_head_loss`) instead of three passes
+    evaluate_only — no optimiser state, no schedule: only `validate()` is usable (`evaluate()`, eval.py)
     """
 
     def __init__(self, model: torch.nn.Module, cfg: TrainConfig, num_labels: Optional[int] = None,
                  void_label=None, save_path: Optional[str] = None, make_input: Optional[Callable] = None,
-                 log: Optional[Callable[[dict], None]] = None, fused_head: bool = False):
+                 log: Optional[Callable[[dict], None]] = None, fused_head: bool = False, evaluate_only: bool = False):
         from . import trainer as T
-        if cfg.optimizer_name != "SGD":
+        if cfg.optimizer_name != "SGD" and not evaluate_only:
             raise NotImplementedError("the fused optimiser step implements SGD (what every reference config selects: "
                                       "co3d_cls.gin:33, scannet_plenoxel.gin:58)")
         self.model, self.cfg, self.save_path, self.log = model, cfg, save_path, log or (lambda d: None)
@@ -336,9 +337,12 @@ class Run:
         if cfg.training_module not in ("SegmentationTraining", "ClassificationTraining"):
             raise AssertionError(f"{cfg.training_module} not in ['SegmentationTraining', 'ClassificationTraining']")
         self.num_labels = num_labels if num_labels is not None else ginlite.query_parameter("get_model.out_channel")
-        self.trainer = T.DataParallelTrainer(model, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
-        self.trainer.initial_lr = cfg.lr
-        self.schedule = cfg.schedule()
+        self.trainer = None
+        self.schedule = None
+        if not evaluate_only:
+            self.trainer = T.DataParallelTrainer(model, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+            self.trainer.initial_lr = cfg.lr
+            self.schedule = cfg.schedule()
         self.global_step = 0
         self.best = -math.inf
         self.make_input = make_input or self._tensor_field
@@ -352,6 +356,8 @@ class Run:
         else:
             self.acc1_meter = AccuracyMeter(self.num_labels, 1)
             self.acc5_meter = AccuracyMeter(self.num_labels, 5)
+        if evaluate_only:
+            return
         if cfg.checkpoint_path is not None and (cfg.load_weights or cfg.load_optimizers or cfg.resume_training):
             ckpt = load_checkpoint(cfg.checkpoint_path, self.trainer, load_weights=cfg.load_weights or cfg.resume_training,
                                    load_optimizers=cfg.load_optimizers or cfg.resume_training,
@@ -543,22 +549,9 @@ def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] =
         ignore_label = _bound(f"{_bound('get_dataset.dataset_name', 'train')}.ignore_label",
                               _bound("train.ignore_label", -100))
     cfg = TrainConfig(max_steps=0, training_module=training_module, ignore_label=ignore_label)
-    # evaluation only: no optimiser state is touched, but the meters / criterion / loop are the trainer's
-    run = Run.__new__(Run)
-    run.model, run.cfg, run.save_path, run.log = model, cfg, save_path, (lambda d: None)
-    run.segmentation = training_module == "SegmentationTraining"
-    run.num_labels = _bound("get_model.out_channel", None)
-    if run.num_labels is None:
-        raise ginlite.GinError("get_model.out_channel is not bound")
-    run.global_step, run.best = int(ckpt.get("global_step", 0)), -math.inf
-    run.make_input = make_input or Run._tensor_field
-    run.fused_head = bool(fused_head)
-    if run.segmentation:
-        from .pipeline import IoUMeter
-        run.criterion = SegLoss(ignore_label, run.num_labels, cfg.void_weight)
-        run.iou_meter = IoUMeter(run.num_labels, ignore_label, _bound("PlenoxelScannetDataset.void_label", None))
-    else:
-        run.acc1_meter, run.acc5_meter = AccuracyMeter(run.num_labels, 1), AccuracyMeter(run.num_labels, 5)
+    run = Run(model, cfg, save_path=save_path, void_label=_bound("PlenoxelScannetDataset.void_label", None),
+              make_input=make_input, fused_head=fused_head, evaluate_only=True)
+    run.global_step = int(ckpt.get("global_step", 0))
     results = run.validate(val_batches() if callable(val_batches) else val_batches)
     results = {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in results.items()}
     with open(json_path, "w") as f:
