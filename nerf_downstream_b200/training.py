@@ -263,6 +263,25 @@ def load_checkpoint(path: str, trainer=None, model: Optional[torch.nn.Module] = 
     return ckpt
 
 
+# ---- batches ---------------------------------------------------------------------------------------------------
+def collate_mink(list_data: Sequence[dict]) -> dict:
+    """`collate_mink` (co3d_3d/src/data/utils.py:25-50): samples `{"coordinates" [n_i, 3], "features" [n_i, C],
+    "labels" ...}` -> one batch with float32 `(b, x, y, z)` coordinates (`ME.utils.sparse_collate(dtype=float32)`),
+    concatenated features, every `*label*` / `*instance*` / `*dists*` entry concatenated, `metadata` / `dataset` /
+    `colors` kept as lists."""
+    from .me import utils as me_utils
+    coordinates_batch, features_batch = me_utils.sparse_collate([d["coordinates"] for d in list_data],
+                                                                [d["features"] for d in list_data], dtype=torch.float32)
+    package = {"coordinates": coordinates_batch, "features": features_batch}
+    for key in list_data[0].keys():
+        if "label" in key or "instance" in key or "dists" in key:
+            package[key] = torch.from_numpy(np.concatenate([np.asarray(d[key]) for d in list_data]))
+    for key in ("metadata", "dataset", "colors"):
+        if key in list_data[0]:
+            package[key] = [d[key] for d in list_data]
+    return package
+
+
 # ---- the run ---------------------------------------------------------------------------------------------------
 class TrainConfig:
     """The `train.*` bindings of a gin file with the defaults of `train()` (co3d_3d/train.py:50-96)."""
@@ -323,11 +342,15 @@ class Run:
     fused_head — segmentation only, for models with `forward_sparse` (models.SparseResUNet): slice, SegLoss and the
                  metric counts run as ONE kernel over the points (`pipeline.seg_head_loss`) instead of three passes
     evaluate_only — no optimiser state, no schedule: only `validate()` is usable (`evaluate()`, eval.py)
+    exception_safe — `ExceptionSafeSegmentationTraining` (segmentation_training.py:233-302): a step or validation batch
+                 that raises RuntimeError (the library reports every failure, incl. out-of-memory, that way) is
+                 counted and skipped; the schedule advances regardless
     """
 
     def __init__(self, model: torch.nn.Module, cfg: TrainConfig, num_labels: Optional[int] = None,
                  void_label=None, save_path: Optional[str] = None, make_input: Optional[Callable] = None,
-                 log: Optional[Callable[[dict], None]] = None, fused_head: bool = False, evaluate_only: bool = False):
+                 log: Optional[Callable[[dict], None]] = None, fused_head: bool = False, evaluate_only: bool = False,
+                 exception_safe: bool = False):
         from . import trainer as T
         if cfg.optimizer_name != "SGD" and not evaluate_only:
             raise NotImplementedError("the fused optimiser step implements SGD (what every reference config selects: "
@@ -347,6 +370,7 @@ class Run:
         self.best = -math.inf
         self.make_input = make_input or self._tensor_field
         self.fused_head = bool(fused_head)
+        self.exception_safe, self.fail_count = bool(exception_safe), 0
         if self.fused_head and not (self.segmentation and hasattr(model, "forward_sparse")):
             raise ValueError("fused_head needs SegmentationTraining and a model with forward_sparse()")
         if self.segmentation:
@@ -380,7 +404,22 @@ class Run:
                 self.trainer.momentum = m
 
     # -- one optimiser step (training_step + backward + optimizer.step + scheduler.step) -------------------------
-    def training_step(self, batch) -> torch.Tensor:
+    def training_step(self, batch) -> Optional[torch.Tensor]:
+        if not self.exception_safe:
+            return self._training_step(batch)
+        try:
+            return self._training_step(batch)
+        except RuntimeError as e:               # segmentation_training.py:276-283
+            self.fail_count += 1
+            print(f"Failed with {e}. Failure rate: {float(self.fail_count) / (self.global_step + 1)}")
+            self.trainer.arena.zero_grad()
+            self.global_step += 1               # "regardless of the failure status, update" the scheduler
+            self._apply_schedule()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            return None
+
+    def _training_step(self, batch) -> torch.Tensor:
         self.model.train()
         labels = batch["labels"].long()
         step_counts = None
@@ -436,28 +475,42 @@ class Run:
             self.acc1_meter.reset()
             self.acc5_meter.reset()
         for batch in batches:
-            labels = batch["labels"].long()
-            if self.fused_head:
-                from . import pipeline
-                field = self.make_input(batch)
-                sparse_out = self.model.forward_sparse(field)
-                dev = sparse_out.F.device
-                step_counts = torch.zeros((3, self.num_labels), dtype=torch.int64, device=dev)
-                crit = self.criterion
-                losses.append(pipeline.seg_head_loss(sparse_out, field, labels.to(dev), crit.ignore_index,
-                                                     crit.weight.to(dev) if crit.weighted else None, step_counts).item())
-                oas.append(metrics_from_counts(step_counts)["OA"])
-                self.iou_meter.counts_buffer(dev).add_(step_counts)
-                continue
-            logits = self.model(self.make_input(batch))
-            if self.segmentation:
-                losses.append(self.criterion(logits, batch).item())
-                oas.append(eval_metrics(logits, labels, logits.shape[1], self.cfg.ignore_label)["OA"])
-                self.iou_meter.update(logits, labels)
+            if self.exception_safe:
+                try:
+                    self._validate_batch(batch, losses, oas)
+                except RuntimeError as e:       # segmentation_training.py:316-326
+                    print(f"Validation step failed with {e}.")
+                    if torch.cuda.is_available():
+                        torch.cuda.synchronize()
             else:
-                losses.append(F.cross_entropy(logits, labels).item())
-                self.acc1_meter(logits, labels)
-                self.acc5_meter(logits, labels)
+                self._validate_batch(batch, losses, oas)
+        return self._validation_epoch_end(losses, oas)
+
+    def _validate_batch(self, batch, losses, oas) -> None:
+        labels = batch["labels"].long()
+        if self.fused_head:
+            from . import pipeline
+            field = self.make_input(batch)
+            sparse_out = self.model.forward_sparse(field)
+            dev = sparse_out.F.device
+            step_counts = torch.zeros((3, self.num_labels), dtype=torch.int64, device=dev)
+            crit = self.criterion
+            losses.append(pipeline.seg_head_loss(sparse_out, field, labels.to(dev), crit.ignore_index,
+                                                 crit.weight.to(dev) if crit.weighted else None, step_counts).item())
+            oas.append(metrics_from_counts(step_counts)["OA"])
+            self.iou_meter.counts_buffer(dev).add_(step_counts)
+            return
+        logits = self.model(self.make_input(batch))
+        if self.segmentation:
+            losses.append(self.criterion(logits, batch).item())
+            oas.append(eval_metrics(logits, labels, logits.shape[1], self.cfg.ignore_label)["OA"])
+            self.iou_meter.update(logits, labels)
+        else:
+            losses.append(F.cross_entropy(logits, labels).item())
+            self.acc1_meter(logits, labels)
+            self.acc5_meter(logits, labels)
+
+    def _validation_epoch_end(self, losses, oas) -> Dict[str, float]:
         assert len(losses) > 0
         out = {"val/loss": float(np.mean(losses)), "global_step": self.global_step}
         if self.segmentation:

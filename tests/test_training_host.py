@@ -536,3 +536,54 @@ def test_evaluate_from_lightning_checkpoint(tmp_path, monkeypatch):
     torch.save(ckpt, tmp_path / "pruned.ckpt")
     with pytest.raises(NotImplementedError, match="pruned"):
         training.evaluate(str(tmp_path / "pruned.ckpt"), val, model=TinyNet(), tag="t2", make_input=lambda b: b["features"])
+
+
+def test_exception_safe_run_survives_failing_batches(monkeypatch):
+    """ExceptionSafeSegmentationTraining (segmentation_training.py:233-326): a step that raises RuntimeError (how the
+    library reports e.g. out-of-memory) is counted and skipped, the schedule still advances; a failing validation
+    batch is skipped."""
+    _cpu_kernels(monkeypatch)
+
+    class Flaky(TinyNet):
+        calls = 0
+
+        def forward(self, x):
+            Flaky.calls += 1
+            if Flaky.calls in (2, 5):
+                raise RuntimeError("CUDA out of memory (simulated)")
+            return super().forward(x)
+
+    ginlite.parse_config("train.max_steps = 6\ntrain.scheduler_name = 'PolyLR'\nPolyLR.poly_exp = 0.9\ntrain.lr = 0.1\n"
+                         "train.ignore_label = -255\nSGD.momentum = 0.9\nget_model.out_channel = 4")
+    data = _batches(60, 6, ignore=-255)
+    run = training.Run(Flaky(), training.TrainConfig(), make_input=lambda b: b["features"], exception_safe=True)
+    before = [p.detach().clone() for p in run.model.parameters()]
+    assert run.training_step(data[0]) is not None
+    after1 = [p.detach().clone() for p in run.model.parameters()]
+    assert run.training_step(data[1]) is None and run.fail_count == 1 and run.global_step == 2
+    assert all(torch.equal(a, b) for a, b in zip(after1, run.model.parameters()))      # the failed step changed nothing
+    assert any(not torch.equal(a, b) for a, b in zip(before, after1))
+    assert abs(run.trainer.lr - 0.1 * (1 - 2 / 7) ** 0.9) < 1e-12                       # the scheduler stepped anyway
+    run.fit(lambda: data[2:])
+    assert run.global_step == 6 and run.fail_count == 2
+    Flaky.calls = 0
+    res = run.validate(data[:3])                                                        # batch 2 of 3 fails, is skipped
+    assert np.isfinite(res["val/loss"])
+    strict = training.Run(Flaky(), training.TrainConfig(), make_input=lambda b: b["features"])
+    Flaky.calls = 1
+    with pytest.raises(RuntimeError, match="out of memory"):
+        strict.training_step(data[0])
+
+
+def test_collate_mink():
+    rng = np.random.default_rng(0)
+    samples = [{"coordinates": rng.uniform(0, 9, (n, 3)).astype(np.float32), "features": rng.standard_normal((n, 5)).astype(np.float32),
+                "labels": rng.integers(0, 4, n), "instance_ids": np.arange(n), "metadata": {"file": f"s{n}"}} for n in (7, 3, 5)]
+    b = training.collate_mink(samples)
+    assert b["coordinates"].dtype == torch.float32 and tuple(b["coordinates"].shape) == (15, 4)
+    assert b["coordinates"][:, 0].tolist() == [0.0] * 7 + [1.0] * 3 + [2.0] * 5                # batch column first
+    assert np.array_equal(b["coordinates"][7:10, 1:].numpy(), samples[1]["coordinates"])
+    assert tuple(b["features"].shape) == (15, 5) and b["features"].dtype == torch.float32
+    assert b["labels"].tolist() == np.concatenate([s["labels"] for s in samples]).tolist()
+    assert b["instance_ids"].shape[0] == 15 and b["metadata"] == [{"file": "s7"}, {"file": "s3"}, {"file": "s5"}]
+    assert "dataset" not in b
