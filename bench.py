@@ -195,7 +195,10 @@ def run_ours(args):
     model = models.Res16UNet34C(27, 20).to(dev).train()
     tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
 
-    coords, feats, labels = synth.room_batch(777 + rank, args.scenes, args.voxels, shuffle=args.shuffle)
+    if args.geometry == "faithful":   # the reference's real ScanNet-plenoxel coordinate transform
+        coords, feats, labels = synth.faithful_room_batch(777 + rank, args.scenes, args.voxels, args.scene_scale)
+    else:
+        coords, feats, labels = synth.room_batch(777 + rank, args.scenes, args.voxels, shuffle=args.shuffle)
     h_coords = torch.from_numpy(coords).pin_memory()
     h_feats = torch.from_numpy(feats).pin_memory()
     h_labels = torch.from_numpy(labels).pin_memory()
@@ -390,7 +393,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"MinkUNet34C (Res16UNet34C 27->20) fwd+bwd+SGD, synthetic ScanNet-shaped "
                                        f"plenoxel scenes, {args.voxels} voxels/scene, {args.scenes} scene(s)/GPU, "
-                                       f"BASELINE.json configs[1]",
+                                       f"BASELINE.json configs[1]"
+                                       + (f" — config 2B geometry, scene_scale {args.scene_scale}"
+                                          if args.geometry == "faithful" else ""),
                            "voxels_per_step_all_gpus": total_voxels, "parallelism": f"dp{world}",
                            "l2_policy": "inputs_exceed_l2 (activations per step >> 126 MB)",
                            "voxel_order": "shuffled" if args.shuffle else "raster (as the reference loaders deliver)",
@@ -426,6 +431,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")
     ap.add_argument("--host-profile", action="store_true", help="cProfile of 3 steps on stderr (host overhead)")
+    ap.add_argument("--geometry", default="dense", choices=["dense", "faithful"],
+                    help="dense = config 2A (headline: dense 2 cm surface); faithful = config 2B (256^3 plenoxel grid, even "
+                         "lattice, (c/256*2-1)/scene_scale/0.02: samples ~2.3 voxels apart, centre-tap-only maps at stride 1)")
+    ap.add_argument("--scene-scale", type=float, default=0.34, help="scene_scale of --geometry faithful (median 0.34)")
     ap.add_argument("--fused-head", action="store_true",
                     help="loss through the fused segmentation head (forward_sparse + spc_seg_head_fwd) instead of "
                          "slice -> cross-entropy; off by default until re-measured inside the step")

@@ -85,6 +85,48 @@ def room_batch(seed: int, n_scenes: int, target_voxels: int, channels: int = 27,
     return np.concatenate(cs), np.concatenate(fs), np.concatenate(ls)
 
 
+def faithful_room_batch(seed: int, n_scenes: int, target_voxels: int, scene_scale: float = 0.34, channels: int = 27,
+                        num_classes: int = 20, ignore_label: int = 255, reso: int = 256, voxel_size: float = 0.02,
+                        downsample_stride: int = 2) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """SURVEY.md §8d "config 2B": the coordinates the reference's PlenoxelScannetDataset really produces.
+
+    A room is drawn on a reso^3 plenoxel grid, thinned to the lattice `c % downsample_stride == 0`
+    (scannet.py:546-549, mode 1), and mapped like `load_data` does (scannet.py:612-615):
+        xyz = (c / reso * 2 - 1) / scene_scale / voxel_size          (float32, torch semantics)
+    so neighbouring samples sit `2 * downsample_stride / (reso * scene_scale * voxel_size)` voxels apart (2.3 at the
+    median scene_scale 0.34): at tensor stride 1 the 3^3 kernel map is (almost) the centre tap only, real
+    neighbourhoods appear at strides 2-4.  Rooms are tiled side by side along x until the scene holds
+    `target_voxels` points.  Returns (coords float32 [N,4], feats float32 [N,C], labels int64 [N])."""
+    rng = np.random.default_rng(seed)
+    cs, fs, ls = [], [], []
+    pitch = 2.0 * downsample_stride / (reso * scene_scale * voxel_size)
+    for b in range(n_scenes):
+        parts, have, tile = [], 0, 0
+        while have < target_voxels:
+            # one plenoxel grid: a room of reso x (0.43 reso) x reso cells, centred in the cube
+            dims = (reso, max(12, int(round(reso * 130 / 300))), reso)
+            cells_wanted = int(dims[0] * dims[1] * dims[2] * 0.2)        # ~1.5 M occupied cells per grid (SURVEY §8d)
+            vox = room_scene(rng, cells_wanted, base=tuple(d * np.sqrt(1.0e6 / cells_wanted) for d in dims))
+            vox = vox + np.array([0, (reso - dims[1]) // 2, 0], np.int32)
+            vox = vox[(vox % downsample_stride == 0).all(1)]
+            xyz = ((vox.astype(np.float32) / np.float32(reso) * np.float32(2) - np.float32(1))
+                   / np.float32(scene_scale) / np.float32(voxel_size)).astype(np.float32)
+            xyz[:, 0] += np.float32(tile * (reso // downsample_stride + 4) * pitch)     # next room beside the last
+            parts.append(xyz)
+            have += xyz.shape[0]
+            tile += 1
+        xyz = np.concatenate(parts)[:target_voxels]
+        c = np.empty((xyz.shape[0], 4), np.float32)
+        c[:, 0] = b
+        c[:, 1:] = xyz
+        lab = rng.integers(0, num_classes, size=xyz.shape[0]).astype(np.int64)
+        lab[rng.random(xyz.shape[0]) < 0.1] = ignore_label
+        cs.append(c)
+        fs.append(sh_features(rng, xyz.shape[0], channels))
+        ls.append(lab)
+    return np.concatenate(cs), np.concatenate(fs), np.concatenate(ls)
+
+
 def co3d_object(rng: np.random.Generator, lattice: int = 128) -> np.ndarray:
     """Integer voxels [n,3]: ellipsoid shell (thickness 3) + 3 solid blobs on a lattice^3 grid."""
     g = np.arange(lattice, dtype=np.float32)

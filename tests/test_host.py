@@ -115,3 +115,29 @@ def test_sparse_collate_float():
     c, f, l = ME.utils.sparse_collate(coords, feats, [torch.tensor([1]), torch.tensor([2, 3])])
     assert c.dtype == torch.int32 and c.tolist() == [[0, 0, -2, 2], [1, 3, 4, 5], [1, 6, 7, 8]]
     assert l.tolist() == [1, 2, 3] and f.shape == (3, 2)
+
+
+def test_faithful_geometry_generator_statistics():
+    """the reference's real ScanNet-plenoxel transform puts samples ~2.3 voxels apart at the
+    median scene_scale, so stride 1 has no collisions and (almost) only the centre tap, stride 2 removes nothing, and
+    real neighbourhoods start at stride 2; a larger scene_scale packs them closer."""
+    import numpy as np
+
+    from nerf_downstream_b200 import synth
+    from oracle import ref_ops as R
+    stats = {}
+    for scale in (0.34, 0.56):
+        c, f, l = synth.faithful_room_batch(3, 2, 30_000, scene_scale=scale)
+        assert c.shape == (60_000, 4) and f.shape == (60_000, 27) and l.shape == (60_000,) and c.dtype == np.float32
+        assert set(np.unique(c[:, 0])) == {0.0, 1.0}
+        uc, _, _ = R.unique_first_np(R.quantize_np(c))
+        nbr = R.kernel_map_np(uc, uc, R.kernel_offsets((3, 3, 3), (1, 1, 1)))
+        uc2 = R.stride_coords_np(uc, (2, 2, 2))
+        nbr2 = R.kernel_map_np(uc2, uc2, R.kernel_offsets((3, 3, 3), (2, 2, 2)))
+        stats[scale] = (uc.shape[0] / c.shape[0], (nbr >= 0).sum() / uc.shape[0], uc2.shape[0] / uc.shape[0],
+                        (nbr2 >= 0).sum() / uc2.shape[0])
+    m1, p1, m2, p2 = stats[0.34]
+    assert m1 == 1.0 and p1 < 1.05 and m2 == 1.0 and p2 > 3.0
+    assert stats[0.56][1] > 2.0 and stats[0.56][3] > p2
+    pitch = 2 * 2 / (256 * 0.34 * 0.02)
+    assert abs(pitch - 2.2978) < 1e-3
