@@ -1,0 +1,210 @@
+"""Host logic of the ME-compatible layer on CPU, through tests/host_harness.py (READ ITS HEADER: the harness answers
+the C-ABI calls with the oracle's numpy restatements so that the Python layer above the ABI — manager, key rules,
+kernel-map caching, lazy BatchNorm fusion, channel padding, bf16 side copies, autograd wiring, training loop — can be
+exercised without a GPU.  It says nothing about the CUDA kernels; tests/test_gpu_*.py cover those through the real
+library).  The product itself still refuses CPU tensors (tests/test_host.py::test_no_cpu_fallback)."""
+import numpy as np
+import pytest
+import torch
+
+from nerf_downstream_b200 import ginlite, models, ops, pipeline, synth, training
+from nerf_downstream_b200 import me as ME
+from oracle import nets
+from oracle import ref_ops as R
+from tests import host_harness
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def _field(coords, feats):
+    return ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats))
+
+
+def _oracle_params(model):
+    return {k: v.detach().double().clone().requires_grad_(v.is_floating_point() and "running" not in k)
+            for k, v in model.state_dict().items()}
+
+
+def test_resnet14_step_matches_oracle_network(monkeypatch):
+    fake = host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(0)
+    coords, feats, labels = synth.co3d_batch(5, 2, lattice=24)
+    model = models.ResNet14(27, 51).train()
+    params = _oracle_params(model)
+    y = torch.from_numpy(labels)
+    ref = nets.resnet_forward(params, coords, torch.from_numpy(feats).double())
+    torch.nn.functional.cross_entropy(ref, y).backward()
+    out = model(_field(coords, feats))
+    ops.cross_entropy(out, y).backward()
+    assert _cos(out.detach(), ref.detach()) >= 0.999999
+    for name, p in model.named_parameters():
+        assert _cos(p.grad, params[name].grad) >= 0.9999, name
+    # ResNet14 has one block per stage: every convolution has its own (map pair, kernel) -> one map each + the pool's
+    n_maps = fake.calls.count("spc_kernel_map")
+    n_convs = fake.calls.count("spc_conv_fwd")
+    assert n_convs == 14 and n_maps <= n_convs + 1
+    # BN + (residual) + ReLU run as ONE apply call per BatchNorm: no separate relu / add launches in the blocks
+    assert fake.calls.count("spc_bn_apply") == 13 and fake.calls.count("spc_add") == 0
+    assert fake.calls.count("spc_relu_fwd") == 0
+
+
+def test_unet_fused_head_and_three_pass_agree_and_match_oracle(monkeypatch):
+    host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(1)
+    coords, feats, labels = synth.room_batch(9, 2, 700, ignore_label=-255)
+    model = models.Res16UNet14A(27, 20).train()
+    params = _oracle_params(model)
+    y = torch.from_numpy(labels)
+    w = torch.ones(20)
+    w[-1] = 0.3
+    ref = nets.resunet_forward(params, coords, torch.from_numpy(feats).double())
+    torch.nn.functional.cross_entropy(ref, y, weight=w.double(), ignore_index=-255).backward()
+
+    logits = model(_field(coords, feats))
+    loss_a = ops.cross_entropy(logits, y, -255, w)
+    loss_a.backward()
+    assert _cos(logits.detach(), ref.detach()) >= 0.99999
+    grads_a = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for name, g in grads_a.items():
+        assert _cos(g, params[name].grad) >= 0.999, name
+
+    model.zero_grad()
+    field = _field(coords, feats)
+    counts = torch.zeros((3, 20), dtype=torch.int64)
+    loss_b = pipeline.seg_head_loss(model.forward_sparse(field), field, y, -255, w, counts)
+    loss_b.backward()
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * abs(loss_a.item())
+    for name, p in model.named_parameters():
+        assert torch.allclose(p.grad, grads_a[name], rtol=1e-4, atol=1e-7), name
+    assert (counts.numpy() == R.iou_counts_np(logits.detach().numpy(), labels, 20, -255)).all()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_tensor_core_modes_pad_channels_and_reuse_bf16_side_copies(monkeypatch, precision):
+    """Large maps (>= 4096 rows) pad 27 -> 32 input and 20 -> 32 output channels for the tensor-core kernels and slice
+    the padding off again; in bf16 mode BatchNorm hands its bf16 side copy to the next convolution (no conversion pass
+    for those rows).  The harness computes in fp32 / bf16-rounded operands, so results must still match the oracle."""
+    fake = host_harness.install(monkeypatch, precision)
+    torch.manual_seed(2)
+    coords, feats = synth.random_cloud(4, 9000, extent=14, n_batch=2, channels=27)
+    x = _field(coords, feats).sparse()
+    assert x.F.shape[0] >= 4096
+    conv1 = ME.MinkowskiConvolution(27, 32, kernel_size=3, dimension=3)
+    bn = ME.MinkowskiBatchNorm(32)
+    relu = ME.MinkowskiReLU()
+    conv2 = ME.MinkowskiConvolution(32, 20, kernel_size=3, bias=True, dimension=3)
+    out = conv2(relu(bn(conv1(x))))
+    out.F.sum().backward()
+    assert out.F.shape == (x.F.shape[0], 20) and conv1.kernel.grad.shape == (27, 27, 32)
+    assert conv2.kernel.grad.shape == (27, 32, 20) and conv2.bias.grad.shape == (1, 20)
+    # oracle of the same two layers
+    uc = x.C.numpy()
+    nbr = R.kernel_map_np(uc, uc, R.kernel_offsets((3, 3, 3), (1, 1, 1)))
+    h = R.conv_forward(x.F.detach().double(), conv1.kernel.detach().double(), nbr)
+    h = torch.relu(R.batch_norm(h, bn.bn.weight.detach().double(), bn.bn.bias.detach().double()))
+    ref = R.conv_forward(h, conv2.kernel.detach().double(), nbr, conv2.bias.detach().double())
+    tol = 1e-5 if precision == "tf32" else 3e-2                  # the harness rounds bf16 operands like the kernels
+    assert (out.F.detach().double() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    conversions = fake.calls.count("spc_to_bf16")
+    if precision == "bf16":
+        # forward: input rows of conv1 only (conv2 takes BatchNorm's side copy); backward: dout of conv2, and the
+        # gradient that reaches conv1 comes out of BatchNorm backward with its bf16 copy attached
+        assert conversions == 2, fake.calls
+    else:
+        assert conversions == 0
+    assert fake.calls.count("spc_tile_mask") >= 1                # tensor-core paths ask for the per-tile offset masks
+
+
+def test_manager_key_rules_and_caching(monkeypatch):
+    fake = host_harness.install(monkeypatch, "fp32")
+    coords, feats = synth.random_cloud(3, 1500, extent=8, n_batch=2, channels=8)
+    x = _field(coords, feats).sparse()
+    mgr = x.coordinate_manager
+    a = ME.MinkowskiConvolution(8, 8, kernel_size=3, stride=2, dimension=3)(x)
+    b = ME.MinkowskiConvolution(8, 8, kernel_size=1, stride=2, dimension=3)(x)
+    assert a.coordinate_map_key == b.coordinate_map_key and a.tensor_stride == [2, 2, 2]
+    assert fake.calls.count("spc_coords_insert") == 2            # field -> voxels, stride-2 map: built once
+    up = ME.MinkowskiConvolutionTranspose(8, 4, kernel_size=2, stride=2, dimension=3)(a)
+    assert up.coordinate_map_key == x.coordinate_map_key
+    n_maps = fake.calls.count("spc_kernel_map")
+    ME.MinkowskiConvolution(8, 8, kernel_size=3, stride=2, dimension=3)(x)       # same (keys, kernel): cached
+    assert fake.calls.count("spc_kernel_map") == n_maps
+    with pytest.raises(AssertionError):
+        ME.cat(a, x)
+    pairs = mgr.kernel_map(x.coordinate_map_key, x.coordinate_map_key, 1, 3, 1)
+    assert bool((pairs[13][0] == pairs[13][1]).all()) and pairs[13].shape[1] == x.F.shape[0]
+    g = ME.MinkowskiGlobalAvgPooling()(a)
+    assert g.F.shape == (2, 8) and g.C.tolist() == [[0, 0, 0, 0], [1, 0, 0, 0]]
+    # out-of-range coordinates surface as a RuntimeError, as from the real library
+    far = coords.copy()
+    far[0, 1] = 3.0e5
+    with pytest.raises(RuntimeError, match="out of the supported range"):
+        _field(far, feats).sparse()
+
+
+@pytest.mark.parametrize("cls", [models.MinkowskiFCNN, models.MinkowskiSplatFCNN])
+def test_fcnn_backbones_run_on_the_surface(monkeypatch, cls):
+    host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(3)
+    coords, feats, labels = synth.co3d_batch(11, 2, channels=3, num_classes=10, lattice=20)
+    net = cls(3, 10, embedding_channel=32, channels=(4, 8, 8, 8, 16)).train()
+    logits = net(_field(coords, feats))
+    assert logits.shape == (2, 10) and torch.isfinite(logits).all()
+    torch.nn.functional.cross_entropy(logits, torch.from_numpy(labels)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_pointnet_matches_torch_restatement(monkeypatch):
+    host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(4)
+    coords, feats = synth.random_cloud(3, 600, extent=6, n_batch=3, channels=5)
+    net = models.MinkowskiPointNet(5, 7, embedding_channel=32).train()
+    net.dp1.module.p = 0.0
+    sd = {k: v.detach().double() for k, v in net.state_dict().items()}
+    logits = net(_field(coords, feats))
+
+    def bn(h, name):
+        return (h - h.mean(0)) / torch.sqrt(h.var(0, unbiased=False) + 1e-5) * sd[f"{name}.1.bn.weight"] + sd[f"{name}.1.bn.bias"]
+    h = torch.from_numpy(feats).double()
+    for name in ("conv1", "conv2", "conv3", "conv4", "conv5"):
+        h = torch.relu(bn(h @ sd[f"{name}.0.linear.weight"].T, name))
+    b = torch.from_numpy(np.floor(coords[:, 0]).astype(np.int64))
+    g = torch.stack([h[b == i].max(0).values for i in range(3)])
+    g = torch.relu(bn(g @ sd["linear1.0.linear.weight"].T, "linear1"))
+    ref = g @ sd["linear2.linear.weight"].T + sd["linear2.linear.bias"]
+    assert _cos(logits.detach(), ref) >= 0.99999
+
+
+def test_gin_driven_run_on_the_surface(monkeypatch, tmp_path):
+    """`training.train` end to end (gin file -> get_model -> fit with the fused head -> Lightning checkpoint ->
+    evaluate) with the real `models.Res16UNet14A` on the ME surface."""
+    host_harness.install(monkeypatch, "fp32")
+    ginlite.clear_config()
+    try:
+        cfg = tmp_path / "tiny.gin"
+        cfg.write_text('get_model.name = "Res16UNet14A"\nget_model.in_channel = 27\nget_model.out_channel = 20\n'
+                       'train.max_steps = 3\ntrain.scheduler_name = "PolyLR"\nPolyLR.poly_exp = 0.9\ntrain.lr = 0.05\n'
+                       'train.ignore_label = -255\ntrain.val_every_n_steps = 3\ntrain.log_every_n_steps = 1\n'
+                       'SGD.momentum = 0.9\n')
+        torch.manual_seed(5)
+
+        def batches(seed, k):
+            out = []
+            for i in range(k):
+                c, f, y = synth.room_batch(seed + i, 1, 400, ignore_label=-255)
+                out.append({"coordinates": torch.from_numpy(c), "features": torch.from_numpy(f), "labels": torch.from_numpy(y)})
+            return out
+        tb, vb = batches(10, 2), batches(20, 1)
+        logs = []
+        run = training.train([str(cfg)], [], lambda: tb, lambda: vb, save_path=str(tmp_path / "run"), device="cpu",
+                             log=logs.append, fused_head=True)
+        assert run.global_step == 3 and [d["global_step"] for d in logs if "train/loss" in d] == [1, 2]
+        last = [d for d in logs if "val/mIoU" in d][-1]
+        res = training.evaluate(str(tmp_path / "run" / "last.ckpt"), vb, model=models.Res16UNet14A(27, 20), tag="e",
+                                fused_head=True)
+        assert abs(res["val/mIoU"] - last["val/mIoU"]) < 1e-3 and abs(res["val/loss"] - last["val/loss"]) < 1e-4
+    finally:
+        ginlite.clear_config()
