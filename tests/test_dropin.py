@@ -71,3 +71,68 @@ def test_reference_resunet_variants_construct():
         assert sum(p.numel() for p in net.parameters()) > 7_000_000
     with pytest.raises(ValueError, match="not supported"):
         ref.ResUNet2(in_channel=27, out_channel=20)            # NORM_TYPE None (common.py:22-33), as with ME itself
+
+
+# ---- the reference's files EXECUTE unchanged (forward + backward) on the surface --------------------------------
+# Through tests/host_harness.py (read its header): the C-ABI calls are answered by the oracle on CPU tensors, so what
+# is tested here is that the reference's own model code drives this repository's MinkowskiEngine package to the same
+# numbers as this repository's model definitions (which the GPU parity tests run on the real kernels).
+def _run(model, coords, feats):
+    import MinkowskiEngine as ME
+    out = model(ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats)))
+    return out if torch.is_tensor(out) else out.F
+
+
+def test_reference_resnet14_and_unet_execute_like_ours(monkeypatch):
+    from nerf_downstream_b200 import models, synth
+    from oracle import nets
+    from tests import host_harness
+    host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(0)
+    rn = ref_harness.load("co3d_3d.src.models.mink.resnet")
+    un = ref_harness.load("co3d_3d.src.models.mink.res16unet")
+    coords, feats, labels = synth.co3d_batch(5, 2, lattice=20)
+    theirs, ours = rn.ResNet14(in_channel=27, out_channel=51).train(), models.ResNet14(27, 51).train()
+    ours.load_state_dict(theirs.state_dict())
+    a, b = _run(theirs, coords, feats), _run(ours, coords, feats)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    params = {k: v.detach().double() for k, v in theirs.state_dict().items()}
+    ref = nets.resnet_forward(params, coords, torch.from_numpy(feats).double())
+    assert torch.allclose(a.detach().double(), ref, rtol=1e-3, atol=1e-4)
+    torch.nn.functional.cross_entropy(a, torch.from_numpy(labels)).backward()
+    torch.nn.functional.cross_entropy(b, torch.from_numpy(labels)).backward()
+    for (n1, p1), (n2, p2) in zip(theirs.named_parameters(), ours.named_parameters()):
+        assert n1 == n2 and torch.allclose(p1.grad, p2.grad, rtol=1e-4, atol=1e-6), n1
+
+    coords, feats, _ = synth.room_batch(3, 1, 500)
+    theirs, ours = un.Res16UNet14A(in_channel=27, out_channel=20).train(), models.Res16UNet14A(27, 20).train()
+    ours.load_state_dict(theirs.state_dict())
+    a, b = _run(theirs, coords, feats), _run(ours, coords, feats)
+    assert a.shape == (500, 20) and torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_reference_other_backbones_execute(monkeypatch):
+    from nerf_downstream_b200 import models, synth
+    from tests import host_harness
+    host_harness.install(monkeypatch, "fp32")
+    torch.manual_seed(1)
+    fc = ref_harness.load("co3d_3d.src.models.mink.fcnn")
+    pn = ref_harness.load("co3d_3d.src.models.mink.pointnet")
+    ru = ref_harness.load("co3d_3d.src.models.mink.resunet")
+    coords, feats, labels = synth.co3d_batch(11, 2, channels=3, num_classes=10, lattice=20)
+    kw = dict(embedding_channel=32, channels=(4, 8, 8, 8, 16))
+    for theirs, ours in [(fc.MinkowskiFCNN(3, 10, **kw), models.MinkowskiFCNN(3, 10, **kw)),
+                         (fc.MinkowskiSplatFCNN(3, 10, **kw), models.MinkowskiSplatFCNN(3, 10, **kw)),
+                         (pn.MinkowskiPointNet(3, 10, embedding_channel=32), models.MinkowskiPointNet(3, 10, embedding_channel=32))]:
+        ours.load_state_dict(theirs.state_dict())
+        theirs.eval()                                             # dropout off: the two must agree exactly
+        ours.eval()
+        a, b = _run(theirs, coords, feats), _run(ours, coords, feats)
+        assert a.shape == (2, 10) and torch.allclose(a, b, rtol=1e-5, atol=1e-6), type(theirs).__name__
+    # instance-norm variant of the feature-matching UNet (3^3 stride-2 down / up convolutions, IN inside the blocks)
+    import MinkowskiEngine as ME
+    net = ru.ResUNetIN2C(in_channel=3, out_channel=16).train()
+    out = net(ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats)).sparse())
+    assert out.F.shape[1] == 16 and torch.isfinite(out.F).all()
+    out.F.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
