@@ -150,6 +150,15 @@ class FakeLib:
         self.tables[_addr(slots)] = uc.copy()
         return 0
 
+    def spc_coords_insert_dev(self, src, n, n_dev, kind, ts, slots, n_slots, out_coords, out_first, out_inverse,
+                              out_count, status, ws, ws_bytes, stream):
+        """rows = min(n, *n_dev): the row count of the parent level is read from ITS status word (stride pyramid)."""
+        rows = n if not _addr(n_dev) else min(int(n), int(view(n_dev, 2, np.int32)[0]))
+        rc = self.spc_coords_insert(src, rows, kind, ts, slots, n_slots, out_coords, out_first, out_inverse, out_count,
+                                    status, ws, ws_bytes, stream)
+        self.calls[-1] = "spc_coords_insert_dev"
+        return rc
+
     def spc_kernel_map(self, in_slots, in_n_slots, out_coords, m_out, offsets, K, nbr, tap_count, stream):
         self._called("spc_kernel_map")
         in_coords = self.tables[_addr(in_slots)]
@@ -534,7 +543,7 @@ class FakeLib:
         return 0
 
 
-def install(monkeypatch, precision: str = "fp32") -> FakeLib:
+def install(monkeypatch, precision: str = "fp32", prefetch_depth: int = 1) -> FakeLib:
     """Route the host layer's library calls to a FakeLib for the duration of a test."""
     from nerf_downstream_b200 import lib as L
     from nerf_downstream_b200 import ops
@@ -554,7 +563,7 @@ def install(monkeypatch, precision: str = "fp32") -> FakeLib:
     monkeypatch.setattr(L, "launch_count", lambda: fake.launches)
     monkeypatch.setattr(ops, "_ptr_rows", lambda x: x.data_ptr())
     monkeypatch.setattr(core, "_require_cuda", lambda dev, what: None)
-    monkeypatch.setattr(core.CoordinateManager, "default_prefetch_depth", 1)   # the pyramid entry point is CUDA-only
+    monkeypatch.setattr(core.CoordinateManager, "default_prefetch_depth", prefetch_depth)   # 4 = the product's pyramid
     monkeypatch.setattr(ops, "_default_precision", ops.PRECISIONS[precision])
     monkeypatch.setattr(ops, "_ws_bytes_cache", {})
     monkeypatch.setattr(ops, "_workspaces", {})

@@ -208,3 +208,27 @@ def test_gin_driven_run_on_the_surface(monkeypatch, tmp_path):
         assert abs(res["val/mIoU"] - last["val/mIoU"]) < 1e-3 and abs(res["val/loss"] - last["val/loss"]) < 1e-4
     finally:
         ginlite.clear_config()
+
+
+def test_stride_pyramid_equals_level_by_level(monkeypatch):
+    """The first stride-2 request builds the 2-4-8-16 maps back to back, each level reading its parent's row count
+    from the parent's status word (one host synchronisation for all levels): maps, parent rows and the network
+    output must equal the level-by-level construction."""
+    outs, sizes, calls = [], [], []
+    for depth in (1, 4):
+        fake = host_harness.install(monkeypatch, "fp32", prefetch_depth=depth)
+        torch.manual_seed(7)
+        coords, feats, _ = synth.room_batch(13, 2, 600)
+        model = models.Res16UNet14A(27, 20).train()
+        field = _field(coords, feats)
+        outs.append(model(field).detach())
+        mgr = field.coordinate_manager
+        sizes.append({tuple(k.get_tensor_stride()): (mgr.size(k), mgr.get_coordinates(k).clone())
+                      for k in mgr._maps if k.get_tensor_stride()[0] in (2, 4, 8, 16)})
+        calls.append((fake.calls.count("spc_coords_insert"), fake.calls.count("spc_coords_insert_dev")))
+    assert calls[0][1] == 0 and calls[1][1] == 4                        # four strided levels in one go
+    assert calls[1][0] == calls[0][0] - 4
+    assert sizes[0].keys() == sizes[1].keys() and len(sizes[0]) == 4
+    for k in sizes[0]:
+        assert sizes[0][k][0] == sizes[1][k][0] and torch.equal(sizes[0][k][1], sizes[1][k][1]), k
+    assert torch.equal(outs[0], outs[1])
