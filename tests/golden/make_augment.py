@@ -38,6 +38,53 @@ SEQUENCES = {
 }
 
 
+PIPELINES = {
+    # PlenoxelScannetDataset.train_transformations (scannet_plenoxel.gin:7-16) with its gin parameters
+    "scannet_plenoxel": [("RandomRotation", dict(upright_axis="y")),
+                         ("RandomCrop", dict(x=60, y=60, z=60)),
+                         ("RandomAffine", dict(upright_axis="y", application_ratio=0.7)),
+                         ("CoordinateDropout", dict()),
+                         ("RandomFeatureJitter", dict(start_ind=4, feature_dim=27)),
+                         ("RandomHorizontalFlip", dict(upright_axis="y")),
+                         ("RandomTranslation", dict()),
+                         ("ElasticDistortion", dict(distortion_params=[(4, 16)], application_ratio=0.7))],
+    # Co3DDatasetBase.train_transformations (co3d_aug3.gin:3-12)
+    "co3d_aug3": [("RandomRotation", dict(upright_axis="y")),
+                  ("RandomAffine", dict(upright_axis="y")),
+                  ("CoordinateDropout", dict(application_ratio=0.9)),
+                  ("RandomHorizontalFlip", dict(upright_axis="y")),
+                  ("CoordinateUniformTranslation", dict(max_translation=0.2)),
+                  ("CoordinateJitter", dict()),
+                  ("RandomScale", dict(scale_ratio=0.4)),
+                  ("RandomFeatureJitter", dict(start_ind=4, feature_dim=27))],
+}
+
+
+def make_pipelines(T):
+    """Full transformation lists (affine AND point-wise) through the reference's Compose -> augment_pipeline_ref.npz."""
+    rng = np.random.default_rng(20261018)
+    n = 400
+    points = rng.uniform(-40, 90, (n, 3))
+    feats = rng.standard_normal((n, 31))
+    labels = rng.integers(0, 20, n)
+    out = {"points": points, "feats": feats, "labels": labels}
+    for name, seq in PIPELINES.items():
+        for seed in range(4):
+            random.seed(seed)
+            np.random.seed(seed)
+            comp = T.Compose([getattr(T, cls)(**kw) for cls, kw in seq])
+            c, f, l = comp(points.copy(), feats.copy(), labels.copy())
+            out[f"{name}/{seed}/coords"] = np.asarray(c, np.float64)
+            out[f"{name}/{seed}/feats"] = np.asarray(f, np.float64)
+            out[f"{name}/{seed}/labels"] = np.asarray(l, np.int64)
+            print(name, seed, c.shape)
+    path = Path(__file__).with_name("augment_pipeline_ref.npz")
+    np.savez_compressed(path, **out)
+    (Path(__file__).with_name("augment_pipeline_ref.json")).write_text(
+        json.dumps({k: [[c, kw] for c, kw in v] for k, v in PIPELINES.items()}))
+    print("wrote", path)
+
+
 def main():
     sys.modules["gin"] = ginlite
     import MinkowskiEngine  # noqa: F401  (this repository's drop-in package; imported by the reference file)
@@ -60,6 +107,7 @@ def main():
     path = Path(__file__).with_name("augment_ref.json")
     path.write_text(json.dumps(out))
     print("wrote", path, len(out["cases"]), "cases")
+    make_pipelines(T)
 
 
 if __name__ == "__main__":

@@ -78,3 +78,46 @@ def test_flip_and_composition_algebra():
     assert np.allclose(got, want) and got[:, 0].min() == pytest.approx(0.0, abs=1e-12)
     d = c.copy().divide(0.02).scale([1.0, 2.0, 3.0])
     assert np.allclose(d.apply(pts), want / 0.02 * [1.0, 2.0, 3.0]) and np.allclose(c.apply(pts), want)
+
+
+def test_full_transformation_lists_match_reference_compose():
+    """Affine AND point-wise transforms through `augment.apply_transformations` (affine runs folded into one matrix,
+    point-wise ones on the tensors) == the reference's `Compose` of its own classes under identical seeds: same rows
+    survive crop / dropout in the same order, coordinates and jittered features agree to rounding."""
+    import torch
+    ref = np.load(GOLDEN.with_name("augment_pipeline_ref.npz"))
+    seqs = json.loads(GOLDEN.with_name("augment_pipeline_ref.json").read_text())
+    pts, feats, labels = ref["points"], ref["feats"], ref["labels"]
+    seen_rows = set()
+    for name, seq in seqs.items():
+        for seed in range(4):
+            random.seed(seed)
+            np.random.seed(seed)
+            c, f, l = augment.apply_transformations([n for n, _ in seq], torch.from_numpy(pts.copy()),
+                                                    torch.from_numpy(feats.copy()), torch.from_numpy(labels.copy()),
+                                                    params={n: kw for n, kw in seq})
+            wc, wf, wl = ref[f"{name}/{seed}/coords"], ref[f"{name}/{seed}/feats"], ref[f"{name}/{seed}/labels"]
+            assert c.shape == wc.shape, (name, seed, c.shape, wc.shape)
+            assert (l.numpy() == wl).all()                                   # identical rows, identical order
+            assert np.abs(c.numpy() - wc).max() <= 1e-9 * max(1.0, np.abs(wc).max()), (name, seed)
+            assert np.abs(f.numpy() - wf).max() <= 1e-12
+            seen_rows.add(c.shape[0])
+    assert len(seen_rows) > 2 and min(seen_rows) < 400                       # crops / dropouts really happened
+
+
+def test_apply_transformations_float32_and_errors():
+    import torch
+    rng = np.random.default_rng(2)
+    pts = torch.from_numpy(rng.uniform(0, 50, (500, 3)).astype(np.float32))
+    random.seed(1)
+    np.random.seed(1)
+    c, f, l = augment.apply_transformations(["RandomRotation", "CoordinateJitter", "RandomScale"], pts,
+                                            params={"RandomRotation": dict(upright_axis="y", application_ratio=1.0),
+                                                    "CoordinateJitter": dict(application_ratio=1.0),
+                                                    "RandomScale": dict(application_ratio=1.0)})
+    assert c.dtype == torch.float32 and c.shape == (500, 3) and f is None and l is None
+    with pytest.raises(KeyError, match="not built"):
+        augment.apply_transformations(["ChromaticJitter"], pts)
+    # a box larger than the cloud leaves it untouched (transforms.py:216-218)
+    same, _, _ = augment.random_crop(pts, None, None, 1000, 1000, 1000)
+    assert same is pts
