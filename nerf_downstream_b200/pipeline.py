@@ -67,6 +67,96 @@ def plenoxel_decode_augmented(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale
     return coords, feats, chain
 
 
+# ---- record -> sample: the reference's Dataset.__getitem__ after the file has been read ------------------------------
+SCANNET_VALID_CLASS_IDS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 24, 28, 33, 34, 36, 39)   # scannet.py:43-64
+SCANNET_NUM_LABELS = 41                                                                              # scannet.py:451
+
+
+def scannet_label_map(ignore_label: int = -100, void_label: Optional[int] = None) -> dict:
+    """NYU40 id -> train id (0..19), everything else -> ignore_label, optional void class = 20 (scannet.py:518-528)."""
+    label_map, n_used = {}, 0
+    for lab in range(SCANNET_NUM_LABELS):
+        if lab in SCANNET_VALID_CLASS_IDS:
+            label_map[lab] = n_used
+            n_used += 1
+        else:
+            label_map[lab] = ignore_label
+    label_map[ignore_label] = ignore_label
+    if void_label is not None and void_label != ignore_label:
+        label_map[void_label] = n_used
+    return label_map
+
+
+def _select_features(features: Sequence[str], available: dict) -> torch.Tensor:
+    """`features.append(eval(f))` over the names of configs/feature_*.gin (co3d.py:217-220, scannet.py:633-636)."""
+    missing = [f for f in features if f not in available]
+    if missing:
+        raise KeyError(f"unknown feature name(s) {missing}; this sample offers {sorted(available)}")
+    return torch.cat([available[f] for f in features], dim=1).float()
+
+
+def co3d_sample(links: torch.Tensor, density: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float,
+                reso: Sequence[int], features: Sequence[str] = ("sh",), transformations: Sequence[str] = (),
+                params: Optional[dict] = None) -> dict:
+    """`Co3DDatasetBase.__getitem__` (co3d.py:178-235) for one record already on the GPU: lattice coordinates and
+    dequantised SH from `spc_plenoxel_decode`, the (per-point, as the reference writes it: `mean(dim=1)`) centred and
+    max-norm-scaled `xyzs`, the train transformations, the configured feature columns."""
+    from . import augment
+    coords4, sh = plenoxel_decode(links, sh_u8, sh_scale, sh_min, reso)
+    coordinates = coords4[:, 1:]
+    xyzs = coordinates - coordinates.mean(dim=1, keepdim=True)
+    xyzs = xyzs / torch.linalg.norm(xyzs, dim=1).max()
+    raw = torch.cat([xyzs, density.to(sh.device).float().view(-1, 1), sh], dim=1).float()
+    if len(transformations) > 0:
+        coordinates, raw, _ = augment.apply_transformations(transformations, coordinates, raw, None, params)
+    xyzs, dens, shf = raw[:, :3], raw[:, 3:4], raw[:, 4:]
+    feats = _select_features(features, {"xyzs": xyzs, "density": dens, "sh": shf, "ones": torch.ones_like(dens)})
+    return {"coordinates": coordinates, "features": feats, "xyzs": xyzs}
+
+
+def scannet_plenoxel_sample(links: torch.Tensor, density: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float,
+                            sh_min: float, reso: Sequence[int], labels: torch.Tensor, dists: torch.Tensor,
+                            scene_scale: float, voxel_size: float = 0.02, downsample_stride: int = 2,
+                            ignore_label: int = -100, void_label: Optional[int] = None, valid_thres: float = 0.05,
+                            ignore_thres: Optional[float] = None, features: Sequence[str] = ("sh",),
+                            transformations: Sequence[str] = (), params: Optional[dict] = None) -> dict:
+    """`PlenoxelScannetDataset.load_data` + `__getitem__` (scannet.py:558-654) for one record on the GPU:
+    void labelling by surface distance, optional distance filter, decode, thinning to the `c % stride == 0` lattice
+    (downsample mode 1), `xyz = (c / reso * 2 - 1) / scene_scale / voxel_size`, train transformations, feature
+    columns, NYU40 -> 20-class label map."""
+    from . import augment
+    dev = links.device
+    labels = labels.to(dev).long().clone().view(-1)
+    dists = dists.to(dev).float().view(-1)
+    density = density.to(dev).float().view(-1, 1)
+    labels[dists > valid_thres] = void_label if void_label is not None else ignore_label
+    if ignore_thres is not None and ignore_thres > 0:
+        keep = dists < ignore_thres
+        links, sh_u8, density, labels = links[keep], sh_u8[keep], density[keep], labels[keep]
+        # (the reference filters `dists` only implicitly — scannet.py:574-579 leaves it unfiltered and would fail in
+        #  `torch.cat`; here the distances follow their voxels)
+        dists = dists[keep]
+    if len(features) > 1:                                     # scannet.py:593-594
+        density = density / (density.abs().max() + 1e-5)
+    coords4, sh = plenoxel_decode(links, sh_u8, sh_scale, sh_min, reso)
+    coordinates = coords4[:, 1:]
+    sel = (coordinates % downsample_stride == 0).all(dim=1)
+    coordinates, sh, density, labels, dists = coordinates[sel], sh[sel], density[sel], labels[sel], dists[sel]
+    r = torch.tensor([float(v) for v in reso], dtype=torch.float32, device=dev)
+    xyzs = (coordinates / r * 2 - 1.0) / scene_scale / voxel_size
+    raw = torch.cat([xyzs, dists.view(-1, 1), density, sh], dim=1).float()
+    if len(transformations) > 0:
+        xyzs, raw, labels = augment.apply_transformations(transformations, xyzs, raw, labels, params)
+    dist_f, dens, shf = raw[:, 3:4], raw[:, 4:5], raw[:, 5:]
+    feats = _select_features(features, {"dists": dist_f, "density": dens, "sh": shf, "ones": torch.ones_like(dens),
+                                        "xyzs": raw[:, :3]})
+    mapped = torch.full_like(labels, ignore_label)            # `label_map[x]` (scannet.py:637-640)
+    for k, v in scannet_label_map(ignore_label, void_label).items():
+        mapped = torch.where(labels == k, torch.full_like(labels, v), mapped)
+    return {"coordinates": xyzs.float(), "features": feats, "xyzs": xyzs.float(), "labels": mapped.to(torch.int32),
+            "dists": dist_f}
+
+
 def seg_counts(logits: torch.Tensor, target: torch.Tensor, ignore_label: int, out: Optional[torch.Tensor] = None):
     """counts[3, C] int64 (+= when `out` is given): per class #seen, #correct, #predicted of argmax(logits)."""
     lib = L.load()

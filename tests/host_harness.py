@@ -474,6 +474,19 @@ class FakeLib:
         p[:] = p - np.float32(lr) * b
         return 0
 
+    def spc_plenoxel_decode(self, links, is64, n, reso, batch_index, affine12, sh_u8, C, sh_scale, sh_min, out_coords,
+                            out_feats, stream):
+        self._called("spc_plenoxel_decode")
+        r = [int(v) for v in view(reso, 3, np.int32)]
+        ln = view(links, n, np.int64 if is64 else np.int32).astype(np.int64)
+        aff = list(view(affine12, 12, np.float32)) if _addr(affine12) else None
+        sh = view(sh_u8, (n, C), np.uint8) if C else np.zeros((n, 0), np.uint8)
+        c, f = R.plenoxel_decode_np(ln, sh, np.float32(sh_scale), np.float32(sh_min), r, batch_index=batch_index, affine=aff)
+        view(out_coords, (n, 4), np.float32)[:] = c
+        if C:
+            view(out_feats, (n, C), np.float32)[:] = f
+        return 0
+
     # ---- instance norm / interpolation ------------------------------------------------------------------------
     def spc_inst_norm_fwd(self, x, coords, m, C, n_batch, gamma, beta, eps, y, mean, rstd, cnt, ws, stream):
         self._called("spc_inst_norm_fwd")

@@ -232,3 +232,50 @@ def test_stride_pyramid_equals_level_by_level(monkeypatch):
     for k in sizes[0]:
         assert sizes[0][k][0] == sizes[1][k][0] and torch.equal(sizes[0][k][1], sizes[1][k][1]), k
     assert torch.equal(outs[0], outs[1])
+
+
+def test_record_to_sample_matches_reference_getitem(monkeypatch):
+    """`pipeline.co3d_sample` / `scannet_plenoxel_sample` against the reference's own `Dataset.__getitem__` code run on
+    the same in-memory plenoxel record (tests/golden/make_samples.py -> samples_ref.npz): decode, void labelling,
+    lattice thinning, normalisation, the train transformations under the same seeds (parameters from gin bindings),
+    feature selection, NYU40 -> 20-class label map.  (Decode kernel emulated by the harness; its GPU parity is
+    tests/test_gpu_parity.py::test_plenoxel_decode_exact.)"""
+    import random
+    from pathlib import Path
+    host_harness.install(monkeypatch, "fp32")
+    gold = Path(__file__).resolve().parent / "golden"
+    ref = np.load(gold / "samples_ref.npz")
+    rec = {k.split("/", 1)[1]: ref[k] for k in ref.files if k.startswith("record/")}
+    links, density = torch.from_numpy(rec["links"]), torch.from_numpy(rec["density"])
+    sh = torch.from_numpy(rec["sh"])
+    scale, mn, reso = float(rec["sh_scale"]), float(rec["sh_min"]), [int(v) for v in rec["reso"]]
+    for case, feats in (("co3d_plain", ["sh"]), ("co3d_xyz_density", ["xyzs", "density", "ones"])):
+        s = pipeline.co3d_sample(links, density, sh, scale, mn, reso, features=feats)
+        assert (s["coordinates"].numpy() == ref[f"{case}/coordinates"]).all()
+        assert np.abs(s["features"].numpy() - ref[f"{case}/features"]).max() <= 1e-6, case
+        assert np.abs(s["xyzs"].numpy() - ref[f"{case}/xyzs"]).max() <= 1e-6
+    ginlite.clear_config()
+    try:
+        ginlite.parse_config((gold / "samples_ref.gin").read_text())
+        labels, dists = torch.from_numpy(rec["labels"]), torch.from_numpy(rec["dists"])
+        names = ["RandomRotation", "RandomCrop", "RandomAffine", "CoordinateDropout", "RandomHorizontalFlip",
+                 "RandomTranslation", "ElasticDistortion"]
+        for case, feats, tf, seed, void in (("scannet_plain", ["sh"], [], 0, None),
+                                            ("scannet_void", ["density", "sh"], [], 0, 40),
+                                            ("scannet_aug", ["sh"], names, 2, None)):
+            random.seed(seed)
+            np.random.seed(seed)
+            s = pipeline.scannet_plenoxel_sample(links, density, sh, scale, mn, reso, labels, dists, scene_scale=0.34,
+                                                 ignore_label=-255, void_label=void, features=feats, transformations=tf)
+            want = ref[f"{case}/coordinates"]
+            assert s["coordinates"].shape == want.shape, (case, s["coordinates"].shape, want.shape)
+            assert (s["labels"].numpy() == ref[f"{case}/labels"]).all(), case
+            tol = 1e-4 if tf else 2e-5                           # float32 chain vs the reference's float64 chain
+            assert np.abs(s["coordinates"].numpy() - want).max() <= tol * max(1.0, np.abs(want).max()), case
+            assert np.abs(s["features"].numpy() - ref[f"{case}/features"]).max() <= 1e-6
+            assert np.abs(s["dists"].numpy() - ref[f"{case}/dists"]).max() <= 1e-7
+        assert (ref["scannet_void/labels"] == 20).any() and (ref["scannet_plain/labels"] == -255).any()
+    finally:
+        ginlite.clear_config()
+    with pytest.raises(KeyError, match="unknown feature"):
+        pipeline.co3d_sample(links, density, sh, scale, mn, reso, features=["rgb"])
