@@ -136,3 +136,37 @@ def test_reference_other_backbones_execute(monkeypatch):
     assert out.F.shape[1] == 16 and torch.isfinite(out.F).all()
     out.F.square().mean().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_reference_weight_sparse_convolution_executes(monkeypatch):
+    """The reference's in-tree pruned-weight inference convolution (sparse_conv.py:267-452: per-offset gather ->
+    sparse / dense W_k product -> scatter, driven by `CoordinateManager.kernel_map` pair lists and
+    `MinkowskiEngine.sparse_matrix_functions.spmm`) runs unchanged on the surface and equals the dense convolution with
+    the same (pruned) kernel — forward and transposed, `strided` and `coo` layouts.  (`csr` fails inside the reference
+    itself on this torch: `torch._sparse_csr_tensor` no longer exists.)"""
+    import MinkowskiEngine as ME
+    from nerf_downstream_b200 import synth
+    from tests import host_harness
+    host_harness.install(monkeypatch, "fp32")
+    sc = ref_harness.load("co3d_3d.src.models.mink.modules.sparse_conv")
+    coords, feats = synth.random_cloud(1, 800, extent=6, n_batch=2, channels=8)
+    x = ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats)).sparse()
+    torch.manual_seed(0)
+    down = ME.MinkowskiConvolution(8, 8, kernel_size=2, stride=2, dimension=3)(x)
+    cases = [(sc.WeightSparseConvolution, ME.MinkowskiConvolution, dict(kernel_size=3, stride=1), x),
+             (sc.WeightSparseConvolution, ME.MinkowskiConvolution, dict(kernel_size=2, stride=2), x),
+             (sc.WeightSparseConvolutionTranspose, ME.MinkowskiConvolutionTranspose, dict(kernel_size=2, stride=2), down)]
+    for layout in ("strided", "coo"):
+        for theirs_cls, ours_cls, kw, inp in cases:
+            theirs = theirs_cls(8, 16, dilation=1, bias=True, dimension=3, **kw)
+            ours = ours_cls(8, 16, bias=True, dimension=3, **kw)
+            with torch.no_grad():
+                theirs.kernel.copy_(torch.randn_like(theirs.kernel) * (torch.rand_like(theirs.kernel) > 0.7))
+                theirs.kernel[1] = 0                                   # a fully pruned offset
+                theirs.bias.copy_(torch.randn(1, 16))
+                ours.kernel.copy_(theirs.kernel)
+                ours.bias.copy_(theirs.bias)
+                theirs.sparsify(layout)
+                a, b = theirs(inp), ours(inp)
+            assert a.coordinate_map_key == b.coordinate_map_key
+            assert torch.allclose(a.F, b.F, rtol=1e-4, atol=1e-5), (layout, theirs_cls.__name__, kw)
