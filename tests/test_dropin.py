@@ -170,3 +170,47 @@ def test_reference_weight_sparse_convolution_executes(monkeypatch):
                 a, b = theirs(inp), ours(inp)
             assert a.coordinate_map_key == b.coordinate_map_key
             assert torch.allclose(a.F, b.F, rtol=1e-4, atol=1e-5), (layout, theirs_cls.__name__, kw)
+
+
+def test_reference_model_zoo_constructs_and_executes(monkeypatch):
+    """Every model class of the reference's resnet.py / res16unet.py constructs on the surface; one of each block
+    family (BasicBlock, Bottleneck, the instance-segmentation variants with their offset head, LayerNorm / PowerNorm
+    modules) executes forward +
+    backward unchanged."""
+    import MinkowskiEngine as ME
+    from nerf_downstream_b200 import synth
+    from tests import host_harness
+    host_harness.install(monkeypatch, "fp32")
+    rn = ref_harness.load("co3d_3d.src.models.mink.resnet")
+    un = ref_harness.load("co3d_3d.src.models.mink.res16unet")
+    built = 0
+    for mod, prefix, args in ((rn, "ResNet", (27, 51)), (un, "Res16UNet", (27, 20))):
+        for name in sorted(n for n in dir(mod) if n.startswith(prefix) and n != prefix and n != prefix + "Base"):
+            cls = getattr(mod, name)
+            # (Res16UNet18/34/50/101 define BLOCK and LAYERS only: PLANES comes with the lettered variants)
+            if isinstance(cls, type) and issubclass(cls, torch.nn.Module) and all(
+                    getattr(cls, a, None) is not None for a in ("BLOCK", "LAYERS", "PLANES")):
+                net = cls(in_channel=args[0], out_channel=args[1])
+                assert sum(p.numel() for p in net.parameters()) > 1_000_000, name
+                built += 1
+    assert built >= 20
+    torch.manual_seed(0)
+    coords, feats, _ = synth.room_batch(3, 1, 300)
+    for cls, cin, cout, rows in ((un.Res16UNet14AIns, 27, 20, 300), (un.Res16UNet18B, 27, 20, 300),
+                                 (rn.ResNet50, 27, 51, 1)):
+        net = cls(in_channel=cin, out_channel=cout).train()
+        out = net(ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats)))
+        outs = out if isinstance(out, tuple) else (out,)        # the *Ins variants return (offsets, logits)
+        outs = [o if torch.is_tensor(o) else o.F for o in outs]
+        assert outs[-1].shape == (rows, cout) and all(torch.isfinite(o).all() for o in outs), cls.__name__
+        sum(o.square().mean() for o in outs).backward()
+        assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+        assert sum(p.grad is not None for p in net.parameters()) > 10
+    ln = ref_harness.load("co3d_3d.src.models.mink.modules.layernorm")
+    pn = ref_harness.load("co3d_3d.src.models.mink.modules.powernorm")
+    f = ME.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats))
+    x = f.sparse()
+    for m in (ln.MinkowskiLayerNorm(27), pn.MinkowskiPowerNorm(27)):
+        a, b = m(x), m(f)
+        assert isinstance(a, ME.SparseTensor) and isinstance(b, ME.TensorField) and torch.isfinite(a.F).all()
+        assert a.coordinate_map_key == x.coordinate_map_key
