@@ -203,6 +203,12 @@ class IoUMeter:
             self.counts = torch.zeros((3, self.num_classes), dtype=torch.int64, device=device)
         return self.counts
 
+    def all_reduce(self, group=None) -> None:
+        """Sum the counts over the ranks of a data-parallel job (`dist_reduce_fx="sum"`, metrics.py:17-28)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and self.counts is not None:
+            dist.all_reduce(self.counts, op=dist.ReduceOp.SUM, group=group)
+
     def compute(self):
         seen, correct, positive = (self.counts[i].to(torch.float32) for i in range(3))
         present = seen != 0

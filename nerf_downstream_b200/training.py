@@ -513,6 +513,12 @@ class Run:
     def _validation_epoch_end(self, losses, oas) -> Dict[str, float]:
         assert len(losses) > 0
         out = {"val/loss": float(np.mean(losses)), "global_step": self.global_step}
+        # epoch metrics are sums over ALL ranks' validation shards (torchmetrics dist_reduce_fx="sum", metrics.py:17-28)
+        if self.segmentation:
+            self.iou_meter.all_reduce()
+        else:
+            self.acc1_meter.all_reduce()
+            self.acc5_meter.all_reduce()
         if self.segmentation:
             miou, ious, macc, accs = self.iou_meter.compute()
             out.update({"val/OA": float(np.mean(oas)), "val/mIoU": float(miou) * 100, "val/mAcc": float(macc) * 100})

@@ -129,7 +129,30 @@ def _fit_worker(rank, world, port, q):
         torch.nn.functional.cross_entropy(ref(x), y).backward()
         opt.step()
     err = max((a - b).abs().max().item() for a, b in zip(run.model.parameters(), ref.parameters()))
-    q.put((rank, err, run.global_step))
+    # epoch metrics: every rank validates ITS shard, the IoU counts are summed over ranks (metrics.py:17-28), so both
+    # ranks report the mIoU of the union — equal to a single process validating all shards
+    from nerf_downstream_b200 import pipeline
+
+    def seg_counts_cpu(logits, target, ignore_label, out=None):
+        C = logits.shape[1]
+        out = torch.zeros((3, C), dtype=torch.int64) if out is None else out
+        keep = target != ignore_label
+        pred, tgt = logits.argmax(1)[keep], target[keep]
+        for c in range(C):
+            out[0, c] += (tgt == c).sum()
+            out[1, c] += ((tgt == c) & (pred == tgt)).sum()
+            out[2, c] += (pred == c).sum()
+        return out
+    pipeline.seg_counts = seg_counts_cpu
+    mine = run.validate(batches(10 + rank)[:2])
+    meter = pipeline.IoUMeter(3, run.cfg.ignore_label)
+    run.model.eval()
+    with torch.no_grad():
+        for r in range(world):
+            for b in batches(10 + r)[:2]:
+                meter.update(run.model(b["features"]), b["labels"])
+    want = float(meter.compute()[0]) * 100
+    q.put((rank, err, run.global_step, abs(mine["val/mIoU"] - want)))
     dist.destroy_process_group()
 
 
@@ -144,5 +167,6 @@ def test_fit_world2_sync_grad_equals_global_batch():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, steps in res:
+    for rank, err, steps, miou_err in res:
         assert steps == 5 and err < 1e-5, (rank, err, steps)
+        assert miou_err < 1e-4, (rank, miou_err)
