@@ -424,26 +424,24 @@ class Run:
         labels = batch["labels"].long()
         step_counts = None
         if self.fused_head:
+            # slice + SegLoss + metric counts in one kernel over the points; logits stay on the voxel rows
             from . import pipeline
             field = self.make_input(batch)
-            out = self.model.forward_sparse(field)
-            logits = out.F
+            sparse_out = self.model.forward_sparse(field)
+            logits = sparse_out.F
             step_counts = torch.zeros((3, logits.shape[1]), dtype=torch.int64, device=logits.device)
             crit = self.criterion
-            loss = pipeline.seg_head_loss(out, field, labels.to(logits.device), crit.ignore_index,
+            loss = pipeline.seg_head_loss(sparse_out, field, labels.to(logits.device), crit.ignore_index,
                                           crit.weight.to(logits.device) if crit.weighted else None, step_counts)
         else:
             logits = self.model(self.make_input(batch))
-        if self.fused_head:
-            if self.cfg.use_sync_grad:
-                loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
-        elif self.segmentation:
-            loss = self.criterion(logits, batch)
-            if self.cfg.use_sync_grad:
-                loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
-        else:
-            from . import ops
-            loss = ops.cross_entropy(logits, labels) if logits.is_cuda else F.cross_entropy(logits, labels)
+            if self.segmentation:
+                loss = self.criterion(logits, batch)
+            else:
+                from . import ops
+                loss = ops.cross_entropy(logits, labels) if logits.is_cuda else F.cross_entropy(logits, labels)
+        if self.segmentation and self.cfg.use_sync_grad:
+            loss = loss * sync_grad_scale(batch["coordinates"].shape[0])
         step = self.global_step
         if step % self.cfg.log_every_n_steps == 0 and step > 0:
             loss_float = loss.detach().cpu().item()
