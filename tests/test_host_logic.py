@@ -279,3 +279,77 @@ def test_record_to_sample_matches_reference_getitem(monkeypatch):
         ginlite.clear_config()
     with pytest.raises(KeyError, match="unknown feature"):
         pipeline.co3d_sample(links, density, sh, scale, mn, reso, features=["rgb"])
+
+
+def test_surface_inventory_of_survey_8b(monkeypatch):
+    """Every MinkowskiEngine symbol / attribute / signature the reference touches (SURVEY.md §8b "Symbols + signatures
+    actually used") exists and behaves: tensors, layers, functional forms, manager, keys, kernel generator, utils."""
+    import MinkowskiEngine as MEpkg
+    import MinkowskiEngine.MinkowskiFunctional as MEF
+    from MinkowskiEngine.MinkowskiCoordinateManager import CoordinateManager
+    from MinkowskiEngine.MinkowskiKernelGenerator import KernelGenerator
+    from MinkowskiEngine.MinkowskiSparseTensor import CoordinateMapKey, SparseTensor
+    from MinkowskiEngineBackend._C import ConvolutionMode, RegionType  # noqa: F401
+    host_harness.install(monkeypatch, "fp32")
+    coords, feats = synth.random_cloud(5, 900, extent=7, n_batch=2, channels=6)
+    f = MEpkg.TensorField(coordinates=torch.from_numpy(coords), features=torch.from_numpy(feats))
+    assert f.F.shape == (900, 6) and f.device == torch.device("cpu") and f.dtype == torch.float32
+    assert f.quantization_mode == MEpkg.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE
+    f2 = MEpkg.TensorField(f.F * 2, coordinate_field_map_key=f.coordinate_field_map_key,
+                           coordinate_manager=f.coordinate_manager, quantization_mode=f.quantization_mode)   # layernorm.py:19-24
+    x = f.sparse()
+    x2 = f2.sparse(quantization_mode=MEpkg.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE)
+    assert isinstance(x, SparseTensor) and x.D == 3 and x.shape == x.F.shape and x.tensor_stride == [1, 1, 1]
+    assert x._manager is x.coordinate_manager and isinstance(x.coordinate_manager, CoordinateManager)
+    assert torch.allclose(x2.F, 2 * x.F)
+    y = MEpkg.SparseTensor(x.F + 1, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager)
+    y += x                                                                            # resnet_block.py:66
+    assert torch.allclose(y.F, 2 * x.F + 1) and y.slice(f).F.shape == (900, 6)
+    s = MEpkg.SparseTensor(features=torch.from_numpy(feats), coordinates=MEpkg.utils.batched_coordinates(
+        [torch.from_numpy(coords[:, 1:])], dtype=torch.float32), device="cpu")       # co3d.py:119, transforms.py:508-512
+    assert s.F.shape[1] == 6 and s.C.dtype == torch.int32
+    # layers + functional forms
+    conv = MEpkg.MinkowskiConvolution(in_channels=6, out_channels=8, kernel_size=3, stride=1, dilation=1, bias=True, dimension=3)
+    assert conv.in_channels == 6 and conv.out_channels == 8 and tuple(conv.kernel.shape) == (27, 6, 8) and conv.bias.shape == (1, 8)
+    kg = conv.kernel_generator
+    assert (kg.kernel_size, kg.kernel_stride, kg.kernel_dilation, kg.kernel_volume) == ([3, 3, 3], [1, 1, 1], [1, 1, 1], 27)
+    assert kg.region_type == RegionType.HYPER_CUBE and kg.expand_coordinates is False
+    assert isinstance(kg.requires_strided_coordinates, bool)
+    h = conv(x)
+    for name in ("MinkowskiReLU", "MinkowskiPReLU", "MinkowskiLeakyReLU", "MinkowskiELU", "MinkowskiCELU", "MinkowskiSELU",
+                 "MinkowskiGELU"):
+        assert getattr(MEpkg, name)()(h).F.shape == h.F.shape, name
+    assert MEpkg.MinkowskiReLU(inplace=True)(h).F.min() >= 0
+    for name in ("relu", "leaky_relu", "prelu", "celu", "selu", "gelu"):
+        fn = getattr(MEF, name)
+        out = fn(h, torch.tensor([0.25])) if name == "prelu" else fn(h)
+        assert out.F.shape == h.F.shape and out.coordinate_map_key == h.coordinate_map_key, name
+    assert MEpkg.MinkowskiSumPooling(kernel_size=2, stride=2, dimension=3)(h).tensor_stride == [2, 2, 2]
+    avg = MEpkg.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)(h)                     # co3d.py:107-111
+    assert avg.C[:, 1:].float().shape[1] == 3 and avg.F.shape[1] == 8
+    assert MEpkg.MinkowskiGlobalAvgPooling()(h).F.shape == (2, 8)
+    lin = MEpkg.MinkowskiLinear(8, 4, bias=False)
+    assert isinstance(lin.linear, torch.nn.Linear) and lin(h).F.shape[1] == 4
+    bn = MEpkg.MinkowskiBatchNorm(8, momentum=0.05)
+    assert isinstance(bn.bn, torch.nn.BatchNorm1d) and bn.bn.momentum == 0.05
+    assert isinstance(MEpkg.MinkowskiNetwork(3), torch.nn.Module) and issubclass(MEpkg.MinkowskiConvolution, MEpkg.MinkowskiModuleBase)
+    net = torch.nn.Sequential(conv, bn)
+    synced = MEpkg.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)                              # train.py:106-107
+    assert isinstance(synced[1], MEpkg.MinkowskiSyncBatchNorm) and synced[1].bn.weight is bn.bn.weight
+    assert MEpkg.cat(h, h).F.shape[1] == 16
+    # manager + keys (sparse_conv.py:80-96,397-405)
+    cm = x.coordinate_manager
+    key = CoordinateMapKey(x.coordinate_map_key.get_coordinate_size())
+    assert not key.is_key_set()
+    key.set_key([2, 2, 2], "")
+    assert cm.stride(x.coordinate_map_key, [2, 2, 2]) == key and cm.size(key) > 0
+    pairs = cm.kernel_map(x.coordinate_map_key, key, [2, 2, 2], [3, 3, 3], [1, 1, 1], is_transpose=False)
+    assert all(p.shape[0] == 2 and p.dtype == torch.int32 for p in pairs.values())
+    assert KernelGenerator(kernel_size=2, stride=2, dilation=1, expand_coordinates=False, dimension=3).kernel_volume == 8
+    # utils
+    cb, fb, lb = MEpkg.utils.sparse_collate([coords[:10, 1:], coords[10:30, 1:]], [feats[:10], feats[10:30]],
+                                            [np.zeros(10), np.ones(20)], dtype=torch.float32)
+    assert cb.shape == (30, 4) and cb.dtype == torch.float32 and fb.shape == (30, 6) and lb.shape[0] == 30
+    w = torch.empty(27, 6, 8)
+    MEpkg.utils.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+    assert abs(float(w.std()) - (2.0 / (27 * 8)) ** 0.5) < 0.02
