@@ -184,8 +184,10 @@ class MinkowskiBatchNorm(nn.Module):
 
 
 class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
-    """Cross-rank statistics via nn.SyncBatchNorm (train.py:106-107).  Off by default in the
-    reference (`use_sync_batchnorm`), so this wrapper simply defers to torch on `.F`."""
+    """Statistics over the rows of all ranks (train.py:106-107; off by default in the reference,
+    `use_sync_batchnorm`).  `self.bn` is an nn.SyncBatchNorm (same state-dict keys, `convert_sync_batchnorm`); in a
+    training forward pass with an initialised process group the work is `ops.SyncBatchNormFn` (our statistics / apply
+    kernels + one all-reduce of 2C + 1 doubles each way), otherwise it is the ordinary batch norm."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True,
                  process_group=None):
@@ -194,7 +196,22 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
                                    track_running_stats=track_running_stats, process_group=process_group)
 
     def forward(self, input):
-        return _wrap_like(input, self.bn(input.F))
+        import torch.distributed as dist
+        bn = self.bn
+        synced = bn.training and dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size(bn.process_group) > 1
+        if not synced:
+            return _wrap_like(input, self._run(input.F))
+        momentum = bn.momentum
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        out = ops.SyncBatchNormFn.apply(input.F, bn.weight, bn.bias,
+                                        bn.running_mean if bn.track_running_stats else None,
+                                        bn.running_var if bn.track_running_stats else None,
+                                        0.0 if momentum is None else momentum, bn.eps, bn.process_group)
+        return _wrap_like(input, out)
 
     @classmethod
     def convert_sync_batchnorm(cls, module, process_group=None):

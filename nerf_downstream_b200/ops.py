@@ -726,6 +726,66 @@ class BatchNormFn(torch.autograd.Function):
                 dres)
 
 
+class SyncBatchNormFn(torch.autograd.Function):
+    """BatchNorm whose statistics span the rows of ALL ranks (ME.MinkowskiSyncBatchNorm, train.py:106-107).
+
+    forward: local per-channel statistics from `spc_bn_stats`, turned into (count, sum, sum of squares) and summed
+    over the ranks with ONE all-reduce of 2C + 1 doubles, then `spc_bn_apply` with the global mean /
+    biased variance; running statistics use the global count (unbiased variance), as torch.nn.SyncBatchNorm.
+    backward: the per-channel sums of dy and dy * xhat are summed over the ranks the same way; the weight / bias
+    gradients stay LOCAL sums (the data-parallel step averages parameter gradients afterwards)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, group):
+        import torch.distributed as dist
+        lib = L.load()
+        x = _feat(x)
+        m, C = x.shape
+        dev = x.device
+        ws_bytes = int(lib.spc_bn_workspace(max(m, 1), C))
+        ws = _workspace(ws_bytes, dev)
+        mean = torch.zeros(C, dtype=torch.float32, device=dev)
+        var = torch.zeros(C, dtype=torch.float32, device=dev)
+        if m > 0:
+            L.check(lib.spc_bn_stats(L.ptr(x), m, C, L.ptr(mean), L.ptr(var), None, None, 0.0, L.ptr(ws), ws_bytes,
+                                     L.stream()), "spc_bn_stats")
+        mu = mean.double()
+        packed = torch.cat([torch.tensor([float(m)], dtype=torch.float64, device=dev), mu * m, (var.double() + mu * mu) * m])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        total = packed[0]
+        gmean = packed[1:1 + C] / total
+        gvar = (packed[1 + C:] / total - gmean * gmean).clamp_min(0)
+        if running_mean is not None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(momentum * gmean.float())
+                running_var.mul_(1 - momentum).add_(momentum * (gvar * total / (total - 1).clamp_min(1)).float())
+        gmean32, gvar32 = gmean.float().contiguous(), gvar.float().contiguous()
+        y = _empty((m, C), torch.float32, dev)
+        if m > 0:
+            L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(gmean32), L.ptr(gvar32), L.ptr(gamma), L.ptr(beta), None, m, C,
+                                     float(eps), 0, L.ptr(y), None, L.stream()), "spc_bn_apply")
+        ctx.save_for_backward(x, gmean32, gvar32, gamma)
+        ctx.cfg = (float(eps), group, total)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        x, gmean, gvar, gamma = ctx.saved_tensors
+        eps, group, total = ctx.cfg
+        C = x.shape[1]
+        rstd = torch.rsqrt(gvar + eps)
+        xhat = (x - gmean) * rstd
+        dbeta = dy.sum(0)
+        dgamma = (dy * xhat).sum(0)
+        packed = torch.cat([dbeta.double(), dgamma.double()])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        s0, s1 = (packed[:C] / total).float(), (packed[C:] / total).float()
+        scale = rstd if gamma is None else rstd * gamma
+        dx = scale * (dy - s0 - xhat * s1)
+        return dx, (dgamma if gamma is not None else None), (dbeta if gamma is not None else None), None, None, None, None, None
+
+
 class ReLUFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -170,3 +170,80 @@ def test_fit_world2_sync_grad_equals_global_batch():
     for rank, err, steps, miou_err in res:
         assert steps == 5 and err < 1e-5, (rank, err, steps)
         assert miou_err < 1e-4, (rank, miou_err)
+
+
+class _Patch:
+    """monkeypatch stand-in for a spawned worker (tests/host_harness.install only needs setattr)."""
+
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _syncbn_worker(rank, world, port, q):
+    """MinkowskiSyncBatchNorm over two ranks with different row counts == nn.BatchNorm1d on the concatenated rows:
+    outputs, input gradients, local weight / bias gradient sums, running statistics.  (Kernels answered by the host
+    harness; the collective is a real gloo all-reduce.)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+
+    from nerf_downstream_b200 import me as ME
+    from tests import host_harness
+    host_harness.install(_Patch(), "fp32")
+    g = torch.Generator().manual_seed(7)
+    rows = [50, 70]
+    xs = [torch.randn(n, 6, generator=g) * 2 + 1 for n in rows]
+    ws = [torch.randn(n, 6, generator=g) for n in rows]
+    coords = torch.zeros(rows[rank], 4)
+    coords[:, 1] = torch.arange(rows[rank])
+    bn = ME.MinkowskiSyncBatchNorm(6, momentum=0.1).train()
+    with torch.no_grad():
+        bn.bn.weight.copy_(torch.linspace(0.5, 1.5, 6))
+        bn.bn.bias.copy_(torch.linspace(-0.2, 0.3, 6))
+    x = xs[rank].clone().requires_grad_(True)
+    field = ME.TensorField(coordinates=coords, features=x)
+    out = bn(field)
+    (out.F * ws[rank]).sum().backward()
+
+    ref = torch.nn.BatchNorm1d(6, momentum=0.1).train()
+    with torch.no_grad():
+        ref.weight.copy_(bn.bn.weight)
+        ref.bias.copy_(bn.bn.bias)
+    xa = torch.cat(xs).clone().requires_grad_(True)
+    oa = ref(xa)
+    (oa * torch.cat(ws)).sum().backward()
+    lo, hi = (0, rows[0]) if rank == 0 else (rows[0], rows[0] + rows[1])
+    xhat = (xa.detach() - xa.detach().mean(0)) / torch.sqrt(xa.detach().var(0, unbiased=False) + 1e-5)
+    errs = {
+        "out": (out.F.detach() - oa.detach()[lo:hi]).abs().max().item(),
+        "dx": (x.grad - xa.grad[lo:hi]).abs().max().item(),
+        "dgamma": (bn.bn.weight.grad - (torch.cat(ws)[lo:hi] * xhat[lo:hi]).sum(0)).abs().max().item(),
+        "dbeta": (bn.bn.bias.grad - torch.cat(ws)[lo:hi].sum(0)).abs().max().item(),
+        "run_mean": (bn.bn.running_mean - ref.running_mean).abs().max().item(),
+        "run_var": (bn.bn.running_var - ref.running_var).abs().max().item(),
+    }
+    # eval mode: running statistics, no collective
+    bn.eval()
+    ev = bn(ME.TensorField(coordinates=coords, features=xs[rank])).F
+    ref.eval()
+    errs["eval"] = (ev - ref(xs[rank])).abs().max().item()
+    q.put((rank, errs, int(bn.bn.num_batches_tracked)))
+    dist.destroy_process_group()
+
+
+def test_sync_batchnorm_world2_equals_batchnorm_on_all_rows():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs, tracked in res:
+        assert tracked == 1
+        for k, v in errs.items():
+            assert v < 2e-5, (rank, k, v)
