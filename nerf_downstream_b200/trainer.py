@@ -52,13 +52,30 @@ class FlatArena:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
 
 
+OPTIMIZERS = ("SGD", "ASGD", "Adam", "AdamW", "Adagrad", "Adadelta", "Adamax", "RMSprop", "Rprop")   # optim.py:57
+
+
 class DataParallelTrainer:
+    """`optimizer_name` "SGD" (what every reference config selects) runs the fused `spc_sgd_step` on the flat arena;
+    the other names of the reference's `get_optimizer` (optim.py:57-69) run the torch optimizer of that name on the
+    arena-backed parameters (`optimizer_kwargs` = its gin bindings), with the same bucketed all-reduce in front."""
+
     def __init__(self, model: torch.nn.Module, lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4,
-                 bucket_mb: float = 25.0, process_group=None):
+                 bucket_mb: float = 25.0, process_group=None, optimizer_name: str = "SGD",
+                 optimizer_kwargs: Optional[dict] = None):
+        if optimizer_name not in OPTIMIZERS:
+            raise ValueError(f"optimizer {optimizer_name} not recognized in {list(OPTIMIZERS)}.")
         self.model = model
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
         self.arena = FlatArena(model)
         self.momentum_buf = torch.zeros_like(self.arena.data)
+        self.optimizer_name = optimizer_name
+        self.torch_optimizer = None
+        if optimizer_name != "SGD":
+            kw = dict(optimizer_kwargs or {})
+            if optimizer_name != "Rprop":
+                kw.setdefault("weight_decay", weight_decay)
+            self.torch_optimizer = getattr(torch.optim, optimizer_name)(self.arena.params, lr=lr, **kw)
         self.steps = 0
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.group = process_group
@@ -113,12 +130,20 @@ class DataParallelTrainer:
                                                          group=self.group, async_op=True))
             for h in self._handles:
                 h.wait()
-        ops.sgd_step(self.arena.data, self.arena.grad, self.momentum_buf, self.lr, self.momentum,
-                     self.weight_decay, 1.0 / self.world, self.steps == 0)
+        if self.torch_optimizer is None:
+            ops.sgd_step(self.arena.data, self.arena.grad, self.momentum_buf, self.lr, self.momentum,
+                         self.weight_decay, 1.0 / self.world, self.steps == 0)
+        else:
+            if self.world > 1:
+                self.arena.grad.mul_(1.0 / self.world)
+            self.torch_optimizer.step()
         self.steps += 1
 
     def set_lr(self, lr: float):
         self.lr = lr
+        if self.torch_optimizer is not None:
+            for group in self.torch_optimizer.param_groups:
+                group["lr"] = lr
 
 
 def cosine_lr(base_lr: float, step: int, max_steps: int, eta_min: float = 0.0) -> float:

@@ -194,6 +194,9 @@ def load_lightning_state_dict(model: torch.nn.Module, state_dict, strict: bool =
 def optimizer_state(trainer) -> dict:
     """`torch.optim.SGD.state_dict()` layout (what Lightning stores in `optimizer_states`): parameters are numbered in
     `model.parameters()` order, each with its `momentum_buffer`."""
+    if getattr(trainer, "torch_optimizer", None) is not None:
+        # torch numbers parameters in the order they were handed over (the arena's); Lightning stores exactly this
+        return trainer.torch_optimizer.state_dict()
     params = [p for p in trainer.model.parameters() if p.requires_grad]
     slot = {id(p): o for p, o in zip(trainer.arena.order, trainer.arena.offsets)}
     state = {}
@@ -210,6 +213,11 @@ def optimizer_state(trainer) -> dict:
 def load_optimizer_state(trainer, opt_state: dict, keep_lr: Optional[float] = None) -> None:
     """Inverse of `optimizer_state`.  `keep_lr`: start from the configured learning rate instead of the stored one
     (the intent of lightning_module_base.py:93-101)."""
+    if getattr(trainer, "torch_optimizer", None) is not None:
+        trainer.torch_optimizer.load_state_dict(opt_state)
+        trainer.set_lr(trainer.torch_optimizer.param_groups[0]["lr"] if keep_lr is None else keep_lr)
+        trainer.steps = max(trainer.steps, 1)
+        return
     params = [p for p in trainer.model.parameters() if p.requires_grad]
     slot = {id(p): o for p, o in zip(trainer.arena.order, trainer.arena.offsets)}
     group = opt_state["param_groups"][0]
@@ -302,6 +310,8 @@ class TrainConfig:
         if self.max_steps is None:
             raise ginlite.GinError("train.max_steps is not bound (required argument of train(), train.py:56)")
         self.momentum = _bound(f"{self.optimizer_name}.momentum", 0.0)
+        self.optimizer_kwargs = {k.split(".", 1)[1]: v for k, v in ginlite.config_dict().items()
+                                 if k.startswith(f"{self.optimizer_name}.")}
         self.scheduler_kwargs = {k.split(".", 1)[1]: v for k, v in ginlite.config_dict().items()
                                  if k.startswith(f"{self.scheduler_name}.")}
 
@@ -352,9 +362,6 @@ class Run:
                  log: Optional[Callable[[dict], None]] = None, fused_head: bool = False, evaluate_only: bool = False,
                  exception_safe: bool = False):
         from . import trainer as T
-        if cfg.optimizer_name != "SGD" and not evaluate_only:
-            raise NotImplementedError("the fused optimiser step implements SGD (what every reference config selects: "
-                                      "co3d_cls.gin:33, scannet_plenoxel.gin:58)")
         self.model, self.cfg, self.save_path, self.log = model, cfg, save_path, log or (lambda d: None)
         self.segmentation = cfg.training_module == "SegmentationTraining"
         if cfg.training_module not in ("SegmentationTraining", "ClassificationTraining"):
@@ -363,7 +370,9 @@ class Run:
         self.trainer = None
         self.schedule = None
         if not evaluate_only:
-            self.trainer = T.DataParallelTrainer(model, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+            self.trainer = T.DataParallelTrainer(model, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay,
+                                                 optimizer_name=cfg.optimizer_name,
+                                                 optimizer_kwargs=None if cfg.optimizer_name == "SGD" else cfg.optimizer_kwargs)
             self.trainer.initial_lr = cfg.lr
             self.schedule = cfg.schedule()
         self.global_step = 0

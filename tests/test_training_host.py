@@ -587,3 +587,35 @@ def test_collate_mink():
     assert b["labels"].tolist() == np.concatenate([s["labels"] for s in samples]).tolist()
     assert b["instance_ids"].shape[0] == 15 and b["metadata"] == [{"file": "s7"}, {"file": "s3"}, {"file": "s5"}]
     assert "dataset" not in b
+
+
+@pytest.mark.parametrize("name,kw", [("Adam", {}), ("AdamW", {"betas": (0.8, 0.99)}), ("RMSprop", {"momentum": 0.5}),
+                                     ("Adagrad", {})])
+def test_other_optimizers_of_get_optimizer(monkeypatch, name, kw):
+    """`get_optimizer` (optim.py:57-69) knows nine torch optimizers; the ones besides SGD run as torch optimizers on
+    the arena-backed parameters with their gin bindings, and the loop / schedule / checkpoint code is the same."""
+    _cpu_kernels(monkeypatch)
+    binds = "".join(f"{name}.{k} = {v!r}\n" for k, v in kw.items())
+    ginlite.parse_config(f"train.max_steps = 5\ntrain.optimizer_name = '{name}'\ntrain.scheduler_name = 'ExponentialLR'\n"
+                         f"ExponentialLR.gamma = 0.9\ntrain.lr = 0.01\ntrain.weight_decay = 1e-3\n"
+                         f"train.training_module = 'ClassificationTraining'\nget_model.out_channel = 4\n{binds}")
+    torch.manual_seed(0)
+    a, b = TinyNet(), TinyNet()
+    b.load_state_dict(a.state_dict())
+    data = _batches(70, 5)
+    run = training.Run(a, training.TrainConfig(), make_input=lambda d: d["features"])
+    run.fit(lambda: data)
+    opt = getattr(torch.optim, name)(b.parameters(), lr=0.01, weight_decay=1e-3, **kw)
+    for t, batch in enumerate(data):
+        for g in opt.param_groups:
+            g["lr"] = 0.01 * 0.9 ** t
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(b(batch["features"]), batch["labels"]).backward()
+        opt.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-6), name
+    st = training.optimizer_state(run.trainer)
+    assert set(st) == {"state", "param_groups"} and len(st["state"]) == len(list(a.parameters()))
+    with pytest.raises(ValueError, match="not recognized"):
+        from nerf_downstream_b200 import trainer as T
+        T.DataParallelTrainer(TinyNet(), optimizer_name="LAMB")
