@@ -338,10 +338,9 @@ def get_model(name: Optional[str] = None, in_channel: Optional[int] = None, out_
     name = name if name is not None else ginlite.query_parameter("get_model.name")
     in_channel = in_channel if in_channel is not None else ginlite.query_parameter("get_model.in_channel")
     out_channel = out_channel if out_channel is not None else ginlite.query_parameter("get_model.out_channel")
-    if not hasattr(models, name):
-        known = sorted(n for n in dir(models) if n.startswith(("ResNet", "Res16UNet")))
-        raise KeyError(f"model {name!r} is not built here (have {known})")
-    return getattr(models, name)(in_channel, out_channel)
+    if name not in models.MODELS:
+        raise KeyError(f"model {name!r} is not built here (have {sorted(models.MODELS)})")
+    return models.MODELS[name](in_channel, out_channel)
 
 
 class Run:
