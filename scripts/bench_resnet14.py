@@ -1,13 +1,17 @@
 """BASELINE.json configs[0] / configs[2] (parity-test cases, not the headline): co3d_3d ResNet14(27 -> 51) sparse
 classifier fwd + bwd + SGD on a synthetic CO3D-shaped plenoxel batch, B objects per GPU (reference: 16,
 co3d_cls.gin:28).  Prints voxels/s and objects/s; `--cpu` also times the CPU restatement on a B=4 batch.
+Under `torchrun --nproc-per-node N` it is SURVEY.md §8d config 3: B objects per GPU (ranks seeded 777 + rank), weak
+scaling, gradient all-reduce over NCCL, time = max over ranks.
 usage: bench_resnet14.py [--batch 16] [--steps 20] [--precision bf16|tf32|fp32] [--cpu]"""
 import argparse
+import os
 import sys
 import time
 from pathlib import Path
 
 import torch
+import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from nerf_downstream_b200 import me as ME  # noqa: E402
@@ -19,12 +23,18 @@ ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--cpu", action="store_true")
 args = ap.parse_args()
-dev = torch.device("cuda:0")
+rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    import datetime
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 ops.set_default_precision(args.precision)
 torch.manual_seed(0)
 model = models.ResNet14(27, 51).to(dev).train()
 tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
-coords, feats, labels = synth.co3d_batch(777, args.batch)
+coords, feats, labels = synth.co3d_batch(777 + rank, args.batch)
 c, f, y = (torch.from_numpy(a).to(dev) for a in (coords, feats, labels))
 
 
@@ -36,19 +46,35 @@ def step():
     return field.coordinate_manager.size(field.coordinate_manager.get_unique_coordinate_map_key(1))
 
 
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
 for _ in range(5):
     vox = step()
-torch.cuda.synchronize()
+barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(args.steps):
     step()
 e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / args.steps
-print(f"ResNet14 fwd+bwd+SGD  B={args.batch}  {vox} voxels/step  {args.precision}: {ms:.3f} ms/step  "
-      f"{vox / ms / 1e3:.2f} M voxels/s  {args.batch / ms * 1e3:.0f} objects/s", flush=True)
-if args.cpu:
+barrier()
+stats = torch.tensor([e0.elapsed_time(e1) / args.steps, float(vox)], device=dev, dtype=torch.float64)
+if world > 1:
+    t = stats[:1].clone()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)            # time = the slowest rank
+    v = stats[1:].clone()
+    dist.all_reduce(v, op=dist.ReduceOp.SUM)            # voxels of the whole job
+    stats = torch.cat([t, v])
+ms, vox = float(stats[0]), int(stats[1])
+if rank == 0:
+    print(f"ResNet14 fwd+bwd+SGD  {world} GPU(s)  B={args.batch}/GPU  {vox} voxels/step  {args.precision}: {ms:.3f} ms/step  "
+          f"{vox / ms / 1e3:.2f} M voxels/s  {world * args.batch / ms * 1e3:.0f} objects/s", flush=True)
+if world > 1:
+    dist.destroy_process_group()
+if args.cpu and rank == 0:
     from oracle import nets
     cc, ff, yy = synth.co3d_batch(777, 4)
     params = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point() and "running" not in k)
