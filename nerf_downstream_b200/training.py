@@ -94,6 +94,27 @@ def metrics_from_counts(counts: torch.Tensor) -> Dict[str, float]:
     return {"OA": oa, "mIoU": float((iu * 100).mean())}
 
 
+def count_parameters(model: torch.nn.Module) -> Dict[str, float]:
+    """`count_parameters` (co3d_3d/src/utils/prune.py:11-23): trainable parameters and the number removed by
+    `torch.nn.utils.prune` masks (`kernel_mask` / `weight_mask` buffers) — logged as val/total_params, val/pruned_params."""
+    return {"total": float(sum(p.numel() for p in model.parameters() if p.requires_grad)),
+            "pruned": float(sum((1 - b.int()).sum() for n, b in model.named_buffers()
+                                if "kernel_mask" in n or "weight_mask" in n))}
+
+
+def get_parameters_to_prune(model: torch.nn.Module):
+    """`get_parameters_to_prune` (utils/prune.py:34-59): (module, parameter name) of every sparse convolution kernel and
+    every MinkowskiLinear weight."""
+    from . import me as ME
+    out = []
+    for _, module in model.named_modules():
+        if isinstance(module, (ME.MinkowskiConvolution, ME.MinkowskiConvolutionTranspose)):
+            out.append((module, "kernel"))
+        elif isinstance(module, ME.MinkowskiLinear):
+            out.append((module.linear, "weight"))
+    return out
+
+
 class AccuracyMeter:
     """torchmetrics `Accuracy(num_classes, top_k)` as the reference uses it (classification_training.py:12-18,59-60,
     67-68): accumulates #correct / #seen over `update(logits, labels)` calls, `compute()` returns the fraction."""
@@ -537,6 +558,8 @@ class Run:
                                "acc": [*(accs * 100).cpu().tolist(), float(macc)]}, f)
         else:
             out.update({"val/acc1": self.acc1_meter.compute(), "val/acc5": self.acc5_meter.compute()})
+        for k, v in count_parameters(self.model).items():          # segmentation_training.py:204-206
+            out[f"val/{k}_params"] = v
         self.log(out)
         return out
 
@@ -594,8 +617,8 @@ def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] =
     """`python eval.py --ginc ... --load_path <ckpt>` (co3d_3d/eval.py:21-103) for one GPU: build `get_model()` in eval
     mode, load `checkpoint["state_dict"]` (Lightning layout), run one validation pass and write `<save_path>/<tag>.json`
     (a list with one result dict, the shape `Trainer.validate` returns).  An existing json is kept unless `replace`
-    (eval.py:42-45).  Checkpoints of pruned networks (`*_mask` / `*_orig` entries, eval.py:51-58) belong to the
-    weight-sparse inference path, which is not built: they raise."""
+    (eval.py:42-45).  Checkpoints of pruned networks (`*_mask` / `*_orig` entries) load through identity pruning and
+    are made permanent, as eval.py:51-74 does."""
     save_path = save_path if save_path is not None else os.path.dirname(load_path)
     if save_path and not os.path.exists(save_path):
         os.makedirs(save_path, exist_ok=True)
@@ -607,9 +630,20 @@ def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] =
         model = get_model().to(device)
     model.eval()
     ckpt = torch.load(load_path, map_location="cpu", weights_only=False)
-    if any("_mask" in k for k in ckpt["state_dict"]):
-        raise NotImplementedError("checkpoint of a pruned network: the weight-sparse inference path is not built")
+    pruned = any("_mask" in k for k in ckpt["state_dict"])
+    if pruned:
+        # eval.py:51-58: identity pruning creates the `*_orig` / `*_mask` entries the checkpoint holds ...
+        import torch.nn.utils.prune as torch_prune
+        to_prune = get_parameters_to_prune(model)
+        for module, name in to_prune:
+            torch_prune.identity(module, name)
     load_lightning_state_dict(model, ckpt["state_dict"])
+    n_params = count_parameters(model)
+    if pruned:
+        # ... and eval.py:71-74 makes the masks permanent.  (The reference then switches its convolutions to sparse
+        # weight layouts, eval.py:76-79; here the dense tensor-core kernels run on the zero-filled kernels: same result.)
+        for module, name in to_prune:
+            torch_prune.remove(module, name)
     if ignore_label is None:
         ignore_label = _bound(f"{_bound('get_dataset.dataset_name', 'train')}.ignore_label",
                               _bound("train.ignore_label", -100))
@@ -618,6 +652,7 @@ def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] =
               make_input=make_input, fused_head=fused_head, evaluate_only=True)
     run.global_step = int(ckpt.get("global_step", 0))
     results = run.validate(val_batches() if callable(val_batches) else val_batches)
+    results["val/total_params"], results["val/pruned_params"] = n_params["total"], n_params["pruned"]
     results = {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in results.items()}
     with open(json_path, "w") as f:
         f.write(json.dumps([results], indent=4))

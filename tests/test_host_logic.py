@@ -353,3 +353,58 @@ def test_surface_inventory_of_survey_8b(monkeypatch):
     w = torch.empty(27, 6, 8)
     MEpkg.utils.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
     assert abs(float(w.std()) - (2.0 / (27 * 8)) ** 0.5) < 0.02
+
+
+def test_torch_prune_on_minkowski_convolution(monkeypatch):
+    """The reference prunes `MinkowskiConvolution.kernel` with torch.nn.utils.prune (utils/prune.py:26-76): the
+    re-parametrised module (`kernel_orig` + `kernel_mask`) still runs, equals the convolution with the masked kernel,
+    trains only the kept weights, and `count_parameters` reports the removed ones."""
+    import torch.nn.utils.prune as torch_prune
+    host_harness.install(monkeypatch, "fp32")
+    coords, feats = synth.random_cloud(8, 700, extent=6, n_batch=2, channels=8)
+    x = _field(coords, feats).sparse()
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(ME.MinkowskiConvolution(8, 16, kernel_size=3, dimension=3), ME.MinkowskiBatchNorm(16),
+                              ME.MinkowskiReLU(), ME.MinkowskiConvolution(16, 4, kernel_size=1, bias=True, dimension=3))
+    dense = net[0].kernel.detach().clone()
+    torch_prune.l1_unstructured(net[0], "kernel", amount=0.5)
+    assert {"kernel_orig"} <= {n for n, _ in net[0].named_parameters()} and "kernel_mask" in dict(net[0].named_buffers())
+    out = net(x)
+    ref_conv = ME.MinkowskiConvolution(8, 16, kernel_size=3, dimension=3)
+    with torch.no_grad():
+        ref_conv.kernel.copy_(dense * net[0].kernel_mask)
+    assert torch.allclose(net[0](x).F, ref_conv(x).F, atol=1e-6)
+    out.F.sum().backward()
+    g = net[0].kernel_orig.grad
+    assert g is not None and float(g[net[0].kernel_mask == 0].abs().max()) == 0.0 and float(g.abs().max()) > 0
+    counts = training.count_parameters(net)
+    assert counts["pruned"] == float((net[0].kernel_mask == 0).sum()) == 27 * 8 * 16 // 2
+    assert counts["total"] == float(sum(p.numel() for p in net.parameters()))
+
+
+def test_evaluate_pruned_checkpoint(monkeypatch, tmp_path):
+    """eval.py:47-74: a Lightning checkpoint of a network pruned with torch.nn.utils.prune (`kernel_orig` /
+    `kernel_mask` entries) evaluates in a fresh model to the pruned network's own numbers."""
+    import torch.nn.utils.prune as torch_prune
+    host_harness.install(monkeypatch, "fp32")
+    ginlite.clear_config()
+    try:
+        ginlite.parse_config("get_model.name = 'Res16UNet14A'\nget_model.in_channel = 27\nget_model.out_channel = 20\n"
+                             "train.ignore_label = -255")
+        torch.manual_seed(3)
+        net = models.Res16UNet14A(27, 20)
+        to_prune = training.get_parameters_to_prune(net)
+        assert len(to_prune) > 20 and all(name == "kernel" for _, name in to_prune)
+        torch_prune.global_unstructured(to_prune, pruning_method=torch_prune.L1Unstructured, amount=0.4)
+        sd = training.lightning_state_dict(net)
+        assert any(k.endswith("kernel_mask") for k in sd) and any(k.endswith("kernel_orig") for k in sd)
+        torch.save({"state_dict": sd, "global_step": 7}, tmp_path / "pruned.ckpt")
+        c, f, y = synth.room_batch(4, 1, 400, ignore_label=-255)
+        val = [{"coordinates": torch.from_numpy(c), "features": torch.from_numpy(f), "labels": torch.from_numpy(y)}]
+        res = training.evaluate(str(tmp_path / "pruned.ckpt"), val, model=models.Res16UNet14A(27, 20), tag="p")
+        want = training.Run(net, training.TrainConfig(max_steps=0, ignore_label=-255), evaluate_only=True).validate(val)
+        assert abs(res["val/mIoU"] - want["val/mIoU"]) < 1e-3 and abs(res["val/loss"] - want["val/loss"]) < 1e-4
+        total = sum(p.numel() for _, p in net.named_parameters())
+        assert res["val/total_params"] == float(total) and abs(res["val/pruned_params"] / sum(m.kernel_mask.numel() for m, _ in to_prune) - 0.4) < 1e-3
+    finally:
+        ginlite.clear_config()

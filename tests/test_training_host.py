@@ -531,11 +531,6 @@ def test_evaluate_from_lightning_checkpoint(tmp_path, monkeypatch):
                              make_input=lambda b: b["features"]) is None                       # kept
     assert training.evaluate(str(tmp_path / "last.ckpt"), val, model=TinyNet(), tag="t1", replace=True,
                              make_input=lambda b: b["features"]) is not None
-    ckpt = torch.load(tmp_path / "last.ckpt", weights_only=False)
-    ckpt["state_dict"]["model.conv.weight_mask"] = torch.ones(1)
-    torch.save(ckpt, tmp_path / "pruned.ckpt")
-    with pytest.raises(NotImplementedError, match="pruned"):
-        training.evaluate(str(tmp_path / "pruned.ckpt"), val, model=TinyNet(), tag="t2", make_input=lambda b: b["features"])
 
 
 def test_exception_safe_run_survives_failing_batches(monkeypatch):
