@@ -214,3 +214,17 @@ def test_reference_model_zoo_constructs_and_executes(monkeypatch):
         a, b = m(x), m(f)
         assert isinstance(a, ME.SparseTensor) and isinstance(b, ME.TensorField) and torch.isfinite(a.F).all()
         assert a.coordinate_map_key == x.coordinate_map_key
+
+
+def test_reference_prune_utils_agree_with_ours():
+    """utils/prune.py imported unchanged: its `get_parameters_to_prune` / `count_parameters` / `count_flops` on a model
+    built on the surface give what `training.get_parameters_to_prune` / `count_parameters` give."""
+    import torch.nn.utils.prune as torch_prune
+    from nerf_downstream_b200 import models, training
+    pr = ref_harness.load("co3d_3d.src.utils.prune")
+    net = models.MinkowskiFCNN(3, 10, embedding_channel=32, channels=(4, 8, 8, 8, 16))
+    theirs, ours = pr.get_parameters_to_prune(net), training.get_parameters_to_prune(net)
+    assert [(id(m), n) for m, n in theirs] == [(id(m), n) for m, n in ours] and len(ours) > 8
+    torch_prune.global_unstructured(ours, pruning_method=torch_prune.L1Unstructured, amount=0.3)
+    assert pr.count_parameters(net) == training.count_parameters(net)
+    assert pr.count_parameters(net)["pruned"] > 0 and pr.count_flops(net) == 0
