@@ -228,3 +228,30 @@ def test_reference_prune_utils_agree_with_ours():
     torch_prune.global_unstructured(ours, pruning_method=torch_prune.L1Unstructured, amount=0.3)
     assert pr.count_parameters(net) == training.count_parameters(net)
     assert pr.count_parameters(net)["pruned"] > 0 and pr.count_flops(net) == 0
+
+
+def test_reference_own_test_cases_run_on_the_surface(monkeypatch):
+    """The only test cases the reference holds for this path: `ResUNetTestCase` (res16unet.py:798-810 —
+    construct `Res16UNet`, run `EncodedRes16UNet` on 1000 random points with ~100 batch indices) and
+    `PositionalEncodingTestCase` (encoding.py:212-218), run UNCHANGED through `unittest` on the surface.  The first
+    two pass; the third dies inside the reference's own constructor call (`MinkowskiPositionalEncoding(3, 6, 0.01)`
+    subscripts a float) before it reaches the engine — with MinkowskiEngine installed it fails identically."""
+    import unittest
+    from tests import host_harness
+    host_harness.install(monkeypatch, "fp32")
+    un = ref_harness.load("co3d_3d.src.models.mink.res16unet")
+    enc = ref_harness.load("co3d_3d.src.models.mink.modules.encoding")
+    torch.manual_seed(0)
+    result = unittest.TestResult()
+    unittest.defaultTestLoader.loadTestsFromTestCase(un.ResUNetTestCase).run(result)
+    assert result.testsRun == 2 and not result.errors and not result.failures, result.errors + result.failures
+    result = unittest.TestResult()
+    unittest.defaultTestLoader.loadTestsFromTestCase(enc.PositionalEncodingTestCase).run(result)
+    assert result.testsRun == 1 and len(result.errors) == 1
+    assert "TypeError: 'float' object is not subscriptable" in result.errors[0][1] and "encoding.py" in result.errors[0][1]
+    # the module itself works on the surface when constructed the way the models construct it
+    import MinkowskiEngine as ME
+    pe = enc.MinkowskiPositionalEncoding(3, 6, include_original_channel_range=(0, 3))
+    x = ME.SparseTensor(coordinates=torch.IntTensor([[0, 0, 0, 0], [0, 0, 0, 1]]), features=torch.rand(2, 3))
+    out = pe(x)
+    assert out.F.shape == (2, pe.out_channels) and out.coordinate_map_key == x.coordinate_map_key
