@@ -30,36 +30,43 @@ class GinError(ValueError):
 
 
 # ---- parsing -----------------------------------------------------------------------------------------------
+def _scan(text: str):
+    """Yield (index, char, inside_string) with backslash escapes inside string literals honoured."""
+    quote, escaped = None, False
+    for i, ch in enumerate(text):
+        if quote:
+            yield i, ch, True
+            if escaped:
+                escaped = False
+            elif ch == "\\":
+                escaped = True
+            elif ch == quote:
+                quote = None
+        else:
+            if ch in "'\"":
+                quote = ch
+                yield i, ch, True
+            else:
+                yield i, ch, False
+
+
 def _strip_comment(line: str) -> str:
     """Remove a trailing `# ...` that is not inside a string literal."""
-    quote = None
-    for i, ch in enumerate(line):
-        if quote:
-            if ch == "\\":
-                continue
-            if ch == quote:
-                quote = None
-        elif ch in "'\"":
-            quote = ch
-        elif ch == "#":
+    for i, ch, in_string in _scan(line):
+        if ch == "#" and not in_string:
             return line[:i]
     return line
 
 
 def _depth(text: str) -> int:
     """Bracket nesting depth at the end of `text`, ignoring brackets inside strings."""
-    depth, quote, prev = 0, None, ""
-    for ch in text:
-        if quote:
-            if ch == quote and prev != "\\":
-                quote = None
-        elif ch in "'\"":
-            quote = ch
-        elif ch in "([{":
-            depth += 1
-        elif ch in ")]}":
-            depth -= 1
-        prev = ch
+    depth = 0
+    for _, ch, in_string in _scan(text):
+        if not in_string:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
     return depth
 
 
