@@ -396,11 +396,13 @@ ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ ta
        i += (long long)gridDim.x * blockDim.x) {
     const long long y = target[i];
     float* g = graw + i * C;
-    if (y == ignore_index) {
+    if (y == ignore_index || y < 0 || y >= C) {
+      // ignored rows and rows with an out-of-range label (flagged: the host raises) contribute no gradient;
+      // graw comes from an uninitialised allocation, so the row must be written either way
+      if (y != ignore_index) *bad_target = 1;
       for (int c = 0; c < C; ++c) g[c] = 0.f;
       continue;
     }
-    if (y < 0 || y >= C) { *bad_target = 1; continue; }
     float v[CMAX];
     float mx = -INFINITY;
 #pragma unroll

@@ -121,6 +121,12 @@ def ptr(t):
         raise RuntimeError("sparseconv_b200 kernels need CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("sparseconv_b200 kernels need contiguous tensors")
+    if t.device.index != torch._C._cuda_getDevice():
+        # launches go to the CURRENT device's current stream: a tensor on another device would be read through a
+        # foreign pointer (illegal address, or an unordered peer access)
+        raise RuntimeError(f"tensor lives on cuda:{t.device.index} but the current device is "
+                           f"cuda:{torch._C._cuda_getDevice()}: call torch.cuda.set_device() for the device "
+                           "the model and batch live on (one process per GPU)")
     return t.data_ptr()
 
 

@@ -971,7 +971,7 @@ class CrossEntropyFn(torch.autograd.Function):
         if e0 is not None:
             _profiler.end("cross_entropy", e0, 0, (8.0 * C + 8.0) * n, f"C{C} N{n}")
         ctx.save_for_backward(graw, stats)
-        ctx.bad = bad
+        _note_bad_flag(bad)
         return (stats[0] / stats[1]).to(torch.float32)
 
     @staticmethod
@@ -1022,7 +1022,7 @@ class SegHeadFn(torch.autograd.Function):
         if e0 is not None:
             _profiler.end("seg_head", e0, 0, 8.0 * C * n + 12.0 * n, f"C{C} N{n}")
         ctx.save_for_backward(graw, stats)
-        ctx.bad = bad
+        _note_bad_flag(bad)
         return (stats[0] / stats[1]).to(torch.float32)
 
     @staticmethod
@@ -1037,10 +1037,38 @@ class SegHeadFn(torch.autograd.Function):
         return dlogits, None, None, None, None, None
 
 
+# `bad_target` flags of the recent loss kernels (device int32 each).  The kernels zero the gradient of a row whose
+# label is outside [0, C) and not ignore_index and raise the flag; reading it needs a host sync, so the training loop
+# checks on log steps / at validation end (`raise_on_bad_targets`), where it synchronises anyway.
+_bad_flags: list = []
+
+
+def _note_bad_flag(flag: torch.Tensor) -> None:
+    _bad_flags.append(flag)
+    if len(_bad_flags) > 4096:  # nobody is checking: keep the newest
+        del _bad_flags[:2048]
+
+
+def raise_on_bad_targets() -> None:
+    """Raise if any loss kernel since the last check saw a label outside [0, C) other than ignore_index (what
+    F.cross_entropy asserts on).  One host synchronisation."""
+    if not _bad_flags:
+        return
+    flags, _bad_flags[:] = list(_bad_flags), []
+    worst = int(torch.stack([f.view(-1)[0] for f in flags]).max().item())
+    if worst:
+        raise RuntimeError("cross-entropy target outside [0, C) that is not ignore_index"
+                           + (" (or an inverse-map entry outside the voxel rows)" if worst == 2 else ""))
+
+
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100,
                   weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.cross_entropy(logits, target, weight=..., ignore_index=...) (mean reduction) on the fused kernels.  Targets
-    outside [0, C) that are not ignore_index set the kernel's `bad_target` flag (no host sync here)."""
+    outside [0, C) that are not ignore_index contribute nothing and set the kernel's `bad_target` flag
+    (`raise_on_bad_targets`; no host sync here).  More than 64 classes: torch's kernel (the fused ones keep a row in
+    registers)."""
+    if logits.shape[1] > 64:
+        return torch.nn.functional.cross_entropy(logits, target, weight=weight, ignore_index=ignore_index)
     if weight is None:
         return CrossEntropyFn.apply(logits, target, ignore_index)
     return SegHeadFn.apply(logits, None, target, ignore_index, weight, None)

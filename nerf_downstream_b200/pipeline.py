@@ -206,7 +206,11 @@ class IoUMeter:
     def all_reduce(self, group=None) -> None:
         """Sum the counts over the ranks of a data-parallel job (`dist_reduce_fx="sum"`, metrics.py:17-28)."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and self.counts is not None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if self.counts is None:
+                # a rank with an empty validation shard (or whose every batch failed) must still enter the collective
+                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+                self.counts = torch.zeros((3, self.num_classes), dtype=torch.int64, device=dev)
             dist.all_reduce(self.counts, op=dist.ReduceOp.SUM, group=group)
 
     def compute(self):

@@ -83,7 +83,21 @@ class DataParallelTrainer:
         self._buckets = []      # (start, end) element ranges in arena order
         self._bucket_of = {}
         self._pending = []
+        self._launched: List[int] = []      # bucket ids in the order their all-reduce was launched this step
+        self._last_order: List[int] = []    # ... of the last complete step
+        # exposed communication: device time between the end of backward and the last bucket's completion
+        # (CUDA events on the compute stream), filled when `time_exposed` is set (scripts/bench_resnet14.py)
+        self.time_exposed = False
+        self.exposed_ms: List[float] = []
+        self._exposed_events = []
         if self.world > 1:
+            # replicas must START equal: DistributedDataParallel (what the reference gets from Lightning's
+            # DDPPlugin, train.py:184) broadcasts rank 0's parameters and buffers at construction
+            dist.broadcast(self.arena.data, src=dist.get_global_rank(process_group, 0) if process_group else 0,
+                           group=process_group)
+            for buf in model.buffers():
+                dist.broadcast(buf.data, src=dist.get_global_rank(process_group, 0) if process_group else 0,
+                               group=process_group)
             self._make_buckets(int(bucket_mb * 1024 * 1024 / 4))
             for i, p in enumerate(self.arena.order):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
@@ -111,6 +125,7 @@ class DataParallelTrainer:
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 s, e, _ = self._buckets[b]
+                self._launched.append(b)
                 self._handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
         return hook
@@ -121,15 +136,25 @@ class DataParallelTrainer:
         if self.world > 1:
             self._pending = [n for (_, _, n) in self._buckets]
             self._handles = []
+            self._launched = []
         loss.backward()
         if self.world > 1:
             for b, left in enumerate(self._pending):  # parameters that received no gradient this step
                 if left > 0:
                     s, e, _ = self._buckets[b]
+                    self._launched.append(b)
                     self._handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM,
                                                          group=self.group, async_op=True))
-            for h in self._handles:
-                h.wait()
+            if self.time_exposed and self.arena.data.is_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for h in self._handles:
+                    h.wait()
+                e1.record()
+                self._exposed_events.append((e0, e1))
+            else:
+                for h in self._handles:
+                    h.wait()
         if self.torch_optimizer is None:
             ops.sgd_step(self.arena.data, self.arena.grad, self.momentum_buf, self.lr, self.momentum,
                          self.weight_decay, 1.0 / self.world, self.steps == 0)
@@ -138,6 +163,47 @@ class DataParallelTrainer:
                 self.arena.grad.mul_(1.0 / self.world)
             self.torch_optimizer.step()
         self.steps += 1
+        if self.world > 1:
+            self._last_order = list(self._launched)
+
+    def abort_step(self):
+        """A step failed on THIS rank (exception-safe training, segmentation_training.py:276-283): drop its
+        gradients.  At world > 1 the other ranks still all-reduce every bucket, so this rank waits for the buckets it
+        has already launched and contributes zeros for the rest — in the launch order of the last complete step, which
+        is the order the peers use — instead of leaving them blocked in `h.wait()`; the zeroed gradients then take part
+        in the peers' averaged update of this step (this rank applies the same update, replicas stay equal)."""
+        if self.world > 1:
+            for h in self._handles:
+                h.wait()
+            launched = set(self._launched)
+            self.arena.grad.zero_()
+            rest = [b for b in (self._last_order or range(len(self._buckets))) if b not in launched]
+            rest += [b for b in range(len(self._buckets)) if b not in launched and b not in rest]
+            hs = []
+            for b in rest:
+                s, e, _ = self._buckets[b]
+                hs.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for h in hs:
+                h.wait()
+            self._handles, self._launched = [], []
+            # the peers step with (their gradients + our zeros) / world: apply the identical update here
+            if self.torch_optimizer is None:
+                ops.sgd_step(self.arena.data, self.arena.grad, self.momentum_buf, self.lr, self.momentum,
+                             self.weight_decay, 1.0 / self.world, self.steps == 0)
+            else:
+                self.arena.grad.mul_(1.0 / self.world)
+                self.torch_optimizer.step()
+            self.steps += 1
+        self.arena.zero_grad()
+
+    def exposed_allreduce_ms(self) -> List[float]:
+        """Per-step device time the compute stream spent waiting for gradient all-reduces after backward had
+        finished (what the overlap did NOT hide).  Synchronises."""
+        if self._exposed_events:
+            torch.cuda.synchronize()
+            self.exposed_ms += [a.elapsed_time(b) for a, b in self._exposed_events]
+            self._exposed_events = []
+        return self.exposed_ms
 
     def set_lr(self, lr: float):
         self.lr = lr

@@ -441,15 +441,25 @@ class Run:
         except RuntimeError as e:               # segmentation_training.py:276-283
             self.fail_count += 1
             print(f"Failed with {e}. Failure rate: {float(self.fail_count) / (self.global_step + 1)}")
-            self.trainer.arena.zero_grad()
+            self.trainer.abort_step()           # zero gradients; at world > 1 keep the collectives matched
             self.global_step += 1               # "regardless of the failure status, update" the scheduler
             self._apply_schedule()
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
             return None
 
+    def _to_device(self, batch):
+        """Lightning moves every tensor of the collated batch to the module's device before training_step /
+        validation_step; `collate_mink` (data/utils.py:25-50) returns host tensors."""
+        dev = next(self.model.parameters()).device
+        if dev.type != "cuda":
+            return batch
+        return {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) and v.device != dev else v)
+                for k, v in batch.items()}
+
     def _training_step(self, batch) -> torch.Tensor:
         self.model.train()
+        batch = self._to_device(batch)
         labels = batch["labels"].long()
         step_counts = None
         if self.fused_head:
@@ -476,6 +486,8 @@ class Run:
             loss_float = loss.detach().cpu().item()
             if not np.isfinite(loss_float):
                 raise ValueError(f"Invalid loss: {loss_float}")
+            from . import ops as _ops
+            _ops.raise_on_bad_targets()         # a label outside [0, C) that is not ignore_index (F.cross_entropy asserts)
             out = {"train/loss": loss_float, "train/lr": self.trainer.lr, "global_step": step}
             if self.segmentation:
                 metrics = metrics_from_counts(step_counts) if step_counts is not None else \
@@ -514,6 +526,7 @@ class Run:
         return self._validation_epoch_end(losses, oas)
 
     def _validate_batch(self, batch, losses, oas) -> None:
+        batch = self._to_device(batch)
         labels = batch["labels"].long()
         if self.fused_head:
             from . import pipeline
@@ -538,6 +551,8 @@ class Run:
             self.acc5_meter(logits, labels)
 
     def _validation_epoch_end(self, losses, oas) -> Dict[str, float]:
+        from . import ops as _ops
+        _ops.raise_on_bad_targets()
         assert len(losses) > 0
         out = {"val/loss": float(np.mean(losses)), "global_step": self.global_step}
         # epoch metrics are sums over ALL ranks' validation shards (torchmetrics dist_reduce_fx="sum", metrics.py:17-28)
@@ -597,12 +612,20 @@ class Run:
         return last_val
 
 
+def _select_device(device) -> None:
+    """The library launches on the CURRENT device's current stream (one process per GPU): make `device` current."""
+    d = torch.device(device)
+    if d.type == "cuda" and torch.cuda.is_available():
+        torch.cuda.set_device(d.index if d.index is not None else torch.cuda.current_device())
+
+
 def train(config_files: Sequence[str], bindings: Sequence[str], train_batches, val_batches=None, model=None,
           save_path: Optional[str] = None, device="cuda", log=None, fused_head: bool = False, **overrides) -> Run:
     """`python -m co3d_3d.train --ginc ... --ginb ...` for one rank (train.py:199-263): parse the gin files and
     bindings, build `get_model()` unless a model is passed, run `fit`."""
     ginlite.parse_config_files_and_bindings(config_files, bindings)
     cfg = TrainConfig(**overrides)
+    _select_device(device)
     if model is None:
         model = get_model().to(device)
     run = Run(model, cfg, save_path=save_path, void_label=_bound("PlenoxelScannetDataset.void_label", None), log=log,
@@ -626,6 +649,7 @@ def evaluate(load_path: str, val_batches, model=None, save_path: Optional[str] =
     if not replace and os.path.isfile(json_path):
         print("====== skip existing experiment =====")
         return None
+    _select_device(device)
     if model is None:
         model = get_model().to(device)
     model.eval()

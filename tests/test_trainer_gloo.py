@@ -247,3 +247,69 @@ def test_sync_batchnorm_world2_equals_batchnorm_on_all_rows():
         assert tracked == 1
         for k, v in errs.items():
             assert v < 2e-5, (rank, k, v)
+
+
+def _worker_divergent_seeds(rank, world, port, q):
+    """Ranks build their replicas from DIFFERENT seeds (per-rank seeding before model construction is common for
+    augmentation): the trainer must broadcast rank 0's parameters and buffers like DistributedDataParallel, and a
+    step that fails on ONE rank (exception-safe training) must not leave the others blocked in their all-reduces."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nerf_downstream_b200 import ops, trainer
+
+    def sgd_cpu(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):
+        d = grad * grad_scale + weight_decay * param
+        buf.copy_(d if first_step else momentum * buf + d)
+        param.sub_(lr * buf)
+
+    ops.sgd_step = sgd_cpu
+    torch.manual_seed(1234 + rank)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    with torch.no_grad():
+        model[1].running_mean.add_(float(rank + 1))
+    tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4, bucket_mb=1e-5)
+
+    def flat():
+        return torch.cat([p.detach().flatten() for p in model.parameters()] + [b.detach().flatten().float() for b in model.buffers()])
+
+    gathered = [torch.zeros_like(flat()) for _ in range(world)]
+    dist.all_gather(gathered, flat())
+    equal_at_start = all(torch.equal(gathered[0], g) for g in gathered)
+    rm_is_rank0 = bool((model[1].running_mean - 1.0).abs().max() < 1e-6)
+    g = torch.Generator().manual_seed(100)
+    xs = [torch.randn(6, 7, generator=g) for _ in range(world)]
+    tr.backward_and_step(model(xs[rank]).pow(2).mean())              # a complete step records the bucket order
+    # step 2: rank 1 "fails" after part of its backward ran; rank 0 completes normally
+    if rank == 1:
+        tr.arena.zero_grad()
+        tr._pending = [n for (_, _, n) in tr._buckets]
+        tr._handles, tr._launched = [], []
+        tr.abort_step()
+    else:
+        tr.backward_and_step(model(xs[rank]).pow(2).mean())
+    gathered = [torch.zeros_like(flat()) for _ in range(world)]
+    params = torch.cat([p.detach().flatten() for p in model.parameters()])
+    gathered = [torch.zeros_like(params) for _ in range(world)]
+    dist.all_gather(gathered, params)
+    equal_after_abort = all(torch.allclose(gathered[0], g, atol=1e-7) for g in gathered)
+    q.put((rank, equal_at_start, rm_is_rank0, equal_after_abort, tr.steps))
+    dist.destroy_process_group()
+
+
+def test_replicas_start_equal_and_abort_keeps_collectives_matched():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_divergent_seeds, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, equal_at_start, rm_is_rank0, equal_after_abort, steps in res:
+        assert equal_at_start, rank
+        assert rm_is_rank0, rank
+        assert equal_after_abort, rank
+        assert steps == 2
