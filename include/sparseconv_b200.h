@@ -146,10 +146,14 @@ int spc_scatter_add_rows(const float* src, const int32_t* index, int64_t n, int6
  *   workspace: spc_conv_workspace(...) bytes (packed weights for the TF32 path).
  */
 void spc_debug_force_mt(int mt);
-void spc_debug_set(int idx, int val); /* test / measurement hook, every knob 0 = default: 1 wgrad dout by LDGSTS instead of
-                                        * TMA, 2 no TMA-store epilogue, 3 epilogue writes nothing (timing only, wrong results),
-                                        * 4-6 wgrad skip-MMA / skip-gather / skip-parts (timing only, wrong results) */
-int spc_debug_read(long long* host, int n); /* test hook: wgrad role cycle counters -> host buffer */
+void spc_debug_set(int idx, int val); /* test / measurement hook, every knob 0 = default: 0 forward: number of producer
+                                        * groups (1, 2, 4, 8); 2 forward: 1 = st.global epilogue instead of TMA stores;
+                                        * 3 forward: epilogue writes nothing (timing only, wrong results); 4 forward: 1 =
+                                        * one 32-channel chunk per stage; 5 wgrad: 1 = one row visit per chunk */
+/* launches per convolution route since the last reset: out3[0] tcgen05 bf16, [1] tcgen05 tf32, [2] CUDA-core fp32
+ * (out3 may be NULL); 1 if spc_conv_fwd (what = 0) / dgrad (1) / wgrad (2) runs the shape on the tensor cores */
+void spc_conv_path_counts(long long* out3, int reset);
+int spc_conv_tensor_core(int what, int K, int c_in, int c_out, int precision);
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision);
 /* fp32 rows -> dense bf16 rows (round to nearest even) for the SPC_PREC_BF16 convolutions: src has `rows` rows of
  * c_src valid columns at a pitch of src_pitch elements (a column slice of a wider tensor is read in place); dst
@@ -173,6 +177,24 @@ int spc_conv_dgrad(const void* dout, const float* w, const int32_t* nbr_t,
 int spc_conv_wgrad(const void* in, const void* dout, const int32_t* nbr,
                    const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision,
                    float* dw, void* workspace, int64_t workspace_bytes, void* stream);
+/* spc_conv_wgrad with `accumulate` != 0: dw is not cleared, the gradient is ADDED to what it holds (a slice of
+ * the trainer's gradient arena, zeroed once per step) — tensor-core shapes only (spc_conv_tensor_core(2, ...)). */
+int spc_conv_wgrad_acc(const void* in, const void* dout, const int32_t* nbr, const uint32_t* tile_mask, int64_t m_in,
+                       int64_t m_out, int c_in, int c_out, int K, int precision, float* dw, int accumulate,
+                       void* stream);
+/* Weights in the tensor-core kernels' shared-memory image ([K][C/32][C'][32] swizzled rows, independent of the
+ * tile shape), so that a layer packs ONCE per optimiser step instead of once per launch: `dgrad` = 0 packs W for
+ * spc_conv_fwd_packed, 1 packs W^T for spc_conv_dgrad_packed.  `packed`: spc_conv_packed_bytes() bytes,
+ * 1024-byte aligned.  precision: SPC_PREC_TF32 or SPC_PREC_BF16; shapes: spc_conv_tensor_core(0 / 1, ...). */
+int64_t spc_conv_packed_bytes(int K, int c_in, int c_out);
+int spc_conv_pack_weights(const float* w, int K, int c_in, int c_out, int dgrad, int precision, void* packed,
+                          void* stream);
+int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
+                        const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                        int precision, float* out, void* stream);
+int spc_conv_dgrad_packed(const void* dout, const void* w_packed_t, const int32_t* nbr_t, const uint32_t* tile_mask_t,
+                          int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision, float* din,
+                          void* stream);
 
 /*
  * BatchNorm over voxel rows (MinkowskiBatchNorm == nn.BatchNorm1d on .F,
@@ -186,6 +208,11 @@ int64_t spc_bn_workspace(int64_t m, int C);
 int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var,
                  float* running_mean, float* running_var, float momentum, /* nullable */
                  void* workspace, int64_t workspace_bytes, void* stream);
+/* spc_bn_stats that also increments nn.BatchNorm1d's num_batches_tracked (device int64, nullable) in the
+ * reduction's last block — no separate one-element launch per BatchNorm layer and step. */
+int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* var, float* running_mean,
+                         float* running_var, float momentum, int64_t* num_batches_tracked, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 /* mean / biased variance (+ running statistics) from the sums written by spc_conv_fwd_stats. */
 int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
                     float* running_var, float momentum, void* stream);
@@ -198,6 +225,13 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16 /* ReLU mask f
                int training, float* dx, void* dx_bf16 /* optional bf16 copy of dx, or NULL */,
                float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* spc_bn_bwd whose dgamma / dbeta (either may be NULL) are ADDED to what the buffers hold when
+ * accumulate_param_grads != 0 (slices of a gradient arena that is zeroed once per step). */
+int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const float* dy, int64_t dy_pitch,
+                   const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+                   int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
+                   int accumulate_param_grads, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* y = relu(x) ; dx = dy * (y > 0) ; y = a + b  (MinkowskiReLU, SparseTensor +=). */
 int spc_relu_fwd(const float* x, int64_t n, float* y, void* stream);

@@ -103,6 +103,8 @@ struct ColFinal {
   float* run_var;
   const float* var;      // MODE 1
   float momentum, eps;
+  int accumulate;        // MODE 1: out0 / out1 += (slices of a gradient arena zeroed once per step) instead of =
+  long long* tracked;    // MODE 0, optional: nn.BatchNorm1d.num_batches_tracked, incremented by the last block
 };
 
 template <int VEC, int MODE>
@@ -118,21 +120,40 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
   // MODE 0 accumulates around a pivot (row 0) so that E[x^2] - E[x]^2 does not cancel
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s0[j] = 0.f; s1[j] = 0.f; mu[j] = MODE == 1 ? mean[c0 + j] : x[c0 + j]; }
-  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
-    const long long off = r * C + c0;
-    Vec<VEC> xv = Vec<VEC>::load(x + off);
-    if (MODE == 0) {
+  // U row groups per iteration: all their loads are issued before the first use, so a thread keeps U (MODE 0) or
+  // up to 3 U (MODE 1) 16-byte loads in flight instead of one per stream (r1: 0.78-0.84 of the HBM peak)
+  constexpr int U = MODE == 0 ? 4 : 2;
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += U * stride) {
+    Vec<VEC> xv[U], g[U], yv[U];
+    bool ok[U];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { float d = xv.v[j] - mu[j]; s0[j] += d; s1[j] += d * d; }
-    } else {
-      Vec<VEC> g = Vec<VEC>::load(dy + r * dy_pitch + c0);
-      if (relu) {
-        Vec<VEC> yv = load_mask_rows<VEC>(y, yb, off);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) if (!(yv.v[j] > 0.f)) g.v[j] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * stride;
+      ok[u] = ru < m;
+      if (ok[u]) {
+        const long long off = ru * C + c0;
+        xv[u] = Vec<VEC>::load(x + off);
+        if (MODE == 1) {
+          g[u] = Vec<VEC>::load(dy + ru * dy_pitch + c0);
+          if (relu) yv[u] = load_mask_rows<VEC>(y, yb, off);
+        }
       }
+    }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s0[j] += g.v[j]; s1[j] += g.v[j] * (xv.v[j] - mu[j]); }
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { float d = xv[u].v[j] - mu[j]; s0[j] += d; s1[j] += d * d; }
+      } else {
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) if (!(yv[u].v[j] > 0.f)) g[u].v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s0[j] += g[u].v[j]; s1[j] += g[u].v[j] * (xv[u].v[j] - mu[j]); }
+      }
     }
   }
 #pragma unroll
@@ -169,10 +190,12 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
     } else {
       fin.raw[c] = (float)a;
       fin.raw[C + c] = (float)b;
-      fin.out0[c] = (float)a;                                                // dbeta
-      fin.out1[c] = (float)(b / sqrt((double)fin.var[c] + (double)fin.eps)); // dgamma
+      const float db = (float)a, dg = (float)(b / sqrt((double)fin.var[c] + (double)fin.eps));
+      if (fin.out0) fin.out0[c] = fin.accumulate ? fin.out0[c] + db : db;    // dbeta
+      if (fin.out1) fin.out1[c] = fin.accumulate ? fin.out1[c] + dg : dg;    // dgamma
     }
   }
+  if (MODE == 0 && fin.tracked && threadIdx.x == 0) *fin.tracked += 1;
 }
 
 template <int VEC>
@@ -191,22 +214,38 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
     sc[j] = g * rsqrtf(var[c0 + j] + eps);
     sh[j] = b - mean[c0 + j] * sc[j];
   }
-  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
-    const long long off = r * C + c0;
-    Vec<VEC> xv = Vec<VEC>::load(x + off), o;
+  constexpr int U = 4;  // row groups per iteration, loads first (see col_reduce_kernel)
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += U * stride) {
+    Vec<VEC> xv[U], rv[U];
+    bool ok[U];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) o.v[j] = fmaf(xv.v[j], sc[j], sh[j]);
-    if (res) {
-      Vec<VEC> rv = Vec<VEC>::load(res + off);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) o.v[j] += rv.v[j];
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * stride;
+      ok[u] = ru < m;
+      if (ok[u]) {
+        xv[u] = Vec<VEC>::load(x + ru * C + c0);
+        if (res) rv[u] = Vec<VEC>::load(res + ru * C + c0);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const long long off = (r + u * stride) * C + c0;
+      Vec<VEC> o;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = fmaf(xv[u].v[j], sc[j], sh[j]);
+      if (res) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o.v[j] += rv[u].v[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
+      }
+      o.store(y + off);
+      if (yb) store_bf16<VEC>(yb + off, o.v);
     }
-    o.store(y + off);
-    if (yb) store_bf16<VEC>(yb + off, o.v);
   }
 }
 
@@ -232,20 +271,37 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
     k0[j] = training ? sums[c0 + j] * inv_m : 0.f;
     k1[j] = training ? sums[C + c0 + j] * inv_m * istd * istd : 0.f;
   }
-  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += (long long)gridDim.x * rows) {
-    const long long off = r * C + c0;
-    Vec<VEC> g = Vec<VEC>::load(dy + r * dy_pitch + c0);
-    if (relu) {
-      Vec<VEC> yv = load_mask_rows<VEC>(y, yb, off);
+  constexpr int U = 2;  // row groups per iteration, loads first (see col_reduce_kernel)
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long r = (long long)blockIdx.x * rows + rl; r < m; r += U * stride) {
+    Vec<VEC> g[U], yv[U], xv[U];
+    bool ok[U];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) if (!(yv.v[j] > 0.f)) g.v[j] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * stride;
+      ok[u] = ru < m;
+      if (ok[u]) {
+        const long long off = ru * C + c0;
+        g[u] = Vec<VEC>::load(dy + ru * dy_pitch + c0);
+        if (relu) yv[u] = load_mask_rows<VEC>(y, yb, off);
+        xv[u] = Vec<VEC>::load(x + off);
+      }
     }
-    if (dres) g.store(dres + off);
-    Vec<VEC> xv = Vec<VEC>::load(x + off), o;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) o.v[j] = sc[j] * (g.v[j] - k0[j] - (xv.v[j] - mu[j]) * k1[j]);
-    o.store(dx + off);
-    if (dxb) store_bf16<VEC>(dxb + off, o.v);
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const long long off = (r + u * stride) * C + c0;
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) if (!(yv[u].v[j] > 0.f)) g[u].v[j] = 0.f;
+      }
+      if (dres) g[u].store(dres + off);
+      Vec<VEC> o;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = sc[j] * (g[u].v[j] - k0[j] - (xv[u].v[j] - mu[j]) * k1[j]);
+      o.store(dx + off);
+      if (dxb) store_bf16<VEC>(dxb + off, o.v);
+    }
   }
 }
 
@@ -531,7 +587,21 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
   ColFinal fin;
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
   fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
-  fin.momentum = momentum; fin.eps = 0.f;
+  fin.momentum = momentum; fin.eps = 0.f; fin.accumulate = 0; fin.tracked = nullptr;
+  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, m, C, 0, fin, stream);
+}
+
+int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* var, float* running_mean,
+                         float* running_var, float momentum, int64_t* num_batches_tracked, void* workspace,
+                         int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
+  SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
+  BnWs w = bn_ws(workspace, C);
+  ColFinal fin;
+  fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
+  fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
+  fin.momentum = momentum; fin.eps = 0.f; fin.accumulate = 0; fin.tracked = (long long*)num_batches_tracked;
   return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, m, C, 0, fin, stream);
 }
 
@@ -565,6 +635,14 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* 
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
                int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream_) {
+  return spc_bn_bwd_acc(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16, dresidual,
+                        dgamma, dbeta, 0, workspace, workspace_bytes, stream_);
+}
+
+int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const float* dy, int64_t dy_pitch,
+                   const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+                   int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
+                   int accumulate_param_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
@@ -575,6 +653,7 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* 
   ColFinal fin;
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = dbeta; fin.out1 = dgamma; fin.raw = sums;
   fin.run_mean = nullptr; fin.run_var = nullptr; fin.var = var; fin.momentum = 0.f; fin.eps = eps;
+  fin.accumulate = accumulate_param_grads; fin.tracked = nullptr;
   int rc = col_reduce_launch(1, x, y, y_bf16, dy, dy_pitch, mean, m, C, relu, fin, stream);
   if (rc) return rc;
   int vec = pick_vec(C, x, y, dy, dx);

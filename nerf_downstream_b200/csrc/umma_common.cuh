@@ -1,0 +1,69 @@
+// umma_common.cuh — pieces shared by the tcgen05 convolution kernels (conv_umma.cu: forward / dgrad,
+// conv_wgrad_umma.cu: wgrad): role layout of the 416-thread CTA, operand-precision traits, tensor-map helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace spc {
+using namespace ptx;
+
+constexpr int kTileM = 128;  // rows per accumulator (UMMA M)
+constexpr int kMaxStages = 8;
+constexpr int kNumProducerWarps = 8;
+constexpr int kNumEpilogueThreads = 128;
+constexpr int kMmaWarp = kNumProducerWarps + 4;
+constexpr int kNumThreads = (kMmaWarp + 1) * 32;  // 8 producer + 4 epilogue + 1 MMA warp
+constexpr int kSmemLimit = 227 * 1024;
+
+template <bool BF16>
+struct Prec {
+  static constexpr int kElt = BF16 ? 2 : 4;             // bytes per element
+  static constexpr int kRowBytes = 32 * kElt;           // one 32-channel chunk of a row
+  static constexpr int kLanesPerRow = kRowBytes / 16;   // 16-byte cp.async pieces per row chunk
+  static constexpr int kMmaPerRow = BF16 ? 2 : 4;       // K = 16 bf16 / 8 tf32 = 32 bytes each
+  // K-major operand (forward): SWIZZLE_64B for 64-byte rows, SWIZZLE_128B for 128-byte rows
+  static constexpr uint32_t kLayoutK = BF16 ? 4u : 2u;
+  static constexpr uint32_t kSboK = 8 * kRowBytes;
+  // MN-major operand (wgrad): 32-bit types must use SWIZZLE_128B_BASE32B, bf16 uses SWIZZLE_64B
+  static constexpr uint32_t kLayoutMN = BF16 ? 4u : 1u;
+  // byte offset of 16-byte piece j of row r inside its row chunk (K-major forward layout)
+  __device__ static __forceinline__ uint32_t swz_k(int j, int r) {
+    return BF16 ? (uint32_t)((j ^ ((r >> 1) & 3)) << 4) : (uint32_t)((j ^ (r & 7)) << 4);
+  }
+  // same for the MN-major wgrad layout (tf32: 32-byte chunks XOR row&3)
+  __device__ static __forceinline__ uint32_t swz_mn(int j, int r) {
+    return BF16 ? (uint32_t)((j ^ ((r >> 1) & 3)) << 4)
+                : (uint32_t)((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4));
+  }
+  __device__ static __forceinline__ uint32_t idesc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return BF16 ? make_idesc_bf16(M, N, a_mn, b_mn) : make_idesc_tf32(M, N, a_mn, b_mn);
+  }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    if (BF16) mma_bf16(d, a, b, id, acc);
+    else mma_tf32(d, a, b, id, acc);
+  }
+};
+
+// test / measurement knobs (spc_debug_set), all 0 = default:
+//   [0] forward: force the number of producer groups (1, 2, 4, 8)      [1] wgrad: dout rows by LDGSTS instead of TMA
+//   [2] forward: 1 = st.global epilogue instead of TMA stores          [3] forward: epilogue writes nothing (timing only)
+//   [4] forward: 1 = one 32-channel chunk per stage (no contiguous multi-chunk row visits)
+//   [5] wgrad: 1 = one row visit per chunk (no grouped visits)
+extern int g_umma_dbg[8];
+extern int g_umma_force_mt;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder();
+// fp32 [rows, C] row-major output, box = 32 columns x 128 rows, SWIZZLE_128B: the forward epilogue's store target
+bool make_out_tile_map(CUtensorMap* map, float* base, int64_t rows, int C);
+// [rows, C] row-major tensor, box = 32 channels x box_rows rows, written in the MN-major UMMA layout of the
+// wgrad operands: bf16 SWIZZLE_64B, fp32 SWIZZLE_128B with 32-byte atoms
+bool make_rows_tile_map(CUtensorMap* map, const void* base, int64_t rows, int C, int box_rows, bool bf16);
+
+}  // namespace spc

@@ -41,7 +41,13 @@ SIGNATURES = {
     "spc_scatter_add_rows": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "spc_debug_force_mt": (None, [c_int]),
     "spc_debug_set": (None, [c_int, c_int]),
-    "spc_debug_read": (c_int, [_P, c_int]),
+    "spc_conv_path_counts": (None, [_P, c_int]),
+    "spc_conv_tensor_core": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "spc_conv_packed_bytes": (c_int64, [c_int, c_int, c_int]),
+    "spc_conv_pack_weights": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "spc_conv_fwd_packed": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "spc_conv_dgrad_packed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "spc_conv_wgrad_acc": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
     "spc_to_bf16": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
@@ -53,6 +59,8 @@ SIGNATURES = {
     "spc_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "spc_bn_apply": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P, _P, _P]),
     "spc_bn_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "spc_bn_bwd_acc": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int64, _P]),
+    "spc_bn_stats_tracked": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, _P, c_int64, _P]),
     "spc_relu_fwd": (c_int, [_P, c_int64, _P, _P]),
     "spc_relu_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "spc_add": (c_int, [_P, _P, c_int64, _P, _P]),

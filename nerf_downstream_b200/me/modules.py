@@ -115,7 +115,7 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
                 out_key = mgr.stride(in_key, kg.kernel_stride)
             km = mgr.get_kernel_map(in_key, out_key, kg, is_transpose=self.is_transpose)
             w = self.kernel
-        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision())
+        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision(), self.kernel)
         return SparseTensor(outfeat, coordinate_map_key=out_key, coordinate_manager=mgr)
 
     def __repr__(self):
@@ -162,12 +162,17 @@ class MinkowskiBatchNorm(nn.Module):
         bn = self.bn
         training = bn.training or not bn.track_running_stats
         momentum = bn.momentum
+        tracked = None
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-            if momentum is None:
+            if momentum is None:     # cumulative moving average: the host needs the count
+                bn.num_batches_tracked.add_(1)
                 momentum = 1.0 / float(bn.num_batches_tracked)
+            elif feats.is_cuda and feats.shape[0] >= 1:
+                tracked = bn.num_batches_tracked   # incremented by the statistics kernel's last block
+            else:
+                bn.num_batches_tracked.add_(1)
         return ops.BatchNormFn.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
-                                     0.0 if momentum is None else momentum, bn.eps, relu, residual)
+                                     0.0 if momentum is None else momentum, bn.eps, relu, residual, tracked)
 
     def forward(self, input):
         if isinstance(input, SparseTensor):

@@ -486,56 +486,120 @@ def to_bf16(x: torch.Tensor, pad_to: int = 0) -> torch.Tensor:
     return out
 
 
-# per-channel (sum, sum of squares) of a convolution output, accumulated by its epilogue for the BatchNorm that
-# follows: data_ptr of the output rows -> (weakref, version, float64 [2 C])
-_stats_side: dict = {}
+# ---------------------------------------------------------------------------------------------------------
+# Packed weights.  The tensor-core kernels read weights as pre-swizzled shared-memory slabs
+# (spc_conv_pack_weights).  The image does not depend on the launch, so a layer packs ONCE per optimiser step per
+# direction (forward: W, dgrad: W^T) instead of once per launch: the cache is keyed on the weight tensor OBJECT (a
+# weak reference: a different tensor that re-uses the address misses), its autograd version counter and
+# `_weights_epoch`, which `sgd_step` bumps because the fused optimiser kernel writes parameters behind autograd's back.
+# ---------------------------------------------------------------------------------------------------------
+_pack_cache: dict = {}
+_weights_epoch = 0
+pack_stats = {"hits": 0, "misses": 0}
 
 
-def _remember_stats(t: torch.Tensor, sums: torch.Tensor) -> None:
-    key = t.data_ptr()
+def invalidate_packed_weights() -> None:
+    """Call after changing parameters through a raw pointer (anything autograd's version counter does not see)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _packed_weights(w3: torch.Tensor, dgrad: bool, precision: int, owner: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`owner`: the long-lived tensor (the layer's Parameter) `w3` is a view of — identity and version are taken
+    from it (a fresh view object per call, or the tensor autograd hands back in backward, would never hit)."""
+    lib = L.load()
+    K, c_in, c_out = w3.shape
+    obj = owner if owner is not None else w3
+    key = (w3.data_ptr(), bool(dgrad), precision, K, c_in, c_out)
+    ver = (obj._version, _weights_epoch)
+    e = _pack_cache.get(key)
+    if e is not None and e[0]() is obj and e[1] == ver:
+        pack_stats["hits"] += 1
+        return e[2]
+    pack_stats["misses"] += 1
+    nbytes = int(lib.spc_conv_packed_bytes(K, c_in, c_out))
+    buf = e[2] if (e is not None and e[2].numel() >= nbytes + 1024) else torch.empty(nbytes + 1024, dtype=torch.uint8,
+                                                                                       device=w3.device)
+    off = (-buf.data_ptr()) % 1024
+    L.check(lib.spc_conv_pack_weights(L.ptr(w3), K, c_in, c_out, int(dgrad), precision, buf.data_ptr() + off,
+                                      L.stream()), "spc_conv_pack_weights")
 
     def _drop(ref, key=key):
-        e = _stats_side.get(key)
+        cur = _pack_cache.get(key)
+        if cur is not None and cur[0] is ref:
+            del _pack_cache[key]
+    _pack_cache[key] = (weakref.ref(obj, _drop), ver, buf)
+    return buf
+
+
+def _packed_ptr(buf: torch.Tensor) -> int:
+    return buf.data_ptr() + ((-buf.data_ptr()) % 1024)
+
+
+_tc_cache: dict = {}
+
+
+def _tensor_core(what: int, K: int, c_in: int, c_out: int, precision: int) -> bool:
+    key = (what, K, c_in, c_out, precision)
+    v = _tc_cache.get(key)
+    if v is None:
+        v = _tc_cache[key] = bool(L.load().spc_conv_tensor_core(what, K, c_in, c_out, precision))
+    return v
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Gradient sinks.  A trainer that keeps every parameter gradient in a flat arena (zeroed once per step) registers its
+# parameters here; the backward kernels then ADD a parameter's gradient straight into its arena slice (wgrad:
+# spc_conv_wgrad_acc; BatchNorm: dgamma / dbeta written by the reduction's last block) and the autograd Function
+# returns None for it, instead of materialising a temporary that autograd adds to `.grad` with one tiny launch per
+# parameter (267 of them per Res16UNet34C step).  `on_ready(param)` is called once the kernel is enqueued — the
+# trainer's bucketed all-reduce hook, which autograd would otherwise fire after its accumulation.
+# ---------------------------------------------------------------------------------------------------------
+_grad_sinks: dict = {}   # id(param) -> (weak reference to the parameter, on_ready); tensors compare elementwise
+
+
+def register_grad_sink(param: torch.Tensor, on_ready) -> None:
+    key = id(param)
+
+    def _drop(ref, key=key):
+        e = _grad_sinks.get(key)
         if e is not None and e[0] is ref:
-            del _stats_side[key]
-    _stats_side[key] = (weakref.ref(t, _drop), t._version, sums)
+            del _grad_sinks[key]
+    _grad_sinks[key] = (weakref.ref(param, _drop), on_ready)
 
 
-def _lookup_stats(t: torch.Tensor):
-    e = _stats_side.get(t.data_ptr())
-    if e is None:
+def clear_grad_sinks() -> None:
+    _grad_sinks.clear()
+
+
+def _sink(param):
+    """(grad tensor to add into, on_ready) if `param` is registered and its .grad is a usable dense fp32 buffer."""
+    if param is None or not _grad_sinks:
         return None
-    ref, version, sums = e
-    o = ref()
-    if o is None or o.shape != t.shape or t._version != version or sums.numel() != 2 * t.shape[1]:
+    e = _grad_sinks.get(id(param))
+    if e is None or e[0]() is not param:
         return None
-    return sums
+    cb = e[1]
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda or not param.requires_grad:
+        return None
+    return g, cb
 
 
-# Convolution epilogues can accumulate the statistics of a following BatchNorm (spc_conv_fwd_stats).  Measured on
-# the 2 x 1 M-voxel UNet step: BatchNorm forward -1.3 ms, convolution forward +1.6 ms — the transposition of the
-# accumulator tile goes through the same LSU / shared-memory pipe that bounds the row gather — so it is OFF by
-# default; `ops.fuse_bn_stats = True` turns it on (tests/test_gpu_parity.py covers it).
-fuse_bn_stats = False
-
-
-def conv_fwd_raw(x, w, bias, km: KernelMap, precision, want_stats: bool = False):
+def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None):
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
-    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
-    ws = _workspace(ws_bytes, x.device)
     mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
-    if want_stats and fuse_bn_stats and precision != L.PREC_FP32 and c_out <= 256 and km.m_out >= 16384:
-        sums = _empty(2 * c_out, torch.float64, x.device)
-        fused = ctypes.c_int32(0)
-        L.check(lib.spc_conv_fwd_stats(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
-                                       c_in, c_out, K, precision, L.ptr(out), L.ptr(sums), ctypes.addressof(fused),
-                                       L.ptr(ws), ws_bytes, L.stream()), "spc_conv_fwd_stats")
-        if fused.value:
-            _remember_stats(out, sums)
+    if _tensor_core(0, K, c_in, c_out, precision):
+        wp = _packed_weights(w, False, precision, w_owner)
+        L.check(lib.spc_conv_fwd_packed(L.ptr(x), _packed_ptr(wp), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in,
+                                        km.m_out, c_in, c_out, K, precision, L.ptr(out), L.stream()),
+                "spc_conv_fwd_packed")
     else:
+        ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
+        ws = _workspace(ws_bytes, x.device)
         L.check(lib.spc_conv_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out,
                                  c_in, c_out, K, precision, L.ptr(out), L.ptr(ws), ws_bytes, L.stream()),
                 "spc_conv_fwd")
@@ -545,33 +609,43 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision, want_stats: bool = False)
     return out
 
 
-def conv_dgrad_raw(g, w, km: KernelMap, precision):
+def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None):
     lib = L.load()
     K, c_in, c_out = w.shape
     din = _empty((km.m_in, c_in), torch.float32, g.device)
-    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
-    ws = _workspace(ws_bytes, g.device)
     mask_t = km.mask_t if precision != L.PREC_FP32 else None
     nbr_t = km.nbr_t
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_conv_dgrad(L.ptr(g), L.ptr(w), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out, c_in,
-                               c_out, K, precision, L.ptr(din), L.ptr(ws), ws_bytes, L.stream()),
-            "spc_conv_dgrad")
+    if _tensor_core(1, K, c_in, c_out, precision):
+        wp = _packed_weights(w, True, precision, w_owner)
+        L.check(lib.spc_conv_dgrad_packed(L.ptr(g), _packed_ptr(wp), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out,
+                                          c_in, c_out, K, precision, L.ptr(din), L.stream()), "spc_conv_dgrad_packed")
+    else:
+        ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
+        ws = _workspace(ws_bytes, g.device)
+        L.check(lib.spc_conv_dgrad(L.ptr(g), L.ptr(w), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out, c_in,
+                                   c_out, K, precision, L.ptr(din), L.ptr(ws), ws_bytes, L.stream()),
+                "spc_conv_dgrad")
     if e0 is not None:
         _profiler.end("conv_dgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
                       f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
     return din
 
 
-def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision):
+def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision, add_into: Optional[torch.Tensor] = None):
+    """dW [K, c_in, c_out]; `add_into` (a dense fp32 buffer of that many elements, tensor-core shapes only): the
+    gradient is ADDED to it (spc_conv_wgrad_acc) and it is returned."""
     lib = L.load()
-    dw = _empty((K, c_in, c_out), torch.float32, x.device)
-    ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
-    ws = _workspace(ws_bytes, x.device)
     mask = km.mask if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_conv_wgrad(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out, K,
-                               precision, L.ptr(dw), L.ptr(ws), ws_bytes, L.stream()), "spc_conv_wgrad")
+    if add_into is not None:
+        dw = add_into
+        L.check(lib.spc_conv_wgrad_acc(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out,
+                                       K, precision, L.ptr(dw), 1, L.stream()), "spc_conv_wgrad_acc")
+    else:
+        dw = _empty((K, c_in, c_out), torch.float32, x.device)
+        L.check(lib.spc_conv_wgrad_acc(L.ptr(x), L.ptr(g), L.ptr(km.nbr), L.ptr(mask), km.m_in, km.m_out, c_in, c_out,
+                                       K, precision, L.ptr(dw), 0, L.stream()), "spc_conv_wgrad")
     if e0 is not None:
         _profiler.end("conv_wgrad", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
                       f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
@@ -582,7 +656,8 @@ class SparseConvFn(torch.autograd.Function):
     """out[o] = sum_k x[nbr[k,o]] @ W[k] (+bias); backward = dgrad / wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, km, precision):
+    def forward(ctx, x, w, bias, km, precision, w_param=None):
+        """`w_param`: the Parameter `w` is (a view of), for the gradient sink (see register_grad_sink)."""
         x = _feat(x)
         w3 = w.contiguous()
         if x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
@@ -607,10 +682,13 @@ class SparseConvFn(torch.autograd.Function):
         if precision == L.PREC_BF16:
             # conversion and channel padding in one pass; the bf16 copy is what backward needs too
             x = to_bf16(x, pad_to=c_in + pad_in)
-        out = conv_fwd_raw(x, w3, b, km, precision, want_stats=not pad_out)
+        own = w_param if (w_param is not None and not pad_in and not pad_out
+                          and w_param.data_ptr() == w3.data_ptr() and w_param.numel() == w3.numel()) else None
+        out = conv_fwd_raw(x, w3, b, km, precision, own)
         if pad_out:
             out = out[:, :c_out].contiguous()
         ctx.save_for_backward(x, w3)
+        ctx.w_param = own
         ctx.km = km
         ctx.precision = precision
         ctx.has_bias = bias is not None
@@ -633,15 +711,20 @@ class SparseConvFn(torch.autograd.Function):
             if pad_out:
                 g = torch.nn.functional.pad(g, (0, pad_out))
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(g, w3, km, prec)
+            dx = conv_dgrad_raw(g, w3, km, prec, ctx.w_param)
             if pad_in:
                 dx = dx[:, :c_in].contiguous()
         if ctx.needs_input_grad[1]:
             K, ci, co = w3.shape
-            dw = conv_wgrad_raw(x, g, km, K, ci, co, prec)
-            if pad_in or pad_out:
-                dw = dw[:, :c_in, :c_out].contiguous()
-        return dx, dw, db, None, None
+            sink = _sink(ctx.w_param) if _tensor_core(2, K, ci, co, prec) else None
+            if sink is not None and sink[0].numel() == K * ci * co:
+                conv_wgrad_raw(x, g, km, K, ci, co, prec, add_into=sink[0])   # straight into the gradient arena
+                sink[1](ctx.w_param)
+            else:
+                dw = conv_wgrad_raw(x, g, km, K, ci, co, prec)
+                if pad_in or pad_out:
+                    dw = dw[:, :c_in, :c_out].contiguous()
+        return dx, dw, db, None, None, None
 
 
 # ---------------------------------------------------------------------------
@@ -651,7 +734,10 @@ class BatchNormFn(torch.autograd.Function):
     """nn.BatchNorm1d semantics on [M,C] rows, optional fused ReLU and residual add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual,
+                tracked=None):
+        """`tracked`: nn.BatchNorm1d.num_batches_tracked (int64 device scalar) to increment inside the statistics
+        kernel, or None."""
         lib = L.load()
         x = _feat(x)
         m, C = x.shape
@@ -666,17 +752,11 @@ class BatchNormFn(torch.autograd.Function):
             mean = _empty(C, torch.float32, dev)
             var = _empty(C, torch.float32, dev)
             upd = training and running_mean is not None
-            sums = _lookup_stats(x)
-            if sums is not None:  # accumulated by the producing convolution's epilogue: no pass over x
-                L.check(lib.spc_bn_finalize(L.ptr(sums), m, C, L.ptr(mean), L.ptr(var),
-                                            L.ptr(running_mean) if upd else None,
-                                            L.ptr(running_var) if upd else None, float(momentum), L.stream()),
-                        "spc_bn_finalize")
-            else:
-                L.check(lib.spc_bn_stats(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
-                                         L.ptr(running_mean) if upd else None,
-                                         L.ptr(running_var) if upd else None, float(momentum), L.ptr(ws), ws_bytes,
-                                         L.stream()), "spc_bn_stats")
+            L.check(lib.spc_bn_stats_tracked(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
+                                             L.ptr(running_mean) if upd else None,
+                                             L.ptr(running_var) if upd else None, float(momentum),
+                                             L.ptr(tracked) if (upd and tracked is not None) else None, L.ptr(ws),
+                                             ws_bytes, L.stream()), "spc_bn_stats")
         else:
             mean, var = running_mean, running_var
         res = _feat(residual) if residual is not None else None
@@ -687,12 +767,13 @@ class BatchNormFn(torch.autograd.Function):
         if yb is not None:
             _remember_bf16(y, yb)
         if e0 is not None:
-            _profiler.end("bn_fwd", e0, 0, ((8.0 if (use_batch and sums is not None) else 12.0)
+            _profiler.end("bn_fwd", e0, 0, ((12.0 if use_batch else 8.0)
                                             + (4.0 if res is not None else 0.0)
                                             + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
         # the ReLU mask of backward comes from the bf16 copy when there is one (2 instead of 4 bytes per value)
         ctx.save_for_backward(x, (yb if yb is not None else y) if relu else None, mean, var, gamma)
         ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
+        ctx.params = (gamma, beta)   # the Parameter objects, for the gradient sinks
         return y
 
     @staticmethod
@@ -708,14 +789,25 @@ class BatchNormFn(torch.autograd.Function):
         dx = _empty((m, C), torch.float32, dev)
         dxb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
         dres = _empty((m, C), torch.float32, dev) if has_res else None
-        dgamma = _empty(C, torch.float32, dev)
-        dbeta = _empty(C, torch.float32, dev)
+        # parameter gradients straight into the trainer's arena when both parameters are registered sinks
+        gp, bp = ctx.params
+        sg, sb = (_sink(gp), _sink(bp)) if affine else (None, None)
+        direct = sg is not None and sb is not None and sg[0].numel() == C and sb[0].numel() == C
+        if direct:
+            dgamma, dbeta = sg[0], sb[0]
+        else:
+            dgamma = _empty(C, torch.float32, dev)
+            dbeta = _empty(C, torch.float32, dev)
         e0 = _profiler.begin() if _profiler else None
         y32, y16 = (None, y) if (y is not None and y.dtype == torch.bfloat16) else (y, None)
-        L.check(lib.spc_bn_bwd(L.ptr(x), L.ptr(y32), L.ptr(y16), _ptr_rows(dy), dy_pitch, L.ptr(mean), L.ptr(var),
-                               L.ptr(gamma), m, C, eps,
-                               relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
-                               L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
+        L.check(lib.spc_bn_bwd_acc(L.ptr(x), L.ptr(y32), L.ptr(y16), _ptr_rows(dy), dy_pitch, L.ptr(mean), L.ptr(var),
+                                   L.ptr(gamma), m, C, eps,
+                                   relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
+                                   int(direct), L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
+        if direct:
+            sg[1](gp)
+            sb[1](bp)
+            dgamma = dbeta = None
         if dxb is not None:
             _remember_bf16(dx, dxb)
         if e0 is not None:
@@ -723,7 +815,7 @@ class BatchNormFn(torch.autograd.Function):
                                             + (2.0 if dxb is not None else 0.0)) * m * C,
                           f"C{C} M{m}")
         return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,
-                dres)
+                dres, None)
 
 
 class SyncBatchNormFn(torch.autograd.Function):
@@ -1213,5 +1305,6 @@ class SplatFn(torch.autograd.Function):
 
 def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_step):
     lib = L.load()
+    invalidate_packed_weights()  # the kernel rewrites every parameter through a raw pointer
     L.check(lib.spc_sgd_step(L.ptr(param), L.ptr(grad), L.ptr(buf), param.numel(), float(lr), float(momentum),
                              float(weight_decay), float(grad_scale), int(first_step), L.stream()), "spc_sgd_step")

@@ -90,6 +90,14 @@ class DataParallelTrainer:
         self.time_exposed = False
         self.exposed_ms: List[float] = []
         self._exposed_events = []
+        # The backward kernels add parameter gradients straight into the arena slices (ops.register_grad_sink):
+        # no temporary + one tiny accumulation launch per parameter.  The callback stands in for autograd's
+        # post-accumulate hook (bucketed all-reduce at world > 1).
+        self._hooks = {}
+        for i, p in enumerate(self.arena.order):
+            hook = self._make_hook(i) if self.world > 1 else None
+            self._hooks[id(p)] = hook
+            ops.register_grad_sink(p, hook if hook is not None else (lambda param: None))
         if self.world > 1:
             # replicas must START equal: DistributedDataParallel (what the reference gets from Lightning's
             # DDPPlugin, train.py:184) broadcasts rank 0's parameters and buffers at construction
@@ -100,7 +108,7 @@ class DataParallelTrainer:
                                group=process_group)
             self._make_buckets(int(bucket_mb * 1024 * 1024 / 4))
             for i, p in enumerate(self.arena.order):
-                p.register_post_accumulate_grad_hook(self._make_hook(i))
+                p.register_post_accumulate_grad_hook(self._hooks[id(p)])
 
     # ---- bucketing ---------------------------------------------------------------
     def _make_buckets(self, bucket_elems: int):

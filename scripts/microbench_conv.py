@@ -63,12 +63,3 @@ for name in args.only.split(","):
     t = sorted(ts)[len(ts) // 2]
     print(f"{name:6s} M_in={km.m_in} M_out={km.m_out} K={K} {args.cin}->{args.cout} P={P} {args.prec}: "
           f"{t:.3f} ms  {flops / t / 1e9:.1f} TFLOP/s  gather {P * args.cin * 4 / t / 1e6:.0f} GB/s", flush=True)
-
-if "wgrad" in args.only and args.prec != "fp32":
-    import ctypes
-    import numpy as np
-    buf = np.zeros(148 * 8, np.int64)
-    L.load().spc_debug_read(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
-    b = buf.reshape(148, 8)
-    names = ["P:a_empty", "P:b_empty", "P:idx_wait", "M:a_full", "M:b_full", "M:t_empty", "P:total", "M:total"]
-    print("wgrad role cycles (mean / max over CTAs):", ", ".join(f"{n}={b[:, i].mean():.0f}/{b[:, i].max()}" for i, n in enumerate(names)))

@@ -291,7 +291,72 @@ class FakeLib:
             d[k] = xin[a[k, o]].T @ g[o] if o.size else 0.0
         return 0
 
+    def spc_conv_wgrad_acc(self, x, dout, nbr, mask, m_in, m_out, c_in, c_out, K, precision, dw, accumulate, stream):
+        if not accumulate:
+            return self.spc_conv_wgrad(x, dout, nbr, mask, m_in, m_out, c_in, c_out, K, precision, dw, None, 0, stream)
+        self._called("spc_conv_wgrad_acc")
+        assert self.spc_conv_tensor_core(2, K, c_in, c_out, precision), "accumulate needs a tensor-core shape"
+        xin = feat_rows(x, m_in, c_in, precision).astype(np.float64)
+        g = feat_rows(dout, m_out, c_out, precision).astype(np.float64)
+        a = view(nbr, (K, m_out), np.int32)
+        d = view(dw, (K, c_in, c_out), np.float32)
+        for k in range(K):
+            o = np.nonzero(a[k] >= 0)[0]
+            if o.size:
+                d[k] += (xin[a[k, o]].T @ g[o]).astype(np.float32)
+        return 0
+
+    # the tensor-core routing rules of conv_api.cu (what: 0 fwd, 1 dgrad, 2 wgrad)
+    def spc_conv_tensor_core(self, what, K, c_in, c_out, precision):
+        if precision == 0 or K > 32:
+            return 0
+        fwd_ok = lambda ck, cn: ck >= 32 and ck % 32 == 0 and cn % 16 == 0   # noqa: E731
+        if what == 0:
+            return int(fwd_ok(c_in, c_out))
+        if what == 1:
+            return int(fwd_ok(c_out, c_in))
+        return int(K * c_in <= 128 * 128 and c_in >= 32 and c_in % 32 == 0 and 32 <= c_out <= 256 and c_out % 32 == 0)
+
+    def spc_conv_packed_bytes(self, K, c_in, c_out):
+        return (K * c_in * c_out * 4 + 1023) // 1024 * 1024
+
+    def spc_conv_path_counts(self, out3, reset):
+        return None
+
+    def spc_conv_pack_weights(self, w, K, c_in, c_out, dgrad, precision, packed, stream):
+        """The harness's "packed image" is the fp32 kernel itself (the real one is a swizzled slab layout)."""
+        self._called("spc_conv_pack_weights")
+        assert _addr(packed) % 1024 == 0
+        view(packed, (K, c_in, c_out), np.float32)[:] = view(w, (K, c_in, c_out), np.float32)
+        return 0
+
+    def spc_conv_fwd_packed(self, x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, stream):
+        assert self.spc_conv_tensor_core(0, K, c_in, c_out, precision)
+        return self.spc_conv_fwd(x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, None, 0, stream)
+
+    def spc_conv_dgrad_packed(self, dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, stream):
+        assert self.spc_conv_tensor_core(1, K, c_in, c_out, precision)
+        return self.spc_conv_dgrad(dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, None, 0, stream)
+
     # ---- batch norm / elementwise -----------------------------------------------------------------------------
+    def spc_bn_stats_tracked(self, x, m, C, mean, var, run_mean, run_var, momentum, tracked, ws, ws_bytes, stream):
+        rc = self.spc_bn_stats(x, m, C, mean, var, run_mean, run_var, momentum, ws, ws_bytes, stream)
+        if _addr(tracked):
+            view(tracked, 1, np.int64)[:] += 1
+        return rc
+
+    def spc_bn_bwd_acc(self, x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16, dres,
+                       dgamma, dbeta, accumulate, ws, ws_bytes, stream):
+        if not accumulate:
+            return self.spc_bn_bwd(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16,
+                                   dres, dgamma, dbeta, ws, ws_bytes, stream)
+        g0, b0 = view(dgamma, C, np.float32).copy(), view(dbeta, C, np.float32).copy()
+        rc = self.spc_bn_bwd(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16,
+                             dres, dgamma, dbeta, ws, ws_bytes, stream)
+        view(dgamma, C, np.float32)[:] += g0
+        view(dbeta, C, np.float32)[:] += b0
+        return rc
+
     def spc_bn_stats(self, x, m, C, mean, var, run_mean, run_var, momentum, ws, ws_bytes, stream):
         self._called("spc_bn_stats")
         xv = view(x, (m, C), np.float32).astype(np.float64)

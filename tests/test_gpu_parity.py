@@ -244,7 +244,7 @@ def test_conv_tf32_tensor_core(cuda_device, ks, stride, cin, cout, transpose, fo
         lib.spc_debug_force_mt(0)
 
 
-BF16_TOL = 2e-2
+BF16_TOL = 3e-3   # tensor-core modes within 3e-3 * max|ref| per layer (measured 2.2e-3 .. 2.7e-3)
 BF16_CONV_CASES = [((3, 3, 3), 1, 32, 32, False), ((3, 3, 3), 1, 64, 96, False), ((3, 3, 3), 1, 128, 96, False),
                    ((3, 3, 3), 1, 96, 96, False), ((3, 3, 3), 1, 256, 256, False), ((3, 3, 3), 2, 64, 128, False),
                    ((2, 2, 2), 2, 96, 96, False), ((2, 2, 2), 2, 256, 128, True), ((1, 1, 1), 2, 128, 256, False)]
@@ -252,7 +252,7 @@ BF16_CONV_CASES = [((3, 3, 3), 1, 32, 32, False), ((3, 3, 3), 1, 64, 96, False),
 
 @pytest.mark.parametrize("ks,stride,cin,cout,transpose", BF16_CONV_CASES)
 def test_conv_bf16_tensor_core(cuda_device, ks, stride, cin, cout, transpose):
-    """kind::f16 path on bf16 copies of the rows; stated bound |d| <= 2e-2 * max|ref| vs the fp64 oracle."""
+    """kind::f16 path on bf16 copies of the rows; stated bound |d| <= 3e-3 * max|ref| vs the fp64 oracle."""
     km, nbr, x, w, b, go = _conv_case(cuda_device, 43, 9000, 11, ks, stride, cin, cout, transpose)
     xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
     ref = R.conv_forward(xr, wr, nbr, b)
@@ -302,27 +302,6 @@ def test_conv_tf32_matches_fp32_kernels_large(cuda_device):
     close_bf16(ops.conv_dgrad_raw(gb, w, km, L.PREC_BF16), db, "bf16 dgrad")
     dw32 = ops.conv_wgrad_raw(x, go, km, 27, 64, 96, L.PREC_FP32)
     close_bf16(ops.conv_wgrad_raw(xb, gb, km, 27, 64, 96, L.PREC_BF16), dw32, "bf16 wgrad")
-    # BatchNorm statistics accumulated by the convolution epilogue (large maps): sums of the output rows
-    for prec, src in ((L.PREC_BF16, xb), (L.PREC_TF32, x)):
-        bias = torch.randn(96, generator=g).to(cuda_device)
-        ops.fuse_bn_stats = True  # (off by default: see ops.py)
-        try:
-            out = ops.conv_fwd_raw(src, w, bias, km, prec, want_stats=True)
-        finally:
-            ops.fuse_bn_stats = False
-        sums = ops._lookup_stats(out)
-        assert sums is not None, "statistics fusion did not engage on a 150 K-row map"
-        ref = torch.cat([out.double().sum(0), (out.double() ** 2).sum(0)])
-        rel = ((sums - ref).abs() / (ref.abs() + 1e-6 * ref.abs().max())).max().item()
-        assert rel <= 1e-6, rel
-        # and BatchNorm fed with them == BatchNorm that computes its own statistics
-        gam, bet = torch.rand(96, generator=g).to(cuda_device) + 0.5, torch.randn(96, generator=g).to(cuda_device)
-        rm1, rv1 = torch.zeros(96, device=cuda_device), torch.ones(96, device=cuda_device)
-        rm2, rv2 = rm1.clone(), rv1.clone()
-        y1 = ops.BatchNormFn.apply(out, gam, bet, rm1, rv1, True, 0.1, 1e-5, True, None)
-        y2 = ops.BatchNormFn.apply(out.clone(), gam, bet, rm2, rv2, True, 0.1, 1e-5, True, None)
-        assert (y1 - y2).abs().max().item() <= 1e-5 * (1 + y2.abs().max().item())
-        assert torch.allclose(rm1, rm2, rtol=1e-5, atol=1e-6) and torch.allclose(rv1, rv2, rtol=1e-5, atol=1e-6)
 
 
 # ---------------------------------------------------------------------------
