@@ -224,6 +224,15 @@ def run_ours(args):
     h_labels = torch.from_numpy(labels).pin_memory()
     d_coords, d_feats, d_labels = h_coords.to(dev), h_feats.to(dev), h_labels.to(dev)
     voxels_per_step = [0]
+    # end-to-end input: the batch as PeRFception stores it (int32 links + uint8 SH + uint8 labels, 32 B / voxel),
+    # decoded on the device into the collated tensors (spc_plenoxel_decode) — --e2e-input float: the float tensors
+    compact = None
+    if args.e2e_input == "compact" and args.geometry == "dense":
+        recs = synth.compact_records(coords, feats, labels)
+        compact = {"recs": [(x[0], x[4], len(x[1])) for x in recs],   # (batch index, grid, rows)
+                   "links": torch.from_numpy(np.concatenate([r[1] for r in recs])).pin_memory(),
+                   "sh": torch.from_numpy(np.concatenate([r[2] for r in recs])).pin_memory(),
+                   "labels": torch.from_numpy(np.concatenate([r[3] for r in recs])).pin_memory()}
 
     def step(c, f, y):
         field = ME.TensorField(coordinates=c, features=f)
@@ -298,13 +307,16 @@ def run_ours(args):
         # the copy of batch i+1 is enqueued on a copy stream while step i computes (two device buffers);
         # batch i+1 is never touched before its copy event, and buffer reuse is safe because loss.item()
         # of step i-1 has synchronised the device.
-        bufs = [tuple(torch.empty_like(t, device=dev) for t in (h_coords, h_feats, h_labels)) for _ in range(2)]
+        host_src = (compact["links"], compact["sh"], compact["labels"]) if compact else (h_coords, h_feats, h_labels)
+        bufs = [tuple(torch.empty_like(t, device=dev) for t in host_src) for _ in range(2)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         turn = [0]
+        dec_c = torch.empty_like(d_coords) if compact else None
+        dec_f = torch.empty_like(d_feats) if compact else None
 
         def enqueue_copy(slot):
             with torch.cuda.stream(copy_stream):
-                for d, h in zip(bufs[slot], (h_coords, h_feats, h_labels)):
+                for d, h in zip(bufs[slot], host_src):
                     d.copy_(h, non_blocking=True)
                 ready[slot].record(copy_stream)
 
@@ -313,7 +325,17 @@ def run_ours(args):
             turn[0] += 1
             torch.cuda.current_stream().wait_event(ready[slot])
             enqueue_copy(slot ^ 1)  # next step's batch, overlapped with this step
-            c, f, y = bufs[slot]
+            if compact:
+                links, sh, lab8 = bufs[slot]
+                row = 0
+                for b, reso, n in compact["recs"]:   # each record decodes into its rows of the collated batch
+                    pipeline.plenoxel_decode(links[row:row + n], sh[row:row + n], 2.0 / 255.0, -1.0, reso, batch_index=b,
+                                             affine=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 0.5, 0.5),
+                                             out_coords=dec_c[row:row + n], out_feats=dec_f[row:row + n])
+                    row += n
+                c, f, y = dec_c, dec_f, lab8.long()
+            else:
+                c, f, y = bufs[slot]
             loss = step(c, f, y)
             return loss.item()  # device -> host read of the step's result
 
@@ -323,7 +345,7 @@ def run_ours(args):
         ms_e2e = timed(e2e_steps, e2e_step)
         torch.cuda.current_stream().wait_stream(copy_stream)
         e2e_value = total_voxels * e2e_steps / (ms_e2e * 1e-3)
-        h2d = h_coords.numel() * 4 + h_feats.numel() * 4 + h_labels.numel() * 8
+        h2d = sum(t.numel() * t.element_size() for t in host_src)
         d2h = 4 + 8 * 5  # loss scalar + the per-level map sizes the host reads back (2 int32 each)
 
         # ---- per-kernel-class device times inside a (separately) timed region -> roofline -------------
@@ -394,7 +416,10 @@ def run_ours(args):
                                        "frac": round(v["bytes"] / t_ / 1e9 / peaks["hbm_gbs"], 3)})
         return {"value": value, "ms_per_step": ms / args.steps, "total_voxels": total_voxels, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / e2e_steps},
+                        "ms_per_step": ms_e2e / e2e_steps,
+                        "input": ("plenoxel records as stored (int32 links + uint8 SH + uint8 labels), decoded on the device "
+                                  "by spc_plenoxel_decode inside the timed region") if compact else
+                                 "collated float32 coordinates + float32 features + int64 labels"},
                 "gpu_launches": int(launches), "host_issue_ms_per_step": 1e3 * host_s[0] / args.steps,
                 # convolution launches per step by route: anything under "cuda_core_fp32" is a shape the tensor-core
                 # kernels do not take (ops.SparseConvFn / conv_api.cu routing), "tf32" under a bf16 run a precision
@@ -481,6 +506,9 @@ def main():
                     help="conv operand precision: bf16 (default; fp32 accumulate), tf32, or fp32 CUDA cores")
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-input", default="compact", choices=["compact", "float"],
+                    help="what the end-to-end leg copies host -> device each step: the plenoxel records as stored on disk "
+                         "(links + u8 SH + u8 labels, decoded on the device) or the collated float tensors")
     ap.add_argument("--no-alt-precision", action="store_true",
                     help="skip the second measurement in the other tensor-core operand precision (alt_precision)")
     ap.add_argument("--detail", action="store_true", help="per-layer kernel times on stderr")

@@ -104,6 +104,12 @@ int spc_kernel_map(const void* in_slots, int64_t in_n_slots,
  */
 int spc_tile_mask(const int32_t* nbr, int64_t m, int K, uint32_t* mask, void* stream);
 
+/* spc_kernel_map for a SELF map (out map == the map the table indexes) with centrally symmetric offsets
+ * (offsets[K-1-k] == -offsets[k], K odd — every odd-kernel stride-1 convolution): nbr[k][o] = i <=> nbr[K-1-k][i] = o,
+ * so only K/2 offsets are probed and the mirrored entries are written by the thread that found them.  Same result
+ * as spc_kernel_map, half the hash probes. */
+int spc_kernel_map_sym(const void* slots, int64_t n_slots, const int32_t* coords, int64_t m,
+                       const int32_t* offsets_host, int K, int32_t* nbr, int32_t* tap_count, void* stream);
 /* Transposed dense map: nbr_t[k*M_in + i] = o  iff  nbr[k*M_out + o] = i. */
 int spc_kernel_map_transpose(const int32_t* nbr, int64_t m_out, int64_t m_in, int K,
                              int32_t* nbr_t, void* stream);
@@ -189,6 +195,10 @@ int spc_conv_wgrad_acc(const void* in, const void* dout, const int32_t* nbr, con
 int64_t spc_conv_packed_bytes(int K, int c_in, int c_out);
 int spc_conv_pack_weights(const float* w, int K, int c_in, int c_out, int dgrad, int precision, void* packed,
                           void* stream);
+/* spc_conv_pack_weights for n_layers (layer, direction) pairs in ONE launch.  desc_dev: DEVICE int64 [n_layers][8] =
+ * { w (fp32 [K, c_in, c_out]), packed (1024-byte aligned), K, Ck, Cn, transpose, bf16, 0 } with (Ck, Cn, transpose) =
+ * (c_in, c_out, 0) for the forward image and (c_out, c_in, 1) for the dgrad image. */
+int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* stream);
 int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
                         const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
                         int precision, float* out, void* stream);

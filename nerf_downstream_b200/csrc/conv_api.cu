@@ -17,6 +17,7 @@ int64_t umma_fwd_workspace(int K, int c_in, int c_out);
 int64_t umma_packed_bytes(int K, int c_in, int c_out);
 int conv_pack_weights(const float* w, int K, int Ck, int Cn, bool transpose, bool bf16, void* packed,
                       cudaStream_t stream);
+int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_t stream);
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
                   bool transpose_w, bool bf16, float* out, void* workspace,
@@ -71,6 +72,10 @@ int spc_conv_pack_weights(const float* w, int K, int c_in, int c_out, int dgrad,
   // forward contracts over Cin (rows of W[k]); dgrad contracts over Cout with W[k]^T
   return dgrad ? conv_pack_weights(w, K, c_out, c_in, true, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream)
                : conv_pack_weights(w, K, c_in, c_out, false, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream);
+}
+
+int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* stream) {
+  return conv_pack_weights_batch((const long long*)desc_dev, n_layers, (cudaStream_t)stream);
 }
 
 int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,

@@ -101,6 +101,45 @@ pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, 
   }
 }
 
+// One launch for every layer of a network (blockIdx.y = layer): the descriptors live in device memory
+// ([n][8] int64: w, packed, K, Ck, Cn, transpose, bf16, unused) and are rebuilt only when the set of layers changes.
+__global__ void __launch_bounds__(256)
+pack_weights_batch_kernel(const long long* __restrict__ desc) {
+  const long long* d = desc + (size_t)blockIdx.y * 8;
+  const float* W = reinterpret_cast<const float*>(d[0]);
+  void* Wp_ = reinterpret_cast<void*>(d[1]);
+  const int K = (int)d[2], Ck = (int)d[3], Cn = (int)d[4], transpose = (int)d[5], bf16 = (int)d[6];
+  const long long total = (long long)K * Ck * Cn;
+  const int kc_count = Ck / 32;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int jj = (int)(e % 32);
+    long long t = e / 32;
+    int n = (int)(t % Cn); t /= Cn;
+    int kc = (int)(t % kc_count);
+    int k = (int)(t / kc_count);
+    int c = kc * 32 + jj;
+    float v = transpose ? W[((long long)k * Cn + n) * Ck + c] : W[((long long)k * Ck + c) * Cn + n];
+    long long row = ((long long)k * kc_count + kc) * Cn + n;
+    if (bf16) {
+      int j = jj >> 3, w = jj & 7;
+      reinterpret_cast<__nv_bfloat16*>(Wp_)[row * 32 + ((j ^ ((n >> 1) & 3)) << 3) + w] = __float2bfloat16_rn(v);
+    } else {
+      int j = jj >> 2, w = jj & 3;
+      reinterpret_cast<float*>(Wp_)[row * 32 + ((j ^ (n & 7)) << 2) + w] = v;
+    }
+  }
+}
+
+int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_t stream) {
+  if (n_layers <= 0) return 0;
+  SPC_REQUIRE(n_layers <= 65535, "too many layers for one launch");
+  dim3 grid(96, (unsigned)n_layers);  // 96 x 256 threads per layer: a 27 x 256 x 256 kernel takes 72 iterations
+  pack_weights_batch_kernel<<<grid, 256, 0, stream>>>(desc_dev);
+  SPC_LAUNCHED("pack_weights_batch_kernel");
+  return 0;
+}
+
 int conv_pack_weights(const float* w, int K, int Ck, int Cn, bool transpose, bool bf16, void* packed,
                       cudaStream_t stream) {
   SPC_REQUIRE(((uintptr_t)packed % 1024) == 0, "packed weights must be 1024-byte aligned");

@@ -229,6 +229,47 @@ kernel_map_kernel(const Slot* __restrict__ slots, unsigned long long bucket_mask
   if (threadIdx.x < K && s_count[threadIdx.x]) atomicAdd(&tap_count[threadIdx.x], s_count[threadIdx.x]);
 }
 
+// Self map with centrally symmetric offsets (every 3^3 / 5^3 stride-1 convolution: in map == out map,
+// offs[K-1-k] == -offs[k]): nbr[k][o] = i  <=>  nbr[K-1-k][i] = o, and the centre offset is the identity.  Only the
+// first K/2 offsets are probed; a hit also writes the mirrored entry (each (K-1-k, i) has exactly one writer; rows
+// K/2+1 .. K-1 are pre-filled with -1).  Half the hash probes — what bounds this kernel — for the map that every
+// stride-1 convolution of a level shares.
+__global__ void __launch_bounds__(256)
+kernel_map_sym_kernel(const Slot* __restrict__ slots, unsigned long long bucket_mask,
+                      const int4* __restrict__ coords, int m, Offsets offs, int K,
+                      int* __restrict__ nbr, int* __restrict__ tap_count) {
+  __shared__ int s_count[kMaxOffsets];
+  const int half = K / 2;
+  if (threadIdx.x < K) s_count[threadIdx.x] = 0;
+  __syncthreads();
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = o < m;
+  const int lane = threadIdx.x & 31;
+  int4 c = valid ? coords[o] : make_int4(0, 0, 0, 0);
+  for (int k = 0; k < half; ++k) {
+    int row = -1;
+    if (valid) {
+      unsigned long long key;
+      if (pack_key(c.x, c.y + offs.v[3 * k], c.z + offs.v[3 * k + 1], c.w + offs.v[3 * k + 2], key))
+        row = table_lookup(slots, bucket_mask, key);
+      nbr[(size_t)k * m + o] = row;
+      if (row >= 0) nbr[(size_t)(K - 1 - k) * m + row] = o;
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0 && bal) atomicAdd(&s_count[k], __popc(bal));
+  }
+  if (valid) nbr[(size_t)half * m + o] = o;
+  __syncthreads();
+  if (threadIdx.x < half && s_count[threadIdx.x]) {
+    atomicAdd(&tap_count[threadIdx.x], s_count[threadIdx.x]);
+    atomicAdd(&tap_count[K - 1 - threadIdx.x], s_count[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
+    const int rows = min(256, m - (int)(blockIdx.x * blockDim.x));
+    if (rows > 0) atomicAdd(&tap_count[half], rows);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 transpose_map_kernel(const int* __restrict__ nbr, int m_out, int m_in, int K,
                      int* __restrict__ nbr_t) {
@@ -451,6 +492,29 @@ int spc_kernel_map(const void* in_slots, int64_t in_n_slots, const int32_t* out_
       (const Slot*)in_slots, (unsigned long long)(in_n_slots / 2 - 1), (const int4*)out_coords,
       (int)m_out, offs, K, nbr, tap_count);
   SPC_LAUNCHED("kernel_map_kernel");
+  return 0;
+}
+
+int spc_kernel_map_sym(const void* slots, int64_t n_slots, const int32_t* coords, int64_t m,
+                       const int32_t* offsets_host, int K, int32_t* nbr, int32_t* tap_count, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(K >= 1 && K <= kMaxOffsets && (K & 1), "kernel volume must be odd and in [1,125]");
+  SPC_REQUIRE(n_slots >= 64 && (n_slots & (n_slots - 1)) == 0, "bad table size");
+  SPC_REQUIRE(m >= 0 && m < (1ll << 31) - 1024, "m out of range");
+  for (int k = 0; k < K; ++k)
+    for (int a = 0; a < 3; ++a)
+      SPC_REQUIRE(offsets_host[3 * k + a] == -offsets_host[3 * (K - 1 - k) + a], "offsets are not centrally symmetric");
+  SPC_CUDA(cudaMemsetAsync(tap_count, 0, (size_t)K * sizeof(int), stream));
+  if (m == 0) return 0;
+  const int half = K / 2;
+  if (half > 0)
+    SPC_CUDA(cudaMemsetAsync(nbr + (size_t)(half + 1) * m, 0xFF, (size_t)half * m * sizeof(int), stream));
+  Offsets offs;
+  memset(&offs, 0, sizeof(offs));
+  memcpy(offs.v, offsets_host, (size_t)K * 3 * sizeof(int));
+  kernel_map_sym_kernel<<<(int)ceil_div(m, 256), 256, 0, stream>>>(
+      (const Slot*)slots, (unsigned long long)(n_slots / 2 - 1), (const int4*)coords, (int)m, offs, K, nbr, tap_count);
+  SPC_LAUNCHED("kernel_map_sym_kernel");
   return 0;
 }
 

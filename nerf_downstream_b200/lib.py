@@ -32,6 +32,7 @@ SIGNATURES = {
     "spc_coords_insert": (c_int, [_P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "spc_coords_insert_dev": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "spc_kernel_map": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, _P, _P, _P]),
+    "spc_kernel_map_sym": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, _P, _P, _P]),
     "spc_tile_mask": (c_int, [_P, c_int64, c_int, _P, _P]),
     "spc_kernel_map_transpose": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "spc_pairs_workspace": (c_int64, [c_int64, c_int]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "spc_conv_tensor_core": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "spc_conv_packed_bytes": (c_int64, [c_int, c_int, c_int]),
     "spc_conv_pack_weights": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "spc_conv_pack_weights_batch": (c_int, [_P, c_int, _P]),
     "spc_conv_fwd_packed": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "spc_conv_dgrad_packed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "spc_conv_wgrad_acc": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P]),

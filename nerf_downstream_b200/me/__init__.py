@@ -10,6 +10,7 @@ from .modules import (MinkowskiAvgPooling, MinkowskiBatchNorm, MinkowskiCELU, Mi
                       MinkowskiGlobalSumPooling, MinkowskiInstanceNorm, MinkowskiInterpolation, MinkowskiLeakyReLU, MinkowskiLinear,
                       MinkowskiMaxPooling, MinkowskiModuleBase, MinkowskiNetwork, MinkowskiNonlinearityBase,
                       MinkowskiPReLU, MinkowskiReLU, MinkowskiSELU, MinkowskiSigmoid, MinkowskiSoftmax,
-                      MinkowskiSumPooling, MinkowskiSyncBatchNorm, MinkowskiTanh, cat)
+                      MinkowskiSumPooling, MinkowskiSyncBatchNorm, MinkowskiTanh, SparseConvMode,
+                      WeightSparseConvolution, WeightSparseConvolutionTranspose, cat)
 
 __version__ = "0.5.4+b200"

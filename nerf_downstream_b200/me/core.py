@@ -627,8 +627,11 @@ class SparseTensor(Tensor):
     def slice(self, X: "TensorField") -> "TensorField":
         """Features of this sparse tensor at the original points of `X` (res16unet.py:435)."""
         assert isinstance(X, TensorField), "slice expects a TensorField"
-        inv = X.inverse_mapping(self.coordinate_map_key)
-        return TensorField(ops.GatherRowsFn.apply(self.F, inv),
+        if self.coordinate_map_key in getattr(X, "_identity_maps", ()):
+            feats = self.F      # one point per voxel: the gather through the inverse map is the identity
+        else:
+            feats = ops.GatherRowsFn.apply(self.F, X.inverse_mapping(self.coordinate_map_key))
+        return TensorField(feats,
                            coordinate_field_map_key=X.coordinate_field_map_key,
                            coordinate_manager=X.coordinate_manager, quantization_mode=X.quantization_mode)
 
@@ -683,6 +686,7 @@ class TensorField(Tensor):
         assert features.ndim == 2, f"features must be [N, C], got {tuple(features.shape)}"
         self.quantization_mode = quantization_mode
         self._inverse_mapping: Dict[CoordinateMapKey, torch.Tensor] = {}
+        self._identity_maps = set()   # sparse maps with one point per voxel: row r of the map IS point r
         if coordinates is not None:
             dev = _resolve_device(features, device)
             _require_cuda(dev, "TensorField")
@@ -731,7 +735,14 @@ class TensorField(Tensor):
         self._inverse_mapping[key] = inverse
         m = mgr.size(key)
         feats = self._F if self._F.dtype == torch.float32 else self._F.float()
-        F = ops.SegmentReduceFn.apply(feats, inverse, count, first, m, code)
+        if m == feats.shape[0] and inverse.shape[0] == m:
+            # No two points share a voxel (what the reference's plenoxel loaders deliver: one record per occupied
+            # cell).  Rows are in first-occurrence order, so the map's row r is point r, the inverse map is the
+            # identity and every reduction of one value is that value: no pass over the features, here or in slice().
+            self._identity_maps.add(key)
+            F = feats.contiguous()
+        else:
+            F = ops.SegmentReduceFn.apply(feats, inverse, count, first, m, code)
         return SparseTensor(F, coordinate_map_key=key, coordinate_manager=mgr)
 
     def splat(self) -> SparseTensor:

@@ -115,8 +115,13 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
                 out_key = mgr.stride(in_key, kg.kernel_stride)
             km = mgr.get_kernel_map(in_key, out_key, kg, is_transpose=self.is_transpose)
             w = self.kernel
-        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision(), self.kernel)
+        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision(), self.kernel,
+                                         None if self.use_mm else self._offset_bits())
         return SparseTensor(outfeat, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def _offset_bits(self) -> Optional[int]:
+        """Kernel offsets that take part (None = all); the weight-sparse subclasses restrict them."""
+        return None
 
     def __repr__(self):
         s = f"(in={self.in_channels}, out={self.out_channels}, kernel_size={self.kernel_generator.kernel_size}, " \
@@ -144,6 +149,66 @@ class MinkowskiConvolutionTranspose(MinkowskiConvolutionBase):
                                           expand_coordinates=expand_coordinates,
                                           convolution_mode=convolution_mode, dimension=dimension)
         self.reset_parameters(True)
+
+
+# ---------------------------------------------------------------------------
+# weight-sparse inference convolution (the reference's co3d_3d/src/models/mink/modules/sparse_conv.py:267-452)
+# ---------------------------------------------------------------------------
+class SparseConvMode:
+    """sparse_conv.py:19-25"""
+    DENSE, SPARSE, ZAXIS, NATIVE, SKIP, SPARSE_DENSE = 0, 1, 2, 3, 4, 5
+
+
+class _WeightSparseMixin:
+    """`sparsify()` (sparse_conv.py:346-379) records `valid_kernel`, the offsets whose pruned kernel W_k still holds
+    a non-zero weight (SparseConvMode.ZAXIS: the three offsets along z, `[4, 13, 22]`, whatever the weights); the
+    forward pass then runs the ordinary gather-GEMM-scatter kernels with those offsets ONLY: the reference loops over
+    `valid_kernel` with one gather + spmm + scatter each (:122-143), here the per-tile offset mask of the tcgen05
+    kernels drops the other offsets' pipeline stages (no gather, no MMA) in the single launch.  Inside a kept offset
+    the product is dense — unstructured zeros in W_k do not change what a tensor-core tile costs."""
+
+    def _init_sparse(self, sparse_mode):
+        self.sparse_mode = int(getattr(sparse_mode, "value", sparse_mode))
+        self.valid_kernel = None
+        self._flops = 0
+
+    def sparsify(self, layout: str = "strided"):
+        if layout not in ("csr", "coo", "strided"):
+            raise ValueError(f"unknown layout {layout}")
+        if self.use_mm:
+            return
+        with torch.no_grad():
+            nz = (self.kernel != 0).flatten(1).any(dim=1).tolist()   # one host read at conversion time
+        self.valid_kernel = [k for k, v in enumerate(nz) if v]
+        if self.sparse_mode == SparseConvMode.ZAXIS:
+            self.valid_kernel = [4, 13, 22]                          # sparse_conv.py:375-379
+
+    def _offset_bits(self):
+        if self.use_mm:
+            return None
+        assert self.valid_kernel is not None, "call sparsify() first (sparse_conv.py:389)"
+        bits = 0
+        for k in self.valid_kernel:
+            bits |= 1 << k
+        return bits
+
+
+class WeightSparseConvolution(_WeightSparseMixin, MinkowskiConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=ConvolutionMode.DEFAULT,
+                 dimension=None, sparse_mode=1):
+        MinkowskiConvolution.__init__(self, in_channels, out_channels, kernel_size, stride, dilation, bias,
+                                      kernel_generator, expand_coordinates, convolution_mode, dimension)
+        self._init_sparse(sparse_mode)
+
+
+class WeightSparseConvolutionTranspose(_WeightSparseMixin, MinkowskiConvolutionTranspose):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=ConvolutionMode.DEFAULT,
+                 dimension=None, sparse_mode=1):
+        MinkowskiConvolutionTranspose.__init__(self, in_channels, out_channels, kernel_size, stride, dilation, bias,
+                                               kernel_generator, expand_coordinates, convolution_mode, dimension)
+        self._init_sparse(sparse_mode)
 
 
 # ---------------------------------------------------------------------------

@@ -263,6 +263,21 @@ class KernelMap:
             self._mask_t = tile_mask(self.nbr_t, self.m_in, self.K)
         return self._mask_t
 
+    def masked(self, bits: Optional[int], transposed: bool = False):
+        """Tile mask restricted to the kernel offsets in `bits` (bit k = offset k is kept; None = all): pruned
+        offsets of a weight-sparse convolution are skipped by the tensor-core kernels like offsets without a
+        neighbour in the tile."""
+        m = self.mask_t if transposed else self.mask
+        if bits is None or m is None:
+            return m
+        key = (int(bits), bool(transposed))
+        cache = self.__dict__.setdefault("_masked", {})
+        v = cache.get(key)
+        if v is None:
+            b = int(bits) & 0xFFFFFFFF
+            v = cache[key] = torch.bitwise_and(m, b - (1 << 32) if b >= (1 << 31) else b)
+        return v
+
     def swapped(self) -> "KernelMap":
         """The same pairs with in/out roles exchanged (transposed convolution)."""
         km = KernelMap(self.nbr_t, self.tap_count, self.K, self.m_out, self.m_in)
@@ -304,6 +319,9 @@ def tile_mask(nbr, m, K):
     return mask
 
 
+symmetric_maps = True   # build self maps of odd stride-1 kernels with spc_kernel_map_sym (tests switch it off to compare)
+
+
 def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
     lib = L.load()
     K = len(offsets)
@@ -312,9 +330,17 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
     nbr = _empty((K, out_map.size), torch.int32, dev)
     tap_count = _empty(K, torch.int32, dev)
     e0 = _profiler.begin() if _profiler else None
-    L.check(lib.spc_kernel_map(L.ptr(in_map.table), in_map.n_slots, L.ptr(out_map.coords), out_map.size,
-                               ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
-                               L.stream()), "spc_kernel_map")
+    # self map with centrally symmetric offsets (odd kernels at stride 1): half the probes, mirrored writes
+    sym = (in_map is out_map and K % 2 == 1 and K <= 125 and symmetric_maps
+           and all(tuple(-v for v in offsets[K - 1 - k]) == tuple(offsets[k]) for k in range(K)))
+    if sym:
+        L.check(lib.spc_kernel_map_sym(L.ptr(in_map.table), in_map.n_slots, L.ptr(out_map.coords), out_map.size,
+                                       ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
+                                       L.stream()), "spc_kernel_map_sym")
+    else:
+        L.check(lib.spc_kernel_map(L.ptr(in_map.table), in_map.n_slots, L.ptr(out_map.coords), out_map.size,
+                                   ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
+                                   L.stream()), "spc_kernel_map")
     if e0 is not None:
         _profiler.end("kernel_map", e0, 0, (16.0 + 8.0 * K + 4.0 * K) * out_map.size,
                       f"K{K} M{out_map.size} ts{in_map.tensor_stride[0]}")
@@ -493,6 +519,7 @@ def to_bf16(x: torch.Tensor, pad_to: int = 0) -> torch.Tensor:
 # weak reference: a different tensor that re-uses the address misses), its autograd version counter and
 # `_weights_epoch`, which `sgd_step` bumps because the fused optimiser kernel writes parameters behind autograd's back.
 # ---------------------------------------------------------------------------------------------------------
+batch_repack = True    # sgd_step re-packs all cached weight images in one launch (off: each layer packs on first use)
 _pack_cache: dict = {}
 _weights_epoch = 0
 pack_stats = {"hits": 0, "misses": 0}
@@ -530,6 +557,38 @@ def _packed_weights(w3: torch.Tensor, dgrad: bool, precision: int, owner: Option
             del _pack_cache[key]
     _pack_cache[key] = (weakref.ref(obj, _drop), ver, buf)
     return buf
+
+
+_pack_desc = {"sig": None, "table": None}
+
+
+def repack_all() -> int:
+    """Re-pack every cached weight image whose owner (a live Parameter) is stale, in ONE launch
+    (spc_conv_pack_weights_batch) — `sgd_step` calls this right after the fused optimiser kernel, so the ~2 x 64
+    per-layer pack launches of a Res16UNet34C step become one.  Returns the number of images packed."""
+    lib = L.load()
+    rows, keys = [], []
+    for key, (ref, ver, buf) in list(_pack_cache.items()):
+        obj = ref()
+        ptr, dgrad, precision, K, c_in, c_out = key
+        if obj is None or not obj.is_cuda or obj.data_ptr() != ptr or obj.numel() != K * c_in * c_out \
+                or not obj.is_contiguous() or obj.device.index != torch.cuda.current_device():
+            continue   # temporaries / moved parameters: packed on demand
+        ck, cn = (c_out, c_in) if dgrad else (c_in, c_out)
+        rows.append((ptr, _packed_ptr(buf), K, ck, cn, int(dgrad), int(precision == L.PREC_BF16), 0))
+        keys.append(key)
+    if not rows:
+        return 0
+    sig = tuple(rows)
+    if _pack_desc["sig"] != sig:
+        _pack_desc["sig"] = sig
+        _pack_desc["table"] = torch.tensor(rows, dtype=torch.int64).to(_pack_cache[keys[0]][2].device)
+    L.check(lib.spc_conv_pack_weights_batch(L.ptr(_pack_desc["table"]), len(rows), L.stream()),
+            "spc_conv_pack_weights_batch")
+    for key in keys:
+        ref, _, buf = _pack_cache[key]
+        _pack_cache[key] = (ref, (ref()._version, _weights_epoch), buf)
+    return len(rows)
 
 
 def _packed_ptr(buf: torch.Tensor) -> int:
@@ -586,11 +645,19 @@ def _sink(param):
     return g, cb
 
 
-def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None):
+def _drop_offsets(w, bits):
+    """CUDA-core kernels take no offset mask: zero the kernels of the dropped offsets instead."""
+    keep = torch.tensor([(int(bits) >> k) & 1 for k in range(w.shape[0])], dtype=w.dtype, device=w.device)
+    return w * keep.view(-1, 1, 1)
+
+
+def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None):
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
-    mask = km.mask if precision != L.PREC_FP32 else None
+    mask = km.masked(offset_bits) if precision != L.PREC_FP32 else None
+    if offset_bits is not None and not _tensor_core(0, K, c_in, c_out, precision):
+        w, w_owner = _drop_offsets(w, offset_bits), None
     e0 = _profiler.begin() if _profiler else None
     if _tensor_core(0, K, c_in, c_out, precision):
         wp = _packed_weights(w, False, precision, w_owner)
@@ -609,11 +676,13 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None):
     return out
 
 
-def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None):
+def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None):
     lib = L.load()
     K, c_in, c_out = w.shape
     din = _empty((km.m_in, c_in), torch.float32, g.device)
-    mask_t = km.mask_t if precision != L.PREC_FP32 else None
+    mask_t = km.masked(offset_bits, transposed=True) if precision != L.PREC_FP32 else None
+    if offset_bits is not None and not _tensor_core(1, K, c_in, c_out, precision):
+        w, w_owner = _drop_offsets(w, offset_bits), None
     nbr_t = km.nbr_t
     e0 = _profiler.begin() if _profiler else None
     if _tensor_core(1, K, c_in, c_out, precision):
@@ -632,11 +701,12 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None):
     return din
 
 
-def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision, add_into: Optional[torch.Tensor] = None):
+def conv_wgrad_raw(x, g, km: KernelMap, K, c_in, c_out, precision, add_into: Optional[torch.Tensor] = None,
+                   offset_bits: Optional[int] = None):
     """dW [K, c_in, c_out]; `add_into` (a dense fp32 buffer of that many elements, tensor-core shapes only): the
     gradient is ADDED to it (spc_conv_wgrad_acc) and it is returned."""
     lib = L.load()
-    mask = km.mask if precision != L.PREC_FP32 else None
+    mask = km.masked(offset_bits) if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
     if add_into is not None:
         dw = add_into
@@ -656,8 +726,9 @@ class SparseConvFn(torch.autograd.Function):
     """out[o] = sum_k x[nbr[k,o]] @ W[k] (+bias); backward = dgrad / wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, km, precision, w_param=None):
-        """`w_param`: the Parameter `w` is (a view of), for the gradient sink (see register_grad_sink)."""
+    def forward(ctx, x, w, bias, km, precision, w_param=None, offset_bits=None):
+        """`w_param`: the Parameter `w` is (a view of), for the gradient sink (see register_grad_sink).
+        `offset_bits`: bit k set = kernel offset k takes part (weight-sparse inference convolution); None = all."""
         x = _feat(x)
         w3 = w.contiguous()
         if x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
@@ -684,7 +755,8 @@ class SparseConvFn(torch.autograd.Function):
             x = to_bf16(x, pad_to=c_in + pad_in)
         own = w_param if (w_param is not None and not pad_in and not pad_out
                           and w_param.data_ptr() == w3.data_ptr() and w_param.numel() == w3.numel()) else None
-        out = conv_fwd_raw(x, w3, b, km, precision, own)
+        out = conv_fwd_raw(x, w3, b, km, precision, own, offset_bits)
+        ctx.offset_bits = offset_bits
         if pad_out:
             out = out[:, :c_out].contiguous()
         ctx.save_for_backward(x, w3)
@@ -711,20 +783,22 @@ class SparseConvFn(torch.autograd.Function):
             if pad_out:
                 g = torch.nn.functional.pad(g, (0, pad_out))
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(g, w3, km, prec, ctx.w_param)
+            dx = conv_dgrad_raw(g, w3, km, prec, ctx.w_param, ctx.offset_bits)
             if pad_in:
                 dx = dx[:, :c_in].contiguous()
         if ctx.needs_input_grad[1]:
             K, ci, co = w3.shape
-            sink = _sink(ctx.w_param) if _tensor_core(2, K, ci, co, prec) else None
+            sink = _sink(ctx.w_param) if (_tensor_core(2, K, ci, co, prec) and ctx.offset_bits is None) else None
             if sink is not None and sink[0].numel() == K * ci * co:
                 conv_wgrad_raw(x, g, km, K, ci, co, prec, add_into=sink[0])   # straight into the gradient arena
                 sink[1](ctx.w_param)
             else:
-                dw = conv_wgrad_raw(x, g, km, K, ci, co, prec)
+                dw = conv_wgrad_raw(x, g, km, K, ci, co, prec, offset_bits=ctx.offset_bits)
+                if ctx.offset_bits is not None and not _tensor_core(2, K, ci, co, prec):
+                    dw = _drop_offsets(dw, ctx.offset_bits)
                 if pad_in or pad_out:
                     dw = dw[:, :c_in, :c_out].contiguous()
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 # ---------------------------------------------------------------------------
@@ -1308,3 +1382,5 @@ def sgd_step(param, grad, buf, lr, momentum, weight_decay, grad_scale, first_ste
     invalidate_packed_weights()  # the kernel rewrites every parameter through a raw pointer
     L.check(lib.spc_sgd_step(L.ptr(param), L.ptr(grad), L.ptr(buf), param.numel(), float(lr), float(momentum),
                              float(weight_decay), float(grad_scale), int(first_step), L.stream()), "spc_sgd_step")
+    if batch_repack and param.is_cuda:
+        repack_all()   # every layer's packed weight images, one launch

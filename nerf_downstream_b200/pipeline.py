@@ -16,9 +16,12 @@ from . import lib as L
 
 
 def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float, reso: Sequence[int],
-                    batch_index: int = 0, affine: Optional[Sequence[float]] = None):
+                    batch_index: int = 0, affine: Optional[Sequence[float]] = None,
+                    out_coords: Optional[torch.Tensor] = None, out_feats: Optional[torch.Tensor] = None):
     """links [n] int32/int64 (flat cell indices), sh_u8 [n, C] uint8 -> coords [n,4] float32 (b,i,j,k), feats [n,C]
-    float32 = sh * scale + min.  `affine` = 12 floats (row-major 3x3, then translation) applied to (i,j,k)."""
+    float32 = sh * scale + min.  `affine` = 12 floats (row-major 3x3, then translation) applied to (i,j,k).
+    `out_coords` / `out_feats`: contiguous [n,4] / [n,C] float32 destinations (e.g. one scene's rows of a batch
+    buffer: the records of a batch decode straight into the collated tensors, no torch.cat)."""
     lib = L.load()
     if links.dtype not in (torch.int32, torch.int64) or links.dim() != 1:
         raise RuntimeError("links must be a 1-D int32 / int64 tensor")
@@ -27,8 +30,10 @@ def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, s
     links, sh_u8 = links.contiguous(), sh_u8.contiguous()
     n, C = sh_u8.shape
     dev = links.device
-    coords = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    feats = torch.empty((n, C), dtype=torch.float32, device=dev)
+    coords = out_coords if out_coords is not None else torch.empty((n, 4), dtype=torch.float32, device=dev)
+    feats = out_feats if out_feats is not None else torch.empty((n, C), dtype=torch.float32, device=dev)
+    if coords.shape != (n, 4) or feats.shape != (n, C) or coords.dtype != torch.float32 or feats.dtype != torch.float32:
+        raise RuntimeError("decode destinations must be float32 [n,4] / [n,C]")
     r = (ctypes.c_int32 * 3)(*[int(v) for v in reso])
     aff = None
     if affine is not None:

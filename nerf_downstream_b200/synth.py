@@ -85,6 +85,33 @@ def room_batch(seed: int, n_scenes: int, target_voxels: int, channels: int = 27,
     return np.concatenate(cs), np.concatenate(fs), np.concatenate(ls)
 
 
+def compact_records(coords: np.ndarray, feats: np.ndarray, labels: np.ndarray, ignore_label: int = 255):
+    """The batch as PeRFception stores it on disk (co3d.py:126-172): per scene int32 `links` (flat cell index of a
+    bounding grid, raster order), uint8 SH codes (`feats = u8 * 2/255 - 1` inverted exactly) and uint8 labels —
+    32 bytes per voxel instead of the 132 of float coordinates + float features + int64 labels.  Decoding with
+    `pipeline.plenoxel_decode(..., affine = identity + 0.5)` gives back coordinates inside the same voxels and
+    bit-identical features.  Returns [(batch_index, links, sh_u8, labels_u8, reso), ...]."""
+    out = []
+    b_col = coords[:, 0].astype(np.int64)
+    for b in np.unique(b_col):
+        sel = b_col == b
+        ijk = np.floor(coords[sel, 1:]).astype(np.int64)
+        if ijk.min() < 0:
+            raise ValueError("compact_records expects non-negative lattice coordinates")
+        reso = tuple(int(v) + 1 for v in ijk.max(0))
+        links = (ijk[:, 0] * reso[1] + ijk[:, 1]) * reso[2] + ijk[:, 2]
+        if links.max() >= 2 ** 31:
+            raise ValueError("grid too large for int32 links")
+        u8 = np.rint((feats[sel].astype(np.float64) + 1.0) * 255.0 / 2.0)
+        if u8.min() < 0 or u8.max() > 255:
+            raise ValueError("features are not u8 * 2/255 - 1 codes")
+        lab = labels[sel]
+        if ((lab < 0) | (lab > 255)).any():
+            raise ValueError("labels do not fit uint8")
+        out.append((int(b), links.astype(np.int32), u8.astype(np.uint8), lab.astype(np.uint8), reso))
+    return out
+
+
 def faithful_room_batch(seed: int, n_scenes: int, target_voxels: int, scene_scale: float = 0.34, channels: int = 27,
                         num_classes: int = 20, ignore_label: int = 255, reso: int = 256, voxel_size: float = 0.02,
                         downsample_stride: int = 2) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

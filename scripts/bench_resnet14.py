@@ -22,6 +22,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--cpu", action="store_true")
+ap.add_argument("--json", default="", help="append a JSON line with the result to this file (rank 0)")
 args = ap.parse_args()
 rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
 torch.cuda.set_device(local_rank)
@@ -34,6 +35,7 @@ ops.set_default_precision(args.precision)
 torch.manual_seed(0)
 model = models.ResNet14(27, 51).to(dev).train()
 tr = trainer.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
+tr.time_exposed = world > 1   # device time the compute stream waits for gradient all-reduces after backward
 coords, feats, labels = synth.co3d_batch(777 + rank, args.batch)
 c, f, y = (torch.from_numpy(a).to(dev) for a in (coords, feats, labels))
 
@@ -61,17 +63,37 @@ for _ in range(args.steps):
     step()
 e1.record()
 barrier()
-stats = torch.tensor([e0.elapsed_time(e1) / args.steps, float(vox)], device=dev, dtype=torch.float64)
+exposed = tr.exposed_allreduce_ms()[-args.steps:] if world > 1 else []
+exposed_ms = sum(exposed) / max(len(exposed), 1)
+stats = torch.tensor([e0.elapsed_time(e1) / args.steps, float(vox), exposed_ms, float(vox), float(vox)], device=dev,
+                     dtype=torch.float64)
 if world > 1:
     t = stats[:1].clone()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)            # time = the slowest rank
-    v = stats[1:].clone()
+    v = stats[1:2].clone()
     dist.all_reduce(v, op=dist.ReduceOp.SUM)            # voxels of the whole job
-    stats = torch.cat([t, v])
-ms, vox = float(stats[0]), int(stats[1])
+    ex = stats[2:3].clone()
+    dist.all_reduce(ex, op=dist.ReduceOp.MAX)           # exposed all-reduce: the worst rank
+    vmax, vmin = stats[3:4].clone(), stats[4:5].clone()
+    dist.all_reduce(vmax, op=dist.ReduceOp.MAX)         # per-rank voxel imbalance (ranks draw different objects)
+    dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+    stats = torch.cat([t, v, ex, vmax, vmin])
+ms, vox, exposed_ms, vmax, vmin = float(stats[0]), int(stats[1]), float(stats[2]), int(stats[3]), int(stats[4])
 if rank == 0:
+    imb = vmax / (vox / world)
     print(f"ResNet14 fwd+bwd+SGD  {world} GPU(s)  B={args.batch}/GPU  {vox} voxels/step  {args.precision}: {ms:.3f} ms/step  "
-          f"{vox / ms / 1e3:.2f} M voxels/s  {world * args.batch / ms * 1e3:.0f} objects/s", flush=True)
+          f"{vox / ms / 1e3:.2f} M voxels/s  {world * args.batch / ms * 1e3:.0f} objects/s  "
+          f"exposed all-reduce {exposed_ms:.3f} ms/step (max over ranks)  voxels per rank min {vmin} max {vmax} "
+          f"(max / mean = {imb:.3f})", flush=True)
+    if args.json:
+        import json
+        with open(args.json, "a") as fh:
+            fh.write(json.dumps({"config": "BASELINE configs[2]: ResNet14(27->51) data parallel, weak scaling",
+                                 "n_gpus": world, "batch_per_gpu": args.batch, "precision": args.precision,
+                                 "voxels_per_step": vox, "ms_per_step": ms, "voxels_per_s": vox / ms * 1e3,
+                                 "objects_per_s": world * args.batch / ms * 1e3, "exposed_allreduce_ms_per_step": exposed_ms,
+                                 "voxels_per_rank_min": vmin, "voxels_per_rank_max": vmax,
+                                 "imbalance_max_over_mean": imb, "gradient_bytes": 4 * tr.arena.numel}) + "\n")
 if world > 1:
     dist.destroy_process_group()
 if args.cpu and rank == 0:

@@ -173,6 +173,11 @@ class FakeLib:
         tc[:] = (res >= 0).sum(1)
         return 0
 
+    def spc_kernel_map_sym(self, slots, n_slots, coords, m, offsets, K, nbr, tap_count, stream):
+        offs = view(offsets, (K, 3), np.int32)
+        assert K % 2 == 1 and (offs == -offs[::-1]).all(), "offsets are not centrally symmetric"
+        return self.spc_kernel_map(slots, n_slots, coords, m, offsets, K, nbr, tap_count, stream)
+
     def spc_kernel_map_transpose(self, nbr, m_out, m_in, K, nbr_t, stream):
         self._called("spc_kernel_map_transpose")
         view(nbr_t, (K, m_in), np.int32)[:] = R.transpose_dense(view(nbr, (K, m_out), np.int32), m_in)
@@ -252,11 +257,25 @@ class FakeLib:
         d[:, :c_src] = f32_to_bf16(rows_view(src, rows, c_src, src_pitch))
         return 0
 
+    @staticmethod
+    def _apply_tile_mask(a, mask, m, K):
+        """The tensor-core kernels skip offset k for a 128-row tile whose mask bit k is clear (spc_tile_mask, or a
+        mask restricted to the offsets of a weight-sparse convolution)."""
+        if not _addr(mask) or K > 32 or m == 0:
+            return a
+        tm = view(mask, ((m + 127) // 128,), np.int32).astype(np.int64) & 0xFFFFFFFF
+        rows_tile = np.arange(m) // 128
+        a = a.copy()
+        for k in range(K):
+            a[k, ((tm[rows_tile] >> k) & 1) == 0] = -1
+        return a
+
     def spc_conv_fwd(self, x, w, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, ws, ws_bytes, stream):
         self._called("spc_conv_fwd")
         xin = feat_rows(x, m_in, c_in, precision).astype(np.float64)
         W = view(w, (K, c_in, c_out), np.float32).astype(np.float64)
         a = view(nbr, (K, m_out), np.int32)
+        a = self._apply_tile_mask(a, mask, m_out, K)
         acc = np.zeros((m_out, c_out), np.float64)
         for k in range(K):
             o = np.nonzero(a[k] >= 0)[0]
@@ -272,6 +291,7 @@ class FakeLib:
         g = feat_rows(dout, m_out, c_out, precision).astype(np.float64)
         W = view(w, (K, c_in, c_out), np.float32).astype(np.float64)
         a = view(nbr_t, (K, m_in), np.int32)
+        a = self._apply_tile_mask(a, mask_t, m_in, K)
         acc = np.zeros((m_in, c_in), np.float64)
         for k in range(K):
             i = np.nonzero(a[k] >= 0)[0]
@@ -328,6 +348,14 @@ class FakeLib:
         self._called("spc_conv_pack_weights")
         assert _addr(packed) % 1024 == 0
         view(packed, (K, c_in, c_out), np.float32)[:] = view(w, (K, c_in, c_out), np.float32)
+        return 0
+
+    def spc_conv_pack_weights_batch(self, desc, n_layers, stream):
+        self._called("spc_conv_pack_weights_batch")
+        d = view(desc, (n_layers, 8), np.int64)
+        for w, packed, K, ck, cn, transpose, bf16, _ in d.tolist():
+            c_in, c_out = (cn, ck) if transpose else (ck, cn)
+            view(packed, (K, c_in, c_out), np.float32)[:] = view(w, (K, c_in, c_out), np.float32)
         return 0
 
     def spc_conv_fwd_packed(self, x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, stream):
