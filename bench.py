@@ -110,7 +110,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: oracle port of ME's CPU algorithm (gather -> sgemm -> scatter, OpenMP kernel maps)
 # ---------------------------------------------------------------------------
-def cpu_step_fn(voxels: int, seed: int = 777):
+def cpu_step_fn(voxels: int, seed: int = 777, forward_only: bool = False):
     import numpy as np
     import torch
     from nerf_downstream_b200 import models, synth
@@ -125,12 +125,16 @@ def cpu_step_fn(voxels: int, seed: int = 777):
     y = torch.from_numpy(labels)
 
     def step():
+        if forward_only:   # the full 1 M-voxel scene on the CPU is timed forward-only (labelled)
+            with torch.no_grad():
+                logits = nets.resunet_forward(params, coords, f, use_c=True)
+                return float(torch.nn.functional.cross_entropy(logits, y, ignore_index=255))
         for p in params.values():
             p.grad = None
         logits = nets.resunet_forward(params, coords, f, use_c=True)
         loss = torch.nn.functional.cross_entropy(logits, y, ignore_index=255)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step, coords.shape[0]
 
@@ -161,7 +165,7 @@ def run_reference(args):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     voxels = args.cpu_voxels
-    step, n = cpu_step_fn(voxels)
+    step, n = cpu_step_fn(voxels, forward_only=args.cpu_forward_only)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -169,14 +173,19 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = (f"each step = Res16UNet34C(27,20) fwd+bwd on one {n}-voxel synthetic room (bounded sample of the "
-              f"{args.voxels}-voxel workload), fp32, oracle port of ME's CPU algorithm (ME not installable)")
+    what = "FORWARD ONLY (fwd+bwd is ~3x; SURVEY 8d prescribes forward-only x3 for the full scene)" if args.cpu_forward_only \
+        else "fwd+bwd"
+    same = n >= 0.95 * args.voxels
+    sample = (f"each step = Res16UNet34C(27,20) {what} on one {n}-voxel synthetic room "
+              + ("(the workload's own scene size)" if same else f"(bounded sample of the {args.voxels}-voxel workload)")
+              + ", fp32, oracle port of ME's CPU algorithm (ME not installable)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"MinkUNet34C (Res16UNet34C 27->20) fwd+bwd, synthetic ScanNet-shaped plenoxel "
                                    f"scenes, {args.voxels} voxels/scene, {args.scenes} scene(s)/GPU",
-                       "sample_voxels": n},
+                       "sample_voxels": n, "same_config": bool(same and not args.cpu_forward_only),
+                       "same_scene_size": bool(same), "forward_only": bool(args.cpu_forward_only)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -505,6 +514,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["tf32", "bf16", "fp32"],
                     help="conv operand precision: bf16 (default; fp32 accumulate), tf32, or fp32 CUDA cores")
     ap.add_argument("--cpu-voxels", type=int, default=20_000, help="scene size of the bounded CPU sample")
+    ap.add_argument("--cpu-forward-only", action="store_true",
+                    help="--impl reference: time the forward pass only (with --cpu-voxels 1000000: the workload's own "
+                         "scene size on the CPU, SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-input", default="compact", choices=["compact", "float"],
                     help="what the end-to-end leg copies host -> device each step: the plenoxel records as stored on disk "

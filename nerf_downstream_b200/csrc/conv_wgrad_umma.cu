@@ -49,8 +49,9 @@ struct UmmaWgradParams {
   const void* in;             // [m_in, Cin] fp32 or bf16
   const int* nbr;             // [K, m_out]
   const uint32_t* tile_mask;  // [ceil(m_out/128)] or null
-  float* dw;                  // [K, Cin, Cout], zeroed (or holding the gradient to accumulate onto)
-  int m_out, Cin, Cout, K;
+  float* dw;                  // [K, Cin, dw_pitch] (+ column offset applied), zeroed (or holding the gradient to add to)
+  int m_out, Cin, Cout, K;    // Cout = width of THIS launch's column group (<= 256)
+  int dw_pitch, col0;         // full output-channel count / first column of the group (dout tile loads start there)
   int ncc, nq;                // chunks per offset, total chunks
   int n_mb, n_pass;
   int n_rb, rb_per_split, n_split;
@@ -244,7 +245,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
           mbar_wait(b_empty(bs), ((b_phase >> bs) & 1u) ^ 1u);
           mbar_arrive_expect_tx(b_full(bs), (uint32_t)b_stage_bytes);
           for (int cbk = 0; cbk < p.Cout / 32; ++cbk)
-            tma_load_2d(dstb + cbk * kWgChunkBlock, &tmap_dout, b_full(bs), cbk * 32, (rb0 + rbi) * kRows);
+            tma_load_2d(dstb + cbk * kWgChunkBlock, &tmap_dout, b_full(bs), p.col0 + cbk * 32, (rb0 + rbi) * kRows);
           b_phase ^= 1u << bs;
           bs ^= 1;
         }
@@ -314,7 +315,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
         const int q = (mb0 + i) * 4 + ew;
         if (q >= p.nq) continue;  // padding chunk of the last M block (warp-uniform)
         const int k = q / p.ncc, cc = q - k * p.ncc;
-        float* dst = p.dw + ((size_t)k * p.Cin + cc * 32 + lane) * p.Cout;
+        float* dst = p.dw + ((size_t)k * p.Cin + cc * 32 + lane) * p.dw_pitch + p.col0;
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(i * p.Cout);
         for (int c0 = 0; c0 < p.Cout; c0 += 16) {
           float v[16];
@@ -343,7 +344,8 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
 }
 
 bool umma_wgrad_supported(int c_in, int c_out) {
-  return c_in >= 32 && c_in % 32 == 0 && c_out >= 32 && c_out % 32 == 0 && c_out <= 256;
+  // (more than 256 output channels: column groups of <= 256, one launch each — ResNet14's 256->512 / 512->512)
+  return c_in >= 32 && c_in % 32 == 0 && c_out >= 32 && c_out % 32 == 0 && c_out <= 1024;
 }
 int64_t umma_wgrad_workspace(int, int, int) { return 256; }
 
@@ -362,6 +364,9 @@ static int launch_wgrad_umma(const UmmaWgradParams& p, const CUtensorMap& tmap, 
 }
 
 extern std::atomic<long long> g_conv_path_counts[4];
+int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
+                         int64_t m_out, int c_in, int c_out_full, int col0, int c_grp, int K, bool bf16, float* dw,
+                         cudaStream_t stream);
 
 // dw: [K, Cin, Cout] fp32.  zero_dw: clear it first (plain gradient); otherwise the partial sums are ADDED to what
 // it holds (the trainer's gradient arena, zeroed once per step: no separate accumulation pass).
@@ -374,10 +379,29 @@ int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint
               "rows must be 16-byte aligned");
   if (zero_dw) SPC_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * c_in * c_out * sizeof(float), stream));
   if (m_out == 0) return 0;
+  if (c_out > 256) {  // column groups: the widest multiple of 32 <= 256 that divides c_out evenly enough
+    int groups = (c_out + 255) / 256;
+    while (c_out % groups || (c_out / groups) % 32) ++groups;
+    const int cg = c_out / groups;
+    for (int g = 0; g < groups; ++g) {
+      int rc = conv_wgrad_umma_cols(in, dout, nbr, tile_mask, m_out, c_in, c_out, g * cg, cg, K, bf16, dw, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  return conv_wgrad_umma_cols(in, dout, nbr, tile_mask, m_out, c_in, c_out, 0, c_out, K, bf16, dw, stream);
+}
+
+// one column group [col0, col0 + c_grp) of the c_out_full output channels
+int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
+                         int64_t m_out, int c_in, int c_out_full, int col0, int c_grp, int K, bool bf16, float* dw,
+                         cudaStream_t stream) {
+  const int c_out = c_grp;
   const int rows = bf16 ? 128 : 64;  // out rows per pipeline step
   UmmaWgradParams p;
   p.in = in; p.nbr = nbr; p.tile_mask = tile_mask; p.dw = dw;
   p.m_out = (int)m_out; p.Cin = c_in; p.Cout = c_out; p.K = K;
+  p.dw_pitch = c_out_full; p.col0 = col0;
   p.ncc = c_in / 32;
   p.nq = K * p.ncc;
   p.n_mb = (p.nq + 3) / 4;
@@ -404,7 +428,7 @@ int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  SPC_REQUIRE(make_rows_tile_map(&tmap, dout, m_out, c_out, rows, bf16), "cuTensorMapEncodeTiled unavailable");
+  SPC_REQUIRE(make_rows_tile_map(&tmap, dout, m_out, c_out_full, rows, bf16), "cuTensorMapEncodeTiled unavailable");
   g_conv_path_counts[bf16 ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
   // row-visit mode: bf16 rows are 64 B per chunk, so visits of 2 / 3 / 4 chunks touch fewer 128-byte lines;
   // tf32 chunks are whole lines already

@@ -739,9 +739,9 @@ class SparseConvFn(torch.autograd.Function):
         # odd widths (27 SH channels, 20 classes) instead of dropping to the CUDA-core kernels.
         pad_in = pad_out = 0
         big = max(km.m_in, km.m_out) >= 4096
-        if precision == L.PREC_BF16 and (K > 32 or c_out > 256 or K * (c_in + (-c_in) % 32) > 128 * 128
+        if precision == L.PREC_BF16 and (K > 32 or c_out > 1024 or K * (c_in + (-c_in) % 32) > 128 * 128
                                          or (not big and (c_in % 32 or c_out % 32))):
-            precision = L.PREC_TF32  # shapes the bf16 kernels are not built for
+            precision = L.PREC_TF32  # shapes the bf16 kernels are not built for (bench.py reports the routes taken)
         if precision != L.PREC_FP32 and K <= 32 and big:
             pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
         if pad_in and precision != L.PREC_BF16:

@@ -335,7 +335,7 @@ class FakeLib:
             return int(fwd_ok(c_in, c_out))
         if what == 1:
             return int(fwd_ok(c_out, c_in))
-        return int(K * c_in <= 128 * 128 and c_in >= 32 and c_in % 32 == 0 and 32 <= c_out <= 256 and c_out % 32 == 0)
+        return int(K * c_in <= 128 * 128 and c_in >= 32 and c_in % 32 == 0 and 32 <= c_out <= 1024 and c_out % 32 == 0)
 
     def spc_conv_packed_bytes(self, K, c_in, c_out):
         return (K * c_in * c_out * 4 + 1023) // 1024 * 1024

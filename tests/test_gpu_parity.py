@@ -247,7 +247,8 @@ def test_conv_tf32_tensor_core(cuda_device, ks, stride, cin, cout, transpose, fo
 BF16_TOL = 3e-3   # tensor-core modes within 3e-3 * max|ref| per layer (measured 2.2e-3 .. 2.7e-3)
 BF16_CONV_CASES = [((3, 3, 3), 1, 32, 32, False), ((3, 3, 3), 1, 64, 96, False), ((3, 3, 3), 1, 128, 96, False),
                    ((3, 3, 3), 1, 96, 96, False), ((3, 3, 3), 1, 256, 256, False), ((3, 3, 3), 2, 64, 128, False),
-                   ((2, 2, 2), 2, 96, 96, False), ((2, 2, 2), 2, 256, 128, True), ((1, 1, 1), 2, 128, 256, False)]
+                   ((2, 2, 2), 2, 96, 96, False), ((2, 2, 2), 2, 256, 128, True), ((1, 1, 1), 2, 128, 256, False),
+                   ((3, 3, 3), 2, 256, 512, False), ((3, 3, 3), 1, 512, 512, False)]   # wgrad in two column groups
 
 
 @pytest.mark.parametrize("ks,stride,cin,cout,transpose", BF16_CONV_CASES)
