@@ -624,7 +624,11 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
 
   UmmaConvParams p;
   p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
+#ifdef SPC_EXPERIMENTS
   p.dbg_skip_store = g_umma_dbg[3];
+#else
+  p.dbg_skip_store = 0;   // (timing experiment, compiled out of the shipped library)
+#endif
   p.m_out = (int)m_out; p.Ck = c_in; p.Cn = c_out; p.K = K;
   p.kc_count = c_in / 32;
   // Chunks per stage: one row visit brings G x 64 contiguous bytes (bf16).  128-byte-aligned pairs when the row
