@@ -190,14 +190,17 @@ int spc_conv_wgrad_acc(const void* in, const void* dout, const int32_t* nbr, con
                        void* stream);
 /* Weights in the tensor-core kernels' shared-memory image ([K][C/32][C'][32] swizzled rows, independent of the
  * tile shape), so that a layer packs ONCE per optimiser step instead of once per launch: `dgrad` = 0 packs W for
- * spc_conv_fwd_packed, 1 packs W^T for spc_conv_dgrad_packed.  `packed`: spc_conv_packed_bytes() bytes,
- * 1024-byte aligned.  precision: SPC_PREC_TF32 or SPC_PREC_BF16; shapes: spc_conv_tensor_core(0 / 1, ...). */
+ * spc_conv_fwd_packed, 1 packs W^T for spc_conv_dgrad_packed, 2 packs W^T with the kernel offsets REVERSED (slab k =
+ * W[K-1-k]^T): on a centrally symmetric self map (odd kernel, stride 1, spc_kernel_map_sym) nbr_t[k] == nbr[K-1-k],
+ * so spc_conv_dgrad_packed is then called with the FORWARD map and tile mask and no transposed map is ever built.
+ * `packed`: spc_conv_packed_bytes() bytes, 1024-byte aligned.  precision: SPC_PREC_TF32 or SPC_PREC_BF16; shapes: spc_conv_tensor_core(0 / 1, ...). */
 int64_t spc_conv_packed_bytes(int K, int c_in, int c_out);
 int spc_conv_pack_weights(const float* w, int K, int c_in, int c_out, int dgrad, int precision, void* packed,
                           void* stream);
 /* spc_conv_pack_weights for n_layers (layer, direction) pairs in ONE launch.  desc_dev: DEVICE int64 [n_layers][8] =
- * { w (fp32 [K, c_in, c_out]), packed (1024-byte aligned), K, Ck, Cn, transpose, bf16, 0 } with (Ck, Cn, transpose) =
- * (c_in, c_out, 0) for the forward image and (c_out, c_in, 1) for the dgrad image. */
+ * { w (fp32 [K, c_in, c_out]), packed (1024-byte aligned), K, Ck, Cn, flags, bf16, 0 } with (Ck, Cn, flags) =
+ * (c_in, c_out, 0) for the forward image, (c_out, c_in, 1) for the dgrad image and (c_out, c_in, 3) for the dgrad
+ * image with reversed offsets. */
 int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* stream);
 int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
                         const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
@@ -228,7 +231,8 @@ int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* va
                     float* running_var, float momentum, void* stream);
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,
-                 int relu, float* y, void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);
+                 int relu, float* y /* NULL: only the bf16 copy is produced */,
+                 void* y_bf16 /* optional bf16 copy of y, or NULL */, void* stream);
 int spc_bn_bwd(const float* x, const float* y, const void* y_bf16 /* ReLU mask from the bf16 copy of y instead of y, or NULL */,
                const float* dy, int64_t dy_pitch /* elements between rows of dy (>= C; a column slice is read in place) */,
                const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
@@ -237,11 +241,20 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16 /* ReLU mask f
                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* spc_bn_bwd whose dgamma / dbeta (either may be NULL) are ADDED to what the buffers hold when
- * accumulate_param_grads != 0 (slices of a gradient arena that is zeroed once per step). */
+ * accumulate_param_grads != 0 (slices of a gradient arena that is zeroed once per step).
+ *   relu = 2 : the ReLU mask is RE-COMPUTED from x with the forward affine (gamma, beta, mean, var: y > 0 <=>
+ *              fma(x, sc, sh) > 0, the expression spc_bn_apply evaluates) — valid when no residual was added before
+ *              the ReLU; y / y_bf16 are then not read at all.  relu = 1 reads y (or y_bf16) as spc_bn_bwd does.
+ *   dx may be NULL when dx_bf16 is given (the consumer is a bf16 convolution's dgrad / wgrad only). */
 int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const float* dy, int64_t dy_pitch,
-                   const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
-                   int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
+                   const float* mean, const float* var, const float* gamma, const float* beta, int64_t m, int C,
+                   float eps, int relu, int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                    int accumulate_param_grads, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* dst[r, 0:row_bytes) = src[r, 0:row_bytes) for pitched rows (pitches in BYTES): ME.cat (res16unet.py:410-425) of the
+ * bf16 operand copies straight into column slices of the concatenated operand. */
+int spc_copy_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t row_bytes, int64_t rows,
+                  void* stream);
 
 /* y = relu(x) ; dx = dy * (y > 0) ; y = a + b  (MinkowskiReLU, SparseTensor +=). */
 int spc_relu_fwd(const float* x, int64_t n, float* y, void* stream);

@@ -15,7 +15,7 @@ int conv_wgrad_simt(const float* in, const float* dout, const int* nbr, int64_t 
 bool umma_fwd_supported(int c_in, int c_out);
 int64_t umma_fwd_workspace(int K, int c_in, int c_out);
 int64_t umma_packed_bytes(int K, int c_in, int c_out);
-int conv_pack_weights(const float* w, int K, int Ck, int Cn, bool transpose, bool bf16, void* packed,
+int conv_pack_weights(const float* w, int K, int Ck, int Cn, int flags, bool bf16, void* packed,
                       cudaStream_t stream);
 int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_t stream);
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
@@ -69,9 +69,11 @@ int spc_conv_pack_weights(const float* w, int K, int c_in, int c_out, int dgrad,
                           void* stream) {
   SPC_REQUIRE(precision == SPC_PREC_TF32 || precision == SPC_PREC_BF16, "packed weights are a tensor-core format");
   SPC_REQUIRE(dgrad ? tc_fwd_ok(K, c_out, c_in) : tc_fwd_ok(K, c_in, c_out), "shape not supported by the tcgen05 path");
-  // forward contracts over Cin (rows of W[k]); dgrad contracts over Cout with W[k]^T
-  return dgrad ? conv_pack_weights(w, K, c_out, c_in, true, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream)
-               : conv_pack_weights(w, K, c_in, c_out, false, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream);
+  SPC_REQUIRE(dgrad >= 0 && dgrad <= 2, "dgrad: 0 forward image, 1 W^T, 2 W^T with the offsets reversed");
+  // forward contracts over Cin (rows of W[k]); dgrad contracts over Cout with W[k]^T; dgrad == 2 additionally stores
+  // W[K-1-k]^T in slab k: the dgrad of a centrally symmetric self map then reads the FORWARD map (nbr_t[k] == nbr[K-1-k])
+  return dgrad ? conv_pack_weights(w, K, c_out, c_in, dgrad == 2 ? 3 : 1, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream)
+               : conv_pack_weights(w, K, c_in, c_out, 0, precision == SPC_PREC_BF16, packed, (cudaStream_t)stream);
 }
 
 int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* stream) {

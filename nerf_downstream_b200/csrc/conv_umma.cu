@@ -78,7 +78,10 @@ int64_t umma_fwd_workspace(int K, int c_in, int c_out) { return umma_packed_byte
 // optimiser step for every launch that uses them.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, int Ck, int Cn, int transpose) {
+pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, int Ck, int Cn, int flags) {
+  // flags: bit 0 = W is [K][Cn][Ck] (dgrad contracts over Cout with W^T); bit 1 = slab k holds W[K-1-k]: on a centrally
+  // symmetric self map nbr_t[k] == nbr[K-1-k], so dgrad reads the forward map with the offsets reversed
+  const int transpose = flags & 1, reverse = flags & 2;
   const long long total = (long long)K * Ck * Cn;
   const int kc_count = Ck / 32;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -89,7 +92,8 @@ pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, 
     int kc = (int)(t % kc_count);
     int k = (int)(t / kc_count);
     int c = kc * 32 + jj;
-    float v = transpose ? W[((long long)k * Cn + n) * Ck + c] : W[((long long)k * Ck + c) * Cn + n];
+    const int ks = reverse ? K - 1 - k : k;
+    float v = transpose ? W[((long long)ks * Cn + n) * Ck + c] : W[((long long)ks * Ck + c) * Cn + n];
     long long row = ((long long)k * kc_count + kc) * Cn + n;
     if (BF16) {
       int j = jj >> 3, w = jj & 7;  // 8 bf16 per 16-byte piece
@@ -102,13 +106,13 @@ pack_weights_kernel(const float* __restrict__ W, void* __restrict__ Wp_, int K, 
 }
 
 // One launch for every layer of a network (blockIdx.y = layer): the descriptors live in device memory
-// ([n][8] int64: w, packed, K, Ck, Cn, transpose, bf16, unused) and are rebuilt only when the set of layers changes.
+// ([n][8] int64: w, packed, K, Ck, Cn, flags (bit 0 transpose, bit 1 reversed offsets), bf16, unused) and are rebuilt only when the set of layers changes.
 __global__ void __launch_bounds__(256)
 pack_weights_batch_kernel(const long long* __restrict__ desc) {
   const long long* d = desc + (size_t)blockIdx.y * 8;
   const float* W = reinterpret_cast<const float*>(d[0]);
   void* Wp_ = reinterpret_cast<void*>(d[1]);
-  const int K = (int)d[2], Ck = (int)d[3], Cn = (int)d[4], transpose = (int)d[5], bf16 = (int)d[6];
+  const int K = (int)d[2], Ck = (int)d[3], Cn = (int)d[4], transpose = (int)d[5] & 1, reverse = (int)d[5] & 2, bf16 = (int)d[6];
   const long long total = (long long)K * Ck * Cn;
   const int kc_count = Ck / 32;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -119,7 +123,8 @@ pack_weights_batch_kernel(const long long* __restrict__ desc) {
     int kc = (int)(t % kc_count);
     int k = (int)(t / kc_count);
     int c = kc * 32 + jj;
-    float v = transpose ? W[((long long)k * Cn + n) * Ck + c] : W[((long long)k * Ck + c) * Cn + n];
+    const int ks = reverse ? K - 1 - k : k;
+    float v = transpose ? W[((long long)ks * Cn + n) * Ck + c] : W[((long long)ks * Ck + c) * Cn + n];
     long long row = ((long long)k * kc_count + kc) * Cn + n;
     if (bf16) {
       int j = jj >> 3, w = jj & 7;
@@ -140,13 +145,13 @@ int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_
   return 0;
 }
 
-int conv_pack_weights(const float* w, int K, int Ck, int Cn, bool transpose, bool bf16, void* packed,
+int conv_pack_weights(const float* w, int K, int Ck, int Cn, int flags, bool bf16, void* packed,
                       cudaStream_t stream) {
   SPC_REQUIRE(((uintptr_t)packed % 1024) == 0, "packed weights must be 1024-byte aligned");
   long long total = (long long)K * Ck * Cn;
   int grid = (int)std::min<long long>(ceil_div(total, 256), kNumSMs * 8);
-  if (bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(w, packed, K, Ck, Cn, transpose ? 1 : 0);
-  else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(w, packed, K, Ck, Cn, transpose ? 1 : 0);
+  if (bf16) pack_weights_kernel<true><<<grid, 256, 0, stream>>>(w, packed, K, Ck, Cn, flags);
+  else pack_weights_kernel<false><<<grid, 256, 0, stream>>>(w, packed, K, Ck, Cn, flags);
   SPC_LAUNCHED("pack_weights_kernel");
   return 0;
 }
@@ -614,7 +619,7 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   if (!Wp) {
     SPC_REQUIRE(w && workspace && workspace_bytes >= umma_fwd_workspace(K, c_in, c_out), "workspace too small");
     void* dstp = (void*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-    int rc = conv_pack_weights(w, K, c_in, c_out, transpose_w, bf16, dstp, stream);
+    int rc = conv_pack_weights(w, K, c_in, c_out, transpose_w ? 1 : 0, bf16, dstp, stream);
     if (rc) return rc;
     Wp = dstp;
   }

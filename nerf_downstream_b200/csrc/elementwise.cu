@@ -86,6 +86,15 @@ __device__ __forceinline__ Vec<VEC> load_mask_rows(const float* y, const __nv_bf
   return r;
 }
 
+// The affine form of BatchNorm as the apply kernel evaluates it: y = fma(x, sc, sh).  Backward re-evaluates exactly
+// this expression to recover the ReLU mask of a BN+ReLU WITHOUT a residual (relu mode 2: y > 0 <=> fma(x, sc, sh) > 0)
+// instead of reading the output rows again, so all three kernels share the one definition.
+__device__ __forceinline__ void bn_scale_shift(float gamma, float beta, float mean, float var, float eps, float& sc,
+                                               float& sh) {
+  sc = gamma * rsqrtf(var + eps);
+  sh = __fmaf_rn(-mean, sc, beta);
+}
+
 // ---------------------------------------------------------------------------
 // column reductions: up to two sums per channel, partials per block, double finalise
 // ---------------------------------------------------------------------------
@@ -111,7 +120,8 @@ template <int VEC, int MODE>
 __global__ void __launch_bounds__(1024)
 col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
                   const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, long long dy_pitch,
-                  const float* __restrict__ mean, long long m, int C, int lanes, int rows, int relu, ColFinal fin) {
+                  const float* __restrict__ mean, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  long long m, int C, int lanes, int rows, int relu, ColFinal fin) {
   extern __shared__ float sm[];  // [rows][2*C]
   __shared__ bool s_last;
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
@@ -120,6 +130,13 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
   // MODE 0 accumulates around a pivot (row 0) so that E[x^2] - E[x]^2 does not cancel
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s0[j] = 0.f; s1[j] = 0.f; mu[j] = MODE == 1 ? mean[c0 + j] : x[c0 + j]; }
+  float sc[VEC], sh[VEC];  // relu mode 2 (MODE 1): the forward affine, to recompute the ReLU mask from x
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sc[j] = 0.f; sh[j] = 0.f;
+    if (MODE == 1 && relu == 2)
+      bn_scale_shift(gamma ? gamma[c0 + j] : 1.f, beta ? beta[c0 + j] : 0.f, mu[j], fin.var[c0 + j], fin.eps, sc[j], sh[j]);
+  }
   // U row groups per iteration: all their loads are issued before the first use, so a thread keeps U (MODE 0) or
   // up to 3 U (MODE 1) 16-byte loads in flight instead of one per stream (r1: 0.78-0.84 of the HBM peak)
   constexpr int U = MODE == 0 ? 4 : 2;
@@ -136,7 +153,7 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
         xv[u] = Vec<VEC>::load(x + off);
         if (MODE == 1) {
           g[u] = Vec<VEC>::load(dy + ru * dy_pitch + c0);
-          if (relu) yv[u] = load_mask_rows<VEC>(y, yb, off);
+          if (relu == 1) yv[u] = load_mask_rows<VEC>(y, yb, off);
         }
       }
     }
@@ -147,9 +164,12 @@ col_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { float d = xv[u].v[j] - mu[j]; s0[j] += d; s1[j] += d * d; }
       } else {
-        if (relu) {
+        if (relu == 1) {
 #pragma unroll
           for (int j = 0; j < VEC; ++j) if (!(yv[u].v[j] > 0.f)) g[u].v[j] = 0.f;
+        } else if (relu == 2) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) if (!(fmaf(xv[u].v[j], sc[j], sh[j]) > 0.f)) g[u].v[j] = 0.f;
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { s0[j] += g[u].v[j]; s1[j] += g[u].v[j] * (xv[u].v[j] - mu[j]); }
@@ -210,9 +230,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
   float sc[VEC], sh[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    float g = gamma ? gamma[c0 + j] : 1.f, b = beta ? beta[c0 + j] : 0.f;
-    sc[j] = g * rsqrtf(var[c0 + j] + eps);
-    sh[j] = b - mean[c0 + j] * sc[j];
+    bn_scale_shift(gamma ? gamma[c0 + j] : 1.f, beta ? beta[c0 + j] : 0.f, mean[c0 + j], var[c0 + j], eps, sc[j], sh[j]);
   }
   constexpr int U = 4;  // row groups per iteration, loads first (see col_reduce_kernel)
   const long long stride = (long long)gridDim.x * rows;
@@ -243,7 +261,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 #pragma unroll
         for (int j = 0; j < VEC; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
       }
-      o.store(y + off);
+      if (y) o.store(y + off);   // (null: only the bf16 operand copy is wanted, see ops.py "hollow" rows)
       if (yb) store_bf16<VEC>(yb + off, o.v);
     }
   }
@@ -255,19 +273,22 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
                     const __nv_bfloat16* __restrict__ yb, const float* __restrict__ dy, long long dy_pitch,
                     const float* __restrict__ mean,
-                    const float* __restrict__ var, const float* __restrict__ gamma,
+                    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ sums /* [2C]: sum dy', sum dy'(x-mean) */,
                     long long m, int C, int lanes, int rows, float eps, int relu, int training,
                     float* __restrict__ dx, float* __restrict__ dres, __nv_bfloat16* __restrict__ dxb) {
   const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
   const int c0 = lane * VEC;
-  float sc[VEC], mu[VEC], k0[VEC], k1[VEC];
+  float sc[VEC], mu[VEC], k0[VEC], k1[VEC], fsc[VEC], fsh[VEC];
   const float inv_m = 1.f / (float)m;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     float istd = rsqrtf(var[c0 + j] + eps);
     sc[j] = (gamma ? gamma[c0 + j] : 1.f) * istd;
     mu[j] = mean[c0 + j];
+    fsc[j] = 0.f; fsh[j] = 0.f;
+    if (relu == 2)
+      bn_scale_shift(gamma ? gamma[c0 + j] : 1.f, beta ? beta[c0 + j] : 0.f, mu[j], var[c0 + j], eps, fsc[j], fsh[j]);
     k0[j] = training ? sums[c0 + j] * inv_m : 0.f;
     k1[j] = training ? sums[C + c0 + j] * inv_m * istd * istd : 0.f;
   }
@@ -283,7 +304,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
       if (ok[u]) {
         const long long off = ru * C + c0;
         g[u] = Vec<VEC>::load(dy + ru * dy_pitch + c0);
-        if (relu) yv[u] = load_mask_rows<VEC>(y, yb, off);
+        if (relu == 1) yv[u] = load_mask_rows<VEC>(y, yb, off);
         xv[u] = Vec<VEC>::load(x + off);
       }
     }
@@ -291,15 +312,18 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
     for (int u = 0; u < U; ++u) {
       if (!ok[u]) continue;
       const long long off = (r + u * stride) * C + c0;
-      if (relu) {
+      if (relu == 1) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) if (!(yv[u].v[j] > 0.f)) g[u].v[j] = 0.f;
+      } else if (relu == 2) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) if (!(fmaf(xv[u].v[j], fsc[j], fsh[j]) > 0.f)) g[u].v[j] = 0.f;
       }
       if (dres) g[u].store(dres + off);
       Vec<VEC> o;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o.v[j] = sc[j] * (g[u].v[j] - k0[j] - (xv[u].v[j] - mu[j]) * k1[j]);
-      o.store(dx + off);
+      if (dx) o.store(dx + off);   // (null: the only consumer is a bf16 convolution reading dxb)
       if (dxb) store_bf16<VEC>(dxb + off, o.v);
     }
   }
@@ -532,6 +556,20 @@ bn_finalize_kernel(const double* __restrict__ gsum, long long m, int C, float* _
 
 using namespace spc;
 
+// rows of `row_bytes` bytes from a pitched source to a pitched destination (channel concatenation of operand
+// copies: dst = a column slice of the wider row).  T = the widest type every pitch / pointer / width is a multiple of.
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(const char* __restrict__ src, long long src_pitch, char* __restrict__ dst, long long dst_pitch,
+                 int per_row, long long rows) {
+  const long long total = rows * per_row;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / per_row;
+    const int j = (int)(e - r * per_row);
+    reinterpret_cast<T*>(dst + r * dst_pitch)[j] = reinterpret_cast<const T*>(src + r * src_pitch)[j];
+  }
+}
+
 #define DISPATCH_VEC(vec, ...)        \
   if ((vec) == 4) { constexpr int VEC = 4; __VA_ARGS__; } \
   else { constexpr int VEC = 1; __VA_ARGS__; }
@@ -558,8 +596,8 @@ static BnWs bn_ws(void* workspace, int C) {
 }
 
 static int col_reduce_launch(int mode, const float* x, const float* y, const void* y_bf16, const float* dy,
-                             int64_t dy_pitch, const float* mean, int64_t m, int C, int relu, ColFinal fin,
-                             cudaStream_t stream) {
+                             int64_t dy_pitch, const float* mean, const float* gamma, const float* beta, int64_t m, int C,
+                             int relu, ColFinal fin, cudaStream_t stream) {
   int vec = pick_vec(C, x, y, dy);
   if (y_bf16 && ((uintptr_t)y_bf16 % 8)) vec = 1;
   if (dy && dy_pitch % 4) vec = 1;
@@ -571,8 +609,8 @@ static int col_reduce_launch(int mode, const float* x, const float* y, const voi
   if (smem > 40 * 1024) return fail("col_reduce", "shared memory");
   SPC_CUDA(cudaMemsetAsync(fin.gsum, 0, (size_t)2 * C * 8 + 64, stream));  // sums + ticket counter
   DISPATCH_VEC(vec,
-    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, m, C, rm.lanes, rm.rows, relu, fin);
-    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, m, C, rm.lanes, rm.rows, relu, fin));
+    if (mode == 0) col_reduce_kernel<VEC, 0><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, gamma, beta, m, C, rm.lanes, rm.rows, relu, fin);
+    else col_reduce_kernel<VEC, 1><<<grid, rm.threads, smem, stream>>>(x, y, yb, dy, dy_pitch, mean, gamma, beta, m, C, rm.lanes, rm.rows, relu, fin));
   SPC_LAUNCHED("col_reduce_kernel");
   return 0;
 }
@@ -588,7 +626,7 @@ int spc_bn_stats(const float* x, int64_t m, int C, float* mean, float* var, floa
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
   fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
   fin.momentum = momentum; fin.eps = 0.f; fin.accumulate = 0; fin.tracked = nullptr;
-  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, m, C, 0, fin, stream);
+  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, m, C, 0, fin, stream);
 }
 
 int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* var, float* running_mean,
@@ -602,7 +640,7 @@ int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* v
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = mean; fin.out1 = var; fin.raw = nullptr;
   fin.run_mean = running_mean; fin.run_var = running_var; fin.var = nullptr;
   fin.momentum = momentum; fin.eps = 0.f; fin.accumulate = 0; fin.tracked = (long long*)num_batches_tracked;
-  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, m, C, 0, fin, stream);
+  return col_reduce_launch(0, x, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, m, C, 0, fin, stream);
 }
 
 int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
@@ -619,6 +657,7 @@ int spc_bn_apply(const float* x, const float* mean, const float* var, const floa
                  float* y, void* y_bf16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(C >= 1, "bad C");
+  SPC_REQUIRE(y || y_bf16, "no output (y and y_bf16 are both null)");
   if (m == 0) return 0;
   int vec = pick_vec(C, x, residual, y);
   if (y_bf16 && ((uintptr_t)y_bf16 % 8)) vec = 1;
@@ -635,18 +674,21 @@ int spc_bn_bwd(const float* x, const float* y, const void* y_bf16, const float* 
                const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
                int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                void* workspace, int64_t workspace_bytes, void* stream_) {
-  return spc_bn_bwd_acc(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16, dresidual,
-                        dgamma, dbeta, 0, workspace, workspace_bytes, stream_);
+  return spc_bn_bwd_acc(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, nullptr, m, C, eps, relu, training, dx, dx_bf16,
+                        dresidual, dgamma, dbeta, 0, workspace, workspace_bytes, stream_);
 }
 
 int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const float* dy, int64_t dy_pitch,
-                   const float* mean, const float* var, const float* gamma, int64_t m, int C, float eps, int relu,
+                   const float* mean, const float* var, const float* gamma, const float* beta, int64_t m, int C,
+                   float eps, int relu,
                    int training, float* dx, void* dx_bf16, float* dresidual, float* dgamma, float* dbeta,
                    int accumulate_param_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1, "empty input");
   SPC_REQUIRE(workspace_bytes >= spc_bn_workspace(m, C), "workspace too small");
-  SPC_REQUIRE(!relu || y || y_bf16, "relu backward needs y (fp32 rows or their bf16 copy)");
+  SPC_REQUIRE(relu >= 0 && relu <= 2, "relu: 0 none, 1 mask from y, 2 mask recomputed from x");
+  SPC_REQUIRE(relu != 1 || y || y_bf16, "relu backward (mode 1) needs y (fp32 rows or their bf16 copy)");
+  SPC_REQUIRE(dx || dx_bf16, "no output (dx and dx_bf16 are both null)");
   SPC_REQUIRE(dy_pitch >= C, "dy pitch smaller than C");
   BnWs w = bn_ws(workspace, C);
   float* sums = w.raw;
@@ -654,7 +696,8 @@ int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const flo
   fin.gsum = w.gsum; fin.counter = w.counter; fin.out0 = dbeta; fin.out1 = dgamma; fin.raw = sums;
   fin.run_mean = nullptr; fin.run_var = nullptr; fin.var = var; fin.momentum = 0.f; fin.eps = eps;
   fin.accumulate = accumulate_param_grads; fin.tracked = nullptr;
-  int rc = col_reduce_launch(1, x, y, y_bf16, dy, dy_pitch, mean, m, C, relu, fin, stream);
+  if (relu != 1) { y = nullptr; y_bf16 = nullptr; }
+  int rc = col_reduce_launch(1, x, y, y_bf16, dy, dy_pitch, mean, gamma, beta, m, C, relu, fin, stream);
   if (rc) return rc;
   int vec = pick_vec(C, x, y, dy, dx);
   if (dresidual && ((uintptr_t)dresidual % 16)) vec = 1;
@@ -665,9 +708,29 @@ int spc_bn_bwd_acc(const float* x, const float* y, const void* y_bf16, const flo
   SPC_REQUIRE(rm.threads <= 1024, "C too large");
   int grid = pick_grid(m, rm.rows, 8);
   DISPATCH_VEC(vec, bn_bwd_apply_kernel<VEC><<<grid, rm.threads, 0, stream>>>(
-      x, y, (const __nv_bfloat16*)y_bf16, dy, dy_pitch, mean, var, gamma, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx,
+      x, y, (const __nv_bfloat16*)y_bf16, dy, dy_pitch, mean, var, gamma, beta, sums, m, C, rm.lanes, rm.rows, eps, relu, training, dx,
       dresidual, (__nv_bfloat16*)dx_bf16));
   SPC_LAUNCHED("bn_bwd_apply_kernel");
+  return 0;
+}
+
+int spc_copy_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t row_bytes, int64_t rows,
+                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(row_bytes >= 0 && rows >= 0 && src_pitch >= row_bytes && dst_pitch >= row_bytes, "bad shape");
+  if (rows == 0 || row_bytes == 0) return 0;
+  const uintptr_t all = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)src_pitch | (uintptr_t)dst_pitch | (uintptr_t)row_bytes;
+  const int w = (all % 16 == 0) ? 16 : (all % 4 == 0 ? 4 : (all % 2 == 0 ? 2 : 1));
+  const int per_row = (int)(row_bytes / w);
+  const int64_t want = ceil_div(rows * per_row, 256);
+  const int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  const char* s = (const char*)src;
+  char* d = (char*)dst;
+  if (w == 16) copy_rows_kernel<uint4><<<grid, 256, 0, stream>>>(s, src_pitch, d, dst_pitch, per_row, rows);
+  else if (w == 4) copy_rows_kernel<uint32_t><<<grid, 256, 0, stream>>>(s, src_pitch, d, dst_pitch, per_row, rows);
+  else if (w == 2) copy_rows_kernel<uint16_t><<<grid, 256, 0, stream>>>(s, src_pitch, d, dst_pitch, per_row, rows);
+  else copy_rows_kernel<uint8_t><<<grid, 256, 0, stream>>>(s, src_pitch, d, dst_pitch, per_row, rows);
+  SPC_LAUNCHED("copy_rows_kernel");
   return 0;
 }
 

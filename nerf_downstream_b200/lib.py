@@ -61,8 +61,9 @@ SIGNATURES = {
     "spc_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "spc_bn_apply": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P, _P, _P]),
     "spc_bn_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
-    "spc_bn_bwd_acc": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int64, _P]),
+    "spc_bn_bwd_acc": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int64, _P]),
     "spc_bn_stats_tracked": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, _P, c_int64, _P]),
+    "spc_copy_rows": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P]),
     "spc_relu_fwd": (c_int, [_P, c_int64, _P, _P]),
     "spc_relu_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "spc_add": (c_int, [_P, _P, c_int64, _P, _P]),

@@ -425,6 +425,49 @@ def _require_cuda(dev: torch.device, what: str):
             "move coordinates/features to a CUDA device or pass device='cuda'.")
 
 
+class _Pending:
+    """Deferred feature rows of a SparseTensor: [convolution] -> [BatchNorm [+ residual] [+ ReLU]].
+
+    `conv` = (input rows, weight, bias, kernel map, precision, weight Parameter, offset bits); `x` = the input rows of
+    a BatchNorm without a pending convolution; `bn` = the MinkowskiBatchNorm module."""
+    __slots__ = ("conv", "x", "bn", "res", "relu", "gone", "grad", "bn_training", "cat")
+
+    def __init__(self, conv=None, x=None, bn=None, cat=None):
+        self.conv, self.x, self.bn = conv, x, bn
+        self.cat = cat      # ME.cat: the parts' rows (possibly hollow)
+        self.res = None
+        self.relu = False
+        self.gone = None
+        # the modules were CALLED in this state; the rows are produced in it, whenever that happens
+        self.grad = torch.is_grad_enabled()
+        self.bn_training = bn.bn.training if bn is not None else None
+
+    def run(self, want_fp32: bool = True) -> torch.Tensor:
+        if self.gone is not None:
+            raise RuntimeError(self.gone)
+        with torch.set_grad_enabled(self.grad):
+            return self._run(want_fp32)
+
+    def _run(self, want_fp32: bool) -> torch.Tensor:
+        # rows that took a residual are a block output: the next block reads them as ITS residual in fp32
+        want_fp32 = want_fp32 or self.res is not None
+        if self.cat is not None:
+            if want_fp32 or not ops.hollow_rows:
+                return torch.cat([ops.ensure_filled(p) for p in self.cat], dim=1)
+            return ops.CatFn.apply(*self.cat)
+        if self.bn is None:
+            x, w, bias, km, precision, w_param, bits = self.conv
+            return ops.SparseConvFn.apply(x, w, bias, km, precision, w_param, bits)
+        if self.conv is not None:
+            x, w, bias, km, precision, w_param, bits = self.conv
+            if ops.conv_bn_fusable(x, w, bias, km, precision, bits):
+                return self.bn._run_fused(x, w, km, w_param, self.relu, self.res, want_fp32, self.bn_training)
+            feats = ops.SparseConvFn.apply(x, w, bias, km, precision, w_param, bits)
+        else:
+            feats = self.x
+        return self.bn._run(feats, self.relu, self.res, want_fp32, self.bn_training)
+
+
 class Tensor:
     """Common base of SparseTensor and TensorField."""
 
@@ -432,21 +475,29 @@ class Tensor:
     _manager: CoordinateManager
     quantization_mode: SparseTensorQuantizationMode
 
-    # Lazily evaluated features: MinkowskiBatchNorm defers its "apply" pass so that a following
-    # `+= residual` and / or ReLU run in the SAME kernel (one read + one write instead of three of
-    # each).  `_lazy(relu, residual)` produces the feature rows; it is resolved by the first reader.
-    _lazy = None
-    _lazy_res = None
+    # Lazily evaluated features.  A convolution or BatchNorm module returns a tensor whose rows are still PENDING
+    # (`_Pending`: conv [+ BatchNorm [+ residual] [+ ReLU]]); the chain is resolved by its first reader, so that
+    #   - a BatchNorm's `+= residual` and / or ReLU run in its apply kernel (one read + one write instead of three),
+    #   - convolution + BatchNorm run as one autograd node (`ops.ConvBNFn`) in bf16 mode,
+    #   - a reader that is itself a bf16 convolution asks for the bf16 operand copy only (`want_fp32=False`).
+    _pending = None
 
-    def _materialize(self, relu: bool = False) -> None:
-        fn, res = self._lazy, self._lazy_res
-        self._lazy = self._lazy_res = None
-        self._F = fn(relu, res)
+    def _materialize(self, want_fp32: bool = True) -> None:
+        pend = self._pending
+        self._pending = None
+        self._F = pend.run(want_fp32)
 
     @property
     def F(self) -> torch.Tensor:
-        if self._F is None and self._lazy is not None:
+        if self._F is None and self._pending is not None:
             self._materialize()
+        return ops.ensure_filled(self._F) if self._F is not None else None
+
+    def _operand(self) -> torch.Tensor:
+        """Feature rows for a consumer that may read their bf16 operand copy instead (a convolution): pending rows
+        are produced without their fp32 image when the precision mode allows, hollow rows are left hollow."""
+        if self._F is None and self._pending is not None:
+            self._materialize(want_fp32=False)
         return self._F
 
     @property
@@ -555,8 +606,8 @@ class SparseTensor(Tensor):
             self._F.requires_grad_(requires_grad)
 
     @classmethod
-    def _deferred(cls, fn, coordinate_map_key, coordinate_manager) -> "SparseTensor":
-        """A tensor whose feature rows are produced on first use by `fn(relu, residual)`."""
+    def _deferred(cls, pending: _Pending, coordinate_map_key, coordinate_manager) -> "SparseTensor":
+        """A tensor whose feature rows are produced on first use by `pending.run()`."""
         t = object.__new__(cls)
         t.quantization_mode = SparseTensorQuantizationMode.RANDOM_SUBSAMPLE
         t.unique_index = None
@@ -564,8 +615,7 @@ class SparseTensor(Tensor):
         t._manager = coordinate_manager
         t.coordinate_map_key = coordinate_map_key
         t._F = None
-        t._lazy = fn
-        t._lazy_res = None
+        t._pending = pending
         return t
 
     def _insert(self, coordinates, tensor_stride):
@@ -601,8 +651,9 @@ class SparseTensor(Tensor):
     def __iadd__(self, other):
         if isinstance(other, SparseTensor):
             self._same_map(other)
-            if self._F is None and self._lazy is not None and self._lazy_res is None:
-                self._lazy_res = other.F  # folded into the deferred BatchNorm apply (resnet_block.py:66)
+            pend = self._pending if self._F is None else None
+            if pend is not None and pend.bn is not None and pend.res is None and not pend.relu and pend.gone is None:
+                pend.res = other.F  # folded into the deferred BatchNorm apply (resnet_block.py:66)
             else:
                 self._F = ops.AddFn.apply(self.F, other.F)
         else:

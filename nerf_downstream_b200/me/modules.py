@@ -16,7 +16,7 @@ from torch.nn import Parameter
 from .. import lib as L
 from .. import ops
 from .core import (ConvolutionMode, CoordinateMapKey, KernelGenerator, RegionType, SparseTensor, TensorField,
-                   _to_list)
+                   _Pending, _to_list)
 
 
 class MinkowskiModuleBase(nn.Module):
@@ -115,9 +115,14 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
                 out_key = mgr.stride(in_key, kg.kernel_stride)
             km = mgr.get_kernel_map(in_key, out_key, kg, is_transpose=self.is_transpose)
             w = self.kernel
-        outfeat = ops.SparseConvFn.apply(input.F, w, self.bias, km, self._precision(), self.kernel,
-                                         None if self.use_mm else self._offset_bits())
-        return SparseTensor(outfeat, coordinate_map_key=out_key, coordinate_manager=mgr)
+        precision = self._precision()
+        # a bf16 convolution reads the operand copy of its input rows: pending / hollow rows stay without fp32 image
+        x = input._operand() if precision == L.PREC_BF16 else input.F
+        conv = (x, w, self.bias, km, precision, self.kernel, None if self.use_mm else self._offset_bits())
+        if ops.fuse_conv_bn:
+            # the rows stay pending: a following MinkowskiBatchNorm takes the convolution into its autograd node
+            return SparseTensor._deferred(_Pending(conv=conv), out_key, mgr)
+        return SparseTensor(ops.SparseConvFn.apply(*conv), coordinate_map_key=out_key, coordinate_manager=mgr)
 
     def _offset_bits(self) -> Optional[int]:
         """Kernel offsets that take part (None = all); the weight-sparse subclasses restrict them."""
@@ -223,28 +228,48 @@ class MinkowskiBatchNorm(nn.Module):
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
                                  track_running_stats=track_running_stats)
 
-    def _run(self, feats, relu=False, residual=None):
+    def _bn_args(self, on_cuda: bool, rows: int, module_training=None):
+        """(training, momentum, tracked) of this forward pass; advances num_batches_tracked on the host when the
+        statistics kernel cannot (cumulative average, CPU harness, empty input).  `module_training`: bn.training as
+        it was when the module was called (deferred rows are produced later)."""
         bn = self.bn
-        training = bn.training or not bn.track_running_stats
+        in_training = bn.training if module_training is None else module_training
+        training = in_training or not bn.track_running_stats
         momentum = bn.momentum
         tracked = None
-        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        if in_training and bn.track_running_stats and bn.num_batches_tracked is not None:
             if momentum is None:     # cumulative moving average: the host needs the count
                 bn.num_batches_tracked.add_(1)
                 momentum = 1.0 / float(bn.num_batches_tracked)
-            elif feats.is_cuda and feats.shape[0] >= 1:
+            elif on_cuda and rows >= 1:
                 tracked = bn.num_batches_tracked   # incremented by the statistics kernel's last block
             else:
                 bn.num_batches_tracked.add_(1)
+        return training, (0.0 if momentum is None else momentum), tracked
+
+    def _run(self, feats, relu=False, residual=None, want_fp32=True, module_training=None):
+        bn = self.bn
+        training, momentum, tracked = self._bn_args(feats.is_cuda, feats.shape[0], module_training)
         return ops.BatchNormFn.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
-                                     0.0 if momentum is None else momentum, bn.eps, relu, residual, tracked)
+                                     momentum, bn.eps, relu, residual, tracked, want_fp32)
+
+    def _run_fused(self, x, w, km, w_param, relu, residual, want_fp32, module_training=None):
+        """convolution + this BatchNorm (+ residual, ReLU) as one autograd node (ops.ConvBNFn)"""
+        bn = self.bn
+        training, momentum, tracked = self._bn_args(x.is_cuda, km.m_out, module_training)
+        return ops.ConvBNFn.apply(x, w, km, w_param, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                  momentum, bn.eps, relu, residual, tracked, want_fp32)
 
     def forward(self, input):
         if isinstance(input, SparseTensor):
-            # defer the apply pass: a following `+= residual` / ReLU is fused into it (_fused_relu)
-            x = input.F
-            return SparseTensor._deferred(lambda relu, res: self._run(x, relu, res), input.coordinate_map_key,
-                                          input.coordinate_manager)
+            # defer the apply pass: a following `+= residual` / ReLU is fused into it (_fused_relu), and a pending
+            # convolution that produced `input` joins the node
+            pend = input._pending if input._F is None else None
+            if pend is not None and pend.bn is None and pend.conv is not None and pend.gone is None:
+                mine = _Pending(conv=pend.conv, bn=self)   # (`input` keeps its own pending convolution)
+            else:
+                mine = _Pending(x=input.F, bn=self)
+            return SparseTensor._deferred(mine, input.coordinate_map_key, input.coordinate_manager)
         return _wrap_like(input, self._run(input.F))
 
     def __repr__(self):
@@ -352,15 +377,13 @@ class MinkowskiNonlinearityBase(MinkowskiModuleBase):
 def _fused_relu(input):
     """ReLU; when `input` is a BatchNorm output whose apply pass is still pending, BN (+ residual add)
     + ReLU run as ONE kernel.  The pre-activation rows of `input` are then never produced."""
-    if isinstance(input, SparseTensor) and input._F is None and input._lazy is not None:
-        input._materialize(relu=True)
-        out = SparseTensor(input._F, coordinate_map_key=input.coordinate_map_key,
-                           coordinate_manager=input.coordinate_manager)
-
-        def _gone(relu, res):
-            raise RuntimeError("the pre-activation features of this BatchNorm output were fused into the "
-                               "following ReLU; read .F before applying the ReLU if you need them")
-        input._F, input._lazy = None, _gone
+    pend = input._pending if (isinstance(input, SparseTensor) and input._F is None) else None
+    if pend is not None and pend.bn is not None and not pend.relu and pend.gone is None:
+        mine = _Pending(conv=pend.conv, x=pend.x, bn=pend.bn)
+        mine.res, mine.relu = pend.res, True
+        out = SparseTensor._deferred(mine, input.coordinate_map_key, input.coordinate_manager)
+        pend.gone = ("the pre-activation features of this BatchNorm output were fused into the "
+                     "following ReLU; read .F before applying the ReLU if you need them")
         return out
     return _wrap_like(input, ops.ReLUFn.apply(input.F))
 
@@ -578,5 +601,8 @@ def cat(*sparse_tensors):
             "Invalid coordinate manager. All inputs must have the same coordinate manager."
         assert key == s.coordinate_map_key, \
             f"Invalid coordinate map key: {key} != {s.coordinate_map_key}. Inputs must share a coordinate map."
+    if ops.lazy_cat and ops.default_precision() == L.PREC_BF16 and all(isinstance(s, SparseTensor) for s in sparse_tensors):
+        # the rows stay pending: a bf16 convolution that reads them asks for the bf16 operand copy only (ops.CatFn)
+        return SparseTensor._deferred(_Pending(cat=[s._operand() for s in sparse_tensors]), key, mgr)
     return SparseTensor(torch.cat([s.F for s in sparse_tensors], dim=1), coordinate_map_key=key,
                         coordinate_manager=mgr)

@@ -233,6 +233,9 @@ class KernelMap:
         self._mask_t = None
         self._pairs = None
         self._n_pairs = None
+        # centrally symmetric self map (odd kernel, stride 1): nbr_t[k] == nbr[K-1-k], so dgrad runs on `nbr` with the
+        # kernel offsets reversed in the packed weights and the transposed map is never built
+        self.symmetric = False
 
     @property
     def n_pairs(self) -> int:
@@ -319,6 +322,11 @@ def tile_mask(nbr, m, K):
     return mask
 
 
+hollow_rows = True           # bf16 mode: BatchNorm outputs that only feed convolutions keep their fp32 rows unwritten
+recompute_relu_mask = True   # BatchNorm backward re-computes the mask of a residual-free ReLU from x
+fuse_conv_bn = True          # ME surface: convolution + BatchNorm (+ residual, ReLU) as one autograd node in bf16 mode
+lazy_cat = True              # bf16 mode: ME.cat assembles the bf16 operand copies, the fp32 concatenation stays hollow
+symmetric_dgrad = True       # dgrad of a symmetric self map reads the forward map with reversed offsets (no transposed map)
 symmetric_maps = True   # build self maps of odd stride-1 kernels with spc_kernel_map_sym (tests switch it off to compare)
 
 
@@ -344,7 +352,9 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
     if e0 is not None:
         _profiler.end("kernel_map", e0, 0, (16.0 + 8.0 * K + 4.0 * K) * out_map.size,
                       f"K{K} M{out_map.size} ts{in_map.tensor_stride[0]}")
-    return KernelMap(nbr, tap_count, K, in_map.size, out_map.size)
+    km = KernelMap(nbr, tap_count, K, in_map.size, out_map.size)
+    km.symmetric = bool(sym)
+    return km
 
 
 # ---------------------------------------------------------------------------
@@ -355,6 +365,7 @@ def _rows_view(x: torch.Tensor):
     (what torch.cat's backward hands out) is read in place instead of being copied to a dense tensor first."""
     if x.dtype != torch.float32:
         raise RuntimeError(f"features must be float32, got {x.dtype}")
+    ensure_filled(x)
     if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1] and x.shape[0] > 1:
         return x, x.stride(0)
     x = x.contiguous()
@@ -371,7 +382,7 @@ def _ptr_rows(x: torch.Tensor):
 def _feat(x: torch.Tensor) -> torch.Tensor:
     if x.dtype != torch.float32:
         raise RuntimeError(f"features must be float32, got {x.dtype}")
-    return x.contiguous()
+    return ensure_filled(x).contiguous()
 
 
 def segment_reduce(feats, inverse, count, m, mode):
@@ -531,13 +542,14 @@ def invalidate_packed_weights() -> None:
     _weights_epoch += 1
 
 
-def _packed_weights(w3: torch.Tensor, dgrad: bool, precision: int, owner: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """`owner`: the long-lived tensor (the layer's Parameter) `w3` is a view of — identity and version are taken
+def _packed_weights(w3: torch.Tensor, dgrad: int, precision: int, owner: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`dgrad`: 0 forward image, 1 W^T, 2 W^T with reversed offsets (symmetric self maps).
+    `owner`: the long-lived tensor (the layer's Parameter) `w3` is a view of — identity and version are taken
     from it (a fresh view object per call, or the tensor autograd hands back in backward, would never hit)."""
     lib = L.load()
     K, c_in, c_out = w3.shape
     obj = owner if owner is not None else w3
-    key = (w3.data_ptr(), bool(dgrad), precision, K, c_in, c_out)
+    key = (w3.data_ptr(), int(dgrad), precision, K, c_in, c_out)
     ver = (obj._version, _weights_epoch)
     e = _pack_cache.get(key)
     if e is not None and e[0]() is obj and e[1] == ver:
@@ -575,7 +587,7 @@ def repack_all() -> int:
                 or not obj.is_contiguous() or obj.device.index != torch.cuda.current_device():
             continue   # temporaries / moved parameters: packed on demand
         ck, cn = (c_out, c_in) if dgrad else (c_in, c_out)
-        rows.append((ptr, _packed_ptr(buf), K, ck, cn, int(dgrad), int(precision == L.PREC_BF16), 0))
+        rows.append((ptr, _packed_ptr(buf), K, ck, cn, (0, 1, 3)[int(dgrad)], int(precision == L.PREC_BF16), 0))
         keys.append(key)
     if not rows:
         return 0
@@ -660,7 +672,7 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits
         w, w_owner = _drop_offsets(w, offset_bits), None
     e0 = _profiler.begin() if _profiler else None
     if _tensor_core(0, K, c_in, c_out, precision):
-        wp = _packed_weights(w, False, precision, w_owner)
+        wp = _packed_weights(w, 0, precision, w_owner)
         L.check(lib.spc_conv_fwd_packed(L.ptr(x), _packed_ptr(wp), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in,
                                         km.m_out, c_in, c_out, K, precision, L.ptr(out), L.stream()),
                 "spc_conv_fwd_packed")
@@ -680,13 +692,19 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None, offset_bits: Op
     lib = L.load()
     K, c_in, c_out = w.shape
     din = _empty((km.m_in, c_in), torch.float32, g.device)
-    mask_t = km.masked(offset_bits, transposed=True) if precision != L.PREC_FP32 else None
-    if offset_bits is not None and not _tensor_core(1, K, c_in, c_out, precision):
+    tc = _tensor_core(1, K, c_in, c_out, precision)
+    # symmetric self map: the forward map with reversed offsets IS the transposed map (no transpose, no second mask)
+    sym = tc and km.symmetric and offset_bits is None and symmetric_dgrad
+    if offset_bits is not None and not tc:
         w, w_owner = _drop_offsets(w, offset_bits), None
-    nbr_t = km.nbr_t
+    if sym:
+        nbr_t, mask_t = km.nbr, km.mask
+    else:
+        nbr_t = km.nbr_t
+        mask_t = km.masked(offset_bits, transposed=True) if precision != L.PREC_FP32 else None
     e0 = _profiler.begin() if _profiler else None
-    if _tensor_core(1, K, c_in, c_out, precision):
-        wp = _packed_weights(w, True, precision, w_owner)
+    if tc:
+        wp = _packed_weights(w, 2 if sym else 1, precision, w_owner)
         L.check(lib.spc_conv_dgrad_packed(L.ptr(g), _packed_ptr(wp), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out,
                                           c_in, c_out, K, precision, L.ptr(din), L.stream()), "spc_conv_dgrad_packed")
     else:
@@ -729,9 +747,8 @@ class SparseConvFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, km, precision, w_param=None, offset_bits=None):
         """`w_param`: the Parameter `w` is (a view of), for the gradient sink (see register_grad_sink).
         `offset_bits`: bit k set = kernel offset k takes part (weight-sparse inference convolution); None = all."""
-        x = _feat(x)
         w3 = w.contiguous()
-        if x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
+        if x.dim() != 2 or x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
             raise RuntimeError(f"conv input {tuple(x.shape)} does not match map rows {km.m_in} / kernel {tuple(w3.shape)}")
         b = bias.contiguous().view(-1) if bias is not None else None
         K, c_in, c_out = w3.shape
@@ -744,6 +761,8 @@ class SparseConvFn(torch.autograd.Function):
             precision = L.PREC_TF32  # shapes the bf16 kernels are not built for (bench.py reports the routes taken)
         if precision != L.PREC_FP32 and K <= 32 and big:
             pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
+        if precision != L.PREC_BF16:
+            x = _feat(x)   # (bf16 mode reads the operand copy: a hollow input is not filled for it)
         if pad_in and precision != L.PREC_BF16:
             x = torch.nn.functional.pad(x, (0, pad_in))
         if pad_in or pad_out:
@@ -801,95 +820,277 @@ class SparseConvFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+def conv_bn_fusable(x, w, bias, km: KernelMap, precision: int, offset_bits) -> bool:
+    """True when convolution + BatchNorm can run as the one autograd node `ConvBNFn`: bf16 operands, tensor-core
+    shapes in all three directions without channel padding, no bias, all offsets."""
+    if not fuse_conv_bn or precision != L.PREC_BF16 or _default_precision != L.PREC_BF16:
+        return False
+    if bias is not None or offset_bits is not None or w.dim() != 3 or not x.is_cuda:
+        return False
+    K, c_in, c_out = w.shape
+    if K > 32 or c_in % 32 or c_out % 32 or c_out > 512 or K * c_in > 128 * 128 or km.m_out < 1:
+        return False
+    return (_tensor_core(0, K, c_in, c_out, precision) and _tensor_core(1, K, c_in, c_out, precision)
+            and _tensor_core(2, K, c_in, c_out, precision))
+
+
+class ConvBNFn(torch.autograd.Function):
+    """MinkowskiConvolution -> MinkowskiBatchNorm (-> += residual) (-> ReLU) as ONE autograd node (bf16 operand mode).
+
+    The convolution output `c` is internal to the node, so backward never materialises its fp32 gradient: BatchNorm
+    backward writes the bf16 operand copy only (4 of its 26 bytes per element less) and dgrad / wgrad read that.
+    Arithmetic and kernels are those of `SparseConvFn` followed by `BatchNormFn`."""
+
+    @staticmethod
+    def forward(ctx, x, w, km, w_param, gamma, beta, running_mean, running_var, training, momentum, eps, relu,
+                residual, tracked, want_fp32):
+        w3 = w.contiguous()
+        K, c_in, c_out = w3.shape
+        if x.dim() != 2 or x.shape[0] != km.m_in or x.shape[1] != c_in:
+            raise RuntimeError(f"conv input {tuple(x.shape)} does not match map rows {km.m_in} / kernel {tuple(w3.shape)}")
+        xb = to_bf16(x)
+        own = w_param if (w_param is not None and w_param.data_ptr() == w3.data_ptr()
+                          and w_param.numel() == w3.numel()) else None
+        c = conv_fwd_raw(xb, w3, None, km, L.PREC_BF16, own)
+        y, yb, mean, var, use_batch = _bn_forward_impl(c, gamma, beta, running_mean, running_var, training, momentum,
+                                                       eps, relu, residual, tracked, want_fp32)
+        relu_mode = 0 if not relu else (2 if (residual is None and recompute_relu_mask) else 1)
+        ctx.save_for_backward(xb, w3, c, ((yb if yb is not None else y) if relu_mode == 1 else None), mean, var,
+                              gamma, beta)
+        ctx.cfg = (float(eps), relu_mode, int(use_batch), residual is not None)
+        ctx.params = (gamma, beta)
+        ctx.w_param = own
+        ctx.km = km
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w3, c, ymask, mean, var, gamma, beta = ctx.saved_tensors
+        eps, relu_mode, use_batch, has_res = ctx.cfg
+        km = ctx.km
+        K, c_in, c_out = w3.shape
+        dc, dcb, dres, dgamma, dbeta = _bn_backward_impl(c, ymask, dy, mean, var, gamma, beta, eps, relu_mode,
+                                                         use_batch, has_res, ctx.params, want_dx32=False)
+        g = dcb if dcb is not None else to_bf16(dc)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad_raw(g, w3, km, L.PREC_BF16, ctx.w_param)
+        if ctx.needs_input_grad[1]:
+            sink = _sink(ctx.w_param)
+            if sink is not None and sink[0].numel() == K * c_in * c_out:
+                conv_wgrad_raw(xb, g, km, K, c_in, c_out, L.PREC_BF16, add_into=sink[0])
+                sink[1](ctx.w_param)
+            else:
+                dw = conv_wgrad_raw(xb, g, km, K, c_in, c_out, L.PREC_BF16)
+        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, dres, None, None
+
+
 # ---------------------------------------------------------------------------
 # batch norm / relu / add
 # ---------------------------------------------------------------------------
+# "Hollow" rows.  In bf16 mode a BatchNorm output that only feeds convolutions is needed as the bf16 operand copy
+# alone; its fp32 tensor still has to exist (it is the autograd output) but is left UNWRITTEN — 4 of the 14 bytes per
+# element the apply pass moves.  `_hollow` maps such a tensor to a closure that writes its fp32 rows on demand
+# (`ensure_filled`, called by every reader of fp32 rows in this module and by `Tensor.F` at the ME surface).
+_hollow: dict = {}   # data_ptr -> (weak reference to the tensor, fill closure)
+hollow_stats = {"made": 0, "filled": 0}
+
+
+def _mark_hollow(t: torch.Tensor, fill) -> None:
+    key = t.data_ptr()
+
+    def _drop(ref, key=key, table=_hollow):
+        e = table.get(key)
+        if e is not None and e[0] is ref:
+            del table[key]
+    _hollow[key] = (weakref.ref(t, _drop), fill)
+    hollow_stats["made"] += 1
+
+
+def is_hollow(t: torch.Tensor) -> bool:
+    e = _hollow.get(t.data_ptr()) if _hollow else None
+    return e is not None and e[0]() is t
+
+
+def ensure_filled(t: torch.Tensor) -> torch.Tensor:
+    """Write the fp32 rows of a hollow tensor (no-op for every other tensor)."""
+    if _hollow:
+        e = _hollow.get(t.data_ptr())
+        if e is not None and e[0]() is t:
+            del _hollow[t.data_ptr()]
+            e[1]()
+            hollow_stats["filled"] += 1
+    return t
+
+
+def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual, tracked,
+                     want_fp32=True):
+    """Statistics + apply.  Returns (y, yb, mean, var, use_batch).  `want_fp32=False`: y may be left hollow."""
+    lib = L.load()
+    m, C = x.shape
+    dev = x.device
+    ws_bytes = int(lib.spc_bn_workspace(m, C))
+    ws = _workspace(ws_bytes, dev)
+    use_batch = training or running_mean is None
+    e0 = _profiler.begin() if _profiler else None
+    if use_batch:
+        if m < 1:
+            raise RuntimeError("batch norm over zero rows")
+        mean = _empty(C, torch.float32, dev)
+        var = _empty(C, torch.float32, dev)
+        upd = training and running_mean is not None
+        L.check(lib.spc_bn_stats_tracked(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
+                                         L.ptr(running_mean) if upd else None,
+                                         L.ptr(running_var) if upd else None, float(momentum),
+                                         L.ptr(tracked) if (upd and tracked is not None) else None, L.ptr(ws),
+                                         ws_bytes, L.stream()), "spc_bn_stats")
+    else:
+        mean, var = running_mean, running_var
+    res = _feat(residual) if residual is not None else None
+    y = _empty((m, C), torch.float32, dev)
+    yb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
+    hollow = yb is not None and not want_fp32 and hollow_rows
+    L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res), m, C,
+                             float(eps), int(relu), None if hollow else L.ptr(y), L.ptr(yb), L.stream()), "spc_bn_apply")
+    if yb is not None:
+        _remember_bf16(y, yb)
+    if hollow:
+        epoch = _weights_epoch
+
+        def fill(x=x, mean=mean, var=var, gamma=gamma, beta=beta, res=res, y=y, eps=float(eps), relu=int(relu)):
+            if epoch != _weights_epoch:
+                raise RuntimeError("fp32 rows of a BatchNorm output were requested after an optimiser step changed its "
+                                   "parameters; read .F before stepping (or set ops.hollow_rows = False)")
+            L.check(L.load().spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res),
+                                          x.shape[0], x.shape[1], eps, relu, L.ptr(y), None, L.stream()),
+                    "spc_bn_apply(fill)")
+        _mark_hollow(y, fill)
+    if e0 is not None:
+        _profiler.end("bn_fwd", e0, 0, ((8.0 if use_batch else 4.0) + (0.0 if hollow else 4.0)
+                                        + (4.0 if res is not None else 0.0)
+                                        + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
+    return y, yb, mean, var, use_batch
+
+
+def _bn_backward_impl(x, ymask, dy, mean, var, gamma, beta, eps, relu_mode, use_batch, has_res, params,
+                      want_dx32=True):
+    """BatchNorm backward.  `relu_mode`: 0 none, 1 mask from `ymask` (fp32 rows or their bf16 copy), 2 mask
+    re-computed from x (no residual before the ReLU: nothing but x and dy is read).  Returns (dx, dxb, dres, dgamma,
+    dbeta); dx is None when `want_dx32` is False and a bf16 copy is produced (fused conv + BN node)."""
+    lib = L.load()
+    dy, dy_pitch = _rows_view(dy)
+    m, C = x.shape
+    dev = x.device
+    ws_bytes = int(lib.spc_bn_workspace(m, C))
+    ws = _workspace(ws_bytes, dev)
+    dxb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
+    dx = _empty((m, C), torch.float32, dev) if (want_dx32 or dxb is None) else None
+    dres = _empty((m, C), torch.float32, dev) if has_res else None
+    # parameter gradients straight into the trainer's arena when both parameters are registered sinks
+    gp, bp = params
+    affine = gamma is not None
+    sg, sb = (_sink(gp), _sink(bp)) if affine else (None, None)
+    direct = sg is not None and sb is not None and sg[0].numel() == C and sb[0].numel() == C
+    if direct:
+        dgamma, dbeta = sg[0], sb[0]
+    else:
+        dgamma = _empty(C, torch.float32, dev)
+        dbeta = _empty(C, torch.float32, dev)
+    e0 = _profiler.begin() if _profiler else None
+    y32, y16 = (None, ymask) if (ymask is not None and ymask.dtype == torch.bfloat16) else (ymask, None)
+    L.check(lib.spc_bn_bwd_acc(L.ptr(x), L.ptr(y32), L.ptr(y16), _ptr_rows(dy), dy_pitch, L.ptr(mean), L.ptr(var),
+                               L.ptr(gamma), L.ptr(beta), m, C, eps,
+                               relu_mode, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
+                               int(direct), L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
+    if direct:
+        sg[1](gp)
+        sb[1](bp)
+        dgamma = dbeta = None
+    if dxb is not None and dx is not None:
+        _remember_bf16(dx, dxb)
+    if e0 is not None:
+        _profiler.end("bn_bwd", e0, 0, (16.0 + ((4.0 if y16 is not None else 8.0) if relu_mode == 1 else 0.0)
+                                        + (4.0 if dx is not None else 0.0) + (4.0 if has_res else 0.0)
+                                        + (2.0 if dxb is not None else 0.0)) * m * C,
+                      f"C{C} M{m}")
+    return dx, dxb, dres, (dgamma if affine else None), (dbeta if affine else None)
+
+
 class BatchNormFn(torch.autograd.Function):
     """nn.BatchNorm1d semantics on [M,C] rows, optional fused ReLU and residual add."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual,
-                tracked=None):
+                tracked=None, want_fp32=True):
         """`tracked`: nn.BatchNorm1d.num_batches_tracked (int64 device scalar) to increment inside the statistics
-        kernel, or None."""
-        lib = L.load()
+        kernel, or None.  `want_fp32=False`: the caller only needs the bf16 operand copy of the output (see
+        "Hollow rows" above)."""
         x = _feat(x)
-        m, C = x.shape
-        dev = x.device
-        ws_bytes = int(lib.spc_bn_workspace(m, C))
-        ws = _workspace(ws_bytes, dev)
-        use_batch = training or running_mean is None
-        e0 = _profiler.begin() if _profiler else None
-        if use_batch:
-            if m < 1:
-                raise RuntimeError("batch norm over zero rows")
-            mean = _empty(C, torch.float32, dev)
-            var = _empty(C, torch.float32, dev)
-            upd = training and running_mean is not None
-            L.check(lib.spc_bn_stats_tracked(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
-                                             L.ptr(running_mean) if upd else None,
-                                             L.ptr(running_var) if upd else None, float(momentum),
-                                             L.ptr(tracked) if (upd and tracked is not None) else None, L.ptr(ws),
-                                             ws_bytes, L.stream()), "spc_bn_stats")
-        else:
-            mean, var = running_mean, running_var
-        res = _feat(residual) if residual is not None else None
-        y = _empty((m, C), torch.float32, dev)
-        yb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
-        L.check(lib.spc_bn_apply(L.ptr(x), L.ptr(mean), L.ptr(var), L.ptr(gamma), L.ptr(beta), L.ptr(res), m, C,
-                                 float(eps), int(relu), L.ptr(y), L.ptr(yb), L.stream()), "spc_bn_apply")
-        if yb is not None:
-            _remember_bf16(y, yb)
-        if e0 is not None:
-            _profiler.end("bn_fwd", e0, 0, ((12.0 if use_batch else 8.0)
-                                            + (4.0 if res is not None else 0.0)
-                                            + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
-        # the ReLU mask of backward comes from the bf16 copy when there is one (2 instead of 4 bytes per value)
-        ctx.save_for_backward(x, (yb if yb is not None else y) if relu else None, mean, var, gamma)
-        ctx.cfg = (float(eps), int(relu), int(use_batch), residual is not None, gamma is not None)
+        y, yb, mean, var, use_batch = _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, momentum,
+                                                       eps, relu, residual, tracked, want_fp32)
+        # ReLU mask of backward: re-computed from x when nothing was added before the ReLU (mode 2); otherwise from
+        # the bf16 copy of y when there is one (2 instead of 4 bytes per value)
+        relu_mode = 0 if not relu else (2 if (residual is None and recompute_relu_mask) else 1)
+        ctx.save_for_backward(x, ((yb if yb is not None else y) if relu_mode == 1 else None), mean, var, gamma, beta)
+        ctx.cfg = (float(eps), relu_mode, int(use_batch), residual is not None)
         ctx.params = (gamma, beta)   # the Parameter objects, for the gradient sinks
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        lib = L.load()
-        x, y, mean, var, gamma = ctx.saved_tensors
-        eps, relu, use_batch, has_res, affine = ctx.cfg
-        dy, dy_pitch = _rows_view(dy)
-        m, C = x.shape
-        dev = x.device
-        ws_bytes = int(lib.spc_bn_workspace(m, C))
-        ws = _workspace(ws_bytes, dev)
-        dx = _empty((m, C), torch.float32, dev)
-        dxb = _empty((m, C), torch.bfloat16, dev) if _want_bf16_side(m, C) else None
-        dres = _empty((m, C), torch.float32, dev) if has_res else None
-        # parameter gradients straight into the trainer's arena when both parameters are registered sinks
-        gp, bp = ctx.params
-        sg, sb = (_sink(gp), _sink(bp)) if affine else (None, None)
-        direct = sg is not None and sb is not None and sg[0].numel() == C and sb[0].numel() == C
-        if direct:
-            dgamma, dbeta = sg[0], sb[0]
-        else:
-            dgamma = _empty(C, torch.float32, dev)
-            dbeta = _empty(C, torch.float32, dev)
-        e0 = _profiler.begin() if _profiler else None
-        y32, y16 = (None, y) if (y is not None and y.dtype == torch.bfloat16) else (y, None)
-        L.check(lib.spc_bn_bwd_acc(L.ptr(x), L.ptr(y32), L.ptr(y16), _ptr_rows(dy), dy_pitch, L.ptr(mean), L.ptr(var),
-                                   L.ptr(gamma), m, C, eps,
-                                   relu, use_batch, L.ptr(dx), L.ptr(dxb), L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta),
-                                   int(direct), L.ptr(ws), ws_bytes, L.stream()), "spc_bn_bwd")
-        if direct:
-            sg[1](gp)
-            sb[1](bp)
-            dgamma = dbeta = None
-        if dxb is not None:
-            _remember_bf16(dx, dxb)
-        if e0 is not None:
-            _profiler.end("bn_bwd", e0, 0, (20.0 + ((4.0 if y16 is not None else 8.0) if relu else 0.0) + (4.0 if has_res else 0.0)
-                                            + (2.0 if dxb is not None else 0.0)) * m * C,
-                          f"C{C} M{m}")
-        return (dx, dgamma if affine else None, dbeta if affine else None, None, None, None, None, None, None,
-                dres, None)
+        x, ymask, mean, var, gamma, beta = ctx.saved_tensors
+        eps, relu_mode, use_batch, has_res = ctx.cfg
+        dx, _, dres, dgamma, dbeta = _bn_backward_impl(x, ymask, dy, mean, var, gamma, beta, eps, relu_mode, use_batch,
+                                                       has_res, ctx.params)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, dres, None, None
+
+
+def cat_rows_bf16(parts) -> torch.Tensor:
+    """bf16 operand copy of the channel concatenation of `parts` ([M, C_i] fp32 rows): each part's bf16 copy (the side
+    output of the kernel that made it, else a conversion pass) is copied into its column slice — 4 bytes per element
+    moved instead of the 8 of an fp32 torch.cat plus the 6 of its conversion."""
+    lib = L.load()
+    m = parts[0].shape[0]
+    C = sum(int(p.shape[1]) for p in parts)
+    out = torch.empty((m, C), dtype=torch.bfloat16, device=parts[0].device)
+    e0 = _profiler.begin() if _profiler else None
+    c0 = 0
+    for p in parts:
+        pb = to_bf16(p)
+        ci = int(p.shape[1])
+        L.check(lib.spc_copy_rows(L.ptr(pb), 2 * ci, out.data_ptr() + 2 * c0, 2 * C, 2 * ci, m, L.stream()),
+                "spc_copy_rows")
+        c0 += ci
+    if e0 is not None:
+        _profiler.end("cat_bf16", e0, 0, 4.0 * m * C, f"C{C} M{m}")
+    return out
+
+
+class CatFn(torch.autograd.Function):
+    """ME.cat along the channels whose consumers are bf16 convolutions: the fp32 result is HOLLOW (allocated for
+    autograd, written only if somebody asks for `.F`), the bf16 operand copy is assembled from the parts' copies."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        m = parts[0].shape[0]
+        widths = [int(p.shape[1]) for p in parts]
+        y = _empty((m, sum(widths)), torch.float32, parts[0].device)
+        yb = cat_rows_bf16(parts)
+        _remember_bf16(y, yb)
+
+        def fill(parts=parts, y=y):
+            torch.cat([ensure_filled(p) for p in parts], dim=1, out=y)
+        _mark_hollow(y, fill)
+        ctx.widths = widths
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        out, c0 = [], 0
+        for w in ctx.widths:
+            out.append(g[:, c0:c0 + w])   # column slices, read in place by the consumers (row pitch)
+            c0 += w
+        return tuple(out)
 
 
 class SyncBatchNormFn(torch.autograd.Function):

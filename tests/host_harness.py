@@ -347,15 +347,17 @@ class FakeLib:
         """The harness's "packed image" is the fp32 kernel itself (the real one is a swizzled slab layout)."""
         self._called("spc_conv_pack_weights")
         assert _addr(packed) % 1024 == 0
-        view(packed, (K, c_in, c_out), np.float32)[:] = view(w, (K, c_in, c_out), np.float32)
+        src = view(w, (K, c_in, c_out), np.float32)
+        view(packed, (K, c_in, c_out), np.float32)[:] = src[::-1] if dgrad == 2 else src   # 2: offsets reversed
         return 0
 
     def spc_conv_pack_weights_batch(self, desc, n_layers, stream):
         self._called("spc_conv_pack_weights_batch")
         d = view(desc, (n_layers, 8), np.int64)
-        for w, packed, K, ck, cn, transpose, bf16, _ in d.tolist():
-            c_in, c_out = (cn, ck) if transpose else (ck, cn)
-            view(packed, (K, c_in, c_out), np.float32)[:] = view(w, (K, c_in, c_out), np.float32)
+        for w, packed, K, ck, cn, flags, bf16, _ in d.tolist():
+            c_in, c_out = (cn, ck) if flags & 1 else (ck, cn)
+            src = view(w, (K, c_in, c_out), np.float32)
+            view(packed, (K, c_in, c_out), np.float32)[:] = src[::-1] if flags & 2 else src
         return 0
 
     def spc_conv_fwd_packed(self, x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, stream):
@@ -373,14 +375,14 @@ class FakeLib:
             view(tracked, 1, np.int64)[:] += 1
         return rc
 
-    def spc_bn_bwd_acc(self, x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16, dres,
-                       dgamma, dbeta, accumulate, ws, ws_bytes, stream):
+    def spc_bn_bwd_acc(self, x, y, y_bf16, dy, dy_pitch, mean, var, gamma, beta, m, C, eps, relu, training, dx, dx_bf16,
+                       dres, dgamma, dbeta, accumulate, ws, ws_bytes, stream):
         if not accumulate:
             return self.spc_bn_bwd(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16,
-                                   dres, dgamma, dbeta, ws, ws_bytes, stream)
+                                   dres, dgamma, dbeta, ws, ws_bytes, stream, beta=beta)
         g0, b0 = view(dgamma, C, np.float32).copy(), view(dbeta, C, np.float32).copy()
         rc = self.spc_bn_bwd(x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16,
-                             dres, dgamma, dbeta, ws, ws_bytes, stream)
+                             dres, dgamma, dbeta, ws, ws_bytes, stream, beta=beta)
         view(dgamma, C, np.float32)[:] += g0
         view(dbeta, C, np.float32)[:] += b0
         return rc
@@ -409,19 +411,27 @@ class FakeLib:
             o = o + view(res, (m, C), np.float32)
         if relu:
             o = np.maximum(o, 0)
-        view(y, (m, C), np.float32)[:] = o
+        if _addr(y):
+            view(y, (m, C), np.float32)[:] = o
         if _addr(y_bf16):
-            view(y_bf16, (m, C), np.uint16)[:] = f32_to_bf16(view(y, (m, C), np.float32))
+            view(y_bf16, (m, C), np.uint16)[:] = f32_to_bf16(o.astype(np.float32))
         return 0
 
     def spc_bn_bwd(self, x, y, y_bf16, dy, dy_pitch, mean, var, gamma, m, C, eps, relu, training, dx, dx_bf16, dres,
-                   dgamma, dbeta, ws, ws_bytes, stream):
+                   dgamma, dbeta, ws, ws_bytes, stream, beta=None):
         self._called("spc_bn_bwd")
         xv = view(x, (m, C), np.float32).astype(np.float64)
         g = np.array(rows_view(dy, m, C, dy_pitch), np.float64)
-        if relu:
+        if relu == 1:
             yv = view(y, (m, C), np.float32) if _addr(y) else bf16_to_f32(view(y_bf16, (m, C), np.uint16))
             g = g * (yv > 0)
+        elif relu == 2:   # mask recomputed from x with the forward affine (no residual before the ReLU)
+            x32 = view(x, (m, C), np.float32)
+            ga = view(gamma, C, np.float32) if _addr(gamma) else np.ones(C, np.float32)
+            be = view(beta, C, np.float32) if _addr(beta) else np.zeros(C, np.float32)
+            sc = (ga / np.sqrt(view(var, C, np.float32) + np.float32(eps))).astype(np.float32)
+            sh = (be - view(mean, C, np.float32) * sc).astype(np.float32)
+            g = g * ((x32 * sc + sh) > 0)
         if _addr(dres):
             view(dres, (m, C), np.float32)[:] = g
         rstd = 1.0 / np.sqrt(view(var, C, np.float32).astype(np.float64) + eps)
@@ -430,9 +440,16 @@ class FakeLib:
         view(dgamma, C, np.float32)[:] = (g * xh).sum(0)
         sc = rstd * (view(gamma, C, np.float32) if _addr(gamma) else 1.0)
         d = sc * (g - g.mean(0) - xh * (g * xh).mean(0)) if training else sc * g
-        view(dx, (m, C), np.float32)[:] = d
+        if _addr(dx):
+            view(dx, (m, C), np.float32)[:] = d
         if _addr(dx_bf16):
-            view(dx_bf16, (m, C), np.uint16)[:] = f32_to_bf16(view(dx, (m, C), np.float32))
+            view(dx_bf16, (m, C), np.uint16)[:] = f32_to_bf16(d.astype(np.float32))
+        return 0
+
+    def spc_copy_rows(self, src, src_pitch, dst, dst_pitch, row_bytes, rows, stream):
+        self._called("spc_copy_rows")
+        for r in range(int(rows)):
+            ctypes.memmove(_addr(dst) + r * int(dst_pitch), _addr(src) + r * int(src_pitch), int(row_bytes))
         return 0
 
     def spc_relu_fwd(self, x, n, y, stream):

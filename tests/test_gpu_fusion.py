@@ -1,0 +1,173 @@
+"""Round-2 byte savings on the real library: every one of them must leave the numbers where they were.
+
+* BatchNorm backward with the ReLU mask RE-COMPUTED from x (relu mode 2) == the mask read from y (mode 1), bit for bit.
+* `spc_bn_apply` without fp32 output (hollow rows) writes the same bf16 copy; a later `.F` fills the fp32 rows.
+* convolution + BatchNorm (+ residual, ReLU) as ONE autograd node (`ops.ConvBNFn`, no fp32 gradient of the
+  convolution output) == the separate nodes.
+* dgrad of a centrally symmetric self map on the FORWARD map with reversed offsets == dgrad on the transposed map.
+* `ME.cat` of bf16 operand copies (`ops.cat_rows_bf16`) == torch.cat of the fp32 rows, converted.
+"""
+import pytest
+import torch
+
+from nerf_downstream_b200 import lib as L
+from nerf_downstream_b200 import me as ME
+from nerf_downstream_b200 import models, ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def bf16_mode():
+    ops.set_default_precision("bf16")
+    yield
+    ops.set_default_precision("tf32")
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "symmetric_dgrad"):
+        setattr(ops, knob, True)
+
+
+def _knobs(value: bool):
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn"):
+        setattr(ops, knob, value)
+
+
+@pytest.mark.parametrize("C,m", [(32, 50_001), (96, 20_000), (20, 3_000)])
+def test_bn_backward_with_the_relu_mask_recomputed_from_x(cuda_device, bf16_mode, C, m):
+    torch.manual_seed(C)
+    x = torch.randn(m, C, device=cuda_device) * 2 + 0.3
+    dy = torch.randn(m, C, device=cuda_device)
+    out = []
+    for recompute in (True, False):
+        ops.recompute_relu_mask = recompute
+        bn = torch.nn.BatchNorm1d(C).to(cuda_device)
+        with torch.no_grad():
+            bn.weight.uniform_(-1, 1)       # negative gammas flip the sign of the mask test
+            bn.bias.uniform_(-0.5, 0.5)
+        xi = x.clone().requires_grad_(True)
+        y = ops.BatchNormFn.apply(xi, bn.weight, bn.bias, bn.running_mean, bn.running_var, True, 0.1, 1e-5, True, None)
+        y.backward(dy)
+        out.append((y.detach(), xi.grad, bn.weight.grad, bn.bias.grad))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    # and against torch
+    bn = torch.nn.BatchNorm1d(C).to(cuda_device)
+    xi = x.clone().requires_grad_(True)
+    torch.relu(bn(xi)).backward(dy)
+    ops.recompute_relu_mask = True
+    bn2 = torch.nn.BatchNorm1d(C).to(cuda_device)
+    xj = x.clone().requires_grad_(True)
+    ops.BatchNormFn.apply(xj, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var, True, 0.1, 1e-5, True, None).backward(dy)
+    assert (xj.grad - xi.grad).abs().max() <= 1e-4 * (1 + xi.grad.abs().max())
+    assert (bn2.weight.grad - bn.weight.grad).abs().max() <= 1e-4 * (1 + bn.weight.grad.abs().max())
+
+
+def test_hollow_rows_are_filled_on_demand(cuda_device, bf16_mode):
+    torch.manual_seed(1)
+    m, C = 30_000, 64
+    x = torch.randn(m, C, device=cuda_device)
+    bn = torch.nn.BatchNorm1d(C).to(cuda_device)
+    args = (bn.weight, bn.bias, None, None, True, 0.1, 1e-5, True, None, None)
+    full = ops.BatchNormFn.apply(x, *args, True)
+    hollow = ops.BatchNormFn.apply(x, *args, False)
+    assert ops.is_hollow(hollow) and not ops.is_hollow(full)
+    assert torch.equal(ops._lookup_bf16(hollow), ops._lookup_bf16(full))      # the operand copy does not depend on it
+    assert torch.equal(ops.to_bf16(hollow), ops._lookup_bf16(full))            # a bf16 consumer does not fill
+    assert ops.is_hollow(hollow)
+    filled = ops.ensure_filled(hollow)
+    assert not ops.is_hollow(hollow) and torch.equal(filled, full)
+
+
+def _stack(cuda_device, coords, feats, fused, seed=3, planes=64):
+    _knobs(fused)
+    torch.manual_seed(seed)
+    net = torch.nn.Sequential(
+        torch.nn.Sequential(ME.MinkowskiConvolution(32, planes, kernel_size=3, dimension=3), ME.MinkowskiBatchNorm(planes),
+                            ME.MinkowskiReLU()),
+        models.ResidualBlock(planes, planes), models._stage(planes, 96, 2),
+        torch.nn.Sequential(ME.MinkowskiConvolution(96, 96, kernel_size=2, stride=2, dimension=3),
+                            ME.MinkowskiBatchNorm(96), ME.MinkowskiReLU()),
+        models.ResidualBlock(96, 96),
+        torch.nn.Sequential(ME.MinkowskiConvolutionTranspose(96, 64, kernel_size=2, stride=2, dimension=3),
+                            ME.MinkowskiBatchNorm(64), ME.MinkowskiReLU()),
+        ME.MinkowskiConvolution(64, 32, kernel_size=1, bias=True, dimension=3)).to(cuda_device).train()
+    f = feats.clone().requires_grad_(True)
+    x = ME.SparseTensor(f, coordinates=coords)
+    out = net(x).F
+    (out * torch.linspace(-1, 1, 32, device=cuda_device)).sum().backward()
+    torch.cuda.synchronize()
+    return out.detach(), f.grad, {n: p.grad.clone() for n, p in net.named_parameters()}, \
+        {n: b.clone() for n, b in net.named_buffers()}
+
+
+def test_fused_conv_bn_node_equals_the_separate_nodes(cuda_device, bf16_mode):
+    c, f, _ = synth.room_batch(11, 1, 60_000)
+    coords = torch.from_numpy(c).to(cuda_device).floor().int()
+    coords = torch.unique(coords, dim=0)
+    feats = torch.randn(coords.shape[0], 32, device=cuda_device)
+    made0 = ops.hollow_stats["made"]
+    out_a, dx_a, g_a, b_a = _stack(cuda_device, coords, feats, True)
+    assert ops.hollow_stats["made"] > made0
+    out_b, dx_b, g_b, b_b = _stack(cuda_device, coords, feats, False)
+    # forward: the same kernels on the same operands
+    assert torch.equal(out_a, out_b)
+    for n in b_a:
+        assert torch.equal(b_a[n], b_b[n]), n
+    # backward: the same kernels too; wgrad's fp32 red.add order is the only freedom
+    scale = dx_b.abs().max()
+    assert (dx_a - dx_b).abs().max() <= 1e-5 * scale
+    for n in g_a:
+        assert (g_a[n] - g_b[n]).abs().max() <= 2e-5 * (g_b[n].abs().max() + 1e-12), n
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_symmetric_dgrad_equals_dgrad_on_the_transposed_map(cuda_device, prec):
+    c, _, _ = synth.room_batch(5, 1, 80_000)
+    cmap, _, _, _ = ops.coords_insert(torch.from_numpy(c).to(cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    assert km.symmetric
+    P = ops.PRECISIONS[prec]
+    torch.manual_seed(2)
+    for cin, cout in ((32, 64), (96, 96)):
+        w = torch.randn(27, cin, cout, device=cuda_device) / (27 * cin) ** 0.5
+        g = torch.randn(cmap.size, cout, device=cuda_device)
+        ga = ops.to_bf16(g) if prec == "bf16" else g
+        ops.symmetric_dgrad = True
+        a = ops.conv_dgrad_raw(ga, w, km, P)
+        assert km._nbr_t is None                       # the transposed map was not built
+        ops.symmetric_dgrad = False
+        b = ops.conv_dgrad_raw(ga, w, km, P)
+        ops.symmetric_dgrad = True
+        assert km._nbr_t is not None
+        assert torch.equal(km.nbr_t, torch.flip(km.nbr, dims=[0]))     # the identity the short cut rests on
+        assert (a - b).abs().max() <= 2e-6 * b.abs().max()              # same products, reversed accumulation order
+
+
+def test_res16unet_step_with_all_savings_equals_the_plain_step(cuda_device, bf16_mode):
+    """Whole Res16UNet14A-sized network, bf16 mode: logits identical, parameter gradients equal up to the fp32
+    accumulation order (symmetric dgrad reverses the offset order; wgrad red.adds are unordered anyway)."""
+    c, f, y = synth.room_batch(21, 2, 40_000)
+    c_d, f_d, y_d = (torch.from_numpy(a).to(cuda_device) for a in (c, f, y))
+
+    def run(on):
+        _knobs(on)
+        ops.symmetric_dgrad = on
+        ops.lazy_cat = on
+        torch.manual_seed(4)
+        net = models.Res16UNet14A(27, 20).to(cuda_device).train()
+        out = net(ME.TensorField(coordinates=c_d, features=f_d))
+        loss = ops.cross_entropy(out, y_d, 255)
+        loss.backward()
+        torch.cuda.synchronize()
+        return out.detach(), float(loss), {n: p.grad.clone() for n, p in net.named_parameters()}
+
+    try:
+        out_a, loss_a, g_a = run(True)
+        out_b, loss_b, g_b = run(False)
+    finally:
+        ops.lazy_cat = True
+    assert torch.equal(out_a, out_b) and loss_a == loss_b
+    va, vb = torch.cat([g.flatten() for g in g_a.values()]), torch.cat([g.flatten() for g in g_b.values()])
+    cos = float(va.double() @ vb.double() / (va.double().norm() * vb.double().norm()))
+    assert cos >= 0.99999, cos
+    for n in g_a:
+        assert (g_a[n] - g_b[n]).abs().max() <= 2e-3 * (g_b[n].abs().max() + 1e-12), n

@@ -408,3 +408,129 @@ def test_evaluate_pruned_checkpoint(monkeypatch, tmp_path):
         assert res["val/total_params"] == float(total) and abs(res["val/pruned_params"] / sum(m.kernel_mask.numel() for m, _ in to_prune) - 0.4) < 1e-3
     finally:
         ginlite.clear_config()
+
+
+def _two_blocks(seed):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(models.ResidualBlock(32, 32), models.ResidualBlock(32, 32))
+
+
+def _run_blocks(monkeypatch, fused: bool):
+    """stem conv (27 -> 32, padded: not fusable) + BN + ReLU, two residual blocks, 1x1 head; returns
+    (logits, {parameter: gradient}, call list)."""
+    from nerf_downstream_b200 import ops as O
+    fake = host_harness.install(monkeypatch, "bf16")
+    for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask"):
+        monkeypatch.setattr(O, knob, fused)
+    torch.manual_seed(5)
+    coords, feats = synth.random_cloud(6, 9000, extent=14, n_batch=2, channels=27)
+    stem = torch.nn.Sequential(ME.MinkowskiConvolution(27, 32, kernel_size=3, dimension=3), ME.MinkowskiBatchNorm(32),
+                               ME.MinkowskiReLU())
+    blocks = _two_blocks(6)
+    head = ME.MinkowskiConvolution(32, 20, kernel_size=1, bias=True, dimension=3)
+    net = torch.nn.Sequential(stem, blocks, head).train()
+    out = net(_field(coords, feats).sparse())
+    logits = out.F
+    (logits * torch.linspace(-1, 1, 20)).sum().backward()
+    return logits.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}, list(fake.calls), net
+
+
+def test_fused_conv_bn_node_hollow_rows_and_recomputed_relu_mask_agree_with_the_separate_nodes(monkeypatch):
+    """bf16 mode: conv + BN (+ residual, ReLU) as ONE autograd node, BatchNorm outputs that only feed convolutions
+    without fp32 rows, ReLU masks re-computed from x — same logits and parameter gradients as conv / BN as separate
+    nodes with every tensor materialised (the harness rounds bf16 operands like the kernels do)."""
+    from nerf_downstream_b200 import ops as O
+    made0 = O.hollow_stats["made"]
+    la, ga, calls_a, net_a = _run_blocks(monkeypatch, True)
+    made = O.hollow_stats["made"] - made0
+    lb, gb, calls_b, net_b = _run_blocks(monkeypatch, False)
+    assert torch.allclose(la, lb, rtol=1e-5, atol=1e-6)
+    for name, g in ga.items():
+        assert torch.allclose(g, gb[name], rtol=2e-4, atol=1e-6), name
+    # running statistics advanced once per BatchNorm in both
+    for (na, ba), (nb, bb) in zip(net_a.named_buffers(), net_b.named_buffers()):
+        assert torch.allclose(ba.float(), bb.float(), rtol=1e-5, atol=1e-7), na
+    # the stem's BN output and bn1 of each block feed one convolution only: hollow; the stem output is then read as
+    # block 1's residual and filled (one extra apply call); block outputs (residual folded in) are never hollow
+    assert made == 3
+    assert calls_a.count("spc_bn_apply") == calls_b.count("spc_bn_apply") + 1
+    # one launch set per layer either way: the fused node adds no kernels
+    for name in ("spc_conv_fwd_packed", "spc_conv_dgrad_packed", "spc_bn_stats_tracked", "spc_bn_bwd"):
+        assert calls_a.count(name) == calls_b.count(name), name
+    # gradients of the conv outputs inside the fused nodes are bf16-only: fewer conversion passes, never more
+    assert calls_a.count("spc_to_bf16") <= calls_b.count("spc_to_bf16")
+
+
+def test_pending_rows_keep_the_grad_mode_and_training_flag_of_the_module_call(monkeypatch):
+    host_harness.install(monkeypatch, "fp32")
+    coords, feats = synth.random_cloud(7, 800, extent=6, n_batch=1, channels=8)
+    x = _field(coords, feats).sparse()
+    conv, bn = ME.MinkowskiConvolution(8, 8, kernel_size=3, dimension=3), ME.MinkowskiBatchNorm(8)
+    with torch.no_grad():
+        y = bn(conv(x))
+    assert not y.F.requires_grad                    # produced outside the no_grad block, but called inside it
+    bn.eval()
+    z = bn(conv(x))
+    bn.train()
+    tracked = int(bn.bn.num_batches_tracked)
+    z.F                                             # an eval-mode call: running statistics, no update
+    assert int(bn.bn.num_batches_tracked) == tracked
+    w = ME.MinkowskiReLU()(bn(conv(x)))
+    with pytest.raises(RuntimeError, match="pre-activation"):
+        _ = bn(conv(x)), None
+        pre = bn(conv(x))
+        ME.MinkowskiReLU()(pre)
+        pre.F
+    assert w.F.min().item() >= 0
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_dgrad_of_a_symmetric_self_map_reads_the_forward_map_with_reversed_offsets(monkeypatch, precision):
+    """nbr_t[k] == nbr[K-1-k] on a centrally symmetric self map: dgrad with the reversed-offset weight image on the
+    forward map equals dgrad on the transposed map, and the transposed map is never built."""
+    from nerf_downstream_b200 import ops as O
+    grads, calls = [], []
+    for sym in (True, False):
+        fake = host_harness.install(monkeypatch, precision)
+        monkeypatch.setattr(O, "symmetric_dgrad", sym)
+        monkeypatch.setattr(O, "_pack_cache", {})
+        torch.manual_seed(8)
+        coords, feats = synth.random_cloud(9, 9000, extent=14, n_batch=2, channels=32)
+        x = _field(coords, feats).sparse()
+        f = x.F.detach().requires_grad_(True)
+        xs = ME.SparseTensor(f, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager)
+        conv = ME.MinkowskiConvolution(32, 64, kernel_size=3, dimension=3)
+        out = conv(xs).F
+        (out * torch.linspace(-1, 1, 64)).sum().backward()
+        grads.append(f.grad.clone())
+        calls.append(list(fake.calls))
+    assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-6)
+    assert calls[0].count("spc_kernel_map_transpose") == 0 and calls[1].count("spc_kernel_map_transpose") == 1
+
+
+def test_unet_in_bf16_mode_with_lazy_cat_and_fused_nodes_matches_the_plain_graph(monkeypatch):
+    """Res16UNet14A on the host harness in bf16 mode: ME.cat assembled from the bf16 operand copies (ops.CatFn, fp32
+    concatenation hollow), conv + BN nodes fused, hollow BatchNorm rows, re-computed ReLU masks, symmetric dgrad — the
+    logits and every parameter gradient equal those of the plain graph (torch.cat, separate nodes, all rows written)."""
+    from nerf_downstream_b200 import ops as O
+    res = []
+    for on in (True, False):
+        fake = host_harness.install(monkeypatch, "bf16")
+        for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "lazy_cat", "symmetric_dgrad"):
+            monkeypatch.setattr(O, knob, on)
+        monkeypatch.setattr(O, "_pack_cache", {})
+        torch.manual_seed(12)
+        coords, feats = synth.random_cloud(13, 6000, extent=12, n_batch=2, channels=27)
+        labels = torch.from_numpy(np.random.RandomState(0).randint(0, 20, size=coords.shape[0]))
+        net = models.Res16UNet14A(27, 20).train()
+        out = net(_field(coords, feats))
+        loss = ops.cross_entropy(out, labels, -255)
+        loss.backward()
+        res.append((out.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}, list(fake.calls)))
+    (la, ga, ca), (lb, gb, cb) = res
+    assert torch.allclose(la, lb, rtol=1e-4, atol=1e-5)
+    for n in ga:
+        assert _cos(ga[n], gb[n]) >= 0.9999, n
+    assert ca.count("spc_copy_rows") == 8 and cb.count("spc_copy_rows") == 0      # 4 skip connections x 2 parts
+    assert ca.count("spc_kernel_map_transpose") < cb.count("spc_kernel_map_transpose")
+    assert ca.count("spc_to_bf16") < cb.count("spc_to_bf16")
