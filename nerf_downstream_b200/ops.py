@@ -892,7 +892,7 @@ class ConvBNFn(torch.autograd.Function):
 # alone; its fp32 tensor still has to exist (it is the autograd output) but is left UNWRITTEN — 4 of the 14 bytes per
 # element the apply pass moves.  `_hollow` maps such a tensor to a closure that writes its fp32 rows on demand
 # (`ensure_filled`, called by every reader of fp32 rows in this module and by `Tensor.F` at the ME surface).
-_hollow: dict = {}   # data_ptr -> (weak reference to the tensor, fill closure)
+_hollow: dict = {}   # data_ptr -> (weak reference to the tensor, fill closure taking the tensor)
 hollow_stats = {"made": 0, "filled": 0}
 
 
@@ -918,7 +918,7 @@ def ensure_filled(t: torch.Tensor) -> torch.Tensor:
         e = _hollow.get(t.data_ptr())
         if e is not None and e[0]() is t:
             del _hollow[t.data_ptr()]
-            e[1]()
+            e[1](t)
             hollow_stats["filled"] += 1
     return t
 
@@ -957,7 +957,8 @@ def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, moment
     if hollow:
         epoch = _weights_epoch
 
-        def fill(x=x, mean=mean, var=var, gamma=gamma, beta=beta, res=res, y=y, eps=float(eps), relu=int(relu)):
+        # (the closure must not hold `y`: the registry entry lives exactly as long as the tensor does)
+        def fill(y, x=x, mean=mean, var=var, gamma=gamma, beta=beta, res=res, eps=float(eps), relu=int(relu)):
             if epoch != _weights_epoch:
                 raise RuntimeError("fp32 rows of a BatchNorm output were requested after an optimiser step changed its "
                                    "parameters; read .F before stepping (or set ops.hollow_rows = False)")
@@ -1078,7 +1079,7 @@ class CatFn(torch.autograd.Function):
         yb = cat_rows_bf16(parts)
         _remember_bf16(y, yb)
 
-        def fill(parts=parts, y=y):
+        def fill(y, parts=parts):
             torch.cat([ensure_filled(p) for p in parts], dim=1, out=y)
         _mark_hollow(y, fill)
         ctx.widths = widths

@@ -534,3 +534,24 @@ def test_unet_in_bf16_mode_with_lazy_cat_and_fused_nodes_matches_the_plain_graph
     assert ca.count("spc_copy_rows") == 8 and cb.count("spc_copy_rows") == 0      # 4 skip connections x 2 parts
     assert ca.count("spc_kernel_map_transpose") < cb.count("spc_kernel_map_transpose")
     assert ca.count("spc_to_bf16") < cb.count("spc_to_bf16")
+
+
+def test_hollow_registry_does_not_keep_tensors_alive(monkeypatch):
+    """A hollow tensor's registry entry (and the rows its fill closure needs) must die with the tensor."""
+    import gc
+    from nerf_downstream_b200 import ops as O
+    host_harness.install(monkeypatch, "bf16")
+    x = torch.randn(64, 32)
+    bn = torch.nn.BatchNorm1d(32)
+    y = O.BatchNormFn.apply(x, bn.weight, bn.bias, None, None, True, 0.1, 1e-5, True, None, None, False)
+    assert O.is_hollow(y)
+    n = len(O._hollow)
+    del y
+    gc.collect()
+    assert len(O._hollow) == n - 1
+    cat = O.CatFn.apply(torch.randn(16, 32), torch.randn(16, 32))
+    assert O.is_hollow(cat)
+    n = len(O._hollow)
+    del cat
+    gc.collect()
+    assert len(O._hollow) == n - 1
