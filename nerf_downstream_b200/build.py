@@ -43,19 +43,29 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:
+    """`experiments=True`: the timing-experiment variant (-DSPC_EXPERIMENTS: debug knobs of the convolution kernels,
+    multi-chunk stages) as libsparseconv_b200_exp.so — used by scripts/ only (SPARSECONV_B200_LIB), never shipped as
+    the product library."""
+    if experiments:
+        return _build_to(PKG_DIR / "libsparseconv_b200_exp.so", PKG_DIR / "build_exp", ["-DSPC_EXPERIMENTS"], verbose)
     digest = _digest()
     if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB_PATH
+    _build_to(LIB_PATH, PKG_DIR / "build", [], verbose)
+    STAMP.write_text(digest)
+    return LIB_PATH
+
+
+def _build_to(lib_path: Path, obj_dir: Path, extra_flags, verbose: bool) -> Path:
     nvcc = _nvcc()
-    obj_dir = PKG_DIR / "build"
     obj_dir.mkdir(exist_ok=True)
     procs = []
     objs = []
     for src in SOURCES:
         obj = obj_dir / (src + ".o")
         objs.append(str(obj))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -70,13 +80,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", str(lib_path), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-cudart", "static"]
     subprocess.run(cmd, check=True)
-    STAMP.write_text(digest)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv)
     print(path)

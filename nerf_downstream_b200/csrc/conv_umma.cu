@@ -39,6 +39,17 @@
 namespace spc {
 
 int g_umma_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef SPC_EXPERIMENTS
+// role timing of the forward kernel (clock64 sums over all CTAs): [0] producer warp 0 loop, [1] its empty-slot waits,
+// [2] its copy issue, [3] its bookkeeping + index prefetch, [4] MMA thread loop, [5] its full-stage waits, [6] its
+// accumulator waits, [7] stages, [8] epilogue warp 0 accumulator waits, [9] its body
+__device__ unsigned long long g_role_cycles[16];
+#define SPC_T(var) const long long var = clock64()
+#define SPC_ACC(i, v) atomicAdd(&g_role_cycles[i], (unsigned long long)(v))
+#else
+#define SPC_T(var)
+#define SPC_ACC(i, v)
+#endif
 int g_umma_force_mt = 0;  // test hook: 0 = auto
 
 struct UmmaConvParams {
@@ -54,6 +65,7 @@ struct UmmaConvParams {
   int out_bufs;              // 16 KB staging blocks of the TMA-store epilogue (0: st.global epilogue)
   int ngroups, wps;          // producer groups, warps per group
   int dbg_skip_store;        // timing experiment only: epilogue does not write the output
+  int dbg_flags;             // timing experiments (-DSPC_EXPERIMENTS): 1 no gather copies, 2 no MMAs, 4 no weight slabs
   int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
   int n_work;                // m_tiles * n_ntiles * ksplit
 };
@@ -199,10 +211,17 @@ int to_bf16(const float* src, int64_t rows, int c_src, int64_t src_pitch, int c_
   return 0;
 }
 
-template <int MT, bool BF16, int G, int WPS>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// NPW = producer warps (8 or 16).  The producers are bound by instruction latency, not by bytes: a stage costs a warp
+// ~450 dependent instructions (index shuffle, address arithmetic, LDGSTS) and with 8 producer warps a scheduler holds
+// two of them (0.37 IPC per scheduler, 330 clocks per stage with neither copies nor MMAs issued —
+// profiles/r2_conv_breakdown.md); 16 warps split every stage in two halves and give each scheduler four.
+constexpr int kFwdMaxThreads = (16 + 4 + 1) * 32;
+template <int MT, bool BF16, int G, int WPS, int NPW>
+__global__ void __launch_bounds__(kFwdMaxThreads, 1)
 conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tmap_out) {
   using PR = Prec<BF16>;
+  constexpr int kNumProducerWarps = NPW;      // (shadow the 8-producer layout of umma_common.cuh)
+  constexpr int kMmaWarp = NPW + 4;
   constexpr int kAStage = kTileM * PR::kRowBytes;  // one 32-channel chunk of one 128-row sub-tile
   extern __shared__ uint8_t smem_raw[];
   // swizzled operands need 1024-byte alignment
@@ -220,10 +239,15 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (REDUX: the warp index as a value ptxas KNOWS to be warp-uniform, so that the role branches below are uniform
+  // control flow and the MMA warp's loop state can live in uniform registers)
+  const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
+#ifdef SPC_EXPERIMENTS
+      if (p.dbg_flags & 128) mbar_init(full_bar(s), WPS + 1); else   // timing experiment: one arrival per warp
+#endif
       mbar_init(full_bar(s), 32 * WPS + 1);             // the lanes of the group's warps + 1 expect_tx
       mbar_init(empty_bar(s), 1);                       // one tcgen05.commit
     }
@@ -240,7 +264,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __reduce_min_sync(0xffffffffu, *tmem_slot_ptr);   // (REDUX: a provably uniform value)
 
   const int rows_per_work = kTileM * MT;
   // work item w -> (m tile, n tile, offset group); w = (mtile * n_ntiles + ntile) * ksplit + kg
@@ -278,7 +302,6 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
     constexpr int NI = RW / 32;             // 32-row groups of a slice
     static_assert(RW >= 32 && RW % 32 == 0, "a warp slice holds whole 32-row groups");
     const char* Bbase = reinterpret_cast<const char*>(p.Bp);
-    const size_t row_pitch = (size_t)p.Ck * PR::kElt;
     const bool leader = elect_one();
 
     // lane-constant pieces of the copy addresses: instruction q of a 32-row group covers flat pieces
@@ -295,64 +318,80 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
       src_tab[q] = (uint32_t)(piece * 16);
     }
 
-    // iterator over the stages this group owns
-    struct It { int w, s, S, ord, n0; uint32_t mask, rest; bool ok; };  // n0 = (first stage of item) % ngroups
-    auto open_item = [&](It& it) {  // first owned stage of item it.w or of a later item
+    // Iterator over the stages this group owns.  Everything per STAGE is incremental — (offset, chunk group) move
+    // by `ngroups` stages with compare / subtract on the item's remaining offset mask; the divisions (work item ->
+    // m tile / n tile, the offset share of a split item) happen once per ITEM.  (r2: the first version located every
+    // stage with four runtime integer divisions; with neither copies nor MMAs issued the kernel still took 0.375 of
+    // its 0.57 ms at 96->96 on 1 M voxels — 330 clocks per stage of dependent integer bookkeeping in eight warps.)
+    struct It { int w, mtile, ntile, cg; uint32_t rest; bool ok; };   // lowest set bit of `rest` = current offset
+    auto open_item = [&](It& it, int skip) {  // stage `skip` (0-based) of item it.w, carried over into later items
       for (;;) {
         if (it.w >= p.n_work || grp >= ngroups) { it.ok = false; return; }
-        it.mask = work_mask(it.w);
-        it.S = __popc(it.mask) * p.kg_count;
-        it.s = grp - it.n0;
-        if (it.s < 0) it.s += ngroups;
-        if (it.s < it.S) { it.rest = it.mask; it.ord = 0; return; }
-        it.n0 = (it.n0 + it.S) % ngroups;
+        uint32_t rest = work_mask(it.w);
+        int cg = skip;
+        while (rest != 0u && cg >= p.kg_count) { cg -= p.kg_count; rest &= rest - 1u; }
+        if (rest != 0u) {
+          it.rest = rest; it.cg = cg;
+          it.mtile = it.w / items_per_mtile;
+          it.ntile = (it.w / p.ksplit) % p.n_ntiles;
+          return;
+        }
+        skip = cg;            // the item has fewer stages than that: the rest of the step lands in the next item
         it.w += gridDim.x;
       }
     };
     auto advance = [&](It& it) {
-      it.s += ngroups;
-      if (it.s >= it.S) {
-        it.n0 = (it.n0 + it.S) % ngroups;
-        it.w += gridDim.x;
-        open_item(it);
-      }
-    };
-    // (k, cg) of the current stage; `rest` / `ord` walk the set bits of the offset mask
-    auto locate = [&](It& it, int& k, int& cg) {
-      const int ord = it.s / p.kg_count;
-      cg = it.s - ord * p.kg_count;
-      while (it.ord < ord) { it.rest &= it.rest - 1u; ++it.ord; }
-      k = __ffs(it.rest) - 1;
+      int cg = it.cg + ngroups;
+      uint32_t rest = it.rest;
+      while (rest != 0u && cg >= p.kg_count) { cg -= p.kg_count; rest &= rest - 1u; }
+      if (rest != 0u) { it.cg = cg; it.rest = rest; return; }
+      it.w += gridDim.x;
+      open_item(it, cg);
     };
     // lane l holds the neighbour row of row l of each 32-row group of this warp's slice
-    auto load_idx = [&](const It& it, int k, int* idx) {
-      const int o0 = (it.w / items_per_mtile) * rows_per_work + sl * RW + lane;
+    auto load_idx = [&](const It& it, int* idx) {
+      const int k = __ffs(it.rest) - 1;
+      const int o0 = it.mtile * rows_per_work + sl * RW + lane;
+      const int* row = p.nbr + (size_t)k * p.m_out;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int o = o0 + i * 32;
-        idx[i] = o < p.m_out ? __ldg(p.nbr + (size_t)k * p.m_out + o) : -1;
+#ifdef SPC_EXPERIMENTS
+        if (p.dbg_flags & 32) { idx[i] = o < p.m_out ? o : -1; continue; }
+#endif
+        idx[i] = o < p.m_out ? __ldg(row + o) : -1;
       }
     };
+    const uint32_t row_pitch32 = (uint32_t)p.Ck * PR::kElt;
 
     It cur;
-    cur.w = blockIdx.x; cur.n0 = 0; cur.ok = true;
-    open_item(cur);
-    int k = 0, cg = 0;
+    cur.w = blockIdx.x; cur.ok = true;
+    open_item(cur, grp);
     int idx[NI];
-    if (cur.ok) { locate(cur, k, cg); load_idx(cur, k, idx); }
+    if (cur.ok) load_idx(cur, idx);
     int slot = grp;  // ring slot / phase of sequence number grp + ngroups * i
     uint32_t phase = 0;
+#ifdef SPC_EXPERIMENTS
+    long long t_wait = 0, t_copy = 0, t_book = 0;
+    const long long t_loop0 = clock64();
+#endif
     while (cur.ok) {
       // indices of the NEXT owned stage: their latency hides behind this stage's slot wait
+      SPC_T(ta);
       It nxt = cur;
       advance(nxt);
-      int k_n = 0, cg_n = 0;
       int idx_n[NI];
-      if (nxt.ok) { locate(nxt, k_n, cg_n); load_idx(nxt, k_n, idx_n); }
+      if (nxt.ok) load_idx(nxt, idx_n);
 
-      const int ntile = (cur.w / p.ksplit) % p.n_ntiles;
+      const int k = __ffs(cur.rest) - 1, cg = cur.cg, ntile = cur.ntile;
+      SPC_T(tb);
       mbar_wait(empty_bar(slot), phase ^ 1u);
+      SPC_T(tc);
       const uint32_t stage_addr = smem_base + (uint32_t)slot * stage_bytes;
+#ifdef SPC_EXPERIMENTS
+      if (sl == 0 && leader && (p.dbg_flags & 4)) mbar_arrive(full_bar(slot));
+      else
+#endif
       if (sl == 0 && leader) {
         mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(G * b_chunk_bytes));
         // slab rows [ntile * cn_tile, +cn_tile) of chunks cg * G .. cg * G + G - 1 of offset k
@@ -367,7 +406,11 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
         }
       }
       __syncwarp();
-      const char* Agrp = reinterpret_cast<const char*>(p.A) + (size_t)cg * (G * PR::kRowBytes);
+      // per-lane source bases of the PPR instruction slots of a 32-row group: row address = base + row * pitch
+      const char* src_q[PPR];
+#pragma unroll
+      for (int q = 0; q < PPR; ++q)
+        src_q[q] = reinterpret_cast<const char*>(p.A) + (size_t)cg * (G * PR::kRowBytes) + src_tab[q];
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int R0 = sl * RW + i * 32;  // first row of this 32-row group among the item's MT x 128 rows
@@ -375,57 +418,102 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
 #pragma unroll
         for (int q = 0; q < PPR; ++q) {
           const int src_row = __shfl_sync(0xffffffffu, idx[i], rr_tab[q]);
-          const char* src = Agrp + (size_t)(src_row >= 0 ? src_row : 0) * row_pitch + src_tab[q];
+          const char* src = src_q[q] + (size_t)(uint32_t)max(src_row, 0) * row_pitch32;   // (IMAD.WIDE.U32)
+#ifdef SPC_EXPERIMENTS
+          if (p.dbg_flags & 1) continue;
+#endif
           cp_async_16(dst_base + dst_tab[q], src, src_row >= 0 ? 16u : 0u);
         }
       }
       // the stage's "full" barrier is signalled by the hardware when this lane's copies have landed:
       // no wait_group, no fence, nothing blocks here
+#ifdef SPC_EXPERIMENTS
+      if (p.dbg_flags & 128) { if (leader) mbar_arrive(full_bar(slot)); } else
+#endif
       cp_async_mbar_arrive_noinc(full_bar(slot));
+#ifdef SPC_EXPERIMENTS
+      { const long long td = clock64(); t_book += tb - ta; t_wait += tc - tb; t_copy += td - tc; }
+#endif
       slot += ngroups;
       if (slot >= p.stages) { slot -= p.stages; phase ^= 1u; }
-      cur = nxt; k = k_n; cg = cg_n;
+      cur = nxt;
 #pragma unroll
       for (int i = 0; i < NI; ++i) idx[i] = idx_n[i];
     }
+#ifdef SPC_EXPERIMENTS
+    if (warp == 0 && lane == 0) {
+      SPC_ACC(0, clock64() - t_loop0); SPC_ACC(1, t_wait); SPC_ACC(2, t_copy); SPC_ACC(3, t_book);
+    }
+#endif
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
-    // ONE elected thread runs the whole loop: under elect.sync the compiler keeps descriptors in
-    // uniform registers and emits back-to-back UTCHMMA (a `lane == 0` branch costs an ELECT /
-    // BRA.U.ANY waterfall around every tcgen05 instruction).
-    if (elect_one()) {
+    // The WHOLE warp runs the loop in uniform control flow and the tcgen05 instructions carry an issue predicate
+    // that is true in one elected lane (ptx.cuh: mma_*_p).  Shared-memory descriptors and barrier addresses advance
+    // incrementally with the ring slot.  (r2: the single-thread `if (elected)` loop kept every counter in vector
+    // registers and moved six of them to uniform registers per stage; with the slot wait and the proxy fence the
+    // issuing thread needed ~390 clocks of its own per stage against 192 clocks of tensor work at 96->96 and was
+    // never waiting for a full stage — profiles/r2_conv_breakdown.md.)
+    {
+      const uint32_t issue = elect_one() ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = PR::idesc(kTileM, (uint32_t)p.cn_tile, 0, 0);
       const uint64_t desc_hi = make_desc(0, 16, PR::kSboK, PR::kLayoutK);
+      const uint32_t sb16 = (uint32_t)stage_bytes >> 4;            // (all shared-memory offsets in 16-byte units)
+      const uint32_t lo0 = smem_base >> 4;
+      constexpr uint32_t kA16 = (uint32_t)kAStage >> 4;
+      const uint32_t bc16 = (uint32_t)b_chunk_bytes >> 4;
+      uint32_t lo = lo0;                                            // slot `stage` starts at lo << 4
+      uint32_t fbar = full_bar(0);
       for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
         const uint32_t mask = work_mask(w);
-        const int n_iters = __popc(mask) * p.kg_count;
+        const int n_iters = (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mask) * p.kg_count));  // (uniform)
+#ifdef SPC_EXPERIMENTS
+        long long m_full = 0;
+        const long long ma = clock64();
+#endif
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+#ifdef SPC_EXPERIMENTS
+        if (issue) { SPC_ACC(6, clock64() - ma); SPC_ACC(7, n_iters); }
+        const long long m_loop0 = clock64();
+#endif
         tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * p.cn_tile);
         for (int it = 0; it < n_iters; ++it) {
-          mbar_wait(full_bar(stage), phase);
+          SPC_T(mb);
+          mbar_wait(fbar, phase);
+#ifdef SPC_EXPERIMENTS
+          m_full += clock64() - mb;
+          if (!(p.dbg_flags & 8))
+#endif
           fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
-          const uint32_t stage_addr = smem_base + (uint32_t)stage * stage_bytes;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t d = tmem_base + (uint32_t)((acc * MT + mt) * p.cn_tile);
+            const uint32_t d = d0 + (uint32_t)(mt * p.cn_tile);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-              const uint64_t adesc = desc_hi | (uint64_t)(((stage_addr + (mt * G + g) * kAStage) >> 4) & 0x3FFFu);
-              const uint64_t bdesc = desc_hi | (uint64_t)(((stage_addr + G * MT * kAStage + g * b_chunk_bytes) >> 4) & 0x3FFFu);
+              const uint64_t adesc = desc_hi | (uint64_t)(lo + (uint32_t)(mt * G + g) * kA16);
+              const uint64_t bdesc = desc_hi | (uint64_t)(lo + (uint32_t)(G * MT) * kA16 + (uint32_t)g * bc16);
 #pragma unroll
-              for (int q = 0; q < PR::kMmaPerRow; ++q)  // 32 bytes of K per MMA
-                PR::mma(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || g > 0 || q > 0) ? 1u : 0u);
+              for (int q = 0; q < PR::kMmaPerRow; ++q) {  // 32 bytes of K per MMA
+#ifdef SPC_EXPERIMENTS
+                if (p.dbg_flags & 2) continue;
+#endif
+                PR::mma_p(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || g > 0 || q > 0) ? 1u : 0u, issue);
+              }
             }
           }
-          mma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          mma_commit_p(fbar + 8u * kMaxStages, issue);  // the slot's "empty" barrier: reusable once these MMAs have read it
+          lo += sb16; fbar += 8u;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; lo = lo0; fbar = full_bar(0); }
         }
-        mma_commit(tfull_bar(acc));
+        mma_commit_p(tfull_bar(acc), issue);
+#ifdef SPC_EXPERIMENTS
+        if (issue) { SPC_ACC(4, clock64() - m_loop0); SPC_ACC(5, m_full); }
+#endif
         if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -442,8 +530,21 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
       const int o0 = mtile * rows_per_work;
       const uint32_t mask = work_mask(w);
       const bool add_bias = p.bias != nullptr && kg == 0;
+      SPC_T(ea);
       mbar_wait_sleep(tfull_bar(acc), acc_phase);
+      SPC_T(eb);
+#ifdef SPC_EXPERIMENTS
+      if (ew == 0 && lane == 0) SPC_ACC(8, eb - ea);
+#endif
       tc_fence_after();
+#ifdef SPC_EXPERIMENTS
+      if (p.dbg_flags & 16) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+#endif
       if (p.out_bufs > 0) {
         // The accumulator tile goes TMEM -> registers -> shared memory (128-byte-swizzled rows: conflict-free
         // 16-byte stores) -> global memory with TMA tensor stores (full 128-byte row segments; rows past
@@ -537,6 +638,9 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+#ifdef SPC_EXPERIMENTS
+      if (ew == 0 && lane == 0) SPC_ACC(9, clock64() - eb);
+#endif
       if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
     }
     if (p.out_bufs > 0 && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -550,16 +654,16 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   }
 }
 
-template <int MT, bool BF16, int G, int WPS>
+template <int MT, bool BF16, int G, int WPS, int NPW>
 static int launch_conv_umma(const UmmaConvParams& p, const CUtensorMap& tmap_out, int grid, size_t smem,
                             cudaStream_t stream) {
-  auto kern = conv_umma_kernel<MT, BF16, G, WPS>;
+  auto kern = conv_umma_kernel<MT, BF16, G, WPS, NPW>;
   static int smem_set = 0;  // (per instantiation) the attribute only ever needs to grow
   if ((int)smem > smem_set) {
     SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = (int)smem;
   }
-  kern<<<grid, kNumThreads, smem, stream>>>(p, tmap_out);
+  kern<<<grid, (NPW + 5) * 32, smem, stream>>>(p, tmap_out);
   SPC_LAUNCHED("conv_umma_kernel");
   return 0;
 }
@@ -631,8 +735,10 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   p.A = in; p.Bp = Wp; p.bias = bias; p.nbr = nbr; p.tile_mask = tile_mask; p.out = out;
 #ifdef SPC_EXPERIMENTS
   p.dbg_skip_store = g_umma_dbg[3];
+  p.dbg_flags = g_umma_dbg[5];
 #else
-  p.dbg_skip_store = 0;   // (timing experiment, compiled out of the shipped library)
+  p.dbg_skip_store = 0;   // (timing experiments, compiled out of the shipped library)
+  p.dbg_flags = 0;
 #endif
   p.m_out = (int)m_out; p.Ck = c_in; p.Cn = c_out; p.K = K;
   p.kc_count = c_in / 32;
@@ -710,12 +816,17 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   SPC_REQUIRE(stages >= 2, "tile does not fit in shared memory");
   p.stages = stages;
   // producer groups: the largest power of two <= min(ring slots, 8); every warp slice holds >= 32 rows
+  // producer warps: 16 split every stage over two warps (more loads in flight while one of them does its
+  // bookkeeping): 32->32 0.173 -> 0.163 ms, 64->64 0.332 -> 0.316, 96->96 0.505 -> 0.493 on 1 M voxels; wider tiles
+  // (stages of >= 24 KB) are better off with 8 (128->128 0.705 vs 0.746).  Knob 6 forces 8 / 16.
+  const int npw = g_umma_dbg[6] == 8 ? 8 : (g_umma_dbg[6] == 16 ? 16 : (p.cn_tile <= 96 ? 16 : 8));
   int ngroups = 1;
-  while (ngroups * 2 <= stages && ngroups * 2 <= kNumProducerWarps) ngroups *= 2;
+  while (ngroups * 2 <= stages && ngroups * 2 <= 8) ngroups *= 2;
   if (g_umma_dbg[0] >= 1 && g_umma_dbg[0] <= stages && g_umma_dbg[0] <= 8 && (g_umma_dbg[0] & (g_umma_dbg[0] - 1)) == 0)
     ngroups = g_umma_dbg[0];
-  int wps = kNumProducerWarps / ngroups;
+  int wps = npw / ngroups;
   if (wps > 4) wps = 4;        // (instantiated: 1, 2, 4 warps per group; every slice holds >= 32 rows)
+  if (kTileM * mt / wps < 32) wps = kTileM * mt / 32;
   p.ngroups = ngroups;
   p.wps = wps;
   const size_t smem = (size_t)stages * stage_bytes + (size_t)p.out_bufs * 16384 + 1024 + 256;
@@ -723,7 +834,9 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   g_conv_path_counts[bf16 ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
   // (MT, precision, G, warps per producer group) -> instantiation
 #define SPC_CONV_CASE(MT_, BF_, G_, W_) \
-  if (mt == MT_ && bf16 == BF_ && G == G_ && wps == W_) return launch_conv_umma<MT_, BF_, G_, W_>(p, tmap_out, grid, smem, stream);
+  if (mt == MT_ && bf16 == BF_ && G == G_ && wps == W_) \
+    return npw == 8 ? launch_conv_umma<MT_, BF_, G_, W_, 8>(p, tmap_out, grid, smem, stream) \
+                    : launch_conv_umma<MT_, BF_, G_, W_, 16>(p, tmap_out, grid, smem, stream);
 #define SPC_CONV_WPS(MT_, BF_, G_) SPC_CONV_CASE(MT_, BF_, G_, 1) SPC_CONV_CASE(MT_, BF_, G_, 2) SPC_CONV_CASE(MT_, BF_, G_, 4)
   SPC_CONV_WPS(1, true, 1) SPC_CONV_WPS(2, true, 1) SPC_CONV_WPS(1, false, 1) SPC_CONV_WPS(2, false, 1)
 #ifdef SPC_EXPERIMENTS   // multi-chunk stages (contiguous 128 / 192-byte row visits): measured slower, see below
@@ -734,6 +847,15 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   return fail("conv_fwd_umma", "no kernel instantiation for this tile configuration");
 }
 
+#ifdef SPC_EXPERIMENTS
+extern "C" int spc_debug_role_cycles(long long* out16, int reset) {
+  unsigned long long h[16];
+  if (cudaMemcpyFromSymbol(h, g_role_cycles, sizeof(h)) != cudaSuccess) return 1;
+  for (int i = 0; i < 16; ++i) out16[i] = (long long)h[i];
+  if (reset) { memset(h, 0, sizeof(h)); if (cudaMemcpyToSymbol(g_role_cycles, h, sizeof(h)) != cudaSuccess) return 1; }
+  return 0;
+}
+#endif
 void umma_set_force_mt(int mt) { g_umma_force_mt = mt; }
 void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_umma_dbg[idx] = val; }
 

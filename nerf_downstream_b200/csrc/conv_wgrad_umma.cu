@@ -91,7 +91,9 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
   uint8_t* s_act = tab_raw + kWgMaxMb * 4 * 2;                        // [2][kWgActBytes] active M blocks per row block
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (REDUX: a warp index ptxas knows to be warp-uniform — the role branches are then uniform control flow and the MMA
+  // warp's loop state lives in uniform registers, see conv_umma_kernel)
+  const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     // full barriers: the 32 lanes of the one warp that fills the stage (cp.async ... arrive.noinc)
@@ -112,7 +114,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __reduce_min_sync(0xffffffffu, *tmem_slot_ptr);   // (REDUX: a provably uniform value)
   const uint32_t all_taps = p.K >= 32 ? 0xFFFFFFFFu : ((1u << p.K) - 1u);
 
   // ---- per-lane constants of the row visits (producer warps): instruction q of a 32-row group covers flat
@@ -141,9 +143,12 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
     return p.act16 ? (uint32_t)reinterpret_cast<const uint16_t*>(act)[rbi] : (uint32_t)act[rbi];
   };
 
-  uint32_t a_phase = 0;        // producer warp: parity of ITS ring slot; MMA thread: one parity bit per slot
-  uint32_t b_phase = 0;        // B warp: bit s = parity of slot s; MMA thread: same
-  uint32_t t_phase = 0;
+  uint32_t a_phase = 0;        // producer warp: parity of ITS ring slot
+  uint32_t b_phase = 0;        // B warp: bit s = parity of slot s
+  uint32_t t_phase = 0;        // epilogue warps
+  // the MMA warp's own copies (one parity bit per A slot / B slot): kept apart from the other roles' so that they are
+  // provably warp-uniform values
+  uint32_t m_a_phase = 0, m_b_phase = 0, m_t_phase = 0;
   int local_item = 0;
   for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++local_item) {
     const int split = w / p.n_pass, pass = w - split * p.n_pass;
@@ -253,45 +258,48 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
       __syncwarp();
     } else if (warp == kMmaWarp) {
       // ============================ MMA issuer ============================
-      // one elected thread runs the whole loop (see conv_umma_kernel)
-      if (elect_one()) {
+      // the whole warp runs the loop in uniform control flow; the tcgen05 instructions carry an issue predicate that
+      // is true in one elected lane (see conv_umma_kernel)
+      {
+        const uint32_t issue = elect_one() ? 1u : 0u;
         const uint32_t idesc = PR::idesc(128, (uint32_t)p.Cout, 1, 1);  // both operands MN-major
         const uint64_t desc_hi = make_desc(0, kWgChunkBlock, 512, PR::kLayoutMN);
-        mbar_wait(t_empty, t_phase ^ 1u);  // epilogue drained the previous item's accumulators
+        mbar_wait(t_empty, m_t_phase ^ 1u);  // epilogue drained the previous item's accumulators
+        m_t_phase ^= 1u;
         tc_fence_after();
         uint32_t touched = 0;
         int as = 0, bs = 0;
         for (int rbi = 0; rbi < n_rbi; ++rbi) {
-          uint32_t a = act_at(act, rbi);
+          uint32_t a = __reduce_or_sync(0xffffffffu, act_at(act, rbi));   // (the same value in every lane: uniform)
           if (!a) continue;
-          mbar_wait(b_full(bs), (b_phase >> bs) & 1u);
-          const uint32_t b_addr = b_base + (uint32_t)bs * b_stage_bytes;
+          mbar_wait(b_full(bs), (m_b_phase >> bs) & 1u);
+          const uint32_t b16 = (b_base + (uint32_t)bs * b_stage_bytes) >> 4;
           while (a) {
             const int i = __ffs(a) - 1;
             a &= a - 1u;
-            mbar_wait(a_full(as), (a_phase >> as) & 1u);
+            mbar_wait(a_full(as), (m_a_phase >> as) & 1u);
             fence_proxy_async_smem();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
             tc_fence_after();
-            const uint32_t a_addr = a_base + (uint32_t)as * kWgAStage;
+            const uint32_t a16 = (a_base + (uint32_t)as * kWgAStage) >> 4;
             const uint32_t d = tmem_base + (uint32_t)(i * p.Cout);
             const uint32_t was = (touched >> i) & 1u;
 #pragma unroll
             for (int r8 = 0; r8 < kMmaPerStep; ++r8) {
               // descriptors differ only in the start address field: 1024 B of rows per MMA = 64 units
-              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr >> 4) + 64u * r8) & 0x3FFFu);
-              const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr >> 4) + 64u * r8) & 0x3FFFu);
-              PR::mma(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u);
+              const uint64_t adesc = desc_hi | (uint64_t)(a16 + 64u * r8);
+              const uint64_t bdesc = desc_hi | (uint64_t)(b16 + 64u * r8);
+              PR::mma_p(d, adesc, bdesc, idesc, (was || r8 > 0) ? 1u : 0u, issue);
             }
-            mma_commit(a_empty(as));
-            a_phase ^= 1u << as;
+            mma_commit_p(a_empty(as), issue);
+            m_a_phase ^= 1u << as;
             if (++as == p.a_stages) as = 0;
             touched |= 1u << i;
           }
-          mma_commit(b_empty(bs));
-          b_phase ^= 1u << bs;
+          mma_commit_p(b_empty(bs), issue);
+          m_b_phase ^= 1u << bs;
           bs ^= 1;
         }
-        mma_commit(t_full);
+        mma_commit_p(t_full, issue);
       }
       __syncwarp();
     } else if (warp >= kNumProducerWarps && warp < kMmaWarp) {
@@ -330,7 +338,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
       tc_fence_before();
       mbar_arrive(t_empty);
     }
-    if (warp == kMmaWarp || (warp >= kNumProducerWarps && warp < kMmaWarp)) t_phase ^= 1u;
+    if (warp >= kNumProducerWarps && warp < kMmaWarp) t_phase ^= 1u;
     // the A / B slot parities of a role that did nothing this item stay as they are; the MMA thread's per-slot
     // bits advanced exactly as the producers' own counters did (every filled slot was consumed)
   }

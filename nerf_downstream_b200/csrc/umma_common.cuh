@@ -45,6 +45,11 @@ struct Prec {
     if (BF16) mma_bf16(d, a, b, id, acc);
     else mma_tf32(d, a, b, id, acc);
   }
+  __device__ static __forceinline__ void mma_p(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc,
+                                               uint32_t issue) {
+    if (BF16) mma_bf16_p(d, a, b, id, acc, issue);
+    else mma_tf32_p(d, a, b, id, acc, issue);
+  }
 };
 
 // test / measurement knobs (spc_debug_set), all 0 = default:
