@@ -236,6 +236,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+  auto turn_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };  // (shared ring slots, see producers)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -250,6 +251,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
 #endif
       mbar_init(full_bar(s), 32 * WPS + 1);             // the lanes of the group's warps + 1 expect_tx
       mbar_init(empty_bar(s), 1);                       // one tcgen05.commit
+      mbar_init(turn_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -369,8 +371,15 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
     open_item(cur, grp);
     int idx[NI];
     if (cur.ok) load_idx(cur, idx);
-    int slot = grp;  // ring slot / phase of sequence number grp + ngroups * i
-    uint32_t phase = 0;
+    // ring slot and revolution of this group's stage sequence number n = grp + ngroups * i (slot = n % stages).
+    // ngroups <= stages: a slot is always refilled by the group that filled it, which waits for the MMA warp to
+    // release it.  ngroups > stages (16 one-warp groups on 8 slots: twice as many warps doing their bookkeeping and
+    // index prefetch while others issue copies): two groups alternate on a slot.  One parity bit cannot tell "the
+    // revolution before mine is not even filled" from "it is already released", so the groups hand the slot to each
+    // other through a third barrier: a group arrives on turn_bar(slot) when it has issued its revolution, and waits
+    // for the other group's arrival before it looks at the slot's "empty" barrier.
+    int slot = grp % p.stages, rev = grp / p.stages;
+    const bool shared_slots = ngroups > p.stages;
 #ifdef SPC_EXPERIMENTS
     long long t_wait = 0, t_copy = 0, t_book = 0;
     const long long t_loop0 = clock64();
@@ -385,7 +394,9 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
 
       const int k = __ffs(cur.rest) - 1, cg = cur.cg, ntile = cur.ntile;
       SPC_T(tb);
-      mbar_wait(empty_bar(slot), phase ^ 1u);
+      const uint32_t par = (uint32_t)(rev - 1) & 1u;
+      if (shared_slots) mbar_wait(turn_bar(slot), par);
+      mbar_wait(empty_bar(slot), par);
       SPC_T(tc);
       const uint32_t stage_addr = smem_base + (uint32_t)slot * stage_bytes;
 #ifdef SPC_EXPERIMENTS
@@ -434,8 +445,9 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
 #ifdef SPC_EXPERIMENTS
       { const long long td = clock64(); t_book += tb - ta; t_wait += tc - tb; t_copy += td - tc; }
 #endif
+      if (shared_slots && sl == 0 && leader) mbar_arrive(turn_bar(slot));
       slot += ngroups;
-      if (slot >= p.stages) { slot -= p.stages; phase ^= 1u; }
+      while (slot >= p.stages) { slot -= p.stages; ++rev; }
       cur = nxt;
 #pragma unroll
       for (int i = 0; i < NI; ++i) idx[i] = idx_n[i];
@@ -826,6 +838,8 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
     ngroups = g_umma_dbg[0];
   int wps = npw / ngroups;
   if (wps > 4) wps = 4;        // (instantiated: 1, 2, 4 warps per group; every slice holds >= 32 rows)
+  // 16 one-warp groups alternating on 8 ring slots (see the producer loop); knob 7 = 1 keeps 8 groups of two warps
+  if (npw == 16 && ngroups == 8 && stages == 8 && g_umma_dbg[7] != 1) { ngroups = 16; wps = 1; }
   if (kTileM * mt / wps < 32) wps = kTileM * mt / 32;
   p.ngroups = ngroups;
   p.wps = wps;

@@ -24,13 +24,13 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {
 // (what template G of conv_umma.cu does); LAYOUT 1: destination rows of PPR*16 B contiguous, 16-byte pieces XORed
 // with (r & 7) (SWIZZLE_128B image for PPR = 8).
 template <int PPR, int LAYOUT, int DEPTH, int RUN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 k(const char* __restrict__ table, int n_rows, int row_bytes, int iters, int miss64, unsigned long long* sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ((uint32_t)__cvta_generic_to_shared(smem) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ROWS = 512 / PPR;   // rows per stage (8 KB / visit width)
-  uint32_t pos = (blockIdx.x * 8 + warp) * 1000003u;
+  uint32_t pos = (blockIdx.x * 16 + warp) * 1000003u;
   for (int it = 0; it < iters; ++it) {
     const uint32_t slot = base + (uint32_t)((warp * DEPTH + it % DEPTH) * 8192);
     // one hash per stage (uniform); the stage's rows are runs of RUN consecutive rows 977 rows apart
@@ -56,27 +56,27 @@ k(const char* __restrict__ table, int n_rows, int row_bytes, int iters, int miss
 }
 
 template <int PPR, int LAYOUT, int DEPTH, int RUN>
-void run(const char* table, int n_rows, int row_bytes, int miss, unsigned long long* sink) {
+void run(const char* table, int n_rows, int row_bytes, int miss, unsigned long long* sink, int NW = 8) {
   const int runlen = RUN;
   const int miss64 = miss * 64 / 100;
-  const size_t smem = 8 * DEPTH * 8192 + 1024;
+  const size_t smem = NW * DEPTH * 8192 + 1024;
   auto kern = k<PPR, LAYOUT, DEPTH, RUN>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int iters = 6000;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  kern<<<148, 256, smem>>>(table, n_rows, row_bytes, 300, miss64, sink);
+  kern<<<148, NW * 32, smem>>>(table, n_rows, row_bytes, 300, miss64, sink);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
-  kern<<<148, 256, smem>>>(table, n_rows, row_bytes, iters, miss64, sink);
+  kern<<<148, NW * 32, smem>>>(table, n_rows, row_bytes, iters, miss64, sink);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   const double clk = ms * 1e-3 * 1.9e9;                 // nominal 1.9 GHz
-  const double visits = 8.0 * iters * (512.0 / PPR);    // per SM
-  printf("visit %3d B layout %d depth %d run %2d miss %2d%%: %7.3f ms  %5.2f clk/visit  %5.2f clk/LDGSTS  %6.1f B/clk/SM (smem bytes)\n",
-         PPR * 16, LAYOUT, DEPTH, runlen, miss, ms, clk / visits, clk / (8.0 * iters * 16), 8.0 * iters * 8192 / clk);
+  const double visits = (double)NW * iters * (512.0 / PPR);    // per SM
+  printf("warps %2d visit %3d B layout %d depth %d run %2d miss %2d%%: %7.3f ms  %5.2f clk/visit  %5.2f clk/LDGSTS  %6.1f B/clk/SM (smem bytes)\n",
+         NW, PPR * 16, LAYOUT, DEPTH, runlen, miss, ms, clk / visits, clk / ((double)NW * iters * 16), (double)NW * iters * 8192 / clk);
 }
 
 int main() {
@@ -97,6 +97,12 @@ int main() {
     run<8, 1, 3, 1>(table, n_rows, row_bytes, miss, sink);
     run<16, 1, 3, 1>(table, n_rows, row_bytes, miss, sink);
   }
+  // warp-count sweep: is the rate per warp or per SM?
+  for (int nw = 1; nw <= 16; nw *= 2) {
+    if (nw * 3 * 8192 + 1024 > 227 * 1024) { run<4, 0, 1, 8>(table, n_rows, row_bytes, 36, sink, nw); continue; }
+    run<4, 0, 3, 8>(table, n_rows, row_bytes, 36, sink, nw);
+  }
+  for (int nw = 1; nw <= 16; nw *= 2) run<4, 0, 1, 8>(table, n_rows, row_bytes, 0, sink, nw);
   // depth sweep on the two candidates
   run<4, 0, 1, 8>(table, n_rows, row_bytes, 36, sink);
   run<4, 0, 2, 8>(table, n_rows, row_bytes, 36, sink);
