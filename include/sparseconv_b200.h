@@ -208,6 +208,12 @@ int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias,
 int spc_conv_dgrad_packed(const void* dout, const void* w_packed_t, const int32_t* nbr_t, const uint32_t* tile_mask_t,
                           int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision, float* din,
                           void* stream);
+/* spc_conv_dgrad_packed with accumulate != 0: din += the input gradient (TMA reduce-add epilogue).  `din` then holds
+ * the gradient that reached the same rows through the block's residual connection (resnet_block.py:53-69: x feeds
+ * conv1 AND `out += residual`), so the sum autograd would form with a separate pass over both is written once. */
+int spc_conv_dgrad_packed_acc(const void* dout, const void* w_packed_t, const int32_t* nbr_t,
+                              const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                              int precision, float* din, int accumulate, void* stream);
 
 /*
  * BatchNorm over voxel rows (MinkowskiBatchNorm == nn.BatchNorm1d on .F,

@@ -21,7 +21,7 @@ int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
                   bool transpose_w, bool bf16, float* out, void* workspace,
-                  int64_t workspace_bytes, cudaStream_t stream);
+                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate = false);
 // conv_wgrad_umma.cu
 bool umma_wgrad_supported(int c_in, int c_out);
 int64_t umma_wgrad_workspace(int K, int c_in, int c_out);
@@ -93,11 +93,18 @@ int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias,
 int spc_conv_dgrad_packed(const void* dout, const void* w_packed_t, const int32_t* nbr_t, const uint32_t* tile_mask_t,
                           int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision, float* din,
                           void* stream) {
+  return spc_conv_dgrad_packed_acc(dout, w_packed_t, nbr_t, tile_mask_t, m_in, m_out, c_in, c_out, K, precision, din, 0,
+                                   stream);
+}
+
+int spc_conv_dgrad_packed_acc(const void* dout, const void* w_packed_t, const int32_t* nbr_t,
+                              const uint32_t* tile_mask_t, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                              int precision, float* din, int accumulate, void* stream) {
   (void)m_out;
   SPC_REQUIRE(precision == SPC_PREC_TF32 || precision == SPC_PREC_BF16, "packed weights are a tensor-core format");
   SPC_REQUIRE(w_packed_t && tc_fwd_ok(K, c_out, c_in), "shape not supported by the tcgen05 path");
   return conv_fwd_umma(dout, nullptr, w_packed_t, nullptr, nbr_t, tile_mask_t, m_in, c_out, c_in, K, true,
-                       precision == SPC_PREC_BF16, din, nullptr, 0, (cudaStream_t)stream);
+                       precision == SPC_PREC_BF16, din, nullptr, 0, (cudaStream_t)stream, accumulate != 0);
 }
 
 int64_t spc_conv_workspace(int K, int c_in, int c_out, int precision) {

@@ -67,6 +67,7 @@ struct UmmaConvParams {
   int dbg_skip_store;        // timing experiment only: epilogue does not write the output
   int dbg_flags;             // timing experiments (-DSPC_EXPERIMENTS): 1 no gather copies, 2 no MMAs, 4 no weight slabs
   int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
+  int reduce_out;            // the epilogue ADDS to `out` (offset-split items, or accumulate: out += result)
   int n_work;                // m_tiles * n_ntiles * ksplit
 };
 
@@ -563,7 +564,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
         // m_out are clipped by the TMA unit), one [128 rows x 32 columns] block per round through a ring of
         // out_bufs staging blocks.  A thread-per-row st.global from the 32x32b TMEM layout is 32 half-written
         // sectors per instruction and competes with the row gather for the LSU (r1: 23 % of the kernel).
-        const bool skip = mask == 0 && !add_bias && p.ksplit > 1;  // nothing to add (uniform over the CTA)
+        const bool skip = mask == 0 && !add_bias && p.reduce_out;  // nothing to add (uniform over the CTA)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int r = ew * 32 + lane;  // row within the sub-tile
@@ -604,7 +605,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
             if (store_leader) {
               if (!skip && !p.dbg_skip_store && row0 < p.m_out) {
                 const int col0 = ntile * p.cn_tile + cb * 32;
-                if (p.ksplit > 1) tma_reduce_add_2d(&tmap_out, blk, col0, row0);
+                if (p.reduce_out) tma_reduce_add_2d(&tmap_out, blk, col0, row0);
                 else tma_store_2d(&tmap_out, blk, col0, row0);
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // (possibly empty: keeps the group count in step)
@@ -631,7 +632,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
               for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ntile * p.cn_tile + c0 + i);
             }
             if (row_ok && !p.dbg_skip_store) {
-              if (p.ksplit > 1) {  // partial sums of several offset groups meet in the (zeroed) output
+              if (p.reduce_out) {  // partial sums of several offset groups meet in the (zeroed) output
                 if (mask != 0 || add_bias) {
 #pragma unroll
                   for (int i = 0; i < 16; i += 4)
@@ -726,7 +727,7 @@ std::atomic<long long> g_conv_path_counts[4];
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
                   bool transpose_w, bool bf16, float* out, void* workspace,
-                  int64_t workspace_bytes, cudaStream_t stream) {
+                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate) {
   if (m_out == 0) return 0;
   SPC_REQUIRE(umma_fwd_supported(c_in, c_out), "shape not supported by the tcgen05 path");
   SPC_REQUIRE(K <= 32, "tcgen05 path supports kernel volume <= 32");
@@ -804,7 +805,10 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   p.kg_count = p.kc_count / G;
   p.k_per = (int)ceil_div(K, p.ksplit);
   p.n_ntiles = c_out / p.cn_tile;
-  if (p.ksplit > 1) SPC_CUDA(cudaMemsetAsync(out, 0, (size_t)m_out * c_out * sizeof(float), stream));
+  // accumulate: `out` already holds the other summand (the gradient that reached the same rows through a residual
+  // connection), every item reduce-adds into it and nothing is cleared
+  if (p.ksplit > 1 && !accumulate) SPC_CUDA(cudaMemsetAsync(out, 0, (size_t)m_out * c_out * sizeof(float), stream));
+  p.reduce_out = (p.ksplit > 1 || accumulate) ? 1 : 0;
 
   const int rows_per_work = kTileM * mt;
   p.n_work = (int)ceil_div(m_out, rows_per_work) * p.n_ntiles * p.ksplit;

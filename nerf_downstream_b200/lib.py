@@ -49,6 +49,7 @@ SIGNATURES = {
     "spc_conv_pack_weights_batch": (c_int, [_P, c_int, _P]),
     "spc_conv_fwd_packed": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "spc_conv_dgrad_packed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "spc_conv_dgrad_packed_acc": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "spc_conv_wgrad_acc": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "spc_conv_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
     "spc_to_bf16": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P]),

@@ -448,6 +448,13 @@ class _Pending:
         with torch.set_grad_enabled(self.grad):
             return self._run(want_fp32)
 
+    @staticmethod
+    def _alias_wanted(src, x) -> bool:
+        """hand the convolution's input back as an alias (ops "Residual gradients") when its rows take a gradient and
+        the SparseTensor that holds them is known"""
+        return bool(ops.fuse_residual_grad and src is not None and src._F is x and x.requires_grad
+                    and torch.is_grad_enabled() and x.is_contiguous())
+
     def _run(self, want_fp32: bool) -> torch.Tensor:
         # rows that took a residual are a block output: the next block reads them as ITS residual in fp32
         want_fp32 = want_fp32 or self.res is not None
@@ -455,14 +462,20 @@ class _Pending:
             if want_fp32 or not ops.hollow_rows:
                 return torch.cat([ops.ensure_filled(p) for p in self.cat], dim=1)
             return ops.CatFn.apply(*self.cat)
-        if self.bn is None:
-            x, w, bias, km, precision, w_param, bits = self.conv
-            return ops.SparseConvFn.apply(x, w, bias, km, precision, w_param, bits)
         if self.conv is not None:
-            x, w, bias, km, precision, w_param, bits = self.conv
-            if ops.conv_bn_fusable(x, w, bias, km, precision, bits):
-                return self.bn._run_fused(x, w, km, w_param, self.relu, self.res, want_fp32, self.bn_training)
-            feats = ops.SparseConvFn.apply(x, w, bias, km, precision, w_param, bits)
+            x, w, bias, km, precision, w_param, bits, src = self.conv
+            alias = self._alias_wanted(src, x)
+            if self.bn is not None and ops.conv_bn_fusable(x, w, bias, km, precision, bits):
+                out = self.bn._run_fused(x, w, km, w_param, self.relu, self.res, want_fp32, self.bn_training, alias)
+                feats = None
+            else:
+                out = ops.SparseConvFn.apply(x, w, bias, km, precision, w_param, bits, alias)
+                feats = out[0] if alias else out
+            if alias:
+                src._F = out[1]     # later readers of the input rows (the residual branch) go through the alias
+                out = out[0]
+            if self.bn is None or feats is None:
+                return out
         else:
             feats = self.x
         return self.bn._run(feats, self.relu, self.res, want_fp32, self.bn_training)

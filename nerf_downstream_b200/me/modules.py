@@ -118,11 +118,11 @@ class MinkowskiConvolutionBase(MinkowskiModuleBase):
         precision = self._precision()
         # a bf16 convolution reads the operand copy of its input rows: pending / hollow rows stay without fp32 image
         x = input._operand() if precision == L.PREC_BF16 else input.F
-        conv = (x, w, self.bias, km, precision, self.kernel, None if self.use_mm else self._offset_bits())
+        conv = (x, w, self.bias, km, precision, self.kernel, None if self.use_mm else self._offset_bits(), input)
         if ops.fuse_conv_bn:
             # the rows stay pending: a following MinkowskiBatchNorm takes the convolution into its autograd node
             return SparseTensor._deferred(_Pending(conv=conv), out_key, mgr)
-        return SparseTensor(ops.SparseConvFn.apply(*conv), coordinate_map_key=out_key, coordinate_manager=mgr)
+        return SparseTensor(_Pending(conv=conv).run(), coordinate_map_key=out_key, coordinate_manager=mgr)
 
     def _offset_bits(self) -> Optional[int]:
         """Kernel offsets that take part (None = all); the weight-sparse subclasses restrict them."""
@@ -253,12 +253,12 @@ class MinkowskiBatchNorm(nn.Module):
         return ops.BatchNormFn.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
                                      momentum, bn.eps, relu, residual, tracked, want_fp32)
 
-    def _run_fused(self, x, w, km, w_param, relu, residual, want_fp32, module_training=None):
+    def _run_fused(self, x, w, km, w_param, relu, residual, want_fp32, module_training=None, alias=False):
         """convolution + this BatchNorm (+ residual, ReLU) as one autograd node (ops.ConvBNFn)"""
         bn = self.bn
         training, momentum, tracked = self._bn_args(x.is_cuda, km.m_out, module_training)
         return ops.ConvBNFn.apply(x, w, km, w_param, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
-                                  momentum, bn.eps, relu, residual, tracked, want_fp32)
+                                  momentum, bn.eps, relu, residual, tracked, want_fp32, alias)
 
     def forward(self, input):
         if isinstance(input, SparseTensor):

@@ -619,6 +619,57 @@ def _tensor_core(what: int, K: int, c_in: int, c_out: int, precision: int) -> bo
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Residual gradients.  In a residual block the input rows x feed conv1 AND the block's `out += residual`
+# (resnet_block.py:53-69), so autograd adds two gradients of x with a separate pass over both (26 such passes per
+# Res16UNet34C step).  Here a convolution node (SparseConvFn / ConvBNFn) hands its input back as a second output — an
+# ALIAS the ME surface swaps into the input's SparseTensor — so the residual branch's gradient arrives at the SAME
+# node as `g_alias`; when that gradient is a buffer one of our backward kernels has just written for exactly this
+# tensor (`_aim_grad`: BatchNorm backward's dres, a convolution's dx), dgrad reduce-adds into it in its epilogue
+# (spc_conv_dgrad_packed_acc) and returns it.  Anything else (a sum formed by autograd, a strided slice of a
+# concatenation's gradient) is added with one ordinary pass.
+# ---------------------------------------------------------------------------------------------------------
+fuse_residual_grad = True
+_grad_aims: dict = {}    # data_ptr of a gradient buffer -> (weak reference to it, data_ptr of the tensor it is the gradient of)
+residual_stats = {"accumulated": 0, "added": 0}
+
+
+def _aim_grad(g: torch.Tensor, target_ptr: int) -> None:
+    key = g.data_ptr()
+
+    def _drop(ref, key=key, table=_grad_aims):
+        e = table.get(key)
+        if e is not None and e[0] is ref:
+            del table[key]
+    _grad_aims[key] = (weakref.ref(g, _drop), target_ptr)
+
+
+def _aimed_at(g: torch.Tensor, target_ptr: int) -> bool:
+    """True (once) if `g` is a dense fp32 buffer written by one of our backward kernels as the gradient of the tensor
+    at `target_ptr` — nobody else holds it, so it may be accumulated into."""
+    e = _grad_aims.get(g.data_ptr())
+    if e is None or e[0]() is not g or e[1] != target_ptr:
+        return False
+    del _grad_aims[g.data_ptr()]
+    return g.dtype == torch.float32 and g.is_contiguous() and g.dim() == 2
+
+
+def _finish_dx(dx_fn, g_alias, x_ptr, shape, tc: bool):
+    """Input gradient of a convolution node whose input alias received `g_alias` (or None).  `dx_fn(add_into)` runs
+    dgrad, into `add_into` when given."""
+    if g_alias is None:
+        dx = dx_fn(None)
+    elif tc and tuple(g_alias.shape) == tuple(shape) and _aimed_at(g_alias, x_ptr):
+        dx = dx_fn(g_alias)
+        residual_stats["accumulated"] += 1
+    else:
+        dx = dx_fn(None)
+        dx.add_(ensure_filled(g_alias))
+        residual_stats["added"] += 1
+    _aim_grad(dx, x_ptr)
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------------
 # Gradient sinks.  A trainer that keeps every parameter gradient in a flat arena (zeroed once per step) registers its
 # parameters here; the backward kernels then ADD a parameter's gradient straight into its arena slice (wgrad:
 # spc_conv_wgrad_acc; BatchNorm: dgamma / dbeta written by the reduction's last block) and the autograd Function
@@ -688,10 +739,12 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits
     return out
 
 
-def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None):
+def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None,
+                   add_into: Optional[torch.Tensor] = None):
+    """`add_into` (tensor-core shapes only): a dense fp32 [m_in, c_in] buffer the input gradient is ADDED to."""
     lib = L.load()
     K, c_in, c_out = w.shape
-    din = _empty((km.m_in, c_in), torch.float32, g.device)
+    din = add_into if add_into is not None else _empty((km.m_in, c_in), torch.float32, g.device)
     tc = _tensor_core(1, K, c_in, c_out, precision)
     # symmetric self map: the forward map with reversed offsets IS the transposed map (no transpose, no second mask)
     sym = tc and km.symmetric and offset_bits is None and symmetric_dgrad
@@ -705,9 +758,12 @@ def conv_dgrad_raw(g, w, km: KernelMap, precision, w_owner=None, offset_bits: Op
     e0 = _profiler.begin() if _profiler else None
     if tc:
         wp = _packed_weights(w, 2 if sym else 1, precision, w_owner)
-        L.check(lib.spc_conv_dgrad_packed(L.ptr(g), _packed_ptr(wp), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out,
-                                          c_in, c_out, K, precision, L.ptr(din), L.stream()), "spc_conv_dgrad_packed")
+        L.check(lib.spc_conv_dgrad_packed_acc(L.ptr(g), _packed_ptr(wp), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out,
+                                              c_in, c_out, K, precision, L.ptr(din), int(add_into is not None),
+                                              L.stream()), "spc_conv_dgrad_packed")
     else:
+        if add_into is not None:
+            raise RuntimeError("conv_dgrad_raw(add_into=...) needs a tensor-core shape")
         ws_bytes = _conv_ws_bytes(lib, K, c_in, c_out, precision)
         ws = _workspace(ws_bytes, g.device)
         L.check(lib.spc_conv_dgrad(L.ptr(g), L.ptr(w), L.ptr(nbr_t), L.ptr(mask_t), km.m_in, km.m_out, c_in,
@@ -744,9 +800,11 @@ class SparseConvFn(torch.autograd.Function):
     """out[o] = sum_k x[nbr[k,o]] @ W[k] (+bias); backward = dgrad / wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, km, precision, w_param=None, offset_bits=None):
+    def forward(ctx, x, w, bias, km, precision, w_param=None, offset_bits=None, alias=False):
         """`w_param`: the Parameter `w` is (a view of), for the gradient sink (see register_grad_sink).
-        `offset_bits`: bit k set = kernel offset k takes part (weight-sparse inference convolution); None = all."""
+        `offset_bits`: bit k set = kernel offset k takes part (weight-sparse inference convolution); None = all.
+        `alias`: also return the input rows as a second output (see "Residual gradients")."""
+        x_in = x
         w3 = w.contiguous()
         if x.dim() != 2 or x.shape[0] != km.m_in or x.shape[1] != w3.shape[1]:
             raise RuntimeError(f"conv input {tuple(x.shape)} does not match map rows {km.m_in} / kernel {tuple(w3.shape)}")
@@ -785,14 +843,21 @@ class SparseConvFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.bias_shape = bias.shape if bias is not None else None
         ctx.dims = (c_in, c_out, pad_in, pad_out)
+        ctx.x_ptr = x_in.data_ptr()
+        ctx.alias = bool(alias)
+        if alias:
+            ctx.set_materialize_grads(False)   # an output nobody used arrives as None in backward, not as zeros
+            return out, x_in.view_as(x_in)
         return out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_alias=None):
         x, w3 = ctx.saved_tensors
         km, prec = ctx.km, ctx.precision
         c_in, c_out, pad_in, pad_out = ctx.dims
         dx = dw = db = None
+        if g is None:   # only the alias was used downstream
+            return (g_alias if ctx.needs_input_grad[0] else None), None, None, None, None, None, None, None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = g.sum(0).view(ctx.bias_shape)
         if prec == L.PREC_BF16:
@@ -802,9 +867,11 @@ class SparseConvFn(torch.autograd.Function):
             if pad_out:
                 g = torch.nn.functional.pad(g, (0, pad_out))
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(g, w3, km, prec, ctx.w_param, ctx.offset_bits)
-            if pad_in:
-                dx = dx[:, :c_in].contiguous()
+            def run_dgrad(add_into):
+                d = conv_dgrad_raw(g, w3, km, prec, ctx.w_param, ctx.offset_bits, add_into=add_into)
+                return d[:, :c_in].contiguous() if pad_in else d
+            tc = (not pad_in) and ctx.offset_bits is None and _tensor_core(1, *w3.shape, prec)
+            dx = _finish_dx(run_dgrad, g_alias, ctx.x_ptr, (km.m_in, c_in), tc)
         if ctx.needs_input_grad[1]:
             K, ci, co = w3.shape
             sink = _sink(ctx.w_param) if (_tensor_core(2, K, ci, co, prec) and ctx.offset_bits is None) else None
@@ -817,7 +884,7 @@ class SparseConvFn(torch.autograd.Function):
                     dw = _drop_offsets(dw, ctx.offset_bits)
                 if pad_in or pad_out:
                     dw = dw[:, :c_in, :c_out].contiguous()
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def conv_bn_fusable(x, w, bias, km: KernelMap, precision: int, offset_bits) -> bool:
@@ -843,7 +910,7 @@ class ConvBNFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, km, w_param, gamma, beta, running_mean, running_var, training, momentum, eps, relu,
-                residual, tracked, want_fp32):
+                residual, tracked, want_fp32, alias=False):
         w3 = w.contiguous()
         K, c_in, c_out = w3.shape
         if x.dim() != 2 or x.shape[0] != km.m_in or x.shape[1] != c_in:
@@ -861,20 +928,29 @@ class ConvBNFn(torch.autograd.Function):
         ctx.params = (gamma, beta)
         ctx.w_param = own
         ctx.km = km
+        ctx.x_ptr = x.data_ptr()
+        ctx.res_ptr = residual.data_ptr() if residual is not None else None
+        if alias:
+            ctx.set_materialize_grads(False)   # an output nobody used arrives as None in backward, not as zeros
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, g_alias=None):
         xb, w3, c, ymask, mean, var, gamma, beta = ctx.saved_tensors
         eps, relu_mode, use_batch, has_res = ctx.cfg
         km = ctx.km
         K, c_in, c_out = w3.shape
+        if dy is None:   # only the alias was used downstream
+            return (g_alias,) + (None,) * 15
         dc, dcb, dres, dgamma, dbeta = _bn_backward_impl(c, ymask, dy, mean, var, gamma, beta, eps, relu_mode,
-                                                         use_batch, has_res, ctx.params, want_dx32=False)
+                                                         use_batch, has_res, ctx.params, want_dx32=False,
+                                                         res_ptr=ctx.res_ptr)
         g = dcb if dcb is not None else to_bf16(dc)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(g, w3, km, L.PREC_BF16, ctx.w_param)
+            dx = _finish_dx(lambda add_into: conv_dgrad_raw(g, w3, km, L.PREC_BF16, ctx.w_param, add_into=add_into),
+                            g_alias, ctx.x_ptr, (km.m_in, c_in), True)
         if ctx.needs_input_grad[1]:
             sink = _sink(ctx.w_param)
             if sink is not None and sink[0].numel() == K * c_in * c_out:
@@ -882,7 +958,7 @@ class ConvBNFn(torch.autograd.Function):
                 sink[1](ctx.w_param)
             else:
                 dw = conv_wgrad_raw(xb, g, km, K, c_in, c_out, L.PREC_BF16)
-        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, dres, None, None
+        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, dres, None, None, None
 
 
 # ---------------------------------------------------------------------------
@@ -907,18 +983,29 @@ def _mark_hollow(t: torch.Tensor, fill) -> None:
     hollow_stats["made"] += 1
 
 
-def is_hollow(t: torch.Tensor) -> bool:
+def _hollow_entry(t: torch.Tensor):
+    """registry entry of `t` or of the tensor `t` is a whole-tensor alias of (ConvBNFn / SparseConvFn hand their input
+    back as a second output, see "Residual gradients")"""
     e = _hollow.get(t.data_ptr()) if _hollow else None
-    return e is not None and e[0]() is t
+    if e is None:
+        return None
+    o = e[0]()
+    if o is t or (o is not None and t._base is o and t.shape == o.shape and t.is_contiguous()):
+        return e
+    return None
+
+
+def is_hollow(t: torch.Tensor) -> bool:
+    return _hollow_entry(t) is not None
 
 
 def ensure_filled(t: torch.Tensor) -> torch.Tensor:
     """Write the fp32 rows of a hollow tensor (no-op for every other tensor)."""
     if _hollow:
-        e = _hollow.get(t.data_ptr())
-        if e is not None and e[0]() is t:
+        e = _hollow_entry(t)
+        if e is not None:
             del _hollow[t.data_ptr()]
-            e[1](t)
+            e[1](e[0]())
             hollow_stats["filled"] += 1
     return t
 
@@ -974,7 +1061,7 @@ def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, moment
 
 
 def _bn_backward_impl(x, ymask, dy, mean, var, gamma, beta, eps, relu_mode, use_batch, has_res, params,
-                      want_dx32=True):
+                      want_dx32=True, res_ptr=None):
     """BatchNorm backward.  `relu_mode`: 0 none, 1 mask from `ymask` (fp32 rows or their bf16 copy), 2 mask
     re-computed from x (no residual before the ReLU: nothing but x and dy is read).  Returns (dx, dxb, dres, dgamma,
     dbeta); dx is None when `want_dx32` is False and a bf16 copy is produced (fused conv + BN node)."""
@@ -1009,6 +1096,8 @@ def _bn_backward_impl(x, ymask, dy, mean, var, gamma, beta, eps, relu_mode, use_
         dgamma = dbeta = None
     if dxb is not None and dx is not None:
         _remember_bf16(dx, dxb)
+    if dres is not None and res_ptr is not None:
+        _aim_grad(dres, res_ptr)   # (a convolution node that handed out the residual rows may accumulate into it)
     if e0 is not None:
         _profiler.end("bn_bwd", e0, 0, (16.0 + ((4.0 if y16 is not None else 8.0) if relu_mode == 1 else 0.0)
                                         + (4.0 if dx is not None else 0.0) + (4.0 if has_res else 0.0)
@@ -1035,6 +1124,7 @@ class BatchNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, ((yb if yb is not None else y) if relu_mode == 1 else None), mean, var, gamma, beta)
         ctx.cfg = (float(eps), relu_mode, int(use_batch), residual is not None)
         ctx.params = (gamma, beta)   # the Parameter objects, for the gradient sinks
+        ctx.res_ptr = residual.data_ptr() if residual is not None else None
         return y
 
     @staticmethod
@@ -1042,7 +1132,7 @@ class BatchNormFn(torch.autograd.Function):
         x, ymask, mean, var, gamma, beta = ctx.saved_tensors
         eps, relu_mode, use_batch, has_res = ctx.cfg
         dx, _, dres, dgamma, dbeta = _bn_backward_impl(x, ymask, dy, mean, var, gamma, beta, eps, relu_mode, use_batch,
-                                                       has_res, ctx.params)
+                                                       has_res, ctx.params, res_ptr=ctx.res_ptr)
         return dx, dgamma, dbeta, None, None, None, None, None, None, dres, None, None
 
 

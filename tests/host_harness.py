@@ -368,6 +368,15 @@ class FakeLib:
         assert self.spc_conv_tensor_core(1, K, c_in, c_out, precision)
         return self.spc_conv_dgrad(dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, None, 0, stream)
 
+    def spc_conv_dgrad_packed_acc(self, dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, accumulate,
+                                  stream):
+        if not accumulate:
+            return self.spc_conv_dgrad_packed(dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, stream)
+        before = view(din, (m_in, c_in), np.float32).copy()
+        rc = self.spc_conv_dgrad_packed(dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, stream)
+        view(din, (m_in, c_in), np.float32)[:] += before
+        return rc
+
     # ---- batch norm / elementwise -----------------------------------------------------------------------------
     def spc_bn_stats_tracked(self, x, m, C, mean, var, run_mean, run_var, momentum, tracked, ws, ws_bytes, stream):
         rc = self.spc_bn_stats(x, m, C, mean, var, run_mean, run_var, momentum, ws, ws_bytes, stream)

@@ -6,6 +6,8 @@
   convolution output) == the separate nodes.
 * dgrad of a centrally symmetric self map on the FORWARD map with reversed offsets == dgrad on the transposed map.
 * `ME.cat` of bf16 operand copies (`ops.cat_rows_bf16`) == torch.cat of the fp32 rows, converted.
+* residual gradients: dgrad reduce-adds into the gradient that reached the same rows through the residual branch
+  (`spc_conv_dgrad_packed_acc`) == the sum autograd forms with a separate pass.
 """
 import pytest
 import torch
@@ -22,7 +24,7 @@ def bf16_mode():
     ops.set_default_precision("bf16")
     yield
     ops.set_default_precision("tf32")
-    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "symmetric_dgrad"):
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "symmetric_dgrad", "fuse_residual_grad"):
         setattr(ops, knob, True)
 
 
@@ -32,7 +34,7 @@ def _cos(a, b):
 
 
 def _knobs(value: bool):
-    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn"):
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "fuse_residual_grad"):
         setattr(ops, knob, value)
 
 
@@ -116,9 +118,12 @@ def test_fused_conv_bn_node_equals_the_separate_nodes(cuda_device, bf16_mode):
     coords = torch.from_numpy(c).to(cuda_device).floor().int()
     coords = torch.unique(coords, dim=0)
     feats = torch.randn(coords.shape[0], 32, device=cuda_device)
-    made0 = ops.hollow_stats["made"]
+    made0, acc0 = ops.hollow_stats["made"], ops.residual_stats["accumulated"]
     out_a, dx_a, g_a, b_a = _stack(cuda_device, coords, feats, True)
     assert ops.hollow_stats["made"] > made0
+    # the four residual blocks' conv1 (and the 1x1 shortcut convolution of the widening block) reduce-add their input
+    # gradient into the buffer BatchNorm backward / the shortcut's dgrad wrote for the same rows
+    assert ops.residual_stats["accumulated"] - acc0 >= 4
     out_b, dx_b, g_b, b_b = _stack(cuda_device, coords, feats, False)
     # the same kernels on the same operands; what is free is the order of the double atomics behind the BatchNorm
     # statistics and of the fp32 red.adds of wgrad / offset-split tiles — last-bit differences that an occasional bf16

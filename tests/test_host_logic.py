@@ -420,7 +420,7 @@ def _run_blocks(monkeypatch, fused: bool):
     (logits, {parameter: gradient}, call list)."""
     from nerf_downstream_b200 import ops as O
     fake = host_harness.install(monkeypatch, "bf16")
-    for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask"):
+    for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "fuse_residual_grad"):
         monkeypatch.setattr(O, knob, fused)
     torch.manual_seed(5)
     coords, feats = synth.random_cloud(6, 9000, extent=14, n_batch=2, channels=27)
@@ -440,9 +440,12 @@ def test_fused_conv_bn_node_hollow_rows_and_recomputed_relu_mask_agree_with_the_
     without fp32 rows, ReLU masks re-computed from x — same logits and parameter gradients as conv / BN as separate
     nodes with every tensor materialised (the harness rounds bf16 operands like the kernels do)."""
     from nerf_downstream_b200 import ops as O
-    made0 = O.hollow_stats["made"]
+    made0, acc0, add0 = O.hollow_stats["made"], O.residual_stats["accumulated"], O.residual_stats["added"]
     la, ga, calls_a, net_a = _run_blocks(monkeypatch, True)
     made = O.hollow_stats["made"] - made0
+    # residual gradients: both blocks' conv1 dgrad reduce-add into the gradient BatchNorm backward wrote for the
+    # residual branch (no separate sum of two activation gradients)
+    assert O.residual_stats["accumulated"] - acc0 == 2 and O.residual_stats["added"] == add0
     lb, gb, calls_b, net_b = _run_blocks(monkeypatch, False)
     assert torch.allclose(la, lb, rtol=1e-5, atol=1e-6)
     for name, g in ga.items():
@@ -516,7 +519,8 @@ def test_unet_in_bf16_mode_with_lazy_cat_and_fused_nodes_matches_the_plain_graph
     res = []
     for on in (True, False):
         fake = host_harness.install(monkeypatch, "bf16")
-        for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "lazy_cat", "symmetric_dgrad"):
+        for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "lazy_cat", "symmetric_dgrad",
+                     "fuse_residual_grad"):
             monkeypatch.setattr(O, knob, on)
         monkeypatch.setattr(O, "_pack_cache", {})
         torch.manual_seed(12)
