@@ -205,6 +205,14 @@ int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* str
 int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
                         const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
                         int precision, float* out, void* stream);
+/* spc_conv_fwd_packed that also leaves the per-column sum and sum of squares of `out` in bn_sums[2 * c_out] (DEVICE
+ * doubles, cleared here) for the BatchNorm that follows (spc_bn_finalize) — the statistics pass over the rows (4 of the
+ * 10-18 bytes per element BatchNorm forward moves) is then not needed.  The epilogue reads the sums back from the
+ * staging blocks of its TMA stores.  *stats_fused (HOST int) = 1 if the sums were produced: large maps (one owner per
+ * output row), c_out <= 256, no bias; otherwise 0 and bn_sums is untouched (run spc_bn_stats). */
+int spc_conv_fwd_packed_stats(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
+                              const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                              int precision, float* out, double* bn_sums, int32_t* stats_fused, void* stream);
 int spc_conv_dgrad_packed(const void* dout, const void* w_packed_t, const int32_t* nbr_t, const uint32_t* tile_mask_t,
                           int64_t m_in, int64_t m_out, int c_in, int c_out, int K, int precision, float* din,
                           void* stream);
@@ -234,7 +242,8 @@ int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* v
                          int64_t workspace_bytes, void* stream);
 /* mean / biased variance (+ running statistics) from the sums written by spc_conv_fwd_stats. */
 int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
-                    float* running_var, float momentum, void* stream);
+                    float* running_var, float momentum, int64_t* num_batches_tracked /* nullable, incremented */,
+                    void* stream);
 int spc_bn_apply(const float* x, const float* mean, const float* var, const float* gamma,
                  const float* beta, const float* residual, int64_t m, int C, float eps,
                  int relu, float* y /* NULL: only the bf16 copy is produced */,

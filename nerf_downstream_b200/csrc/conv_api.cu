@@ -21,7 +21,8 @@ int conv_pack_weights_batch(const long long* desc_dev, int n_layers, cudaStream_
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
                   bool transpose_w, bool bf16, float* out, void* workspace,
-                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate = false);
+                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate = false, double* stats = nullptr,
+                  int* stats_fused = nullptr);
 // conv_wgrad_umma.cu
 bool umma_wgrad_supported(int c_in, int c_out);
 int64_t umma_wgrad_workspace(int K, int c_in, int c_out);
@@ -83,11 +84,22 @@ int spc_conv_pack_weights_batch(const int64_t* desc_dev, int n_layers, void* str
 int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
                         const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
                         int precision, float* out, void* stream) {
+  return spc_conv_fwd_packed_stats(in, w_packed, bias, nbr, tile_mask, m_in, m_out, c_in, c_out, K, precision, out,
+                                   nullptr, nullptr, stream);
+}
+
+int spc_conv_fwd_packed_stats(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
+                              const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
+                              int precision, float* out, double* bn_sums, int32_t* stats_fused, void* stream) {
   (void)m_in;
   SPC_REQUIRE(precision == SPC_PREC_TF32 || precision == SPC_PREC_BF16, "packed weights are a tensor-core format");
   SPC_REQUIRE(w_packed && tc_fwd_ok(K, c_in, c_out), "shape not supported by the tcgen05 path");
-  return conv_fwd_umma(in, nullptr, w_packed, bias, nbr, tile_mask, m_out, c_in, c_out, K, false,
-                       precision == SPC_PREC_BF16, out, nullptr, 0, (cudaStream_t)stream);
+  SPC_REQUIRE(bn_sums == nullptr || stats_fused != nullptr, "bn_sums needs stats_fused");
+  int fused = 0;
+  int rc = conv_fwd_umma(in, nullptr, w_packed, bias, nbr, tile_mask, m_out, c_in, c_out, K, false,
+                         precision == SPC_PREC_BF16, out, nullptr, 0, (cudaStream_t)stream, false, bn_sums, &fused);
+  if (stats_fused) *stats_fused = fused;
+  return rc;
 }
 
 int spc_conv_dgrad_packed(const void* dout, const void* w_packed_t, const int32_t* nbr_t, const uint32_t* tile_mask_t,

@@ -68,6 +68,7 @@ struct UmmaConvParams {
   int dbg_flags;             // timing experiments (-DSPC_EXPERIMENTS): 1 no gather copies, 2 no MMAs, 4 no weight slabs
   int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
   int reduce_out;            // the epilogue ADDS to `out` (offset-split items, or accumulate: out += result)
+  double* stats;             // [2 * Cn] per-column sum / sum of squares of `out` for the BatchNorm that follows, or null
   int n_work;                // m_tiles * n_ntiles * ksplit
 };
 
@@ -238,6 +239,8 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
   auto turn_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };  // (shared ring slots, see producers)
+  // per-CTA column sums of the output tile (p.stats): [2 * cn_tile] doubles behind the barrier area
+  double* s_stats = reinterpret_cast<double*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -245,6 +248,8 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   // control flow and the MMA warp's loop state can live in uniform registers)
   const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), lane = threadIdx.x & 31;
 
+  if (p.stats != nullptr)
+    for (int c = threadIdx.x; c < 2 * p.cn_tile; c += blockDim.x) s_stats[c] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
 #ifdef SPC_EXPERIMENTS
@@ -602,6 +607,24 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
               fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) reads
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.stats != nullptr && !skip && mask != 0) {
+              // BatchNorm statistics of this [128 rows x 32 columns] block, read back from the staging block the
+              // tensor store is about to read as well: thread (ew, lane) sums column `lane` over rows 32 ew .. + 31
+              // (a warp reads the 32 words of one row: conflict-free), one shared-memory double add per thread and sum.
+              // Rows past m_out are zero (their gathers were zero-filled, there is no bias in this mode).
+              float s0 = 0.f, s1 = 0.f;
+              const int jj = lane >> 2, ww = lane & 3;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const int rw = ew * 32 + rr;
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(blk + (uint32_t)rw * 128u + (uint32_t)(((jj ^ (rw & 7)) << 4) + ww * 4)));
+                s0 += v;
+                s1 = fmaf(v, v, s1);
+              }
+              atomicAdd(&s_stats[cb * 32 + lane], (double)s0);
+              atomicAdd(&s_stats[p.cn_tile + cb * 32 + lane], (double)s1);
+            }
             if (store_leader) {
               if (!skip && !p.dbg_skip_store && row0 < p.m_out) {
                 const int col0 = ntile * p.cn_tile + cb * 32;
@@ -657,6 +680,13 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
       if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
     }
     if (p.out_bufs > 0 && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.stats != nullptr) {   // this CTA's column sums -> the layer's (n_ntiles == 1: the tile spans all columns)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = (warp & 3) * 32 + lane; c < 2 * p.cn_tile; c += 128) {
+        const double v = s_stats[c];
+        if (v != 0.0) atomicAdd(p.stats + c, v);
+      }
+    }
   }
 
   tc_fence_before();
@@ -727,7 +757,8 @@ std::atomic<long long> g_conv_path_counts[4];
 int conv_fwd_umma(const void* in, const float* w, const void* packed, const float* bias, const int* nbr,
                   const uint32_t* tile_mask, int64_t m_out, int c_in, int c_out, int K,
                   bool transpose_w, bool bf16, float* out, void* workspace,
-                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate) {
+                  int64_t workspace_bytes, cudaStream_t stream, bool accumulate, double* stats, int* stats_fused) {
+  if (stats_fused) *stats_fused = 0;
   if (m_out == 0) return 0;
   SPC_REQUIRE(umma_fwd_supported(c_in, c_out), "shape not supported by the tcgen05 path");
   SPC_REQUIRE(K <= 32, "tcgen05 path supports kernel volume <= 32");
@@ -765,7 +796,9 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
 #ifdef SPC_EXPERIMENTS
   if (bf16 && g_umma_dbg[4] == 2) G = (c_in % 64 == 0) ? 2 : (c_in % 96 == 0 ? 3 : 1);
 #endif
-  const int budget = kSmemLimit - 1024 - 256;
+  // (4 KB behind the barrier area for the epilogue's column sums when statistics are asked for)
+  const int stats_smem = (stats != nullptr && c_out <= 256) ? 4096 : 0;
+  const int budget = kSmemLimit - 1024 - 256 - stats_smem;
   // Tile shape: MT sub-tiles of 128 rows x cn_tile output channels per work item, and on small maps
   // (deep UNet levels: too few row tiles for 148 SMs) the K offsets split over `ksplit` items whose
   // partial sums meet in the zeroed output through fp32 reduce-adds.  Chosen to minimise the
@@ -847,7 +880,15 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   if (kTileM * mt / wps < 32) wps = kTileM * mt / 32;
   p.ngroups = ngroups;
   p.wps = wps;
-  const size_t smem = (size_t)stages * stage_bytes + (size_t)p.out_bufs * 16384 + 1024 + 256;
+  // BatchNorm statistics in the epilogue: one owner per output row (no offset split, no accumulation), the tile spans
+  // all columns, no bias, TMA-store epilogue (the sums are read back from its staging blocks)
+  p.stats = nullptr;
+  if (stats_smem && p.ksplit == 1 && !accumulate && p.n_ntiles == 1 && bias == nullptr && p.out_bufs > 0) {
+    SPC_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * c_out * sizeof(double), stream));
+    p.stats = stats;
+    if (stats_fused) *stats_fused = 1;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + (size_t)p.out_bufs * 16384 + 1024 + 256 + stats_smem;
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
   g_conv_path_counts[bf16 ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
   // (MT, precision, G, warps per producer group) -> instantiation

@@ -537,8 +537,9 @@ ce_bwd_kernel(const float* __restrict__ graw, const double* __restrict__ stats,
 // accumulated in double by the convolution epilogue (spc_conv_fwd_stats)
 __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const double* __restrict__ gsum, long long m, int C, float* __restrict__ mean,
-                   float* __restrict__ var, float* run_mean, float* run_var, float momentum) {
+                   float* __restrict__ var, float* run_mean, float* run_var, float momentum, long long* tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && tracked) *tracked += 1;
   if (c >= C) return;
   const double mu = gsum[c] / (double)m;
   double v = gsum[C + c] / (double)m - mu * mu;
@@ -644,10 +645,11 @@ int spc_bn_stats_tracked(const float* x, int64_t m, int C, float* mean, float* v
 }
 
 int spc_bn_finalize(const double* sums, int64_t m, int C, float* mean, float* var, float* running_mean,
-                    float* running_var, float momentum, void* stream_) {
+                    float* running_var, float momentum, int64_t* num_batches_tracked, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPC_REQUIRE(m >= 1 && C >= 1 && sums, "empty input");
-  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, stream>>>(sums, m, C, mean, var, running_mean, running_var, momentum);
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, stream>>>(sums, m, C, mean, var, running_mean, running_var, momentum,
+                                                          (long long*)num_batches_tracked);
   SPC_LAUNCHED("bn_finalize_kernel");
   return 0;
 }

@@ -55,7 +55,8 @@ SIGNATURES = {
     "spc_to_bf16": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "spc_conv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_fwd_stats": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
-    "spc_bn_finalize": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P]),
+    "spc_bn_finalize": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, c_float, _P, _P]),
+    "spc_conv_fwd_packed_stats": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "spc_conv_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_conv_wgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "spc_bn_workspace": (c_int64, [c_int64, c_int]),

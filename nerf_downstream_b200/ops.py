@@ -629,6 +629,7 @@ def _tensor_core(what: int, K: int, c_in: int, c_out: int, precision: int) -> bo
 # concatenation's gradient) is added with one ordinary pass.
 # ---------------------------------------------------------------------------------------------------------
 fuse_residual_grad = True
+fuse_bn_stats = True         # ConvBNFn: BatchNorm statistics from the convolution's epilogue (no statistics pass over the rows)
 _grad_aims: dict = {}    # data_ptr of a gradient buffer -> (weak reference to it, data_ptr of the tensor it is the gradient of)
 residual_stats = {"accumulated": 0, "added": 0}
 
@@ -714,7 +715,11 @@ def _drop_offsets(w, bits):
     return w * keep.view(-1, 1, 1)
 
 
-def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None):
+def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits: Optional[int] = None,
+                 bn_sums: Optional[torch.Tensor] = None):
+    """`bn_sums` (float64 [2 * c_out], tensor-core shapes): ask the kernel's epilogue for the per-column sum / sum of
+    squares of the output; returns (out, fused) then — fused False: the sums were not produced (small map, wide or
+    biased layer) and the caller runs the statistics pass."""
     lib = L.load()
     K, c_in, c_out = w.shape
     out = _empty((km.m_out, c_out), torch.float32, x.device)
@@ -724,6 +729,16 @@ def conv_fwd_raw(x, w, bias, km: KernelMap, precision, w_owner=None, offset_bits
     e0 = _profiler.begin() if _profiler else None
     if _tensor_core(0, K, c_in, c_out, precision):
         wp = _packed_weights(w, 0, precision, w_owner)
+        if bn_sums is not None:
+            fused = ctypes.c_int32(0)
+            L.check(lib.spc_conv_fwd_packed_stats(L.ptr(x), _packed_ptr(wp), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask),
+                                                  km.m_in, km.m_out, c_in, c_out, K, precision, L.ptr(out),
+                                                  L.ptr(bn_sums), ctypes.byref(fused), L.stream()),
+                    "spc_conv_fwd_packed_stats")
+            if e0 is not None:
+                _profiler.end("conv_fwd", e0, 2.0 * km.n_pairs * c_in * c_out, _conv_bytes(km, K, c_in, c_out),
+                              f"K{K} {c_in}->{c_out} M{km.m_out} P{km.n_pairs}")
+            return out, bool(fused.value)
         L.check(lib.spc_conv_fwd_packed(L.ptr(x), _packed_ptr(wp), L.ptr(bias), L.ptr(km.nbr), L.ptr(mask), km.m_in,
                                         km.m_out, c_in, c_out, K, precision, L.ptr(out), L.stream()),
                 "spc_conv_fwd_packed")
@@ -892,7 +907,7 @@ def conv_bn_fusable(x, w, bias, km: KernelMap, precision: int, offset_bits) -> b
     shapes in all three directions without channel padding, no bias, all offsets."""
     if not fuse_conv_bn or precision != L.PREC_BF16 or _default_precision != L.PREC_BF16:
         return False
-    if bias is not None or offset_bits is not None or w.dim() != 3 or not x.is_cuda:
+    if bias is not None or offset_bits is not None or w.dim() != 3:
         return False
     K, c_in, c_out = w.shape
     if K > 32 or c_in % 32 or c_out % 32 or c_out > 512 or K * c_in > 128 * 128 or km.m_out < 1:
@@ -918,9 +933,16 @@ class ConvBNFn(torch.autograd.Function):
         xb = to_bf16(x)
         own = w_param if (w_param is not None and w_param.data_ptr() == w3.data_ptr()
                           and w_param.numel() == w3.numel()) else None
-        c = conv_fwd_raw(xb, w3, None, km, L.PREC_BF16, own)
+        sums = None
+        if fuse_bn_stats and (training or running_mean is None) and c_out <= 256 and km.m_out >= 1:
+            sums = _empty(2 * c_out, torch.float64, x.device)
+            c, fused = conv_fwd_raw(xb, w3, None, km, L.PREC_BF16, own, bn_sums=sums)
+            if not fused:
+                sums = None
+        else:
+            c = conv_fwd_raw(xb, w3, None, km, L.PREC_BF16, own)
         y, yb, mean, var, use_batch = _bn_forward_impl(c, gamma, beta, running_mean, running_var, training, momentum,
-                                                       eps, relu, residual, tracked, want_fp32)
+                                                       eps, relu, residual, tracked, want_fp32, sums)
         relu_mode = 0 if not relu else (2 if (residual is None and recompute_relu_mask) else 1)
         ctx.save_for_backward(xb, w3, c, ((yb if yb is not None else y) if relu_mode == 1 else None), mean, var,
                               gamma, beta)
@@ -1011,8 +1033,10 @@ def ensure_filled(t: torch.Tensor) -> torch.Tensor:
 
 
 def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual, tracked,
-                     want_fp32=True):
-    """Statistics + apply.  Returns (y, yb, mean, var, use_batch).  `want_fp32=False`: y may be left hollow."""
+                     want_fp32=True, sums=None):
+    """Statistics + apply.  Returns (y, yb, mean, var, use_batch).  `want_fp32=False`: y may be left hollow.
+    `sums` (float64 [2C]): per-column sum / sum of squares already produced by the convolution's epilogue — the
+    statistics pass over x is replaced by spc_bn_finalize."""
     lib = L.load()
     m, C = x.shape
     dev = x.device
@@ -1026,11 +1050,17 @@ def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, moment
         mean = _empty(C, torch.float32, dev)
         var = _empty(C, torch.float32, dev)
         upd = training and running_mean is not None
-        L.check(lib.spc_bn_stats_tracked(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
-                                         L.ptr(running_mean) if upd else None,
-                                         L.ptr(running_var) if upd else None, float(momentum),
-                                         L.ptr(tracked) if (upd and tracked is not None) else None, L.ptr(ws),
-                                         ws_bytes, L.stream()), "spc_bn_stats")
+        if sums is not None:
+            L.check(lib.spc_bn_finalize(L.ptr(sums), m, C, L.ptr(mean), L.ptr(var),
+                                        L.ptr(running_mean) if upd else None, L.ptr(running_var) if upd else None,
+                                        float(momentum), L.ptr(tracked) if (upd and tracked is not None) else None,
+                                        L.stream()), "spc_bn_finalize")
+        else:
+            L.check(lib.spc_bn_stats_tracked(L.ptr(x), m, C, L.ptr(mean), L.ptr(var),
+                                             L.ptr(running_mean) if upd else None,
+                                             L.ptr(running_var) if upd else None, float(momentum),
+                                             L.ptr(tracked) if (upd and tracked is not None) else None, L.ptr(ws),
+                                             ws_bytes, L.stream()), "spc_bn_stats")
     else:
         mean, var = running_mean, running_var
     res = _feat(residual) if residual is not None else None
@@ -1054,7 +1084,7 @@ def _bn_forward_impl(x, gamma, beta, running_mean, running_var, training, moment
                     "spc_bn_apply(fill)")
         _mark_hollow(y, fill)
     if e0 is not None:
-        _profiler.end("bn_fwd", e0, 0, ((8.0 if use_batch else 4.0) + (0.0 if hollow else 4.0)
+        _profiler.end("bn_fwd", e0, 0, ((8.0 if (use_batch and sums is None) else 4.0) + (0.0 if hollow else 4.0)
                                         + (4.0 if res is not None else 0.0)
                                         + (2.0 if yb is not None else 0.0)) * m * C, f"C{C} M{m}")
     return y, yb, mean, var, use_batch

@@ -364,6 +364,34 @@ class FakeLib:
         assert self.spc_conv_tensor_core(0, K, c_in, c_out, precision)
         return self.spc_conv_fwd(x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, None, 0, stream)
 
+    def spc_conv_fwd_packed_stats(self, x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, bn_sums,
+                                  stats_fused, stream):
+        rc = self.spc_conv_fwd_packed(x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, stream)
+        fused = int(_addr(bn_sums) != 0 and not _addr(bias) and c_out <= 256 and m_out >= 4096)  # (large maps only)
+        if fused:
+            o = view(out, (m_out, c_out), np.float32).astype(np.float64)
+            s = view(bn_sums, 2 * c_out, np.float64)
+            s[:c_out] = o.sum(0)
+            s[c_out:] = (o * o).sum(0)
+        if stats_fused is not None:
+            stats_fused._obj.value = fused
+        return rc
+
+    def spc_bn_finalize(self, sums, m, C, mean, var, run_mean, run_var, momentum, tracked, stream):
+        self._called("spc_bn_finalize")
+        s = view(sums, 2 * C, np.float64)
+        mu = s[:C] / m
+        v = np.maximum(s[C:] / m - mu * mu, 0.0)
+        view(mean, C, np.float32)[:] = mu
+        view(var, C, np.float32)[:] = v
+        if _addr(run_mean):
+            rm, rv = view(run_mean, C, np.float32), view(run_var, C, np.float32)
+            rm[:] = (1 - momentum) * rm + momentum * mu
+            rv[:] = (1 - momentum) * rv + momentum * (v * m / max(m - 1, 1))
+        if _addr(tracked):
+            view(tracked, 1, np.int64)[:] += 1
+        return 0
+
     def spc_conv_dgrad_packed(self, dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, stream):
         assert self.spc_conv_tensor_core(1, K, c_in, c_out, precision)
         return self.spc_conv_dgrad(dout, wp, nbr_t, mask_t, m_in, m_out, c_in, c_out, K, precision, din, None, 0, stream)

@@ -6,6 +6,8 @@
   convolution output) == the separate nodes.
 * dgrad of a centrally symmetric self map on the FORWARD map with reversed offsets == dgrad on the transposed map.
 * `ME.cat` of bf16 operand copies (`ops.cat_rows_bf16`) == torch.cat of the fp32 rows, converted.
+* BatchNorm statistics from the convolution's epilogue (`spc_conv_fwd_packed_stats` + `spc_bn_finalize`) == the
+  statistics pass over the rows, to 1e-6 relative in mean and variance.
 * residual gradients: dgrad reduce-adds into the gradient that reached the same rows through the residual branch
   (`spc_conv_dgrad_packed_acc`) == the sum autograd forms with a separate pass.
 """
@@ -24,7 +26,8 @@ def bf16_mode():
     ops.set_default_precision("bf16")
     yield
     ops.set_default_precision("tf32")
-    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "symmetric_dgrad", "fuse_residual_grad"):
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "symmetric_dgrad", "fuse_residual_grad",
+                 "fuse_bn_stats"):
         setattr(ops, knob, True)
 
 
@@ -34,7 +37,7 @@ def _cos(a, b):
 
 
 def _knobs(value: bool):
-    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "fuse_residual_grad"):
+    for knob in ("hollow_rows", "recompute_relu_mask", "fuse_conv_bn", "fuse_residual_grad", "fuse_bn_stats"):
         setattr(ops, knob, value)
 
 
@@ -89,6 +92,31 @@ def test_hollow_rows_are_filled_on_demand(cuda_device, bf16_mode):
     assert ops.is_hollow(hollow)
     filled = ops.ensure_filled(hollow)
     assert not ops.is_hollow(hollow) and torch.equal(filled, full)
+
+
+@pytest.mark.parametrize("cin,cout,m", [(32, 32, 120_000), (64, 96, 70_000), (96, 96, 19_000), (128, 256, 25_000)])
+def test_batchnorm_statistics_from_the_convolution_epilogue(cuda_device, bf16_mode, cin, cout, m):
+    c, _, _ = synth.room_batch(31, 1, m)
+    cmap, _, _, _ = ops.coords_insert(torch.from_numpy(c).to(cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    torch.manual_seed(cin + cout)
+    x = ops.to_bf16(torch.randn(cmap.size, cin, device=cuda_device) + 0.5)      # a mean well away from zero
+    w = torch.randn(27, cin, cout, device=cuda_device) / (27 * cin) ** 0.5
+    sums = torch.full((2 * cout,), float("nan"), dtype=torch.float64, device=cuda_device)
+    out, fused = ops.conv_fwd_raw(x, w, None, km, L.PREC_BF16, bn_sums=sums)
+    ref = ops.conv_fwd_raw(x, w, None, km, L.PREC_BF16)
+    assert torch.equal(out, ref)
+    assert fused == (cmap.size >= 148 * 128)           # small maps split the offsets: no single owner per row
+    if fused:
+        o = ref.double()
+        s0, s1 = o.sum(0), (o * o).sum(0)
+        assert (sums[:cout] - s0).abs().max() <= 1e-6 * s0.abs().max()
+        assert (sums[cout:] - s1).abs().max() <= 1e-6 * s1.abs().max()
+        mean, var = torch.empty(cout, device=cuda_device), torch.empty(cout, device=cuda_device)
+        L.check(L.load().spc_bn_finalize(L.ptr(sums), cmap.size, cout, L.ptr(mean), L.ptr(var), None, None, 0.1, None,
+                                         L.stream()), "spc_bn_finalize")
+        assert (mean.double() - o.mean(0)).abs().max() <= 1e-6 * (1 + o.mean(0).abs().max())
+        assert (var.double() - o.var(0, unbiased=False)).abs().max() <= 1e-5 * o.var(0, unbiased=False).max()
 
 
 def _stack(cuda_device, coords, feats, fused, seed=3, planes=64):

@@ -420,7 +420,7 @@ def _run_blocks(monkeypatch, fused: bool):
     (logits, {parameter: gradient}, call list)."""
     from nerf_downstream_b200 import ops as O
     fake = host_harness.install(monkeypatch, "bf16")
-    for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "fuse_residual_grad"):
+    for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "fuse_residual_grad", "fuse_bn_stats"):
         monkeypatch.setattr(O, knob, fused)
     torch.manual_seed(5)
     coords, feats = synth.random_cloud(6, 9000, extent=14, n_batch=2, channels=27)
@@ -458,8 +458,12 @@ def test_fused_conv_bn_node_hollow_rows_and_recomputed_relu_mask_agree_with_the_
     assert made == 3
     assert calls_a.count("spc_bn_apply") == calls_b.count("spc_bn_apply") + 1
     # one launch set per layer either way: the fused node adds no kernels
-    for name in ("spc_conv_fwd_packed", "spc_conv_dgrad_packed", "spc_bn_stats_tracked", "spc_bn_bwd"):
+    for name in ("spc_conv_fwd_packed", "spc_conv_dgrad_packed", "spc_bn_bwd"):
         assert calls_a.count(name) == calls_b.count(name), name
+    # the four fused nodes take their BatchNorm statistics from the convolution's epilogue (spc_bn_finalize); the
+    # stem (padded channels: separate nodes) still runs the statistics pass
+    assert calls_a.count("spc_bn_finalize") == 4 and calls_a.count("spc_bn_stats") == 1
+    assert calls_b.count("spc_bn_finalize") == 0 and calls_b.count("spc_bn_stats") == 5
     # gradients of the conv outputs inside the fused nodes are bf16-only: fewer conversion passes, never more
     assert calls_a.count("spc_to_bf16") <= calls_b.count("spc_to_bf16")
 
@@ -520,7 +524,7 @@ def test_unet_in_bf16_mode_with_lazy_cat_and_fused_nodes_matches_the_plain_graph
     for on in (True, False):
         fake = host_harness.install(monkeypatch, "bf16")
         for knob in ("fuse_conv_bn", "hollow_rows", "recompute_relu_mask", "lazy_cat", "symmetric_dgrad",
-                     "fuse_residual_grad"):
+                     "fuse_residual_grad", "fuse_bn_stats"):
             monkeypatch.setattr(O, knob, on)
         monkeypatch.setattr(O, "_pack_cache", {})
         torch.manual_seed(12)
