@@ -209,7 +209,7 @@ int spc_conv_fwd_packed(const void* in, const void* w_packed, const float* bias,
  * doubles, cleared here) for the BatchNorm that follows (spc_bn_finalize) — the statistics pass over the rows (4 of the
  * 10-18 bytes per element BatchNorm forward moves) is then not needed.  The epilogue reads the sums back from the
  * staging blocks of its TMA stores.  *stats_fused (HOST int) = 1 if the sums were produced: large maps (one owner per
- * output row), c_out <= 256, no bias; otherwise 0 and bn_sums is untouched (run spc_bn_stats). */
+ * output row), c_out <= 128, no bias; otherwise 0 and bn_sums is untouched (run spc_bn_stats). */
 int spc_conv_fwd_packed_stats(const void* in, const void* w_packed, const float* bias, const int32_t* nbr,
                               const uint32_t* tile_mask, int64_t m_in, int64_t m_out, int c_in, int c_out, int K,
                               int precision, float* out, double* bn_sums, int32_t* stats_fused, void* stream);

@@ -239,7 +239,8 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
   auto turn_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };  // (shared ring slots, see producers)
-  // per-CTA column sums of the output tile (p.stats): [2 * cn_tile] doubles behind the barrier area
+  // column sums of the output tiles this CTA writes (p.stats): [4 epilogue warps][2 * cn_tile] doubles behind the
+  // barrier area — every epilogue thread owns its slots (plain loads / stores, no atomics)
   double* s_stats = reinterpret_cast<double*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -249,7 +250,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
   const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (p.stats != nullptr)
-    for (int c = threadIdx.x; c < 2 * p.cn_tile; c += blockDim.x) s_stats[c] = 0.0;
+    for (int c = threadIdx.x; c < 8 * p.cn_tile; c += blockDim.x) s_stats[c] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
 #ifdef SPC_EXPERIMENTS
@@ -610,7 +611,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
             if (p.stats != nullptr && !skip && mask != 0) {
               // BatchNorm statistics of this [128 rows x 32 columns] block, read back from the staging block the
               // tensor store is about to read as well: thread (ew, lane) sums column `lane` over rows 32 ew .. + 31
-              // (a warp reads the 32 words of one row: conflict-free), one shared-memory double add per thread and sum.
+              // (a warp reads the 32 words of one row: conflict-free), one private double slot per thread and sum.
               // Rows past m_out are zero (their gathers were zero-filled, there is no bias in this mode).
               float s0 = 0.f, s1 = 0.f;
               const int jj = lane >> 2, ww = lane & 3;
@@ -622,8 +623,9 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
                 s0 += v;
                 s1 = fmaf(v, v, s1);
               }
-              atomicAdd(&s_stats[cb * 32 + lane], (double)s0);
-              atomicAdd(&s_stats[p.cn_tile + cb * 32 + lane], (double)s1);
+              double* mine = s_stats + (size_t)ew * 2 * p.cn_tile + cb * 32 + lane;
+              mine[0] += (double)s0;
+              mine[p.cn_tile] += (double)s1;
             }
             if (store_leader) {
               if (!skip && !p.dbg_skip_store && row0 < p.m_out) {
@@ -683,7 +685,7 @@ conv_umma_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMap tma
     if (p.stats != nullptr) {   // this CTA's column sums -> the layer's (n_ntiles == 1: the tile spans all columns)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = (warp & 3) * 32 + lane; c < 2 * p.cn_tile; c += 128) {
-        const double v = s_stats[c];
+        const double v = s_stats[c] + s_stats[2 * p.cn_tile + c] + s_stats[4 * p.cn_tile + c] + s_stats[6 * p.cn_tile + c];
         if (v != 0.0) atomicAdd(p.stats + c, v);
       }
     }
@@ -797,7 +799,7 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
   if (bf16 && g_umma_dbg[4] == 2) G = (c_in % 64 == 0) ? 2 : (c_in % 96 == 0 ? 3 : 1);
 #endif
   // (4 KB behind the barrier area for the epilogue's column sums when statistics are asked for)
-  const int stats_smem = (stats != nullptr && c_out <= 256) ? 4096 : 0;
+  const int stats_smem = (stats != nullptr && c_out <= 128) ? 64 * c_out : 0;   // [4 warps][2 C] doubles
   const int budget = kSmemLimit - 1024 - 256 - stats_smem;
   // Tile shape: MT sub-tiles of 128 rows x cn_tile output channels per work item, and on small maps
   // (deep UNet levels: too few row tiles for 148 SMs) the K offsets split over `ksplit` items whose

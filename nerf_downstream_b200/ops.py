@@ -934,7 +934,7 @@ class ConvBNFn(torch.autograd.Function):
         own = w_param if (w_param is not None and w_param.data_ptr() == w3.data_ptr()
                           and w_param.numel() == w3.numel()) else None
         sums = None
-        if fuse_bn_stats and (training or running_mean is None) and c_out <= 256 and km.m_out >= 1:
+        if fuse_bn_stats and (training or running_mean is None) and c_out <= 128 and km.m_out >= 1:
             sums = _empty(2 * c_out, torch.float64, x.device)
             c, fused = conv_fwd_raw(xb, w3, None, km, L.PREC_BF16, own, bn_sums=sums)
             if not fused:

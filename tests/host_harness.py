@@ -367,7 +367,7 @@ class FakeLib:
     def spc_conv_fwd_packed_stats(self, x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, bn_sums,
                                   stats_fused, stream):
         rc = self.spc_conv_fwd_packed(x, wp, bias, nbr, mask, m_in, m_out, c_in, c_out, K, precision, out, stream)
-        fused = int(_addr(bn_sums) != 0 and not _addr(bias) and c_out <= 256 and m_out >= 4096)  # (large maps only)
+        fused = int(_addr(bn_sums) != 0 and not _addr(bias) and c_out <= 128 and m_out >= 4096)  # (large maps only)
         if fused:
             o = view(out, (m_out, c_out), np.float32).astype(np.float64)
             s = view(bn_sums, 2 * c_out, np.float64)
