@@ -334,6 +334,25 @@ int spc_plenoxel_decode(const void* links, int links_is_int64, int64_t n, const 
 int spc_seg_metrics(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_label,
                     uint64_t* counts, void* stream);
 
+/* Row selections of a plenoxel record on the device: the reference's RandomCrop and CoordinateDropout
+ * (co3d_3d/src/data/transforms.py:195-265) drop points BEFORE the network sees them; here they become a row list and
+ * the record is decoded once, for the kept rows only, in the reference's row order.
+ * spc_plenoxel_decode_rows: spc_plenoxel_decode for output row j <- record rows[j] (rows: DEVICE int32 [n_rows]; a
+ *   CoordinateDropout's `np.random.choice` index list, or the list spc_plenoxel_crop_select wrote).
+ * spc_plenoxel_crop_select: RandomCrop.__call__ for one draw of the box position.  Over the records rows[0..n) (NULL:
+ *   all n records) with lattice coordinates mapped through affine12 (HOST float[12] or NULL: the affine chain applied
+ *   before the crop): extent, then keep the points with  u * clip(max - min - size, 0) < p - min < ... + size  on every
+ *   axis (u3, size3: HOST float[3]; float32 arithmetic), stable compaction of the kept record numbers into out_rows
+ *   (DEVICE int32 [n]).  result2 (DEVICE int32 [2]) = { rows kept, 1 if the box covers the extent on every axis (the
+ *   reference then returns its input unchanged) }.  The caller reads result2 once (RandomCrop retries an empty box). */
+int spc_plenoxel_decode_rows(const void* links, int links_is_int64, const int32_t* rows, int64_t n_rows,
+                             const int32_t* reso, int32_t batch_index, const float* affine12, const uint8_t* sh_u8, int C,
+                             float sh_scale, float sh_min, float* out_coords, float* out_feats, void* stream);
+int64_t spc_plenoxel_crop_workspace(int64_t n);
+int spc_plenoxel_crop_select(const void* links, int links_is_int64, const int32_t* rows, int64_t n, const int32_t* reso,
+                             const float* affine12, const float* u3, const float* size3, int32_t* out_rows,
+                             int32_t* result2, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- segmentation head --------------------------------------------------------------------
  * spc_seg_head_fwd: `out.slice(x).F` (res16unet.py:435) -> `SegLoss` (segmentation_training.py:27-44) ->
  *   `IoUMeter.update` (metrics.py:29-41) in ONE pass over the n points.

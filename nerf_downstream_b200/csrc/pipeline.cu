@@ -6,6 +6,8 @@
 //                     float features  sh * scale + min                      (co3d_3d/src/data/co3d.py:164-172,196-203)
 //   seg_metrics     : per-class seen / correct / predicted counts of argmax(logits) against the labels with an ignore
 //                     label — IoUMeter.update                                (co3d_3d/src/metrics.py:29-41)
+#include <climits>
+
 #include "common.cuh"
 
 namespace spc {
@@ -19,12 +21,14 @@ struct Affine {
 __global__ void __launch_bounds__(256)
 plenoxel_decode_kernel(const long long* __restrict__ links64, const int* __restrict__ links32, long long n,
                        int r1, int r2, float batch, Affine aff, const unsigned char* __restrict__ sh_u8, int C,
-                       float sh_scale, float sh_min, float* __restrict__ coords, float* __restrict__ feats) {
+                       float sh_scale, float sh_min, float* __restrict__ coords, float* __restrict__ feats,
+                       const int* __restrict__ rows) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long plane = (long long)r1 * r2;
   for (long long i = t0; i < n; i += stride) {
-    const long long l = links64 ? links64[i] : (long long)links32[i];
+    const long long src = rows ? (long long)rows[i] : i;   // output row i <- record rows[i] (crop / dropout selections)
+    const long long l = links64 ? links64[src] : (long long)links32[src];
     // torch.div(links, r1*r2, 'trunc'), torch.div(links % (r1*r2), r2, 'trunc'), links % r2   (co3d.py:196-203)
     const float x = (float)(l / plane), y = (float)((l % plane) / r2), z = (float)(l % r2);
     float4 c;
@@ -37,6 +41,28 @@ plenoxel_decode_kernel(const long long* __restrict__ links64, const int* __restr
       c.y = x; c.z = y; c.w = z;
     }
     reinterpret_cast<float4*>(coords)[i] = c;
+  }
+  if (rows) {   // gathered rows: one thread per (row, 4-byte group) when C % 4 == 0, else per element
+    const bool v4 = C % 4 == 0 && ((uintptr_t)sh_u8 % 4 == 0) && ((uintptr_t)feats % 16 == 0);
+    const int per = v4 ? C / 4 : C;
+    const long long tot = n * (long long)per;
+    for (long long q = t0; q < tot; q += stride) {
+      const long long i = q / per;
+      const int j = (int)(q - i * per);
+      const long long src = (long long)rows[i];
+      if (v4) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(sh_u8 + src * C)[j];
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn((float)u.x, sh_scale), sh_min);
+        o.y = __fadd_rn(__fmul_rn((float)u.y, sh_scale), sh_min);
+        o.z = __fadd_rn(__fmul_rn((float)u.z, sh_scale), sh_min);
+        o.w = __fadd_rn(__fmul_rn((float)u.w, sh_scale), sh_min);
+        reinterpret_cast<float4*>(feats + i * C)[j] = o;
+      } else {
+        feats[i * C + j] = __fadd_rn(__fmul_rn((float)sh_u8[src * C + j], sh_scale), sh_min);
+      }
+    }
+    return;
   }
   // features: flat over n * C bytes, 4 per thread where alignment allows;  sh.float() * scale + min  (co3d.py:169)
   const long long total = n * (long long)C;
@@ -52,6 +78,127 @@ plenoxel_decode_kernel(const long long* __restrict__ links64, const int* __restr
     reinterpret_cast<float4*>(feats)[q] = o;
   }
   for (long long e = n4 * 4 + t0; e < total; e += stride) feats[e] = __fadd_rn(__fmul_rn((float)sh_u8[e], sh_scale), sh_min);
+}
+
+// ---- RandomCrop on the device (co3d_3d/src/data/transforms.py:195-243) ---------------------------------------------
+// The crop keeps the points strictly inside a box of size `size` whose corner is u * max(extent - size, 0) above the
+// minimum of the (already transformed) coordinates.  Three small kernels over the current row selection of a record:
+// extent (ordered-int atomic min / max), flags + per-block counts, stable compaction into a row list — the decode
+// kernel then gathers exactly the kept records (plenoxel_decode_kernel, `rows`), in the reference's order.
+__device__ __forceinline__ int float_order(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;     // monotone float -> int
+}
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__device__ __forceinline__ void plenoxel_point(long long l, long long plane, int r2, const Affine& aff, float& px, float& py,
+                                               float& pz) {
+  const float x = (float)(l / plane), y = (float)((l % plane) / r2), z = (float)(l % r2);
+  if (aff.enabled) {
+    px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[0], x), __fmul_rn(aff.m[1], y)), __fmul_rn(aff.m[2], z)), aff.t[0]);
+    py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[3], x), __fmul_rn(aff.m[4], y)), __fmul_rn(aff.m[5], z)), aff.t[1]);
+    pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(aff.m[6], x), __fmul_rn(aff.m[7], y)), __fmul_rn(aff.m[8], z)), aff.t[2]);
+  } else {
+    px = x; py = y; pz = z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+crop_extent_kernel(const long long* __restrict__ links64, const int* __restrict__ links32, const int* __restrict__ rows,
+                   long long n, int r1, int r2, Affine aff, int* __restrict__ ext /* [6] ordered ints: min xyz, max xyz */) {
+  const long long plane = (long long)r1 * r2;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long src = rows ? (long long)rows[i] : i;
+    float p[3];
+    plenoxel_point(links64 ? links64[src] : (long long)links32[src], plane, r2, aff, p[0], p[1], p[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { const int o = float_order(p[a]); lo[a] = min(lo[a], o); hi[a] = max(hi[a], o); }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(ext + a, lo[a]); atomicMax(ext + 3 + a, hi[a]); }
+  }
+}
+
+struct CropBox { float u[3], size[3]; };
+
+// keep flag of a point: norm = p - min; box corner = u * clip(max - min - size, 0); strict inequalities.
+// (float32 arithmetic in the reference's order of operations; the reference computes in float64 when the coordinates
+// are float64 — pipeline.py documents the dtype it mirrors)
+__device__ __forceinline__ bool crop_keep(const float* p, const int* __restrict__ ext, const CropBox& box) {
+  bool keep = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float mn = order_float(ext[a]), mx = order_float(ext[3 + a]);
+    const float norm = __fsub_rn(p[a], mn);
+    const float range = fmaxf(__fsub_rn(__fsub_rn(mx, mn), box.size[a]), 0.f);
+    const float lo = __fmul_rn(box.u[a], range), hi = __fadd_rn(lo, box.size[a]);
+    keep = keep && norm > lo && norm < hi;
+  }
+  return keep;
+}
+
+constexpr int kCropBlock = 1024;   // records per block of the count / compaction kernels
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kCropBlock)
+crop_select_kernel(const long long* __restrict__ links64, const int* __restrict__ links32, const int* __restrict__ rows,
+                   long long n, int r1, int r2, Affine aff, const int* __restrict__ ext, CropBox box,
+                   int* __restrict__ block_counts /* WRITE: exclusive offsets */, int* __restrict__ out_rows) {
+  __shared__ int s_warp[kCropBlock / 32];
+  const long long plane = (long long)r1 * r2;
+  const long long i = (long long)blockIdx.x * kCropBlock + threadIdx.x;
+  bool keep = false;
+  long long src = 0;
+  if (i < n) {
+    src = rows ? (long long)rows[i] : i;
+    float p[3];
+    plenoxel_point(links64 ? links64[src] : (long long)links32[src], plane, r2, aff, p[0], p[1], p[2]);
+    keep = crop_keep(p, ext, box);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = __popc(ballot);
+  __syncthreads();
+  if (wid == 0) {   // exclusive scan of the 32 warp counts
+    int v = s_warp[lane], incl = v;
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    s_warp[lane] = incl - v;
+    if (!WRITE && lane == 31) block_counts[blockIdx.x] = incl;
+  }
+  if (!WRITE) return;
+  __syncthreads();
+  if (keep) out_rows[block_counts[blockIdx.x] + s_warp[wid] + __popc(ballot & ((1u << lane) - 1u))] = (int)src;
+}
+
+// exclusive scan of the block counts in place (one block; <= a few thousand blocks), total and "box fits" flag
+__global__ void __launch_bounds__(1024)
+crop_scan_kernel(int* __restrict__ block_counts, int n_blocks, const int* __restrict__ ext, CropBox box,
+                 int* __restrict__ result /* [2]: rows kept, 1 if the box covers the extent on every axis */) {
+  __shared__ int s_part[1024];
+  const int per = (n_blocks + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(b0 + per, n_blocks);
+  int sum = 0;
+  for (int b = b0; b < b1; ++b) sum += block_counts[b];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < 1024; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
+    result[0] = run;
+    bool fits = true;
+    for (int a = 0; a < 3; ++a)
+      fits = fits && !(__fsub_rn(__fsub_rn(order_float(ext[3 + a]), order_float(ext[a])), box.size[a]) > 0.f);
+    result[1] = fits ? 1 : 0;
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for (int b = b0; b < b1; ++b) { const int v = block_counts[b]; block_counts[b] = run; run += v; }
 }
 
 // counts[0][c] = #(target == c), counts[1][c] = #(target == c and argmax == c), counts[2][c] = #(argmax == c),
@@ -183,8 +330,72 @@ int spc_plenoxel_decode(const void* links, int links_is_int64, int64_t n, const 
   plenoxel_decode_kernel<<<grid, 256, 0, stream>>>(links_is_int64 ? (const long long*)links : nullptr,
                                                     links_is_int64 ? nullptr : (const int*)links, n, reso[1], reso[2],
                                                     (float)batch_index, aff, sh_u8, C, sh_scale, sh_min, out_coords,
-                                                    out_feats);
+                                                    out_feats, nullptr);
   SPC_LAUNCHED("plenoxel_decode_kernel");
+  return 0;
+}
+
+static Affine make_affine(const float* affine12) {
+  Affine aff;
+  memset(&aff, 0, sizeof(aff));
+  if (affine12) {
+    memcpy(aff.m, affine12, 9 * sizeof(float));
+    memcpy(aff.t, affine12 + 9, 3 * sizeof(float));
+    aff.enabled = 1;
+  }
+  return aff;
+}
+
+int spc_plenoxel_decode_rows(const void* links, int links_is_int64, const int32_t* rows, int64_t n_rows,
+                             const int32_t* reso, int32_t batch_index, const float* affine12, const uint8_t* sh_u8, int C,
+                             float sh_scale, float sh_min, float* out_coords, float* out_feats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(n_rows >= 0 && C >= 0 && rows && reso && reso[1] > 0 && reso[2] > 0, "bad arguments");
+  SPC_REQUIRE(((uintptr_t)out_coords % 16) == 0, "coordinates must be 16-byte aligned");
+  if (n_rows == 0) return 0;
+  int64_t want = ceil_div(n_rows * (C >= 4 ? C / 4 : 1), 256);
+  int grid = (int)(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  plenoxel_decode_kernel<<<grid, 256, 0, stream>>>(links_is_int64 ? (const long long*)links : nullptr,
+                                                    links_is_int64 ? nullptr : (const int*)links, n_rows, reso[1], reso[2],
+                                                    (float)batch_index, make_affine(affine12), sh_u8, C, sh_scale, sh_min,
+                                                    out_coords, out_feats, rows);
+  SPC_LAUNCHED("plenoxel_decode_kernel");
+  return 0;
+}
+
+int64_t spc_plenoxel_crop_workspace(int64_t n) { return 64 + 4 * (ceil_div(n > 0 ? n : 1, kCropBlock) + 8); }
+
+int spc_plenoxel_crop_select(const void* links, int links_is_int64, const int32_t* rows, int64_t n, const int32_t* reso,
+                             const float* affine12, const float* u3, const float* size3, int32_t* out_rows,
+                             int32_t* result2, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(n >= 0 && reso && reso[1] > 0 && reso[2] > 0 && u3 && size3 && out_rows && result2, "bad arguments");
+  SPC_REQUIRE(workspace && workspace_bytes >= spc_plenoxel_crop_workspace(n), "workspace too small");
+  SPC_REQUIRE(n < (1ll << 31), "too many rows");
+  if (n == 0) { SPC_CUDA(cudaMemsetAsync(result2, 0, 8, stream)); return 0; }
+  const long long* l64 = links_is_int64 ? (const long long*)links : nullptr;
+  const int* l32 = links_is_int64 ? nullptr : (const int*)links;
+  const Affine aff = make_affine(affine12);
+  int* ext = (int*)(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
+  int* block_counts = ext + 8;
+  const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  SPC_CUDA(cudaMemcpyAsync(ext, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  CropBox box;
+  memcpy(box.u, u3, 12);
+  memcpy(box.size, size3, 12);
+  int64_t want = ceil_div(n, 256 * 4);
+  int grid = (int)(want < kNumSMs * 8 ? (want > 0 ? want : 1) : kNumSMs * 8);
+  crop_extent_kernel<<<grid, 256, 0, stream>>>(l64, l32, rows, n, reso[1], reso[2], aff, ext);
+  SPC_LAUNCHED("crop_extent_kernel");
+  const int n_blocks = (int)ceil_div(n, kCropBlock);
+  crop_select_kernel<false><<<n_blocks, kCropBlock, 0, stream>>>(l64, l32, rows, n, reso[1], reso[2], aff, ext, box,
+                                                                  block_counts, nullptr);
+  SPC_LAUNCHED("crop_select_kernel");
+  crop_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, n_blocks, ext, box, result2);
+  SPC_LAUNCHED("crop_scan_kernel");
+  crop_select_kernel<true><<<n_blocks, kCropBlock, 0, stream>>>(l64, l32, rows, n, reso[1], reso[2], aff, ext, box,
+                                                                 block_counts, out_rows);
+  SPC_LAUNCHED("crop_select_kernel");
   return 0;
 }
 

@@ -78,6 +78,9 @@ SIGNATURES = {
     "spc_pool_max_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "spc_global_max_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "spc_plenoxel_decode": (c_int, [_P, c_int, c_int64, _P, c_int, _P, _P, c_int, c_float, c_float, _P, _P, _P]),
+    "spc_plenoxel_decode_rows": (c_int, [_P, c_int, _P, c_int64, _P, c_int, _P, _P, c_int, c_float, c_float, _P, _P, _P]),
+    "spc_plenoxel_crop_workspace": (c_int64, [c_int64]),
+    "spc_plenoxel_crop_select": (c_int, [_P, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "spc_seg_metrics": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
     "spc_seg_head_fwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     "spc_inst_norm_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P, _P]),

@@ -17,11 +17,16 @@ from . import lib as L
 
 def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float, reso: Sequence[int],
                     batch_index: int = 0, affine: Optional[Sequence[float]] = None,
-                    out_coords: Optional[torch.Tensor] = None, out_feats: Optional[torch.Tensor] = None):
+                    out_coords: Optional[torch.Tensor] = None, out_feats: Optional[torch.Tensor] = None,
+                    rows: Optional[torch.Tensor] = None):
     """links [n] int32/int64 (flat cell indices), sh_u8 [n, C] uint8 -> coords [n,4] float32 (b,i,j,k), feats [n,C]
     float32 = sh * scale + min.  `affine` = 12 floats (row-major 3x3, then translation) applied to (i,j,k).
     `out_coords` / `out_feats`: contiguous [n,4] / [n,C] float32 destinations (e.g. one scene's rows of a batch
-    buffer: the records of a batch decode straight into the collated tensors, no torch.cat)."""
+    buffer: the records of a batch decode straight into the collated tensors, no torch.cat).
+    `rows` (int32 [m]): decode only these records, output row j <- record rows[j] (`plenoxel_select_rows`: the
+    reference's RandomCrop / CoordinateDropout as a row list instead of boolean-mask copies of decoded tensors)."""
+    if rows is not None:
+        return _plenoxel_decode_rows(links, sh_u8, sh_scale, sh_min, reso, batch_index, affine, rows)
     lib = L.load()
     if links.dtype not in (torch.int32, torch.int64) or links.dim() != 1:
         raise RuntimeError("links must be a 1-D int32 / int64 tensor")
@@ -45,6 +50,104 @@ def plenoxel_decode(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, s
                                     L.ptr(sh_u8), C, float(sh_scale), float(sh_min), L.ptr(coords), L.ptr(feats),
                                     L.stream()), "spc_plenoxel_decode")
     return coords, feats
+
+
+def _affine12(affine):
+    if affine is None:
+        return None
+    if len(affine) != 12:
+        raise RuntimeError("affine must hold 12 floats (3x3 row-major + translation)")
+    return (ctypes.c_float * 12)(*[float(v) for v in affine])
+
+
+def _plenoxel_decode_rows(links, sh_u8, sh_scale, sh_min, reso, batch_index, affine, rows):
+    lib = L.load()
+    if rows.dtype != torch.int32 or rows.dim() != 1:
+        raise RuntimeError("rows must be a 1-D int32 tensor")
+    links, sh_u8, rows = links.contiguous(), sh_u8.contiguous(), rows.contiguous()
+    m, C = rows.shape[0], sh_u8.shape[1]
+    coords = torch.empty((m, 4), dtype=torch.float32, device=links.device)
+    feats = torch.empty((m, C), dtype=torch.float32, device=links.device)
+    r = (ctypes.c_int32 * 3)(*[int(v) for v in reso])
+    aff = _affine12(affine)
+    L.check(lib.spc_plenoxel_decode_rows(L.ptr(links), int(links.dtype == torch.int64), L.ptr(rows), m,
+                                         ctypes.cast(r, ctypes.c_void_p), int(batch_index),
+                                         ctypes.cast(aff, ctypes.c_void_p) if aff is not None else None, L.ptr(sh_u8), C,
+                                         float(sh_scale), float(sh_min), L.ptr(coords), L.ptr(feats), L.stream()),
+            "spc_plenoxel_decode_rows")
+    return coords, feats
+
+
+def plenoxel_crop_rows(links: torch.Tensor, reso: Sequence[int], size3: Sequence[float], u3: Sequence[float],
+                       rows: Optional[torch.Tensor] = None, affine: Optional[Sequence[float]] = None):
+    """One draw of RandomCrop (transforms.py:206-226) over the records `rows` (None: all) of a plenoxel record, the
+    lattice coordinates mapped through `affine` first.  Returns (kept record numbers int32 [k], fits): `fits` = the box
+    covers the extent on every axis (the reference returns its input unchanged).  One host synchronisation."""
+    lib = L.load()
+    links = links.contiguous()
+    n = int(rows.shape[0]) if rows is not None else int(links.shape[0])
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=links.device)
+    res = torch.empty(2, dtype=torch.int32, device=links.device)
+    ws_bytes = int(lib.spc_plenoxel_crop_workspace(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=links.device)
+    r = (ctypes.c_int32 * 3)(*[int(v) for v in reso])
+    aff = _affine12(affine)
+    u = (ctypes.c_float * 3)(*[float(v) for v in u3])
+    sz = (ctypes.c_float * 3)(*[float(v) for v in size3])
+    L.check(lib.spc_plenoxel_crop_select(L.ptr(links), int(links.dtype == torch.int64),
+                                         L.ptr(rows.contiguous()) if rows is not None else None, n,
+                                         ctypes.cast(r, ctypes.c_void_p),
+                                         ctypes.cast(aff, ctypes.c_void_p) if aff is not None else None,
+                                         ctypes.cast(u, ctypes.c_void_p), ctypes.cast(sz, ctypes.c_void_p), L.ptr(out),
+                                         L.ptr(res), L.ptr(ws), ws_bytes, L.stream()), "spc_plenoxel_crop_select")
+    kept, fits = res.tolist()
+    return out[:kept], bool(fits)
+
+
+def plenoxel_select_rows(links: torch.Tensor, reso: Sequence[int], steps: Sequence[tuple],
+                         affine: Optional[Sequence[float]] = None) -> Optional[torch.Tensor]:
+    """The point-dropping transformations of the reference's train lists as ONE row list of the record, drawn in the
+    reference's RNG order (python `random` for the application ratios, numpy for the draws):
+      ("RandomCrop", dict(x=, y=, z=, application_ratio=1, max_retries=10))        transforms.py:195-243
+      ("CoordinateDropout", dict(dropout_ratio=0.2, application_ratio=0.2))        transforms.py:247-264
+    `affine`: the affine chain in front of these steps.  Returns int32 record numbers in the reference's row order, or
+    None when every step left the rows as they were.  The record is then decoded once for those rows
+    (`plenoxel_decode(..., rows=...)`), instead of being decoded in full and copied through boolean masks."""
+    import random as py_random
+
+    import numpy as np
+    rows = None
+    n = int(links.shape[0])
+    for name, kw in steps:
+        cur = n if rows is None else int(rows.shape[0])
+        if name == "RandomCrop":
+            if py_random.random() > kw.get("application_ratio", 1):
+                continue
+            size3 = (kw["x"], kw["y"], kw["z"])
+            retries, chosen = 0, None
+            while True:
+                state = np.random.get_state()
+                u3 = np.random.rand(1, 3)[0]
+                kept, fits = plenoxel_crop_rows(links, reso, size3, u3, rows, affine)
+                if fits:                      # `np.prod(coord_range == 0)`: the reference returns BEFORE its first draw
+                    np.random.set_state(state)
+                    break
+                if kept.shape[0] > 0:
+                    chosen = kept
+                    break
+                retries += 1
+                if retries >= kw.get("max_retries", 10):
+                    break
+            if chosen is not None:
+                rows = chosen
+        elif name == "CoordinateDropout":
+            if py_random.random() < kw.get("application_ratio", 0.2):
+                inds = np.random.choice(cur, int(cur * (1 - kw.get("dropout_ratio", 0.2))), replace=False)
+                idx = torch.from_numpy(inds.astype(np.int64)).to(links.device)
+                rows = idx.to(torch.int32) if rows is None else rows[idx]
+        else:
+            raise KeyError(f"{name} does not drop points (RandomCrop / CoordinateDropout do)")
+    return rows
 
 
 def plenoxel_decode_augmented(links: torch.Tensor, sh_u8: torch.Tensor, sh_scale: float, sh_min: float,

@@ -346,6 +346,23 @@ def plenoxel_decode_np(links: np.ndarray, sh_u8: np.ndarray, sh_scale: float, sh
     return coords, feats.astype(np.float32)
 
 
+def random_crop_select_np(xyz: np.ndarray, u3, size3):
+    """RandomCrop.__call__ for ONE draw `u3` of the box position (co3d_3d/src/data/transforms.py:206-226): returns
+    (indices of the kept rows in their order, fits) — `fits`: the box covers the extent on every axis, the reference then
+    returns its input unchanged (:217-218).  float32 arithmetic in the reference's order of operations."""
+    c = np.asarray(xyz, np.float32)
+    mn = c.min(0, keepdims=True)
+    norm = (c - mn).astype(np.float32)
+    max_coords = norm.max(0, keepdims=True)
+    size = np.asarray(size3, np.float32).reshape(1, 3)
+    rng = np.clip((max_coords - size).astype(np.float32), 0, np.inf).astype(np.float32)
+    fits = bool(np.prod(rng == 0))
+    lo = (np.asarray(u3, np.float32).reshape(1, 3) * rng).astype(np.float32)
+    hi = (lo + size).astype(np.float32)
+    sel = np.logical_and(np.prod(norm > lo, 1), np.prod(norm < hi, 1)).astype(bool)
+    return np.nonzero(sel)[0].astype(np.int32), fits
+
+
 def iou_counts_np(logits: np.ndarray, target: np.ndarray, num_classes: int, ignore_label: int) -> np.ndarray:
     """IoUMeter.update (co3d_3d/src/metrics.py:29-41) on preds = argmax(logits): [3, C] seen / correct / positive."""
     preds = logits.argmax(1)

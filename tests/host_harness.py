@@ -634,6 +634,38 @@ class FakeLib:
             view(out_feats, (n, C), np.float32)[:] = f
         return 0
 
+    def spc_plenoxel_decode_rows(self, links, is64, rows, n_rows, reso, batch_index, affine12, sh_u8, C, sh_scale, sh_min,
+                                 out_coords, out_feats, stream):
+        self._called("spc_plenoxel_decode_rows")
+        r = [int(v) for v in view(reso, 3, np.int32)]
+        rw = view(rows, n_rows, np.int32).astype(np.int64)
+        n_rec = int(rw.max()) + 1 if n_rows else 0
+        ln = view(links, n_rec, np.int64 if is64 else np.int32).astype(np.int64)[rw]
+        aff = list(view(affine12, 12, np.float32)) if _addr(affine12) else None
+        sh = view(sh_u8, (n_rec, C), np.uint8)[rw] if C else np.zeros((n_rows, 0), np.uint8)
+        c, f = R.plenoxel_decode_np(ln, sh, np.float32(sh_scale), np.float32(sh_min), r, batch_index=batch_index, affine=aff)
+        view(out_coords, (n_rows, 4), np.float32)[:] = c
+        if C:
+            view(out_feats, (n_rows, C), np.float32)[:] = f
+        return 0
+
+    def spc_plenoxel_crop_workspace(self, n):
+        return 256
+
+    def spc_plenoxel_crop_select(self, links, is64, rows, n, reso, affine12, u3, size3, out_rows, result2, ws, ws_bytes,
+                                 stream):
+        self._called("spc_plenoxel_crop_select")
+        r = [int(v) for v in view(reso, 3, np.int32)]
+        rw = view(rows, n, np.int32).astype(np.int64) if _addr(rows) else np.arange(n, dtype=np.int64)
+        n_rec = int(rw.max()) + 1 if n else 0
+        ln = view(links, n_rec, np.int64 if is64 else np.int32).astype(np.int64)[rw]
+        aff = list(view(affine12, 12, np.float32)) if _addr(affine12) else None
+        c, _ = R.plenoxel_decode_np(ln, np.zeros((n, 0), np.uint8), 1.0, 0.0, r, affine=aff)
+        keep, fits = R.random_crop_select_np(c[:, 1:], view(u3, 3, np.float32), view(size3, 3, np.float32))
+        view(out_rows, n, np.int32)[:len(keep)] = rw[keep]
+        view(result2, 2, np.int32)[:] = (len(keep), int(fits))
+        return 0
+
     # ---- instance norm / interpolation ------------------------------------------------------------------------
     def spc_inst_norm_fwd(self, x, coords, m, C, n_batch, gamma, beta, eps, y, mean, rstd, cnt, ws, stream):
         self._called("spc_inst_norm_fwd")

@@ -563,3 +563,37 @@ def test_hollow_registry_does_not_keep_tensors_alive(monkeypatch):
     del cat
     gc.collect()
     assert len(O._hollow) == n - 1
+
+
+def test_row_selections_of_a_plenoxel_record_follow_the_reference_transforms(monkeypatch):
+    """RandomCrop / CoordinateDropout as a row list + one decode of the kept records == decoding everything and pushing
+    the tensors through the (reference-pinned) transforms of augment.py with the same RNG state."""
+    import random as py_random
+
+    from nerf_downstream_b200 import augment
+    fake = host_harness.install(monkeypatch, "fp32")
+    rng = np.random.RandomState(3)
+    reso = (64, 48, 40)
+    links = torch.from_numpy(np.sort(rng.choice(reso[0] * reso[1] * reso[2], 5000, replace=False)).astype(np.int32))
+    sh = torch.from_numpy(rng.randint(0, 256, size=(5000, 27)).astype(np.uint8))
+    aff = [1.0, 0.05, 0, -0.05, 1.0, 0, 0, 0, 1.0, 2.0, -1.0, 0.5]
+    steps = [("RandomCrop", dict(x=30, y=25, z=100, application_ratio=1.0)),
+             ("CoordinateDropout", dict(dropout_ratio=0.3, application_ratio=1.0))]
+    py_random.seed(7)
+    np.random.seed(7)
+    rows = pipeline.plenoxel_select_rows(links, reso, steps, aff)
+    assert rows is not None and rows.dtype == torch.int32
+    c_a, f_a = pipeline.plenoxel_decode(links, sh, 2.0 / 255, -1.0, reso, affine=aff, rows=rows)
+    # the same through the transforms on fully decoded tensors
+    py_random.seed(7)
+    np.random.seed(7)
+    c_all, f_all = pipeline.plenoxel_decode(links, sh, 2.0 / 255, -1.0, reso, affine=aff)
+    xyz, f_b, _ = augment.random_crop(c_all[:, 1:], f_all, None, 30, 25, 100, 1.0)
+    xyz, f_b, _ = augment.coordinate_dropout(xyz, f_b, None, 0.3, 1.0)
+    assert 0 < xyz.shape[0] < 5000
+    assert torch.equal(c_a[:, 1:], xyz) and torch.equal(f_a, f_b)
+    assert fake.calls.count("spc_plenoxel_decode_rows") == 1 and fake.calls.count("spc_plenoxel_crop_select") >= 1
+    # a box larger than the extent: the reference returns its input and draws nothing
+    state = np.random.get_state()[1].copy()
+    assert pipeline.plenoxel_select_rows(links, reso, [("RandomCrop", dict(x=500, y=500, z=500))], aff) is None
+    assert (np.random.get_state()[1] == state).all()
