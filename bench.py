@@ -302,6 +302,17 @@ def run_ours(args):
 
         ms = timed(args.steps, host_timed_step)
         launches = L.launch_count() - launches0
+        # host time to ISSUE one step with an idle device in front of it: inside the timed region the map-size
+        # read-backs make the host wait for the previous step's kernels, so `host_issue_ms_per_step` there tracks the
+        # device time; this one is what the Python layer itself costs per step (median of 3)
+        iso = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step(d_coords, d_feats, d_labels)
+            iso.append(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+        host_isolated_ms = 1e3 * sorted(iso)[1]
         routes = path_counts(False)
         clocks = sampler.stop() if (rank == 0 and with_clocks) else None
         vox = torch.tensor([float(voxels_per_step[0])], device=dev)
@@ -430,6 +441,7 @@ def run_ours(args):
                                   "by spc_plenoxel_decode inside the timed region") if compact else
                                  "collated float32 coordinates + float32 features + int64 labels"},
                 "gpu_launches": int(launches), "host_issue_ms_per_step": 1e3 * host_s[0] / args.steps,
+                "host_issue_ms_isolated_step": host_isolated_ms,
                 # convolution launches per step by route: anything under "cuda_core_fp32" is a shape the tensor-core
                 # kernels do not take (ops.SparseConvFn / conv_api.cu routing), "tf32" under a bf16 run a precision
                 # fallback — both would be silent otherwise
@@ -484,6 +496,7 @@ def run_ours(args):
                 "e2e": main_res["e2e"],
                 "gpu_launches": main_res["gpu_launches"],
                 "host_issue_ms_per_step": main_res["host_issue_ms_per_step"],
+                "host_issue_ms_isolated_step": main_res["host_issue_ms_isolated_step"],
                 "conv_routes_per_step": main_res["conv_routes_per_step"],
                 "roofline": main_res["roofline"],
                 "kernel_map_build_ms": main_res["kernel_map_build_ms"],
