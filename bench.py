@@ -35,7 +35,10 @@ UNIT = "voxels/s"
 PARITY_NOTE = {
     "bf16": {"per_layer_bar": "|d| <= 3e-3 * max|ref| (fwd, dgrad, wgrad; measured 2.2e-3 .. 2.7e-3)",
              "test": "tests/test_gpu_parity.py::test_conv_bf16_tensor_core, tests/test_gpu_scale.py",
-             "whole_network_at_scale": "logits cos 0.9993, all-parameter gradient cos 0.907 (tf32: 0.99999 / 0.985)"},
+             "whole_network_at_scale": "logits cos 0.9993, all-parameter gradient cos 0.903 (tf32: 0.99999 / 0.985)",
+             "graph": "conv + BatchNorm as one autograd node, hollow rows, re-computed ReLU masks, epilogue statistics, "
+                      "symmetric dgrad, residual gradients in dgrad's epilogue (ops.<knob>; held to the plain graph in "
+                      "tests/test_gpu_fusion.py)"},
     "tf32": {"per_layer_bar": "|d| <= 3e-3 * max|ref| (measured 7.4e-4 .. 8.5e-4)",
              "test": "tests/test_gpu_parity.py::test_conv_tf32_tensor_core, tests/test_gpu_scale.py",
              "whole_network_at_scale": "logits cos 0.99999, all-parameter gradient cos 0.985"},
