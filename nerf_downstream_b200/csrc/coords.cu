@@ -28,13 +28,57 @@ std::atomic<long long> g_launch_count{0};
 constexpr int kScanThreads = 1024;
 
 // ---------------------------------------------------------------------------
-// 1. insert: quantise, pack, probe, claim a slot, remember the smallest source row
+// 1. insert: quantise, pack, claim a slot, remember the smallest source row
 // ---------------------------------------------------------------------------
+// A slot is claimed with ONE 128-bit compare-and-swap {empty} -> {key, first = i, row = unset} (atom.cas.b128, sm_90+):
+// for a source without duplicates (what the plenoxel loaders deliver) that is the only L2 transaction of the point
+// besides its coalesced reads / writes — r1 / r2 spent a volatile read, a 64-bit CAS and an atomicMin on it.  A failed
+// CAS returns the slot: the same key -> atomicMin on `first` (only if the snapshot is larger), another key -> next slot.
+__device__ __forceinline__ void cas_slot(Slot* s, unsigned long long new_lo, unsigned long long new_hi,
+                                         unsigned long long& old_lo, unsigned long long& old_hi) {
+  const unsigned long long ones = kEmptyKey;
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 c, n, o;\n\t"
+      "mov.b128 c, {%2, %2};\n\t"
+      "mov.b128 n, {%3, %4};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 o, [%5], c, n;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t"
+      "}"
+      : "=l"(old_lo), "=l"(old_hi)
+      : "l"(ones), "l"(new_lo), "l"(new_hi), "l"(s)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// PEEK: look at the slot before trying to claim it — a stride map sees every parent voxel ~5 times, so most points
+// find their key already there and an atomicMin (often not even that: `first` is read with the key) is all they need.
 template <int SRC>
 __global__ void __launch_bounds__(256)
 insert_kernel(const void* __restrict__ src, int n, const int* __restrict__ n_dev, int3 ts, Slot* slots,
-              unsigned long long bucket_mask, int* __restrict__ slot_of, int* status) {
+              unsigned long long bucket_mask, int* __restrict__ slot_of, int* status,
+              int* __restrict__ out_count, unsigned long long* __restrict__ scan_state, int n_state) {
+  constexpr bool PEEK = SRC == SPC_SRC_STRIDE;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // this launch also clears what the row-assignment kernel behind it accumulates into: the per-voxel multiplicities
+  // and the look-back words of its single-pass scan (n_state words: ticket counter + one per block)
+  if (i < n) out_count[i] = 0;
+  if (i < n_state) scan_state[i] = 0ull;
   if (n_dev) n = min(n, *n_dev);  // row count produced on the device by the previous level
   if (i >= n) return;
   int b, x, y, z;
@@ -69,18 +113,27 @@ insert_kernel(const void* __restrict__ src, int n, const int* __restrict__ n_dev
     slot_of[i] = -1;
     return;
   }
+  const unsigned long long mine_hi = (unsigned long long)(unsigned)i | 0xFFFFFFFF00000000ull;  // first = i, row unset
   unsigned long long bucket = hash_key(key) & bucket_mask;
   for (;;) {
     Slot* s = slots + 2 * bucket;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&s[j].key);
-      if (k == kEmptyKey) {
-        k = atomicCAS(&s[j].key, kEmptyKey, key);
-        if (k == kEmptyKey) k = key;
+      unsigned long long k, hi;
+      bool have = false;
+      if (PEEK) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(hi) : "l"(&s[j]) : "memory");
+        have = k != kEmptyKey;
+      }
+      if (!have) {
+        cas_slot(&s[j], key, mine_hi, k, hi);
+        if (k == kEmptyKey) {   // claimed (an empty key means an empty slot: the other fields change only under a key)
+          slot_of[i] = (int)(2 * bucket + j);
+          return;
+        }
       }
       if (k == key) {
-        atomicMin(&s[j].first, (unsigned)i);
+        if ((unsigned)hi > (unsigned)i) atomicMin(&s[j].first, (unsigned)i);   // (`first` only ever decreases)
         slot_of[i] = (int)(2 * bucket + j);
         return;
       }
@@ -89,23 +142,27 @@ insert_kernel(const void* __restrict__ src, int n, const int* __restrict__ n_dev
   }
 }
 
-__device__ __forceinline__ bool is_first(const Slot* slots, const int* slot_of, int i, int n) {
-  if (i >= n) return false;
-  int s = slot_of[i];
-  return s >= 0 && slots[s].first == (unsigned)i;
+// block-wide exclusive prefix of a predicate using warp ballots
+__device__ __forceinline__ int block_ballot_prefix(bool flag, int* warp_sum /*[32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned bal = __ballot_sync(0xffffffffu, flag);
+  int lane_prefix = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_sum[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sum[lane], x = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    warp_sum[lane] = x - w;  // exclusive
+  }
+  __syncthreads();
+  return warp_sum[warp] + lane_prefix;
 }
 
-// 2. per-block number of first occurrences
-__global__ void __launch_bounds__(kScanThreads)
-count_first_kernel(const Slot* __restrict__ slots, const int* __restrict__ slot_of, int n,
-                   const int* __restrict__ n_dev, int* __restrict__ block_count) {
-  int i = blockIdx.x * kScanThreads + threadIdx.x;
-  if (n_dev) n = min(n, *n_dev);
-  int c = __syncthreads_count(is_first(slots, slot_of, i, n));
-  if (threadIdx.x == 0) block_count[blockIdx.x] = c;
-}
-
-// 3. single-block exclusive scan (in place) of `nb` ints, total -> *total_out
+// single-block exclusive scan (in place) of `nb` ints, total -> *total_out (pair-list export)
 __global__ void __launch_bounds__(kScanThreads)
 scan_blocks_kernel(int* __restrict__ data, int nb, int* __restrict__ total_out) {
   __shared__ int warp_sum[32];
@@ -141,58 +198,85 @@ scan_blocks_kernel(int* __restrict__ data, int nb, int* __restrict__ total_out) 
   if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
-// block-wide exclusive prefix of a predicate using warp ballots
-__device__ __forceinline__ int block_ballot_prefix(bool flag, int* warp_sum /*[32]*/) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned bal = __ballot_sync(0xffffffffu, flag);
-  int lane_prefix = __popc(bal & ((1u << lane) - 1u));
-  if (lane == 0) warp_sum[warp] = __popc(bal);
-  __syncthreads();
-  if (warp == 0) {
-    int w = warp_sum[lane], x = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    warp_sum[lane] = x - w;  // exclusive
-  }
-  __syncthreads();
-  return warp_sum[warp] + lane_prefix;
-}
-
-// 4. give every first occurrence its row; emit coordinates and unique_index
+// 2. rows in first-occurrence order, coordinates, unique_index, inverse map and multiplicities in ONE pass
+// (r1 / r2: count_first + scan_blocks + assign_rows + inverse kernels, each with its own random read of the slots).
+// A block takes a ticket t (so that lower tickets are always resident or done), owns source rows [1024 t, 1024 t + 1024),
+// counts its first occurrences and gets the number of those in front of it by decoupled look-back over the per-block
+// words (status << 32 | value; status 1 = the block's own count, 2 = its inclusive prefix) — the stream is read once.
+// A source row that is NOT the first of its voxel finds the voxel's row in the slot: written by a thread of this
+// block before the barrier, or by a block with a lower ticket (the first occurrence has the smaller index), which
+// never waits for a higher one — so spinning on the slot's `row` field terminates.
 __global__ void __launch_bounds__(kScanThreads)
 assign_rows_kernel(Slot* slots, const int* __restrict__ slot_of, int n, const int* __restrict__ n_dev,
-                   const int* __restrict__ block_offset, int4* __restrict__ out_coords,
-                   int* __restrict__ out_first) {
+                   unsigned long long* scan_state, int4* __restrict__ out_coords, int* __restrict__ out_first,
+                   int* __restrict__ inverse, int* __restrict__ count, int* __restrict__ status) {
   __shared__ int warp_sum[32];
-  int i = blockIdx.x * kScanThreads + threadIdx.x;
+  __shared__ int s_ticket, s_prefix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (n_dev) n = min(n, *n_dev);
-  bool flag = is_first(slots, slot_of, i, n);
-  int row = block_offset[blockIdx.x] + block_ballot_prefix(flag, warp_sum);
+  if (threadIdx.x == 0) s_ticket = (int)atomicAdd(scan_state, 1ull);
+  __syncthreads();
+  const int t = s_ticket;
+  unsigned long long* state = scan_state + 1;
+  const int last = n > 0 ? (n - 1) / kScanThreads : 0;
+  if (t > last) return;   // (nothing in this block's range, and no block that works looks at its word)
+  const int i = t * kScanThreads + threadIdx.x;
+  const int s = i < n ? slot_of[i] : -1;
+  bool flag = false;
+  unsigned long long key = 0;
+  if (s >= 0) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(slots + s);   // key, first (final since the insert launch)
+    key = v.x;
+    flag = (unsigned)v.y == (unsigned)i;
+  }
+  const int local = block_ballot_prefix(flag, warp_sum);
+  const int agg = __syncthreads_count(flag);
+  if (warp == 0) {
+    int excl = 0;
+    if (t == 0) {
+      if (lane == 0) st_relaxed_u64(state, (2ull << 32) | (unsigned)agg);
+    } else {
+      if (lane == 0) st_relaxed_u64(state + t, (1ull << 32) | (unsigned)agg);
+      for (int j = t - 1;; j -= 32) {
+        const int idx = j - lane;
+        unsigned long long w = 2ull << 32;   // in front of block 0: inclusive prefix 0
+        if (idx >= 0) {
+          do { w = ld_relaxed_u64(state + idx); } while ((w >> 32) == 0ull);
+        }
+        const unsigned done = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
+        int v = (int)(unsigned)w;
+        if (done && lane > __ffs(done) - 1) v = 0;   // blocks behind the nearest inclusive prefix are inside it
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (done) break;
+      }
+      if (lane == 0) st_relaxed_u64(state + t, (2ull << 32) | (unsigned)(excl + agg));
+    }
+    if (lane == 0) s_prefix = excl;
+  }
+  __syncthreads();
+  const int row = s_prefix + local;
   if (flag) {
-    Slot* s = slots + slot_of[i];
-    s->row = (unsigned)row;
-    out_coords[row] = unpack_key(s->key);
+    st_relaxed_u32(&slots[s].row, (unsigned)row);
+    out_coords[row] = unpack_key(key);
     out_first[row] = i;
   }
-}
-
-// 5. inverse map and per-voxel multiplicity
-__global__ void __launch_bounds__(256)
-inverse_kernel(const Slot* __restrict__ slots, const int* __restrict__ slot_of, int n,
-               const int* __restrict__ n_dev, int* __restrict__ inverse, int* __restrict__ count) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  int s = slot_of[i];
-  int row = -1;
-  if (s >= 0) {
-    row = (int)slots[s].row;
-    atomicAdd(&count[row], 1);
+  if (t == last && threadIdx.x == 0) status[0] = s_prefix + agg;
+  __syncthreads();
+  if (i < n) {
+    int r = -1;
+    if (s >= 0) {
+      if (flag) r = row;
+      else {
+        unsigned v;
+        do { v = ld_relaxed_u32(&slots[s].row); } while (v == 0xFFFFFFFFu);
+        r = (int)v;
+      }
+      atomicAdd(&count[r], 1);
+    }
+    inverse[i] = r;
   }
-  inverse[i] = row;
 }
 
 // ---------------------------------------------------------------------------
@@ -423,7 +507,7 @@ int64_t spc_table_slots(int64_t n) {
 
 int64_t spc_coords_insert_workspace(int64_t n) {
   int64_t nb = ceil_div(n > 0 ? n : 1, kScanThreads);
-  return align_up(n * 4, 256) + align_up(nb * 4, 256) + 256;
+  return align_up(n * 4, 256) + align_up((nb + 1) * 8, 256) + 256;   // slot of every source row + look-back words
 }
 
 int spc_coords_insert(const void* src, int64_t n, int src_kind, const int32_t* ts, void* slots,
@@ -448,31 +532,27 @@ int spc_coords_insert_dev(const void* src, int64_t n, const int32_t* n_dev, int 
   SPC_CUDA(cudaMemsetAsync(slots, 0xFF, (size_t)n_slots * sizeof(Slot), stream));
   SPC_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int), stream));
   if (n == 0) return 0;
-  SPC_CUDA(cudaMemsetAsync(out_count, 0, (size_t)n * sizeof(int), stream));
   char* ws = (char*)workspace;
   int* slot_of = (int*)ws;
-  int* block_off = (int*)(ws + align_up(n * 4, 256));
+  unsigned long long* scan_state = (unsigned long long*)(ws + align_up(n * 4, 256));   // [0] ticket counter, [1 + t] block t
   const int nb = (int)ceil_div(n, kScanThreads);
   const unsigned long long bucket_mask = (unsigned long long)(n_slots / 2 - 1);
   const int3 t3 = make_int3(ts[0], ts[1], ts[2]);
-  const int grid256 = (int)ceil_div(n, 256);
+  const int grid256 = (int)ceil_div(n, 256);   // (>= nb + 1 threads: the launch also clears the look-back words)
   Slot* sl = (Slot*)slots;
   if (src_kind == SPC_SRC_FLOAT)
-    insert_kernel<SPC_SRC_FLOAT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_FLOAT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status,
+                                                              out_count, scan_state, nb + 1);
   else if (src_kind == SPC_SRC_INT)
-    insert_kernel<SPC_SRC_INT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_INT><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status,
+                                                            out_count, scan_state, nb + 1);
   else
-    insert_kernel<SPC_SRC_STRIDE><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status);
+    insert_kernel<SPC_SRC_STRIDE><<<grid256, 256, 0, stream>>>(src, (int)n, n_dev, t3, sl, bucket_mask, slot_of, status,
+                                                               out_count, scan_state, nb + 1);
   SPC_LAUNCHED("insert_kernel");
-  count_first_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, n_dev, block_off);
-  SPC_LAUNCHED("count_first_kernel");
-  scan_blocks_kernel<<<1, kScanThreads, 0, stream>>>(block_off, nb, status);
-  SPC_LAUNCHED("scan_blocks_kernel");
-  assign_rows_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, n_dev, block_off,
-                                                      (int4*)out_coords, out_first);
+  assign_rows_kernel<<<nb, kScanThreads, 0, stream>>>(sl, slot_of, (int)n, n_dev, scan_state, (int4*)out_coords,
+                                                      out_first, out_inverse, out_count, status);
   SPC_LAUNCHED("assign_rows_kernel");
-  inverse_kernel<<<grid256, 256, 0, stream>>>(sl, slot_of, (int)n, n_dev, out_inverse, out_count);
-  SPC_LAUNCHED("inverse_kernel");
   return 0;
 }
 

@@ -21,6 +21,8 @@ ap.add_argument("--prec", default="tf32")
 ap.add_argument("--only", default="fwd,dgrad,wgrad")
 ap.add_argument("--shuffle", action="store_true")
 ap.add_argument("--dbg", default="", help="idx=val,... passed to spc_debug_set")
+ap.add_argument("--sort-window", type=int, default=0,
+                help="re-insert the voxels sorted by their 27-bit neighbour mask inside windows of W rows (0 = raster)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 for kv in filter(None, args.dbg.split(",")):
@@ -29,6 +31,14 @@ for kv in filter(None, args.dbg.split(",")):
 prec = ops.PRECISIONS[args.prec]
 c, _, _ = synth.room_batch(777, 1, args.voxels, channels=1, shuffle=args.shuffle)
 cmap, _, _, _ = ops.coords_insert(torch.from_numpy(c).to(dev), L.SRC_FLOAT, (1, 1, 1))
+if args.sort_window > 0:
+    # what an engine-side row order would do to the (tile, offset) skipping: same voxels, rows grouped by mask
+    km0 = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    bits = (km0.nbr >= 0).to(torch.int64) << torch.arange(27, device=dev).view(27, 1)
+    key = (torch.arange(cmap.size, device=dev) // args.sort_window << 27) | bits.sum(0)
+    perm = torch.sort(key, stable=True)[1]
+    cmap, _, _, _ = ops.coords_insert(cmap.coords[perm].contiguous(), L.SRC_INT, (1, 1, 1))
+    del km0, bits, key
 out_map = cmap
 if args.stride > 1:
     out_map, _, _, _ = ops.coords_insert(cmap.coords, L.SRC_STRIDE, (args.stride,) * 3)
