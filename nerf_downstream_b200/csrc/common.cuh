@@ -76,13 +76,21 @@ __device__ __forceinline__ int4 unpack_key(unsigned long long key) {
   return c;
 }
 // splitmix64 finaliser; buckets are pairs of slots (one 32-byte sector).
-__device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
+// Tables larger than the L2 (>= 2^22 buckets = 128 MB: maps of more than ~2 M voxels) leave the lowest bit of z out of
+// the hash, so that the voxels (.., z even) and (.., z + 1) share a home bucket: the reference's loaders deliver
+// voxels in raster order (z fastest) and neighbouring lanes' probes then read the same DRAM sector half of the time
+// (3^3 map at 10 M voxels 2.36 -> 1.91 ms).  A pair fills its bucket, so look-ups take 1.44 instead of 1.17 probes
+// (simulated on the 1 M-voxel room) — on an L2-resident table that costs more than the shared sectors save (1 M
+// voxels: 0.136 -> 0.171 ms), hence the size rule.  Measured: profiles/r2_row_order_experiments.md.
+constexpr unsigned long long kPairHashBuckets = 1ull << 22;
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k, unsigned long long bucket_mask) {
+  if (bucket_mask >= kPairHashBuckets - 1) k >>= 1;
   k ^= k >> 30;
   k *= 0xbf58476d1ce4e5b9ull;
   k ^= k >> 27;
   k *= 0x94d049bb133111ebull;
   k ^= k >> 31;
-  return k;
+  return k & bucket_mask;
 }
 
 // One 256-bit read-only load (LDG.E.256, sm_100+): a whole 32-byte bucket = both slots in ONE instruction and
@@ -98,7 +106,7 @@ __device__ __forceinline__ void ldg256(const void* p, unsigned long long (&v)[4]
 __device__ __forceinline__ int table_lookup(const Slot* __restrict__ slots,
                                             unsigned long long bucket_mask,
                                             unsigned long long key) {
-  unsigned long long b = hash_key(key) & bucket_mask;
+  unsigned long long b = hash_key(key, bucket_mask);
   for (;;) {
     unsigned long long v[4];  // {key0, first0 | row0 << 32, key1, first1 | row1 << 32}
     ldg256(slots + 2 * b, v);

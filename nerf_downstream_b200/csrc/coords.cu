@@ -114,7 +114,7 @@ insert_kernel(const void* __restrict__ src, int n, const int* __restrict__ n_dev
     return;
   }
   const unsigned long long mine_hi = (unsigned long long)(unsigned)i | 0xFFFFFFFF00000000ull;  // first = i, row unset
-  unsigned long long bucket = hash_key(key) & bucket_mask;
+  unsigned long long bucket = hash_key(key, bucket_mask);
   for (;;) {
     Slot* s = slots + 2 * bucket;
 #pragma unroll

@@ -2,6 +2,7 @@
 plus the bandwidth-bound row kernels (BN, ReLU, pooling) at the same sizes.  Prints ms and the achieved
 ALGORITHMIC GB/s (formulas: DESIGN.md §3) against the measured HBM peak."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -39,7 +40,7 @@ def line(name, m, ms, nbytes):
 
 sizes = [int(s) for s in sys.argv[1:]] or [100_000, 300_000, 1_000_000, 3_000_000, 10_000_000]
 for n in sizes:
-    c, _, _ = synth.room_batch(777, 1, n, channels=1)
+    c, _, _ = synth.room_batch(777, 1, n, channels=1, shuffle=bool(os.environ.get("SWEEP_SHUFFLE")))   # raster order unless asked
     cg = torch.from_numpy(c).to(dev)
     ms = timed(lambda: ops.coords_insert(cg, L.SRC_FLOAT, (1, 1, 1)))       # includes the host read of M
     cmap, first, inv, cnt = ops.coords_insert(cg, L.SRC_FLOAT, (1, 1, 1))
