@@ -38,7 +38,7 @@
 
 namespace spc {
 
-int g_umma_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_umma_dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #ifdef SPC_EXPERIMENTS
 // role timing of the forward kernel (clock64 sums over all CTAs): [0] producer warp 0 loop, [1] its empty-slot waits,
 // [2] its copy issue, [3] its bookkeeping + index prefetch, [4] MMA thread loop, [5] its full-stage waits, [6] its
@@ -51,26 +51,11 @@ __device__ unsigned long long g_role_cycles[16];
 #define SPC_ACC(i, v)
 #endif
 int g_umma_force_mt = 0;  // test hook: 0 = auto
-
-struct UmmaConvParams {
-  const void* A;             // [*, Ck] fp32 or bf16
-  const void* Bp;            // packed weights [K][Ck/32][Cn][32] (swizzled rows)
-  const float* bias;         // [Cn] or null
-  const int* nbr;            // [K, m_out]
-  const uint32_t* tile_mask; // [ceil(m_out/128)] or null (all offsets active)
-  float* out;                // [m_out, Cn]
-  int m_out, Ck, Cn, K;
-  int cn_tile, n_ntiles, kc_count, kg_count;  // 32-channel chunks / chunk groups (stages) per offset
-  int stages, acc_bufs, tmem_cols;
-  int out_bufs;              // 16 KB staging blocks of the TMA-store epilogue (0: st.global epilogue)
-  int ngroups, wps;          // producer groups, warps per group
-  int dbg_skip_store;        // timing experiment only: epilogue does not write the output
-  int dbg_flags;             // timing experiments (-DSPC_EXPERIMENTS): 1 no gather copies, 2 no MMAs, 4 no weight slabs
-  int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
-  int reduce_out;            // the epilogue ADDS to `out` (offset-split items, or accumulate: out += result)
-  double* stats;             // [2 * Cn] per-column sum / sum of squares of `out` for the BatchNorm that follows, or null
-  int n_work;                // m_tiles * n_ntiles * ksplit
-};
+bool conv_umma_pair_eligible(int64_t m_out, int c_in, int c_out, int K, bool bf16, const float* bias, const void* packed,
+                             const float* out);
+int conv_fwd_umma_pair(const void* in, const void* packed, const int* nbr, const uint32_t* tile_mask, int64_t m_out,
+                       int c_in, int c_out, int K, float* out, cudaStream_t stream, bool accumulate, double* stats,
+                       int* stats_fused);
 
 static inline int pick_cn_tile(int Cn) {
   for (int t = 256; t >= 16; t -= 16)
@@ -774,6 +759,9 @@ int conv_fwd_umma(const void* in, const float* w, const void* packed, const floa
     Wp = dstp;
   }
   SPC_REQUIRE(((uintptr_t)Wp % 1024) == 0, "packed weights must be 1024-byte aligned");
+  // large bf16 maps: CTA pairs (cta_group::2), each CTA stages and reads half of every weight slab (conv_umma_pair.cu)
+  if (packed != nullptr && g_umma_force_mt != 1 && conv_umma_pair_eligible(m_out, c_in, c_out, K, bf16, bias, Wp, out))
+    return conv_fwd_umma_pair(in, Wp, nbr, tile_mask, m_out, c_in, c_out, K, out, stream, accumulate, stats, stats_fused);
   const int row_bytes = bf16 ? 64 : 128;
   const int a_stage = kTileM * row_bytes;
 
@@ -918,6 +906,6 @@ extern "C" int spc_debug_role_cycles(long long* out16, int reset) {
 }
 #endif
 void umma_set_force_mt(int mt) { g_umma_force_mt = mt; }
-void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 8) g_umma_dbg[idx] = val; }
+void umma_debug_set(int idx, int val) { if (idx >= 0 && idx < 16) g_umma_dbg[idx] = val; }
 
 }  // namespace spc

@@ -57,8 +57,31 @@ struct Prec {
 //   [2] forward: 1 = st.global epilogue instead of TMA stores          [3] forward: epilogue writes nothing (timing only)
 //   [4] forward: 1 = one 32-channel chunk per stage (no contiguous multi-chunk row visits)
 //   [5] wgrad: 1 = one row visit per chunk (no grouped visits)
-extern int g_umma_dbg[8];
+//   [6] forward: producer warps 8 / 16 (0 = by tile width)             [7] forward: 1 = no shared ring slots (8 groups x 2 warps)
+//   [8] forward: 1 = never the CTA-pair kernel (conv_umma_pair.cu), 2 = always where it is eligible
+extern int g_umma_dbg[16];
 extern int g_umma_force_mt;
+
+struct UmmaConvParams {
+  const void* A;             // [*, Ck] fp32 or bf16
+  const void* Bp;            // packed weights [K][Ck/32][Cn][32] (swizzled rows)
+  const float* bias;         // [Cn] or null
+  const int* nbr;            // [K, m_out]
+  const uint32_t* tile_mask; // [ceil(m_out/128)] or null (all offsets active)
+  float* out;                // [m_out, Cn]
+  int m_out, Ck, Cn, K;
+  int cn_tile, n_ntiles, kc_count, kg_count;  // 32-channel chunks / chunk groups (stages) per offset
+  int stages, acc_bufs, tmem_cols;
+  int out_bufs;              // 16 KB staging blocks of the TMA-store epilogue (0: st.global epilogue)
+  int ngroups, wps;          // producer groups, warps per group
+  int dbg_skip_store;        // timing experiment only: epilogue does not write the output
+  int dbg_flags;             // timing experiments (-DSPC_EXPERIMENTS): 1 no gather copies, 2 no MMAs, 4 no weight slabs
+  int ksplit, k_per;         // offsets split over ksplit work items of k_per offsets each (small maps)
+  int reduce_out;            // the epilogue ADDS to `out` (offset-split items, or accumulate: out += result)
+  double* stats;             // [2 * Cn] per-column sum / sum of squares of `out` for the BatchNorm that follows, or null
+  int n_work;                // m_tiles * n_ntiles * ksplit
+};
+
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -643,3 +643,50 @@ def test_batched_weight_packing_and_gradient_sinks(cuda_device):
             assert ops.pack_stats["misses"] - before["misses"] <= 4, (before, ops.pack_stats)
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=2e-4, atol=2e-6)
+
+
+PAIR_CASES = [(9001, 32, 32), (20_000, 96, 96), (70_001, 64, 96), (33_000, 128, 128), (12_345, 256, 256),
+              (150_000, 128, 96), (200_000, 96, 96)]
+
+
+@pytest.mark.parametrize("voxels,cin,cout", PAIR_CASES)
+def test_cta_pair_conv_kernel_equals_the_single_cta_kernel(cuda_device, voxels, cin, cout):
+    """conv_umma_pair.cu (tcgen05 cta_group::2: two CTAs share every weight slab) against conv_umma_kernel on the same
+    map: every output row sees the same sequence of MMAs, so forward and dgrad are BIT-identical; the epilogue
+    statistics (double atomics in a free order) agree to 1e-12 relative; the accumulate form (dgrad adding into the
+    residual branch's gradient) too.  Row counts that are not multiples of the 512-row pair item included."""
+    lib = L.load()
+    c, _, _ = synth.room_batch(17, 1, voxels, channels=1)
+    cmap, _, _, _ = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    g = torch.Generator(device="cpu").manual_seed(voxels)
+    xb = ops.to_bf16(torch.randn(cmap.size, cin, generator=g).to(cuda_device))
+    gb = ops.to_bf16(torch.randn(cmap.size, cout, generator=g).to(cuda_device))
+    w = (torch.randn(27, cin, cout, generator=g) / (27 * cin) ** 0.5).to(cuda_device)
+    base = torch.randn(cmap.size, cin, generator=g).to(cuda_device)
+
+    def run(knob):
+        lib.spc_debug_set(8, knob)
+        try:
+            out = ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16)
+            sums = torch.zeros(2 * cout, dtype=torch.float64, device=cuda_device)
+            out_s, fused = ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16, bn_sums=sums)
+            din = ops.conv_dgrad_raw(gb, w, km, L.PREC_BF16)
+            acc = base.clone()
+            ops.conv_dgrad_raw(gb, w, km, L.PREC_BF16, add_into=acc)
+            torch.cuda.synchronize()
+        finally:
+            lib.spc_debug_set(8, 0)
+        return out, out_s, (sums if fused else None), din, acc
+
+    a, b = run(1), run(2)
+    if voxels >= 150_000:     # (on smaller maps the single-CTA kernel splits the offsets over several CTAs: partial sums)
+        assert torch.equal(a[0], b[0]), "forward"
+        assert torch.equal(a[1], b[1]), "forward with statistics"
+        assert torch.equal(a[3], b[3]), "dgrad"
+    for i, what in ((0, "forward"), (1, "forward with statistics"), (3, "dgrad")):
+        assert (a[i] - b[i]).abs().max() <= 1e-5 * a[i].abs().max(), what
+    assert (a[4] - b[4]).abs().max() <= 1e-5 * a[4].abs().max(), "dgrad accumulate"   # (reduce-adds into fp32 rows)
+    assert (a[2] is None) == (b[2] is None)
+    if a[2] is not None:
+        assert ((a[2] - b[2]).abs() <= 1e-9 * a[2].abs() + 1e-9).all(), "epilogue statistics"
