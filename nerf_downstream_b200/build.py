@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libsparseconv_b200.so"
 STAMP = PKG_DIR / "build" / "stamp.txt"
 
-SOURCES = ["coords.cu", "elementwise.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_pair.cu", "conv_wgrad_umma.cu", "conv_api.cu", "pipeline.cu", "head.cu", "interp.cu"]
+SOURCES = ["coords.cu", "elementwise.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_pair.cu", "conv_wgrad_umma.cu", "conv_wgrad_umma_pair.cu", "conv_api.cu", "pipeline.cu", "head.cu", "interp.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "umma_common.cuh", "../../include/sparseconv_b200.h"]
 
 NVCC_FLAGS = [

@@ -30,73 +30,6 @@ namespace spc {
 
 namespace {
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// all threads of both CTAs (also orders shared-memory / mbarrier initialisation across the pair)
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_pair() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A[128 rows of each CTA] * B[N/2 rows of each CTA], bf16 operands, issue predicate as in
-// ptx.cuh (mma_bf16_p)
-__device__ __forceinline__ void mma_bf16_pair_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-// arrive on the barrier at this shared-memory offset in BOTH CTAs once the tcgen05.mma issued so far have completed
-__device__ __forceinline__ void mma_commit_pair_p(uint32_t bar, uint32_t issue) {
-  const uint16_t both = 3;
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
-      "r"(issue), "h"(both)
-      : "memory");
-}
-
 constexpr int kPairBarBytes = 512;   // barrier area (the single-CTA kernel's 256 B + the peer_full barriers)
 
 }  // namespace
@@ -233,7 +166,7 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
       const int k = __ffs(cur.rest) - 1, cg = cur.cg;
       const uint32_t par = (uint32_t)(rev - 1) & 1u;
       if (shared_slots) mbar_wait(turn_bar(slot), par);
-      mbar_wait_cluster(empty_bar(slot), par);     // (released by rank 0's multicast commit)
+      mbar_wait(empty_bar(slot), par);             // (released by rank 0's multicast commit)
       const uint32_t stage_addr = smem_base + (uint32_t)slot * stage_bytes;
       if (leader) {
         mbar_arrive_expect_tx(full_bar(slot), (uint32_t)b_half_bytes);
@@ -283,13 +216,13 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
       for (int w = cid; w < p.n_work; w += n_cl) {
         const uint32_t mask = work_mask(w);
         const int n_iters = (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mask) * p.kg_count));
-        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * p.cn_tile);
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(fbar, phase);                                       // this CTA's rows and slab half
-          mbar_wait_cluster(fbar + 8u * (3 * kMaxStages + 5), phase);   // the peer's (peer_full_bar)
-          fence_proxy_async_all();
+          mbar_wait(fbar + 8u * (3 * kMaxStages + 5), phase);           // the peer's (peer_full_bar)
+          fence_proxy_async_smem();
           tc_fence_after();
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -316,7 +249,7 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
         const int n_iters = (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mask) * p.kg_count));
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(fbar, phase);
-          fence_proxy_async_all();
+          fence_proxy_async_smem();
           if (issue) mbar_arrive_cluster(map_to_rank(fbar + 8u * (3 * kMaxStages + 5), 0u));
           fbar += 8u;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; fbar = full_bar(0); }
@@ -428,7 +361,7 @@ std::atomic<long long> g_conv_pair_launches{0};
 // convolutions in front of a BatchNorm), packed weights.
 bool conv_umma_pair_eligible(int64_t m_out, int c_in, int c_out, int K, bool bf16, const float* bias, const void* packed,
                              const float* out) {
-  constexpr bool kPairByDefault = false;   // (until the kernel has been validated on the hardware: knob 8 = 2 asks for it)
+  constexpr bool kPairByDefault = true;    // (knob 8: 1 = never, 2 = on every eligible shape whatever the map size)
   if (g_umma_dbg[8] == 1 || (g_umma_dbg[8] == 0 && !kPairByDefault)) return false;
   if (!bf16 || bias != nullptr || packed == nullptr) return false;
   if (c_in < 32 || c_in % 32 || c_out % 32 || c_out > 256 || K > 32) return false;

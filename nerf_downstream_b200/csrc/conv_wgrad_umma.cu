@@ -372,6 +372,9 @@ static int launch_wgrad_umma(const UmmaWgradParams& p, const CUtensorMap& tmap, 
 }
 
 extern std::atomic<long long> g_conv_path_counts[4];
+bool conv_wgrad_pair_eligible(int64_t m_out, int c_in, int c_grp, int K, bool bf16);
+int conv_wgrad_pair_cols(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask, int64_t m_out,
+                         int c_in, int c_out_full, int col0, int c_grp, int K, float* dw, cudaStream_t stream);
 int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
                          int64_t m_out, int c_in, int c_out_full, int col0, int c_grp, int K, bool bf16, float* dw,
                          cudaStream_t stream);
@@ -404,6 +407,10 @@ int conv_wgrad_umma(const void* in, const void* dout, const int* nbr, const uint
 int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const uint32_t* tile_mask,
                          int64_t m_out, int c_in, int c_out_full, int col0, int c_grp, int K, bool bf16, float* dw,
                          cudaStream_t stream) {
+  // large bf16 maps: CTA pairs (conv_wgrad_umma_pair.cu) — each CTA stages half of the dout columns, twice the M
+  // blocks per pass
+  if (conv_wgrad_pair_eligible(m_out, c_in, c_grp, K, bf16))
+    return conv_wgrad_pair_cols(in, dout, nbr, tile_mask, m_out, c_in, c_out_full, col0, c_grp, K, dw, stream);
   const int c_out = c_grp;
   const int rows = bf16 ? 128 : 64;  // out rows per pipeline step
   UmmaWgradParams p;

@@ -52,6 +52,63 @@ struct Prec {
   }
 };
 
+// ---- CTA pairs (tcgen05 cta_group::2; conv_umma_pair.cu, conv_wgrad_umma_pair.cu) ----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of both CTAs (also orders shared-memory / mbarrier initialisation across the pair)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// (relaxed: a release at cluster scope is a MEMBAR.ALL.GPU in front of every arrival — the first version of this
+// kernel ran 4x slower than the single-CTA kernel with cluster-scope acquires / releases and an unqualified
+// fence.proxy.async in the per-stage paths: L1 invalidations and GPU-wide membars in the producer and relay warps.  What
+// has to be ordered here is shared memory against the async proxy (fence.proxy.async.shared::cta in front of the
+// arrival) and tcgen05 operations (tcgen05.fence), not generic global memory.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows of each CTA] * B[N/2 rows of each CTA], bf16 operands, issue predicate as in
+// ptx.cuh (mma_bf16_p)
+__device__ __forceinline__ void mma_bf16_pair_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once the tcgen05.mma issued so far have completed
+__device__ __forceinline__ void mma_commit_pair_p(uint32_t bar, uint32_t issue) {
+  const uint16_t both = 3;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
+      "r"(issue), "h"(both)
+      : "memory");
+}
+
+
 // test / measurement knobs (spc_debug_set), all 0 = default:
 //   [0] forward: force the number of producer groups (1, 2, 4, 8)      [1] wgrad: dout rows by LDGSTS instead of TMA
 //   [2] forward: 1 = st.global epilogue instead of TMA stores          [3] forward: epilogue writes nothing (timing only)
@@ -59,6 +116,7 @@ struct Prec {
 //   [5] wgrad: 1 = one row visit per chunk (no grouped visits)
 //   [6] forward: producer warps 8 / 16 (0 = by tile width)             [7] forward: 1 = no shared ring slots (8 groups x 2 warps)
 //   [8] forward: 1 = never the CTA-pair kernel (conv_umma_pair.cu), 2 = always where it is eligible
+//   [9] wgrad: the same for conv_wgrad_umma_pair.cu
 extern int g_umma_dbg[16];
 extern int g_umma_force_mt;
 

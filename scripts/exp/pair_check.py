@@ -69,3 +69,35 @@ if "--time" in sys.argv:
             t = sorted(ts)[3]
             print(f"{tag:6s} {name:5s} {cin}->{cout} M={km.m_out}: {t:.3f} ms  {2.0 * km.n_pairs * cin * cout / t / 1e9:.1f} TFLOP/s", flush=True)
 lib.spc_debug_set(8, 0)
+
+# ---- wgrad: pair kernel (knob 9) against the single-CTA kernel: fp32 red.adds in a free order -> tolerance ----
+def wgrad(knob):
+    lib.spc_debug_set(9, knob)
+    dw = ops.conv_wgrad_raw(xb, gb, km, 27, cin, cout, prec)
+    torch.cuda.synchronize()
+    return dw
+
+
+wa = wgrad(1)
+print("single-CTA wgrad done", flush=True)
+wb = wgrad(2)
+print("pair wgrad done", flush=True)
+werr = float((wa - wb).abs().max() / wa.abs().max())
+print(f"wgrad      max |diff| / max |ref| {werr:.3e}", flush=True)
+print("PAIR WGRAD", "OK" if werr < 1e-4 else "MISMATCH", flush=True)
+if "--time" in sys.argv:
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    for knob, tag in ((1, "single"), (2, "pair")):
+        lib.spc_debug_set(9, knob)
+        fn = lambda: ops.conv_wgrad_raw(xb, gb, km, 27, cin, cout, prec)
+        fn()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[3]
+        print(f"{tag:6s} wgrad {cin}->{cout} M={km.m_out}: {t:.3f} ms  {2.0 * km.n_pairs * cin * cout / t / 1e9:.1f} TFLOP/s", flush=True)
+lib.spc_debug_set(9, 0)

@@ -667,7 +667,9 @@ def test_cta_pair_conv_kernel_equals_the_single_cta_kernel(cuda_device, voxels, 
 
     def run(knob):
         lib.spc_debug_set(8, knob)
+        lib.spc_debug_set(9, knob)
         try:
+            dw = ops.conv_wgrad_raw(xb, gb, km, 27, cin, cout, L.PREC_BF16)
             out = ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16)
             sums = torch.zeros(2 * cout, dtype=torch.float64, device=cuda_device)
             out_s, fused = ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16, bn_sums=sums)
@@ -677,7 +679,8 @@ def test_cta_pair_conv_kernel_equals_the_single_cta_kernel(cuda_device, voxels, 
             torch.cuda.synchronize()
         finally:
             lib.spc_debug_set(8, 0)
-        return out, out_s, (sums if fused else None), din, acc
+            lib.spc_debug_set(9, 0)
+        return out, out_s, (sums if fused else None), din, acc, dw
 
     a, b = run(1), run(2)
     if voxels >= 150_000:     # (on smaller maps the single-CTA kernel splits the offsets over several CTAs: partial sums)
@@ -687,6 +690,11 @@ def test_cta_pair_conv_kernel_equals_the_single_cta_kernel(cuda_device, voxels, 
     for i, what in ((0, "forward"), (1, "forward with statistics"), (3, "dgrad")):
         assert (a[i] - b[i]).abs().max() <= 1e-5 * a[i].abs().max(), what
     assert (a[4] - b[4]).abs().max() <= 1e-5 * a[4].abs().max(), "dgrad accumulate"   # (reduce-adds into fp32 rows)
-    assert (a[2] is None) == (b[2] is None)
-    if a[2] is not None:
+    if a[2] is not None and b[2] is not None:
         assert ((a[2] - b[2]).abs() <= 1e-9 * a[2].abs() + 1e-9).all(), "epilogue statistics"
+    if b[2] is not None:     # (the forced pair kernel fuses them on maps where the single-CTA kernel splits offsets)
+        o = b[1].double()
+        want = torch.cat([o.sum(0), (o * o).sum(0)])
+        assert ((b[2] - want).abs() <= 1e-5 * want.abs() + 1e-6 * want.abs().max()).all(), "epilogue statistics vs the rows"
+    # wgrad (conv_wgrad_umma_pair.cu): fp32 partial sums meet in dW through red.add in a free order
+    assert (a[5] - b[5]).abs().max() <= 1e-4 * a[5].abs().max(), "wgrad"
