@@ -31,6 +31,7 @@ namespace spc {
 namespace {
 
 constexpr int kPairBarBytes = 512;   // barrier area (the single-CTA kernel's 256 B + the peer_full barriers)
+constexpr int kPairMaxStages = 12;   // ring slots: the pair's stages are smaller (half a slab) and the relay hop wants depth
 
 }  // namespace
 
@@ -49,12 +50,12 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
   const uint32_t out_stage = smem_base + (uint32_t)p.stages * stage_bytes;
   const uint32_t bar_base = out_stage + (uint32_t)p.out_bufs * 16384u;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
-  auto turn_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };
-  auto peer_full_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + 5 + s); };   // used in rank 0
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kPairMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kPairMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kPairMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kPairMaxStages + 4);
+  auto turn_bar = [&](int s) { return bar_base + 8u * (2 * kPairMaxStages + 5 + s); };
+  auto peer_full_bar = [&](int s) { return bar_base + 8u * (3 * kPairMaxStages + 5 + s); };   // used in rank 0
   double* s_stats = reinterpret_cast<double*>(smem_raw + (bar_base + kPairBarBytes - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -221,7 +222,7 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
         const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * p.cn_tile);
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(fbar, phase);                                       // this CTA's rows and slab half
-          mbar_wait(fbar + 8u * (3 * kMaxStages + 5), phase);           // the peer's (peer_full_bar)
+          mbar_wait(fbar + 8u * (3 * kPairMaxStages + 5), phase);           // the peer's (peer_full_bar)
           fence_proxy_async_smem();
           tc_fence_after();
 #pragma unroll
@@ -233,7 +234,7 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
             for (int q = 0; q < PR::kMmaPerRow; ++q)
               mma_bf16_pair_p(d, adesc + 2u * q, bdesc + 2u * q, idesc, (it > 0 || q > 0) ? 1u : 0u, issue);
           }
-          mma_commit_pair_p(fbar + 8u * kMaxStages, issue);   // "empty" of this slot in both CTAs
+          mma_commit_pair_p(fbar + 8u * kPairMaxStages, issue);   // "empty" of this slot in both CTAs
           lo += sb16; fbar += 8u;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; lo = lo0; fbar = full_bar(0); }
         }
@@ -250,7 +251,7 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(fbar, phase);
           fence_proxy_async_smem();
-          if (issue) mbar_arrive_cluster(map_to_rank(fbar + 8u * (3 * kMaxStages + 5), 0u));
+          if (issue) mbar_arrive_cluster(map_to_rank(fbar + 8u * (3 * kPairMaxStages + 5), 0u));
           fbar += 8u;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; fbar = full_bar(0); }
         }
@@ -410,14 +411,16 @@ int conv_fwd_umma_pair(const void* in, const void* packed, const int* nbr, const
   memset(&tmap_out, 0, sizeof(tmap_out));
   SPC_REQUIRE(make_out_tile_map(&tmap_out, out, m_out, c_out), "cuTensorMapEncodeTiled unavailable");
   p.out_bufs = (budget - 32768) / stage_bytes >= std::min(4, budget / stage_bytes) ? 2 : 1;
+  if (g_umma_dbg[11] == 1) p.out_bufs = 1;   // (knob 11: one staging block, one more ring slot)
   int stages = (budget - p.out_bufs * 16384) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > kPairMaxStages) stages = kPairMaxStages;
   SPC_REQUIRE(stages >= 2, "pair tile does not fit in shared memory");
   p.stages = stages;
   const int npw = g_umma_dbg[6] == 8 ? 8 : (g_umma_dbg[6] == 16 ? 16 : (c_out <= 96 ? 16 : 8));
-  int ngroups = 1;
-  while (ngroups * 2 <= stages && ngroups * 2 <= 8) ngroups *= 2;
-  if (npw == 16 && ngroups == 8 && stages == 8 && g_umma_dbg[7] != 1) ngroups = 16;   // two groups alternate on a slot
+  if (g_umma_dbg[10] >= 2 && g_umma_dbg[10] < stages) { stages = g_umma_dbg[10]; p.stages = stages; }   // (knob 10: ring slots)
+  // one-warp groups: as many as ring slots (a group is never two revolutions ahead), or 16 alternating on 8 slots
+  int ngroups = std::min(stages, npw);
+  if (npw == 16 && stages == 8 && g_umma_dbg[7] != 1) ngroups = 16;   // two groups alternate on a slot
   p.ngroups = ngroups; p.wps = 1;
   p.stats = nullptr;
   if (stats_smem && !accumulate) {

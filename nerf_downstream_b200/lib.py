@@ -116,6 +116,10 @@ def load():
         fn.argtypes = argtypes
     if lib.spc_abi_version() != 1:
         raise SparseConvLibraryError("ABI version mismatch")
+    # measurement knobs of the convolution kernels (spc_debug_set; all 0 by default), e.g. "8=1" = no CTA-pair kernel
+    for kv in filter(None, os.environ.get("SPARSECONV_B200_DEBUG_SET", "").split(",")):
+        idx, val = kv.split("=")
+        lib.spc_debug_set(int(idx), int(val))
     _lib = lib
     return lib
 
