@@ -14,15 +14,16 @@
 // floor(512 / Cout) accumulators; a work item = (row range, pass over a group of M blocks) and ends with an fp32
 // red.global.add of its partial dW — the only atomics of the convolution path.
 //
-// Roles (416 threads, one persistent CTA per SM):
-//   warps 0..a_stages-1  one warp per A ring slot: step j of an item is gathered by warp j % a_stages.  Chunks of
+// Roles (512 threads, one persistent CTA per SM; see the role-layout constants below — since the end of r2 two producer
+// warps share an A ring slot when a step has two or more row visits):
+//   warps 0..             A producers: step j of an item is gathered by the warp(s) of slot j % a_stages.  Chunks of
 //                        an M block that belong to the same offset are consecutive channels of the same input row,
 //                        so they are fetched by ONE row visit of RM x 64 contiguous bytes (bf16; the L1 handles an
 //                        LDGSTS one 128-byte line at a time: a 128-byte visit costs one line where two 64-byte
 //                        visits cost two);
-//   warp a_stages        dout row blocks by TMA tile loads (hardware swizzle = the MN-major UMMA layout), 2 slots;
-//   warps 8-11           epilogue: tcgen05.ld + red.global.add.v4 of the item's partial dW;
-//   warp 12              one elected thread issues every tcgen05.mma / commit.
+//   warp 10              dout row blocks by TMA tile loads (hardware swizzle = the MN-major UMMA layout), 2 slots;
+//   warps 11-14          epilogue: tcgen05.ld + red.global.add.v4 of the item's partial dW;
+//   warp 15              the MMA issuer (tcgen05.mma / commit under an issue predicate true in one lane).
 // Which (row block, M block) steps exist is data (the per-128-row offset masks: offsets without a neighbour in a
 // row block are skipped — on the faithful ScanNet geometry 26 of 27).  r1 walked the masks from global memory in
 // every role (each producer warp walked ALL steps to find its own: ~3000 cycles of dependent loads per step with
@@ -44,6 +45,20 @@ constexpr int kWgMaxMb = 128;    // M blocks (K * Cin / 128): 27 offsets x 512 c
 // all: with more, Cout = 128 loses its fifth and Cout = 256 its third A ring slot (measured: 256->256 2.68 -> 3.03 ms).
 constexpr int kWgActBytes = 384;
 constexpr int kWgTabBytes = kWgMaxMb * 4 * 2 + 2 * kWgActBytes;
+// role layout (16 warps = 512 threads x 128 registers): warps 0..9 A producers — TWO per ring slot when a step has at
+// least two row visits (each warp gathers half of the visits; at most 5 slots then), warp 10 the dout producer, warps
+// 11..14 the epilogue (warp & 3 = its TMEM lane group), warp 15 the MMA issuer.  r2 had one warp per slot: a producer's
+// step is latency — index loads, 64 dependent LDGSTS, the slot wait — and five warps in flight needed ~950 clocks per
+// step at 96->96 where shared memory allows ~730.  Measured (1 M voxels, bf16, profiles/r2_row_order_experiments.md
+// section 6): 96->96 0.533 -> 0.497 ms, 32->32 0.167 -> 0.161, tf32 96->96 1.054 -> 0.972.  A first version with 18
+// warps was capped at 96 registers, spilled, and was 7 % SLOWER; splitting the ROWS of every visit between the two
+// warps instead of the visits was 1-3 % slower than this.
+constexpr int kWgAWarps = 10;
+constexpr int kWgBWarp = kWgAWarps;
+constexpr int kWgEpiWarp0 = kWgBWarp + 1;
+constexpr int kWgMmaWarp = kWgEpiWarp0 + 4;
+constexpr int kWgThreads = (kWgMmaWarp + 1) * 32;
+constexpr int kWgTableThreads = (kWgBWarp + 2) * 32;   // producers + MMA warp build and read the step tables
 
 struct UmmaWgradParams {
   const void* in;             // [m_in, Cin] fp32 or bf16
@@ -65,7 +80,7 @@ struct UmmaWgradParams {
 // mixed visits for Cin = 96 ((3 + 1) / (2 + 2) / (1 + 3) chunks of two offsets) were SLOWER (0.554 -> 0.698) and
 // are not built.
 template <bool BF16, int RM>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensorMap tmap_dout) {
   using PR = Prec<BF16>;
   constexpr int kRows = kWgChunkBlock / PR::kRowBytes;      // 64 (tf32) / 128 (bf16) rows per step
@@ -73,6 +88,8 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
   constexpr int LPR = PR::kLanesPerRow;
   constexpr int NI = kRows / 32;                            // neighbour indices per lane and row visit
   constexpr int NR = 4 / RM;                                // row visits per M block
+  constexpr int WPA = NR >= 2 ? 2 : 1;                      // producer warps per A ring slot
+  constexpr int NRW = NR / WPA;                             // row visits per producer warp and step
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = (p.Cout / 32) * kWgChunkBlock;
@@ -97,14 +114,14 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
 
   if (threadIdx.x == 0) {
     // full barriers: the 32 lanes of the one warp that fills the stage (cp.async ... arrive.noinc)
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 32); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 32 * WPA); mbar_init(a_empty(s), 1); }
     // b_full: one expect_tx arrival (TMA tile loads of the dout rows)
     for (int s = 0; s < kWgBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(t_full, 1);
     mbar_init(t_empty, kNumEpilogueThreads);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
+  if (warp == kWgMmaWarp) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
   // row visit r of M block mb covers chunks 4 mb + r RM .. + RM - 1, all of one offset (ncc % RM == 0)
   for (int e = threadIdx.x; e < p.n_mb * 4; e += blockDim.x) {
     const int mb = e >> 2, r = e & 3;
@@ -157,8 +174,9 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
     const int n_rbi = rb1 - rb0;
     uint8_t* act = s_act + (local_item & 1) * kWgActBytes;
     // ---- step table of the item: bit i of act[rbi] = M block mb0 + i has a neighbour in row block rb0 + rbi ----
-    const int filler = warp == kMmaWarp ? kNumProducerWarps * 32 + lane : threadIdx.x;  // 0..287 among the 9 warps
-    for (int rbi = filler; rbi < n_rbi && (warp < kNumProducerWarps || warp == kMmaWarp); rbi += 288) {
+    const bool tabler = warp <= kWgBWarp || warp == kWgMmaWarp;
+    const int filler = warp == kWgMmaWarp ? (kWgBWarp + 1) * 32 + lane : threadIdx.x;  // 0..383 among the 12 warps
+    for (int rbi = filler; rbi < n_rbi && tabler; rbi += kWgTableThreads) {
       const uint32_t m = p.tile_mask ? (p.tile_mask[((rb0 + rbi) * kRows) >> 7] & all_taps) : all_taps;
       uint32_t a = 0;
       for (int mb = mb0; mb < mb1; ++mb)
@@ -170,13 +188,14 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
     // gather starts while they still drain this item's accumulators.  Two tables alternate: a role that runs ahead
     // fills the next item's table while a slower role may still read this one; every one of the 288 threads has
     // passed this barrier before any of them reaches the one after the next.)
-    if (warp < kNumProducerWarps || warp == kMmaWarp) asm volatile("bar.sync 2, 288;" ::: "memory");
+    if (tabler) asm volatile("bar.sync 2, %0;" ::"n"(kWgTableThreads) : "memory");
 
-    if (warp < p.a_stages) {
+    if (warp < kWgAWarps && warp / WPA < p.a_stages) {
+      const int aslot = warp / WPA, ahalf = warp - aslot * WPA;   // this warp gathers row visits ahalf * NRW .. + NRW - 1
       // ============================ A producers ============================
       const char* in_base = reinterpret_cast<const char*>(p.in);
       const size_t in_pitch = (size_t)p.Cin * PR::kElt;
-      const uint32_t stage_addr = a_base + (uint32_t)warp * kWgAStage;
+      const uint32_t stage_addr = a_base + (uint32_t)aslot * kWgAStage;
       // walker over this warp's steps j = warp, warp + a_stages, ... of the item
       struct Walk { int rbi, c, j; bool ok; int mb; };
       auto seek = [&](Walk& s) {  // position on step s.j (>= the steps before row block s.rbi = s.c)
@@ -191,13 +210,13 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
       };
       auto load_idx = [&](const Walk& s, int* idx) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const uint32_t d = s_run[s.mb * 4 + r];
+        for (int rw = 0; rw < NRW; ++rw) {
+          const uint32_t d = s_run[s.mb * 4 + ahalf * NRW + rw];
           const int k = (int)(d & 63u);
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
             const int o = (rb0 + s.rbi) * kRows + i * 32 + lane;
-            idx[r * NI + i] = (k != 63 && o < p.m_out) ? __ldg(p.nbr + (size_t)k * p.m_out + o) : -1;
+            idx[rw * NI + i] = (k != 63 && o < p.m_out) ? __ldg(p.nbr + (size_t)k * p.m_out + o) : -1;
           }
         }
       };
@@ -218,27 +237,30 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
         }
       };
       Walk cur;
-      cur.rbi = 0; cur.c = 0; cur.j = warp; cur.ok = false; cur.mb = 0;
+      cur.rbi = 0; cur.c = 0; cur.j = aslot; cur.ok = false; cur.mb = 0;
       seek(cur);
-      int idx[NR * NI];
+      int idx[NRW * NI];
       if (cur.ok) load_idx(cur, idx);
       while (cur.ok) {
         Walk nxt = cur;
         nxt.j += p.a_stages;
         seek(nxt);
-        int idx_n[NR * NI];
+        int idx_n[NRW * NI];
         if (nxt.ok) load_idx(nxt, idx_n);  // latency hides behind this stage's slot wait
 
-        mbar_wait(a_empty(warp), a_phase ^ 1u);
+        mbar_wait(a_empty(aslot), a_phase ^ 1u);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) gather(r, idx + r * NI, s_run[cur.mb * 4 + r]);
-        cp_async_mbar_arrive_noinc(a_full(warp));
+        for (int rw = 0; rw < NRW; ++rw) {
+          const int r = ahalf * NRW + rw;
+          gather(r, idx + rw * NI, s_run[cur.mb * 4 + r]);
+        }
+        cp_async_mbar_arrive_noinc(a_full(aslot));
         a_phase ^= 1u;
         cur = nxt;
 #pragma unroll
-        for (int i = 0; i < NR * NI; ++i) idx[i] = idx_n[i];
+        for (int i = 0; i < NRW * NI; ++i) idx[i] = idx_n[i];
       }
-    } else if (warp == p.a_stages) {
+    } else if (warp == kWgBWarp) {
       // ============================ B producer ============================
       // the dout rows of one row block (contiguous rows, all Cout channels): Cout / 32 tile loads (32 channels x
       // kRows rows, hardware swizzle = the MN-major UMMA layout) issued by one lane; rows past m_out are zero-filled
@@ -256,7 +278,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
         }
       }
       __syncwarp();
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kWgMmaWarp) {
       // ============================ MMA issuer ============================
       // the whole warp runs the loop in uniform control flow; the tcgen05 instructions carry an issue predicate that
       // is true in one elected lane (see conv_umma_kernel)
@@ -302,7 +324,7 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
         mma_commit_p(t_full, issue);
       }
       __syncwarp();
-    } else if (warp >= kNumProducerWarps && warp < kMmaWarp) {
+    } else if (warp >= kWgEpiWarp0 && warp < kWgMmaWarp) {
       // ============================ epilogue ============================
       const int ew = warp & 3;
       // which accumulators received at least one MMA (same rule as the step table: the offsets of the M block
@@ -338,14 +360,14 @@ conv_wgrad_umma_kernel(const UmmaWgradParams p, const __grid_constant__ CUtensor
       tc_fence_before();
       mbar_arrive(t_empty);
     }
-    if (warp >= kNumProducerWarps && warp < kMmaWarp) t_phase ^= 1u;
+    if (warp >= kWgEpiWarp0 && warp < kWgMmaWarp) t_phase ^= 1u;
     // the A / B slot parities of a role that did nothing this item stay as they are; the MMA thread's per-slot
     // bits advanced exactly as the producers' own counters did (every filled slot was consumed)
   }
   cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kWgMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -366,7 +388,7 @@ static int launch_wgrad_umma(const UmmaWgradParams& p, const CUtensorMap& tmap, 
     SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = (int)smem;
   }
-  kern<<<grid, kNumThreads, smem, stream>>>(p, tmap);
+  kern<<<grid, kWgThreads, smem, stream>>>(p, tmap);
   SPC_LAUNCHED("conv_wgrad_umma_kernel");
   return 0;
 }
@@ -438,6 +460,12 @@ int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const
   int a_stages = (kSmemLimit - 1024 - 256 - kWgTabBytes - kWgBStages * b_stage_bytes) / kWgAStage;
   if (a_stages > kWgMaxAStages) a_stages = kWgMaxAStages;  // one producer warp per A stage + the B warp <= 8 warps
   SPC_REQUIRE(a_stages >= 2, "wgrad tile does not fit in shared memory");
+  // row-visit mode: bf16 rows are 64 B per chunk, so visits of 2 / 4 chunks touch fewer 128-byte lines; tf32 chunks are
+  // whole lines already.  Two producer warps share a slot when a step has >= 2 visits: 10 A warps = 5 slots then
+  int rm = 1;
+  if (bf16 && g_umma_dbg[5] != 1) rm = (p.ncc % 4 == 0) ? 4 : (p.ncc % 2 == 0 ? 2 : 1);
+  const int wpa = (4 / rm >= 2) ? 2 : 1;
+  if (a_stages > kWgAWarps / wpa) a_stages = kWgAWarps / wpa;
   p.a_stages = a_stages;
   const size_t smem = (size_t)a_stages * kWgAStage + (size_t)kWgBStages * b_stage_bytes + 1024 + 256 + kWgTabBytes;
   const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
@@ -445,10 +473,6 @@ int conv_wgrad_umma_cols(const void* in, const void* dout, const int* nbr, const
   memset(&tmap, 0, sizeof(tmap));
   SPC_REQUIRE(make_rows_tile_map(&tmap, dout, m_out, c_out_full, rows, bf16), "cuTensorMapEncodeTiled unavailable");
   g_conv_path_counts[bf16 ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
-  // row-visit mode: bf16 rows are 64 B per chunk, so visits of 2 / 3 / 4 chunks touch fewer 128-byte lines;
-  // tf32 chunks are whole lines already
-  int rm = 1;
-  if (bf16 && g_umma_dbg[5] != 1) rm = (p.ncc % 4 == 0) ? 4 : (p.ncc % 2 == 0 ? 2 : 1);
   if (!bf16) return launch_wgrad_umma<false, 1>(p, tmap, grid, smem, stream);
   switch (rm) {
     case 4: return launch_wgrad_umma<true, 4>(p, tmap, grid, smem, stream);
