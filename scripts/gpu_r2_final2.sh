@@ -2,7 +2,7 @@
 # Round-2 final evidence pass, second edition (CTA-pair forward kernel, 2-kernel coordinate insert; one GPU): tests, bench lines (default / variants / CPU arm), ResNet14 configs, map and
 # layer sweeps, ncu --set full captures of the dominant kernels, launch list of two bench steps.
 mkdir -p gpurun_out
-P=gpurun_out/r2g
+P=gpurun_out/r2h
 timeout 1500 python -m pytest tests -m gpu -q -s --timeout 600 > ${P}_tests.log 2>&1
 timeout 600 python bench.py --steps 10 --warmup 3 > ${P}_bench.log 2> ${P}_bench.err
 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-alt-precision --detail > ${P}_bench_detail.log 2> ${P}_bench_per_layer.txt
