@@ -155,7 +155,12 @@ void spc_debug_force_mt(int mt);
 void spc_debug_set(int idx, int val); /* test / measurement hook, every knob 0 = default: 0 forward: number of producer
                                         * groups (1, 2, 4, 8); 2 forward: 1 = st.global epilogue instead of TMA stores;
                                         * 3 forward: epilogue writes nothing (timing only, wrong results); 4 forward: 1 =
-                                        * one 32-channel chunk per stage; 5 wgrad: 1 = one row visit per chunk */
+                                        * one 32-channel chunk per stage; 5 wgrad: 1 = one row visit per chunk;
+                                        * 6 forward: producer warps (8 / 16); 7 forward: 1 = no shared ring slots;
+                                        * 8 forward / dgrad: 1 = never the CTA-pair kernel (cta_group::2), 2 = on every
+                                        * eligible shape whatever the map size; 9 wgrad: 2 = the CTA-pair wgrad kernel;
+                                        * 10 pair kernel: ring slots; 11 pair kernel: 1 = one staging block.  Results do
+                                        * not depend on knobs 0, 2, 4-11. */
 /* launches per convolution route since the last reset: out3[0] tcgen05 bf16, [1] tcgen05 tf32, [2] CUDA-core fp32
  * (out3 may be NULL); 1 if spc_conv_fwd (what = 0) / dgrad (1) / wgrad (2) runs the shape on the tensor cores */
 void spc_conv_path_counts(long long* out3, int reset);
