@@ -355,11 +355,11 @@ conv_umma_pair_kernel(const UmmaConvParams p, const __grid_constant__ CUtensorMa
 
 bool make_out_tile_map(CUtensorMap* map, float* base, int64_t rows, int C);
 extern std::atomic<long long> g_conv_path_counts[4];
-std::atomic<long long> g_conv_pair_launches{0};
 
-// Eligible: bf16 rows, one n tile of <= 256 channels whose halves keep the swizzle phase (multiples of 16 rows... of
-// 8), 32-column store blocks, a map large enough that every pair gets work, no bias (the shapes that reach here are
-// convolutions in front of a BatchNorm), packed weights.
+// Eligible: bf16 rows and packed weights; one n tile of <= 256 output channels that is a multiple of 32 (32-column
+// store blocks; each CTA's half of a slab is then a multiple of 16 rows, which keeps the 64-byte swizzle phase and is
+// a legal N / 2 of a cta_group::2 instruction); no bias (what reaches this path are convolutions in front of a
+// BatchNorm); a map large enough that every pair gets at least two work items.
 bool conv_umma_pair_eligible(int64_t m_out, int c_in, int c_out, int K, bool bf16, const float* bias, const void* packed,
                              const float* out) {
   constexpr bool kPairByDefault = true;    // (knob 8: 1 = never, 2 = on every eligible shape whatever the map size)
@@ -431,7 +431,6 @@ int conv_fwd_umma_pair(const void* in, const void* packed, const int* nbr, const
   const size_t smem = (size_t)stages * stage_bytes + (size_t)p.out_bufs * 16384 + 1024 + kPairBarBytes + stats_smem;
   int grid = 2 * std::min(p.n_work, kNumSMs / 2);
   g_conv_path_counts[0].fetch_add(1, std::memory_order_relaxed);
-  g_conv_pair_launches.fetch_add(1, std::memory_order_relaxed);
   return npw == 8 ? launch_pair<8>(p, tmap_out, grid, smem, stream) : launch_pair<16>(p, tmap_out, grid, smem, stream);
 }
 
