@@ -459,6 +459,50 @@ def test_full_size_round_trips(cuda_device):
     assert m2b.size == m2.size and bool((parent_b == torch.arange(m2.size, device=cuda_device)).all())
 
 
+def test_tables_beyond_the_l2_use_pair_buckets_and_stay_exact(cuda_device):
+    """More than 2^21 points -> a table of >= 2^22 buckets, where `hash_key` leaves the lowest bit of z out (z pairs
+    share a home bucket, csrc/common.cuh).  3 M points with duplicates (two rooms on top of each other): unique /
+    inverse / first / count against an on-device restatement built on torch.unique of the packed keys, the self map by
+    its properties, and every voxel found again through the general (non-symmetric) probe kernel."""
+    c, _, _ = synth.room_batch(5, 1, 2_000_000, channels=1)
+    c2, _, _ = synth.room_batch(6, 1, 1_000_000, channels=1)
+    pts = torch.cat([gpu(c, cuda_device), gpu(c2, cuda_device)])
+    n = pts.shape[0]
+    assert L.load().spc_table_slots(n) // 2 >= 1 << 22
+    cmap, first, inverse, count = ops.coords_insert(pts, L.SRC_FLOAT, (1, 1, 1))
+    q = torch.floor(pts).long()
+    key = ((q[:, 0] << 54) | ((q[:, 1] + 131072) << 36) | ((q[:, 2] + 131072) << 18) | (q[:, 3] + 131072))
+    uk, inv_sorted, cnt_sorted = torch.unique(key, return_inverse=True, return_counts=True)   # (sorted by key)
+    m = uk.numel()
+    assert cmap.size == m and m < n                                   # the two rooms share voxels
+    # first occurrence of every key, then ranks in first-occurrence order = the row order of the map
+    idx = torch.arange(n, device=cuda_device)
+    first_sorted = torch.full((m,), n, device=cuda_device, dtype=torch.long).scatter_reduce_(0, inv_sorted, idx, "amin")
+    order = torch.argsort(first_sorted)                               # sorted-key id of row r
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(m, device=cuda_device)
+    assert bool((first.long() == first_sorted[order]).all())
+    assert bool((inverse.long() == rank[inv_sorted]).all())
+    assert bool((count.long() == cnt_sorted[order]).all())
+    assert bool((cmap.coords.long() == q[first.long()]).all())
+    km = ops.build_kernel_map(cmap, cmap, ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1)))
+    ar = torch.arange(m, device=cuda_device, dtype=torch.int32)
+    assert bool((km.nbr[13] == ar).all())
+    assert bool((km.nbr_t == km.nbr.flip(0)).all())
+    offs = ops.kernel_offsets((3, 3, 3), (1, 1, 1), (1, 1, 1))
+    for k in (1, 12, 22):
+        o = torch.nonzero(km.nbr[k] >= 0).view(-1)
+        d = cmap.coords[km.nbr[k][o].long()] - cmap.coords[o]
+        assert bool((d == torch.tensor([0, *offs[k]], device=cuda_device, dtype=torch.int32)).all())
+        # ... and no pair is missing: the neighbour exists iff its key is in the set
+        want = torch.isin(key[first.long()] + ((offs[k][0] << 36) + (offs[k][1] << 18) + offs[k][2]), uk)
+        inside = ((cmap.coords[:, 1:].long() + torch.tensor(offs[k], device=cuda_device)).abs() < 131072).all(1)
+        assert bool(((km.nbr[k] >= 0) == (want & inside)).all())
+    # the general probe kernel (what stride-2 / transposed maps use) on the same table: every voxel finds itself
+    probe = ops.build_kernel_map(cmap, ops.CoordMap(cmap.coords, None, 0, m, (1, 1, 1)), [(0, 0, 0)])
+    assert bool((probe.nbr[0] == ar).all())
+
+
 @pytest.mark.parametrize("n,C", [(1, 20), (777, 20), (50_000, 20), (4096, 51), (100, 3)])
 def test_cross_entropy_matches_torch(cuda_device, n, C):
     """fused CE (mean over non-ignored rows) vs torch's fp64 cross_entropy; |d| <= 1e-5 * (1 + |ref|)."""
