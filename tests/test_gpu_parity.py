@@ -742,3 +742,37 @@ def test_cta_pair_conv_kernel_equals_the_single_cta_kernel(cuda_device, voxels, 
         assert ((b[2] - want).abs() <= 1e-5 * want.abs() + 1e-6 * want.abs().max()).all(), "epilogue statistics vs the rows"
     # wgrad (conv_wgrad_umma_pair.cu): fp32 partial sums meet in dW through red.add in a free order
     assert (a[5] - b[5]).abs().max() <= 1e-4 * a[5].abs().max(), "wgrad"
+
+
+def test_cta_pair_kernel_on_stride_2_and_transposed_maps(cuda_device):
+    """The pair kernel on maps that are not self maps: 2^3 stride-2 convolution (fine -> coarse), its dgrad (coarse ->
+    fine: one contribution per fine row) and the transposed convolution on the swapped map (coarse -> fine), K = 8."""
+    lib = L.load()
+    c, _, _ = synth.room_batch(23, 1, 320_000, channels=1)
+    fine, _, _, _ = ops.coords_insert(gpu(c, cuda_device), L.SRC_FLOAT, (1, 1, 1))
+    coarse, _, _, _ = ops.coords_insert(fine.coords, L.SRC_STRIDE, (2, 2, 2))
+    km = ops.build_kernel_map(fine, coarse, ops.kernel_offsets((2, 2, 2), (1, 1, 1), (1, 1, 1)))
+    up = km.swapped()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    cin, cout = 64, 96
+    xb = ops.to_bf16(torch.randn(fine.size, cin, generator=g).to(cuda_device))
+    gb = ops.to_bf16(torch.randn(coarse.size, cout, generator=g).to(cuda_device))
+    xc = ops.to_bf16(torch.randn(coarse.size, cin, generator=g).to(cuda_device))
+    w = (torch.randn(8, cin, cout, generator=g) / (8 * cin) ** 0.5).to(cuda_device)
+
+    def run(knob):
+        lib.spc_debug_set(8, knob)
+        try:
+            down = ops.conv_fwd_raw(xb, w, None, km, L.PREC_BF16)          # [coarse, cout]
+            din = ops.conv_dgrad_raw(gb, w, km, L.PREC_BF16)               # [fine, cin]
+            upo = ops.conv_fwd_raw(xc, w, None, up, L.PREC_BF16)           # [fine, cout]
+            torch.cuda.synchronize()
+        finally:
+            lib.spc_debug_set(8, 0)
+        return down, din, upo
+
+    a, b = run(1), run(2)
+    assert a[0].shape == (coarse.size, cout) and a[1].shape == (fine.size, cin) and a[2].shape == (fine.size, cout)
+    for i, what in enumerate(("stride-2 forward", "stride-2 dgrad", "transposed forward")):
+        assert (a[i] - b[i]).abs().max() <= 1e-5 * a[i].abs().max(), what
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])     # fine-side outputs: large maps, one owner per row
