@@ -411,6 +411,19 @@ int spc_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
                  float momentum, float weight_decay, float grad_scale, int first_step,
                  void* stream);
 
+/*
+ * Engine-side row order (no ME counterpart: MinkowskiEngine's GPU maps leave the row order unspecified).  A tensor-core
+ * convolution executes an offset for a whole 128-row tile if ANY row of the tile has a neighbour there; on thin
+ * geometry (the faithful ScanNet-plenoxel lattices: 5-8 neighbours per voxel, but 24-27 offsets per raster-ordered
+ * tile) grouping rows with equal neighbourhoods inside windows lets the tile masks skip most of that.
+ *   spc_row_masks     row_mask[o] = bit set of offsets k with nbr[k, o] >= 0 (K <= 32); *executed_dev (DEVICE int64) =
+ *                     number of (tile, offset) pairs executed on the CURRENT row order
+ *   spc_table_relabel every occupied slot's map row r becomes pos[r] (pos: DEVICE int32 [M], a permutation): after the
+ *                     caller has permuted the coordinate rows, look-ups and kernel maps come out in the new order
+ */
+int spc_row_masks(const int32_t* nbr, int64_t m, int K, uint32_t* row_mask, int64_t* executed_dev, void* stream);
+int spc_table_relabel(void* slots, int64_t n_slots, const int32_t* pos, void* stream);
+
 /* Number of kernels launched through this library since load (bench `gpu_launches`). */
 int64_t spc_launch_count(void);
 

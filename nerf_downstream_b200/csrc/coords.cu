@@ -376,6 +376,31 @@ tile_mask_kernel(const int* __restrict__ nbr, int m, int K, unsigned* __restrict
   if (threadIdx.x == 0) mask[blockIdx.x] = mm;
 }
 
+// per-ROW bitmask of offsets with a neighbour (bit k; K <= 32) + the number of (128-row tile, offset) pairs a
+// tensor-core kernel would execute on this row order (sum over tiles of popcount(OR of the tile's row masks)):
+// what the engine-side row re-ordering (ops.reorder_rows_by_mask) sorts by and decides on
+__global__ void __launch_bounds__(128)
+row_masks_kernel(const int* __restrict__ nbr, int m, int K, unsigned* __restrict__ row_mask,
+                 unsigned long long* __restrict__ executed) {
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  unsigned mine = 0, tile = 0;
+  for (int k = 0; k < K; ++k) {
+    const int v = (o < m) && nbr[(size_t)k * m + o] >= 0;
+    if (v) mine |= 1u << k;
+    if (__syncthreads_or(v)) tile |= 1u << k;
+  }
+  if (o < m) row_mask[o] = mine;
+  if (threadIdx.x == 0 && tile) atomicAdd(executed, (unsigned long long)__popc(tile));
+}
+
+// rows of a coordinate map re-numbered: row r becomes pos[r] in every occupied slot of its hash table
+__global__ void __launch_bounds__(256)
+table_relabel_kernel(Slot* slots, long long n_slots, const int* __restrict__ pos) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  if (slots[i].key != kEmptyKey) slots[i].row = (unsigned)pos[slots[i].row];
+}
+
 // pair-list export: count / scan / write, stable in out row
 __global__ void __launch_bounds__(kScanThreads)
 pairs_count_kernel(const int* __restrict__ nbr, int m_out, int nblk, int* __restrict__ block_count) {
@@ -616,6 +641,26 @@ int spc_tile_mask(const int32_t* nbr, int64_t m, int K, uint32_t* mask, void* st
   if (m == 0) return 0;
   tile_mask_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, stream>>>(nbr, (int)m, K, mask);
   SPC_LAUNCHED("tile_mask_kernel");
+  return 0;
+}
+
+int spc_row_masks(const int32_t* nbr, int64_t m, int K, uint32_t* row_mask, int64_t* executed_dev, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(K >= 1 && K <= 32, "row masks support kernel volume <= 32");
+  SPC_REQUIRE(m >= 0 && m < (1ll << 31) - 1024, "m out of range");
+  SPC_CUDA(cudaMemsetAsync(executed_dev, 0, sizeof(int64_t), stream));
+  if (m == 0) return 0;
+  row_masks_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, stream>>>(nbr, (int)m, K, row_mask,
+                                                                   (unsigned long long*)executed_dev);
+  SPC_LAUNCHED("row_masks_kernel");
+  return 0;
+}
+
+int spc_table_relabel(void* slots, int64_t n_slots, const int32_t* pos, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_REQUIRE(n_slots >= 64 && (n_slots & (n_slots - 1)) == 0, "bad table size");
+  table_relabel_kernel<<<(unsigned)ceil_div(n_slots, 256), 256, 0, stream>>>((Slot*)slots, (long long)n_slots, pos);
+  SPC_LAUNCHED("table_relabel_kernel");
   return 0;
 }
 

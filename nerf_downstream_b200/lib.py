@@ -40,6 +40,8 @@ SIGNATURES = {
     "spc_segment_reduce": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P]),
     "spc_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "spc_scatter_add_rows": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
+    "spc_row_masks": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    "spc_table_relabel": (c_int, [_P, c_int64, _P, _P]),
     "spc_debug_force_mt": (None, [c_int]),
     "spc_debug_set": (None, [c_int, c_int]),
     "spc_conv_path_counts": (None, [_P, c_int]),

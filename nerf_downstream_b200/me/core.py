@@ -204,6 +204,7 @@ class CoordinateManager:
         self._identity_maps: Dict[CoordinateMapKey, ops.KernelMap] = {}
         self._interp_maps: Dict[tuple, tuple] = {}             # (field key, map key) -> (rows [8,N], weights [8,N])
         self._field_batch: Dict[CoordinateMapKey, torch.Tensor] = {}
+        self._row_perm: Dict[CoordinateMapKey, torch.Tensor] = {}   # maps whose rows were re-ordered: new row -> creation row
         self._n_batch: Optional[int] = None
         self._field_counter = 0
         self.prefetch_depth = CoordinateManager.default_prefetch_depth
@@ -216,6 +217,30 @@ class CoordinateManager:
             n += 1
             key = CoordinateMapKey(ts, f"{string_id}-{n}" if string_id else f"{n}")
         return key
+
+    def _maybe_reorder(self, key, cmap, first, inverse, count, parent_perm=None, parent_pos=None):
+        """Engine-side row order (ops.reorder_rows_by_mask): called once, right after a map has been created and before
+        anything refers to its rows.  `first` / `inverse` / `count` are the map's creation aux arrays; for a strided
+        map they refer to the PARENT's rows, which may themselves just have been re-numbered (`parent_perm`,
+        `parent_pos`).  The 3^3 stride-1 self map the decision needs is the one every convolution of the level uses:
+        it is cached under its ME key, in the order the map ends up with.  Returns (first, inverse, count, perm, pos)."""
+        if parent_perm is not None:
+            inverse = inverse[parent_perm]                # indexed by parent rows: follow their new numbering
+            first = parent_pos[first.long()]              # values are parent rows
+        if not ops.sort_rows or cmap.size < ops.sort_min_rows:
+            return first, inverse, count, None, None
+        kg = KernelGenerator(kernel_size=3, stride=1, dilation=1, dimension=self.D)
+        offs = ops.kernel_offsets(kg.kernel_size, cmap.tensor_stride, kg.kernel_dilation)
+        km = ops.build_kernel_map(cmap, cmap, offs)
+        res = ops.reorder_rows_by_mask(cmap, km)
+        if res is not None:
+            perm, pos = res
+            first, count = first[perm], count[perm]
+            safe = inverse.clamp_min(0).long()
+            inverse = torch.where(inverse >= 0, pos[safe], inverse)   # (-1: a point outside the supported range)
+            km = ops.build_kernel_map(cmap, cmap, offs)               # the same map in the new order
+        self._kernel_maps[(key, key, kg.cache_key(), False, False)] = km
+        return (first, inverse, count) + (res if res is not None else (None, None))
 
     def insert_and_map(self, coordinates: torch.Tensor, tensor_stride=1, string_id: str = ""):
         """int32 coordinates -> new map.  Returns (key, (unique_index, inverse_mapping)) (int64)."""
@@ -246,6 +271,9 @@ class CoordinateManager:
         cmap, first, inverse, count = ops.coords_insert(field.coords, L.SRC_FLOAT, ts)
         key = self._unique_key(ts, sparse_string_id, self._maps)
         self._maps[key] = cmap
+        first, inverse, count, perm, _ = self._maybe_reorder(key, cmap, first, inverse, count)
+        if perm is not None:
+            self._row_perm[key] = perm
         self._insert_aux[key] = (first, inverse, count)
         self._field_to_sparse[(field_key, key)] = inverse
         return key, (first, inverse, count)
@@ -342,10 +370,14 @@ class CoordinateManager:
         else:
             built = ops.coords_insert_pyramid(in_map, chain)
         parent = in_key
+        p_perm = p_pos = None     # (the levels were built from each other's creation order: re-number as we go down)
         for ts_l, (cmap, first, inverse, count) in zip(chain, built):
             key = CoordinateMapKey(ts_l, string_id)
             cmap.tensor_stride = tuple(ts_l)
             self._maps[key] = cmap
+            first, inverse, count, p_perm, p_pos = self._maybe_reorder(key, cmap, first, inverse, count, p_perm, p_pos)
+            if p_perm is not None:
+                self._row_perm[key] = p_perm
             self._insert_aux[key] = (first, inverse, count)
             self._stride_parent[key] = (parent, inverse, count)
             parent = key
@@ -799,7 +831,11 @@ class TensorField(Tensor):
         self._inverse_mapping[key] = inverse
         m = mgr.size(key)
         feats = self._F if self._F.dtype == torch.float32 else self._F.float()
-        if m == feats.shape[0] and inverse.shape[0] == m:
+        perm = mgr._row_perm.get(key)
+        if m == feats.shape[0] and inverse.shape[0] == m and perm is not None:
+            # one point per voxel, rows re-ordered by the engine (ops.reorder_rows_by_mask): row j is point perm[j]
+            F = ops.GatherRowsFn.apply(feats.contiguous(), perm.int() if perm.dtype != torch.int32 else perm)
+        elif m == feats.shape[0] and inverse.shape[0] == m:
             # No two points share a voxel (what the reference's plenoxel loaders deliver: one record per occupied
             # cell).  Rows are in first-occurrence order, so the map's row r is point r, the inverse map is the
             # identity and every reduction of one value is that value: no pass over the features, here or in slice().

@@ -358,6 +358,51 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
 
 
 # ---------------------------------------------------------------------------
+# engine-side row order
+# ---------------------------------------------------------------------------
+# The tensor-core kernels execute a kernel offset for a whole 128-row tile when ANY row of the tile has a neighbour there.
+# On the dense synthetic rooms that wastes ~1.45x; on the geometry the reference's ScanNet-plenoxel loader really produces
+# (samples 2.3 voxels apart, 5-8 neighbours per voxel at stride 2) a raster-ordered tile touches
+# 24-27 offsets for rows that have 5-8 each.  MinkowskiEngine's GPU backend does not define the row order of a map, so
+# the engine may choose one: rows with equal neighbour masks are grouped inside windows of `sort_window` rows (windows keep
+# the gathers' L2 locality; a global sort loses it — profiles/r2_row_order_experiments.md) when that cuts the executed
+# (tile, offset) volume enough to pay for the second map build.  `.C`, `.F`, `unique_index`, `inverse_mapping` and the
+# kernel maps of such a map are all in the new order (consistent with each other); results at the points of a
+# TensorField (`slice`) do not depend on it.
+sort_rows = True             # False: maps keep first-occurrence order everywhere
+sort_min_rows = 1 << 18      # smaller maps are not worth a second kernel-map build
+sort_window = 1 << 16
+sort_min_ratio = 2.0         # executed / useful (tile, offset) volume on the first-occurrence order above which rows are re-ordered
+sort_stats = {"considered": 0, "reordered": 0}
+
+
+def reorder_rows_by_mask(cmap: CoordMap, km: KernelMap):
+    """Decide from the self map `km` (first-occurrence order) whether grouping rows by neighbour mask pays, and if so
+    permute the map in place: coordinates, hash-table rows.  Returns (perm, pos) — new row j' is old row perm[j'], old
+    row r is new row pos[r] (int64 / int32 device tensors) — or None when the order is kept.  One host synchronisation."""
+    lib = L.load()
+    m, K = cmap.size, km.K
+    dev = cmap.coords.device
+    sort_stats["considered"] += 1
+    rmask = _empty(m, torch.int32, dev)
+    stat = _empty(1, torch.int64, dev)
+    L.check(lib.spc_row_masks(L.ptr(km.nbr), m, K, L.ptr(rmask), L.ptr(stat), L.stream()), "spc_row_masks")
+    executed = int(stat.item()) * 128          # (host sync)
+    useful = max(km.n_pairs, 1)
+    if executed < sort_min_ratio * useful:
+        return None
+    window = torch.arange(m, device=dev, dtype=torch.int64) // int(sort_window)
+    key = (window << 32) | (rmask.to(torch.int64) & 0xFFFFFFFF)
+    perm = torch.sort(key, stable=True)[1]
+    pos = torch.empty(m, dtype=torch.int32, device=dev)
+    pos[perm] = torch.arange(m, device=dev, dtype=torch.int32)
+    cmap.coords = cmap.coords[perm].contiguous()
+    L.check(lib.spc_table_relabel(L.ptr(cmap.table), cmap.n_slots, L.ptr(pos), L.stream()), "spc_table_relabel")
+    sort_stats["reordered"] += 1
+    return perm, pos
+
+
+# ---------------------------------------------------------------------------
 # feature-row ops
 # ---------------------------------------------------------------------------
 def _rows_view(x: torch.Tensor):

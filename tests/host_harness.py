@@ -183,6 +183,28 @@ class FakeLib:
         view(nbr_t, (K, m_in), np.int32)[:] = R.transpose_dense(view(nbr, (K, m_out), np.int32), m_in)
         return 0
 
+    def spc_row_masks(self, nbr, m, K, row_mask, executed_dev, stream):
+        self._called("spc_row_masks")
+        nb = view(nbr, (K, m), np.int32)
+        bits = np.zeros(m, np.uint32)
+        for k in range(K):
+            bits |= (nb[k] >= 0).astype(np.uint32) << np.uint32(k)
+        view(row_mask, m, np.uint32)[:] = bits
+        pad = np.concatenate([bits, np.zeros((-m) % 128, np.uint32)]).reshape(-1, 128)
+        tile = np.bitwise_or.reduce(pad, axis=1)
+        view(executed_dev, 1, np.int64)[0] = int(sum(bin(int(t)).count("1") for t in tile))
+        return 0
+
+    def spc_table_relabel(self, slots, n_slots, pos, stream):
+        """the fake table IS the coordinate array in row order: old row r moves to pos[r]"""
+        self._called("spc_table_relabel")
+        coords = self.tables[_addr(slots)]
+        p = view(pos, coords.shape[0], np.int32)
+        new = np.empty_like(coords)
+        new[p] = coords
+        self.tables[_addr(slots)] = new
+        return 0
+
     def spc_tile_mask(self, nbr, m, K, mask, stream):
         self._called("spc_tile_mask")
         n_tiles = (m + 127) // 128

@@ -597,3 +597,48 @@ def test_row_selections_of_a_plenoxel_record_follow_the_reference_transforms(mon
     state = np.random.get_state()[1].copy()
     assert pipeline.plenoxel_select_rows(links, reso, [("RandomCrop", dict(x=500, y=500, z=500))], aff) is None
     assert (np.random.get_state()[1] == state).all()
+
+
+def test_engine_side_row_order_leaves_results_at_the_points_unchanged(monkeypatch):
+    """ops.reorder_rows_by_mask on the host layer (harness): a sparse cloud (few neighbours per voxel, every raster tile
+    touching most offsets) is re-ordered, strided levels follow their parents' new numbering, and the network's output
+    at the points of the TensorField, the loss and the parameter gradients equal those of the first-occurrence order."""
+    def run(sort):
+        fake = host_harness.install(monkeypatch, "fp32", prefetch_depth=4)
+        monkeypatch.setattr(ops, "sort_rows", sort)
+        monkeypatch.setattr(ops, "sort_min_rows", 512)
+        monkeypatch.setattr(ops, "sort_window", 1024)
+        monkeypatch.setattr(ops, "sort_min_ratio", 1.2)
+        monkeypatch.setattr(ops, "sort_stats", {"considered": 0, "reordered": 0})
+        torch.manual_seed(11)
+        coords, feats = synth.random_cloud(7, 6000, extent=30, n_batch=2, channels=27)
+        labels = torch.from_numpy(np.random.default_rng(3).integers(0, 20, size=coords.shape[0]))
+        model = models.Res16UNet14A(27, 20).train()
+        field = _field(coords, feats)
+        out = model(field)
+        loss = ops.cross_entropy(out, labels)
+        loss.backward()
+        mgr = field.coordinate_manager
+        return (out.detach().clone(), float(loss), {n: p.grad.clone() for n, p in model.named_parameters()},
+                dict(ops.sort_stats), mgr, fake)
+
+    out_a, loss_a, g_a, stats_a, mgr_a, _ = run(False)
+    out_b, loss_b, g_b, stats_b, mgr_b, fake_b = run(True)
+    assert stats_a["reordered"] == 0 and stats_b["reordered"] >= 1, (stats_a, stats_b)
+    assert fake_b.calls.count("spc_table_relabel") == stats_b["reordered"]
+    assert torch.allclose(out_a, out_b, rtol=1e-4, atol=1e-5)
+    assert abs(loss_a - loss_b) <= 1e-5 * abs(loss_a)
+    for name in g_a:
+        assert _cos(g_a[name], g_b[name]) >= 0.9999, name
+    # the re-ordered map holds the same voxels, and a stride-2 level built from it is consistent with it
+    k1 = mgr_b.get_unique_coordinate_map_key(1)
+    ca, cb = mgr_a.get_coordinates(mgr_a.get_unique_coordinate_map_key(1)), mgr_b.get_coordinates(k1)
+    assert not torch.equal(ca, cb)
+    assert sorted(map(tuple, ca.tolist())) == sorted(map(tuple, cb.tolist()))
+    k2 = mgr_b.get_unique_coordinate_map_key(2)
+    first2, inv2, cnt2 = mgr_b._insert_aux[k2]
+    c2 = mgr_b.get_coordinates(k2)
+    want = cb.clone()
+    want[:, 1:] = torch.div(want[:, 1:], 2, rounding_mode="floor") * 2
+    assert torch.equal(c2[inv2.long()], want)                      # parent row -> child row, in both new numberings
+    assert torch.equal(want[first2.long()], c2) and int(cnt2.sum()) == cb.shape[0]
