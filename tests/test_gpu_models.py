@@ -127,3 +127,60 @@ def test_manager_semantics(cuda_device):
     assert mgr.size(x.coordinate_map_key) == x.F.shape[0]
     k2 = mgr.stride(x.coordinate_map_key, [2, 2, 2])
     assert k2 == a.coordinate_map_key
+
+
+@pytest.mark.gpu
+def test_engine_side_row_order_on_the_faithful_geometry(cuda_device):
+    """ops.reorder_rows_by_mask on the real library: a faithful ScanNet-plenoxel scene (few
+    neighbours per voxel, raster tiles touching most offsets) is re-ordered at the levels where it pays; logits at the
+    points, loss and parameter gradients equal those of the first-occurrence order (fp32 CUDA-core path: only the
+    order of sums differs), the re-ordered maps hold the same voxels, and the executed (tile, offset) volume drops."""
+    from nerf_downstream_b200 import lib as L
+    c, f, y = synth.faithful_room_batch(5, 1, 150_000, scene_scale=0.56)
+    c_d, f_d, y_d = (torch.from_numpy(a).to(cuda_device) for a in (c, f, y))
+    saved = (ops.sort_rows, ops.sort_min_rows, ops.sort_window, dict(ops.sort_stats))
+
+    def run(sort):
+        ops.sort_rows, ops.sort_min_rows, ops.sort_window = sort, 20_000, 16_384
+        ops.sort_stats.update(considered=0, reordered=0)
+        ops.set_default_precision("fp32")
+        torch.manual_seed(8)
+        net = models.Res16UNet14A(27, 20).to(cuda_device).train()
+        field = ME.TensorField(coordinates=c_d, features=f_d)
+        out = net(field)
+        loss = ops.cross_entropy(out, y_d, 255)
+        loss.backward()
+        torch.cuda.synchronize()
+        mgr = field.coordinate_manager
+        vol = {}
+        for ts in (1, 2):
+            key = mgr.get_unique_coordinate_map_key(ts)
+            km = mgr.get_kernel_map(key, key, ME.KernelGenerator(kernel_size=3, stride=1, dilation=1, dimension=3))
+            vol[ts] = (int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in km.mask.tolist())) * 128, km.n_pairs,
+                       mgr.get_coordinates(key).clone())
+        return out.detach().clone(), float(loss), torch.cat([p.grad.flatten() for p in net.parameters()]), vol, dict(ops.sort_stats)
+
+    try:
+        out_a, loss_a, g_a, vol_a, st_a = run(False)
+        out_b, loss_b, g_b, vol_b, st_b = run(True)
+    finally:
+        ops.sort_rows, ops.sort_min_rows, ops.sort_window = saved[:3]
+        ops.sort_stats.update(saved[3])
+        ops.set_default_precision("tf32")
+    assert st_a["reordered"] == 0 and st_b["reordered"] >= 1, (st_a, st_b)
+    assert (out_a - out_b).abs().max() <= 1e-4 * out_a.abs().max()
+    assert abs(loss_a - loss_b) <= 1e-5 * abs(loss_a)
+    a, b = g_a.double(), g_b.double()
+    assert float(a @ b / (a.norm() * b.norm())) >= 0.99999
+    improved = 0
+    for ts in (1, 2):
+        ex_a, p_a, ca = vol_a[ts]
+        ex_b, p_b, cb = vol_b[ts]
+        assert p_a == p_b and ca.shape == cb.shape
+        ka = (ca[:, 0].long() << 54) | ((ca[:, 1].long() + 131072) << 36) | ((ca[:, 2].long() + 131072) << 18) | (ca[:, 3].long() + 131072)
+        kb = (cb[:, 0].long() << 54) | ((cb[:, 1].long() + 131072) << 36) | ((cb[:, 2].long() + 131072) << 18) | (cb[:, 3].long() + 131072)
+        assert torch.equal(torch.sort(ka)[0], torch.sort(kb)[0])          # the same voxels
+        assert ex_b <= ex_a
+        improved += ex_b < 0.8 * ex_a
+        print(f"ts{ts}: executed / useful {ex_a / p_a:.2f} -> {ex_b / p_b:.2f}")
+    assert improved >= 1
