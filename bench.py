@@ -222,6 +222,8 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = L.load()
+    if args.sort_rows:
+        ops.sort_rows = True
 
     torch.manual_seed(0)
     model = models.Res16UNet34C(27, 20).to(dev).train()
@@ -491,6 +493,7 @@ def run_ours(args):
                            "voxels_per_step_all_gpus": main_res["total_voxels"], "parallelism": f"dp{world}",
                            "l2_policy": "inputs_exceed_l2 (activations per step >> 126 MB)",
                            "voxel_order": "shuffled" if args.shuffle else "raster (as the reference loaders deliver)",
+                           "engine_row_order": ("on: " + str(ops.sort_stats)) if ops.sort_rows else "off (first occurrence, as ME's CPU maps)",
                            "precision": args.precision},
                 # which bar the operand precision of `value` meets (tensor-core modes within
                 # 3e-3 * max|ref| per layer) and the test that proves it; whole-network agreement at realistic scale
@@ -548,6 +551,9 @@ def main():
     ap.add_argument("--fused-head", action="store_true",
                     help="loss through the fused segmentation head (forward_sparse + spc_seg_head_fwd) instead of "
                          "slice -> cross-entropy; off by default until re-measured inside the step")
+    ap.add_argument("--sort-rows", action="store_true",
+                    help="engine-side row order (ops.sort_rows): rows of large thin maps grouped by neighbour mask; pays on "
+                         "--geometry faithful, never triggers on the dense default workload")
     ap.add_argument("--shuffle", action="store_true",
                     help="deliver voxels in random order instead of the loaders' raster order (adversarial locality)")
     args = ap.parse_args()

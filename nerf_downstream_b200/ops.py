@@ -370,7 +370,9 @@ def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
 # (tile, offset) volume enough to pay for the second map build.  `.C`, `.F`, `unique_index`, `inverse_mapping` and the
 # kernel maps of such a map are all in the new order (consistent with each other); results at the points of a
 # TensorField (`slice`) do not depend on it.
-sort_rows = os.environ.get("SPARSECONV_B200_SORT_ROWS", "1") != "0"   # False: maps keep first-occurrence order everywhere
+# OPT-IN: a re-ordered map's exported rows (`.C`, `.F`, kernel-map pair lists) are no longer in MinkowskiEngine's CPU
+# (first-occurrence) order, which is the order the bit-exact parity tests pin — so the default keeps that order everywhere.
+sort_rows = os.environ.get("SPARSECONV_B200_SORT_ROWS", "0") == "1"
 sort_min_rows = 1 << 18      # smaller maps are not worth a second kernel-map build
 sort_window = 1 << 16
 sort_min_ratio = 2.0         # executed / useful (tile, offset) volume on the first-occurrence order above which rows are re-ordered
