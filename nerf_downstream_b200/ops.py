@@ -331,17 +331,30 @@ symmetric_dgrad = True       # dgrad of a symmetric self map reads the forward m
 symmetric_maps = True   # build self maps of odd stride-1 kernels with spc_kernel_map_sym (tests switch it off to compare)
 
 
+_offset_cache: dict = {}   # offsets tuple -> (ctypes int32 [3K] array, centrally symmetric?)  (a few dozen entries per network)
+
+
+def _offsets_ctypes(offsets):
+    key = tuple(tuple(int(v) for v in off) for off in offsets)
+    hit = _offset_cache.get(key)
+    if hit is None:
+        K = len(key)
+        flat = (ctypes.c_int32 * (3 * K))(*[v for off in key for v in off])
+        central = K % 2 == 1 and all(tuple(-v for v in key[K - 1 - k]) == key[k] for k in range(K))
+        hit = _offset_cache[key] = (flat, central)
+    return hit
+
+
 def build_kernel_map(in_map: CoordMap, out_map: CoordMap, offsets) -> KernelMap:
     lib = L.load()
     K = len(offsets)
     dev = out_map.coords.device
-    flat = (ctypes.c_int32 * (3 * K))(*[int(v) for off in offsets for v in off])
+    flat, central = _offsets_ctypes(offsets)
     nbr = _empty((K, out_map.size), torch.int32, dev)
     tap_count = _empty(K, torch.int32, dev)
     e0 = _profiler.begin() if _profiler else None
     # self map with centrally symmetric offsets (odd kernels at stride 1): half the probes, mirrored writes
-    sym = (in_map is out_map and K % 2 == 1 and K <= 125 and symmetric_maps
-           and all(tuple(-v for v in offsets[K - 1 - k]) == tuple(offsets[k]) for k in range(K)))
+    sym = in_map is out_map and K <= 125 and symmetric_maps and central
     if sym:
         L.check(lib.spc_kernel_map_sym(L.ptr(in_map.table), in_map.n_slots, L.ptr(out_map.coords), out_map.size,
                                        ctypes.cast(flat, ctypes.c_void_p), K, L.ptr(nbr), L.ptr(tap_count),
